@@ -1,0 +1,188 @@
+/*
+ * smmd.h -- C ABI of libsmmd.so: the B200-native (sm_100a) replacement for the data-parallel hot path
+ * of playHing/Scaled-MMD-GAN: the pairwise-kernel MMD^2 loss (+ feature gradients) and the
+ * cubic-polynomial KID score.
+ *
+ * The reference has no FFI / plugin registry: its boundary is a set of Python call signatures
+ * (SURVEY.md section 8b).  Every entry point below names the reference interface it replaces
+ * (file:line relative to the reference repo root).  The Python drop-in with the reference's own
+ * names/kwargs lives in scaled-mmd-gan_b200/smmd/{mmd,compute_scores}.py and binds this header via
+ * ctypes.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller; the library never allocates or
+ *     frees user memory and only uses the caller-supplied workspace.  Matrices are row-major.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises
+ *     the host, and is re-entrant as long as workspaces are distinct.
+ *   - Returns 0 (SMMD_OK) or a negative smmd_status; never throws, never aborts.  Shape / dtype /
+ *     architecture problems are reported before anything is launched.
+ *   - There is no CPU fallback: on a device that is not sm_100 the calls return SMMD_EARCH.
+ */
+#ifndef SMMD_H_
+#define SMMD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SMMD_API __attribute__((visibility("default")))
+#else
+#define SMMD_API
+#endif
+
+#define SMMD_VERSION 100 /* 0.1.0 */
+#define SMMD_MAX_PARAMS 8
+#define SMMD_NUM_SCALARS 16
+
+typedef enum smmd_status {
+  SMMD_OK = 0,
+  SMMD_EINVAL = -1,       /* null pointer / bad enum / bad parameter value                      */
+  SMMD_ESHAPE = -2,       /* m, n, d, ld* or subset shape not acceptable                        */
+  SMMD_EDTYPE = -3,       /* dtype not supported by the selected precision path                 */
+  SMMD_EARCH = -4,        /* current device is not sm_100 (B200)                                */
+  SMMD_EWORKSPACE = -5,   /* workspace NULL, misaligned or smaller than *_workspace_bytes()     */
+  SMMD_ECUDA = -6,        /* a CUDA runtime/driver call failed (see smmd_last_cuda_error())     */
+  SMMD_EUNSUPPORTED = -7  /* combination not implemented on the requested precision path        */
+} smmd_status;
+
+typedef enum smmd_dtype { SMMD_F32 = 0, SMMD_BF16 = 1 } smmd_dtype;
+
+/* Kernel families = the `_<name>_kernel` zoo of gan/core/mmd.py:18-188 (selected by name string in
+ * gan/core/model.py:314 and gan/core/smmd.py:11).  The mix_rq_*dot wrappers (mmd.py:119-136) are
+ * SMMD_K_MIX_RQ with add_dot set; SMMD_K_RBF is SMMD_K_MIX_RBF with one sigma (mmd.py:55-82). */
+typedef enum smmd_kernel_id {
+  SMMD_K_DISTANCE = 0,      /* mmd.py:18-37   */
+  SMMD_K_TANH_DISTANCE = 1, /* mmd.py:40-41   */
+  SMMD_K_DOT = 2,           /* mmd.py:44-52   */
+  SMMD_K_RBF = 3,           /* mmd.py:55-82   params[0]=sigma, wts[0]=wt          */
+  SMMD_K_MIX_RBF = 4,       /* mmd.py:85-116  params=sigmas, wts                  */
+  SMMD_K_MIX_RQ = 5,        /* mmd.py:143-188 params=alphas, wts, add_dot         */
+  SMMD_K_TANH_MIX_RQ = 6,   /* mmd.py:139-140 */
+  SMMD_K_POLY = 7           /* compute_scores.py:232-244 / sklearn polynomial_kernel:
+                               params[0]=gamma (<=0 -> 1/d), params[1]=coef0, degree in `degree` */
+} smmd_kernel_id;
+
+/* Arithmetic path.  FP32: exact fp32 SIMT kernels (tolerance tier rel 1e-5 vs the oracle).
+ * BF16: tcgen05 tensor cores, bf16 operands / fp32 accumulate (tier rel 1e-3).
+ * BF16X3: tcgen05 with a 3-term split-bf16 Gram (hi*hi + lo*hi + hi*lo), forward-only paths
+ * (KID, value-only MMD^2); ~fp32-accurate Gram at 3x the tensor work.
+ * AUTO: FP32 for small problems, BF16 otherwise. */
+typedef enum smmd_precision {
+  SMMD_PREC_FP32 = 0,
+  SMMD_PREC_BF16 = 1,
+  SMMD_PREC_BF16X3 = 2,
+  SMMD_PREC_AUTO = 3
+} smmd_precision;
+
+/* One MMD^2 problem: X = generated/fake features [m,d], Y = real features [n,d] -- the reference's
+ * argument order kernel(G, images) (model.py:315). */
+typedef struct smmd_problem {
+  int64_t m, n, d;                 /* rows of X, rows of Y, feature dim (all >= 1; m,n >= 2 if !biased) */
+  int64_t ldx, ldy;                /* row strides of X / Y in elements (>= d)                  */
+  int32_t dtype;                   /* smmd_dtype of X and Y                                    */
+  int32_t kernel_id;               /* smmd_kernel_id                                           */
+  int32_t nparams;                 /* number of sigmas / alphas (<= SMMD_MAX_PARAMS)           */
+  float params[SMMD_MAX_PARAMS];   /* sigmas (rbf), alphas (rq), {gamma, coef0} (poly)         */
+  float wts[SMMD_MAX_PARAMS];      /* mixture weights                                          */
+  float add_dot;                   /* mix_rq add_dot (mmd.py:143,170-171,183-185)              */
+  int32_t degree;                  /* polynomial degree (SMMD_K_POLY)                          */
+  int32_t biased;                  /* mmd2(K, biased) (mmd.py:194)                             */
+  int32_t precision;               /* smmd_precision                                           */
+  /* Row sharding for one process per GPU: X and Y passed to the call are the FULL (all-gathered)
+   * matrices on every rank; rank r owns X rows [m*r/world, m*(r+1)/world) and Y rows
+   * [n*r/world, n*(r+1)/world), computes only those rows of the Gram against all columns and
+   * returns partial sums (+ complete gradients for its rows).  world=1 -> single GPU. */
+  int32_t rank, world;
+} smmd_problem;
+
+/* scalars[] layout (device, double[SMMD_NUM_SCALARS]) written by smmd_mmd2_fwd_bwd: */
+enum {
+  SMMD_S_MMD2 = 0,     /* final MMD^2 (only meaningful when world == 1)                       */
+  SMMD_S_SUM_XX = 1,   /* sum of K_XX over owned rows, diagonal excluded                      */
+  SMMD_S_SUM_YY = 2,   /* sum of K_YY over owned rows, diagonal excluded                      */
+  SMMD_S_SUM_XY = 3,   /* sum of K_XY over owned X rows x all Y columns                       */
+  SMMD_S_SUM_YX = 4,   /* sum of K_YX over owned Y rows x all X columns                       */
+  SMMD_S_DIAG_X = 5,   /* sum_i K_XX[i,i] over owned rows (analytic diagonal)                 */
+  SMMD_S_DIAG_Y = 6,   /* sum_i K_YY[i,i] over owned rows                                     */
+  SMMD_S_NONFINITE = 7,/* != 0 when a NaN/Inf reached the sums (model.py:537 asserts on it)   */
+  SMMD_S_VAR = 8,      /* variance estimate   (smmd_mmd2_and_ratio only)                      */
+  SMMD_S_RATIO = 9     /* mmd2/sqrt(max(var,min_var_est)) (smmd_mmd2_and_ratio only)          */
+};
+
+SMMD_API int smmd_version(void);
+SMMD_API const char* smmd_strerror(int status);
+/* Text of the last CUDA error seen by this thread inside the library ("" if none). */
+SMMD_API const char* smmd_last_cuda_error(void);
+/* 1 if the current device can run the library (compute capability 10.x), else 0. */
+SMMD_API int smmd_device_supported(void);
+
+/* Replaces: mmd2(kernel(X, Y, ...), biased) + tf.gradients of it w.r.t. X and Y
+ *   gan/core/mmd.py:18-220 (kernels + _mmd2), called from gan/core/model.py:313-319 and
+ *   gan/core/smmd.py:10-19; autodiff at gan/core/model.py:446,452.
+ * scalars: device double[SMMD_NUM_SCALARS].  dX [owned_m, d] / dY [owned_n, d] fp32 row-major
+ * (ld = d) receive dMMD2/dX, dMMD2/dY for the owned rows; both NULL = forward only. */
+SMMD_API size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad);
+SMMD_API int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars,
+                      float* dX, float* dY, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Multi-GPU: after all-reducing scalars[1..7] over ranks, turn the summed partials into MMD^2
+ * (same arithmetic as the single-GPU finalisation).  sums/out are device pointers; out[0] = MMD^2. */
+SMMD_API int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream);
+
+/* Replaces: mmd2_and_ratio(K, biased, min_var_est) -- gan/core/mmd.py:223-293 (+ ops.sq_sum / ops.dot,
+ * gan/core/ops.py:209-225).  Requires m == n (mmd.py:237).  Reproduces the reference's unbiased
+ * branch that keeps the diagonal (mmd.py:273-276).  scalars[MMD2, VAR, RATIO] are written. */
+SMMD_API int smmd_mmd2_and_ratio(const smmd_problem* p, const void* X, const void* Y, double min_var_est,
+                        double* scalars, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: kernel(X, Y, K_XY_only=True) -- e.g. gan/core/mmd.py:31-32,72-73,106-107,172-173, the
+ * witness term of the gradient penalty (gan/core/model.py:336).  K [m, n] fp32 row-major, ld = ldk. */
+SMMD_API int smmd_kernel_xy(const smmd_problem* p, const void* X, const void* Y, float* K, int64_t ldk,
+                   void* stream);
+/* VJP of the above: given dK [m,n] returns dX [m,d], dY [n,d] (fp32, ld = d). */
+SMMD_API int smmd_kernel_xy_bwd(const smmd_problem* p, const void* X, const void* Y, const float* dK,
+                       int64_t lddk, float* dX, float* dY, void* stream);
+
+/* KID: polynomial_mmd_averages over subsets given by explicit row indices.
+ *   Replaces gan/compute_scores.py:211-229 (subset loop + fancy-index gather), :232-244
+ *   (polynomial_mmd = 3x sklearn polynomial_kernel) and :252-335 (_mmd2_and_variance), as called
+ *   from gan/utils/scorer.py:103-109 and the CLI (compute_scores.py:489-493).
+ * The reference draws the subsets from numpy's global RNG (compute_scores.py:221-222); the library
+ * has no hidden RNG: the caller passes the indices (int32, [n_subsets, subset_size]). */
+typedef enum smmd_mmd_est { SMMD_EST_UNBIASED = 0, SMMD_EST_BIASED = 1, SMMD_EST_USTAT = 2 } smmd_mmd_est;
+
+typedef struct smmd_kid_problem {
+  int64_t n_g, n_r, d;             /* rows of codes_g, rows of codes_r, feature dim           */
+  int64_t ldg, ldr;                /* row strides (elements)                                  */
+  int32_t dtype;                   /* smmd_dtype of the codes (F32)                           */
+  int32_t n_subsets, subset_size;  /* S, m                                                    */
+  int32_t degree;                  /* 3                                                       */
+  float gamma;                     /* <= 0 -> 1/d (sklearn gamma=None)                        */
+  float coef0;                     /* 1                                                       */
+  int64_t var_at_m;                /* compute_scores.py:213,223 (min(len_g,len_r)); <=0 -> m  */
+  int32_t mmd_est;                 /* smmd_mmd_est (compute_scores.py:290-300)                */
+  int32_t ret_var;                 /* also compute the variance estimate (:305-333)           */
+  int32_t precision;               /* smmd_precision (AUTO -> BF16X3)                         */
+  int32_t first_subset, n_local;   /* subset shard of this rank: [first, first+n_local); n_local<=0 -> all */
+} smmd_kid_problem;
+
+SMMD_API size_t smmd_kid_workspace_bytes(const smmd_kid_problem* p);
+/* mmd2_out / var_out: device double[n_subsets] (entries of the local shard are written);
+ * var_out may be NULL when ret_var == 0. */
+SMMD_API int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void* codes_r,
+                     const int32_t* idx_g, const int32_t* idx_r, double* mmd2_out, double* var_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Introspection for tests/bench: number of kernels the last call on this thread launched, and the
+ * name of the code path it took ("simt_fp32", "tc_bf16_fused", "tc_bf16_fwd", ...). */
+SMMD_API int smmd_last_launch_count(void);
+SMMD_API const char* smmd_last_path(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMMD_H_ */

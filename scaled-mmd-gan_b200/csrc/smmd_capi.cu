@@ -1,0 +1,389 @@
+// smmd_capi.cu -- the extern "C" boundary declared in include/smmd.h: argument validation, path
+// selection (exact-fp32 SIMT vs tcgen05 tensor-core kernels), workspace carving and launches.
+// No CPU fallback exists: unsupported devices get SMMD_EARCH.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include "smmd_internal.h"
+#include "smmd_tc.h"
+
+using namespace smmd;
+
+namespace {
+thread_local char g_cuda_err[256] = "";
+thread_local int g_launches = 0;
+thread_local const char* g_path = "none";
+
+int cuda_fail(cudaError_t e) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return SMMD_ECUDA;
+}
+#define SMMD_CUDA(x)                        \
+  do {                                      \
+    cudaError_t e__ = (x);                  \
+    if (e__ != cudaSuccess) return cuda_fail(e__); \
+    ++g_launches;                           \
+  } while (0)
+
+int device_ok() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+// Translate the public problem into the device-side kernel description.  Returns smmd_status.
+int build_kernel_fn(int kernel_id, int nparams, const float* params, const float* wts, float add_dot, int degree,
+                    int64_t d, KernelFn* out) {
+  KernelFn k;
+  memset(&k, 0, sizeof(k));
+  k.np = 0;
+  k.degree = 0;
+  switch (kernel_id) {
+    case SMMD_K_TANH_DISTANCE: k.tanh_features = 1;  // fallthrough
+    case SMMD_K_DISTANCE: k.family = FAM_DISTANCE; break;
+    case SMMD_K_DOT: k.family = FAM_DOT; break;
+    case SMMD_K_RBF:
+    case SMMD_K_MIX_RBF: {
+      k.family = FAM_RBF;
+      int np = kernel_id == SMMD_K_RBF ? 1 : nparams;
+      if (np < 1 || np > SMMD_MAX_PARAMS) return SMMD_EINVAL;
+      k.np = np;
+      double cd = 0;
+      for (int i = 0; i < np; ++i) {
+        if (!(params[i] > 0.f) || !std::isfinite(params[i]) || !std::isfinite(wts[i])) return SMMD_EINVAL;
+        double gamma = 1.0 / (2.0 * (double)params[i] * (double)params[i]);
+        k.p0[i] = (float)gamma;
+        k.p1[i] = (float)(-gamma * 1.4426950408889634);
+        k.w[i] = wts[i];
+        cd += wts[i];
+      }
+      k.const_diag = (float)cd;
+      k.has_const_diag = 1;
+      break;
+    }
+    case SMMD_K_TANH_MIX_RQ: k.tanh_features = 1;  // fallthrough
+    case SMMD_K_MIX_RQ: {
+      k.family = FAM_RQ;
+      if (nparams < 1 || nparams > SMMD_MAX_PARAMS) return SMMD_EINVAL;
+      k.np = nparams;
+      double cd = 0;
+      for (int i = 0; i < nparams; ++i) {
+        if (!(params[i] > 0.f) || !std::isfinite(params[i]) || !std::isfinite(wts[i])) return SMMD_EINVAL;
+        k.p0[i] = (float)(1.0 / (2.0 * (double)params[i]));
+        k.p1[i] = params[i];
+        k.w[i] = wts[i];
+        cd += wts[i];
+      }
+      if (!std::isfinite(add_dot) || add_dot < 0.f) return SMMD_EINVAL;
+      k.add_dot = add_dot;
+      k.const_diag = (float)cd;  // quirk kept: add_dot is NOT part of const_diagonal (mmd.py:186-188)
+      k.has_const_diag = 1;
+      break;
+    }
+    case SMMD_K_POLY: {
+      k.family = FAM_POLY;
+      if (degree < 1 || degree > 8) return SMMD_EINVAL;
+      k.degree = degree;
+      k.poly_gamma = (nparams >= 1 && params[0] > 0.f) ? params[0] : (float)(1.0 / (double)d);
+      k.poly_coef0 = nparams >= 2 ? params[1] : 1.f;
+      break;
+    }
+    default: return SMMD_EINVAL;
+  }
+  *out = k;
+  return SMMD_OK;
+}
+
+int validate_problem(const smmd_problem* p) {
+  if (!p) return SMMD_EINVAL;
+  if (p->m < 1 || p->n < 1 || p->d < 1) return SMMD_ESHAPE;
+  if (!p->biased && (p->m < 2 || p->n < 2)) return SMMD_ESHAPE;
+  if (p->ldx < p->d || p->ldy < p->d) return SMMD_ESHAPE;
+  if (p->m + p->n > (int64_t)1 << 24 || p->d > 1 << 16) return SMMD_ESHAPE;
+  if (p->dtype != SMMD_F32 && p->dtype != SMMD_BF16) return SMMD_EDTYPE;
+  if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return SMMD_EINVAL;
+  if (p->precision < SMMD_PREC_FP32 || p->precision > SMMD_PREC_AUTO) return SMMD_EINVAL;
+  if (p->kernel_id < 0 || p->kernel_id > SMMD_K_POLY) return SMMD_EINVAL;
+  return SMMD_OK;
+}
+
+Geometry make_geometry(const smmd_problem* p) {
+  Geometry g;
+  g.m = p->m;
+  g.n = p->n;
+  g.d = p->d;
+  g.x0 = p->m * p->rank / p->world;
+  g.x1 = p->m * (p->rank + 1) / p->world;
+  g.y0 = p->n * p->rank / p->world;
+  g.y1 = p->n * (p->rank + 1) / p->world;
+  g.biased = p->biased;
+  return g;
+}
+
+// AUTO: tensor cores only pay off once the Gram is big and the contraction deep enough.
+int resolve_precision(const smmd_problem* p, int want_grad) {
+  int prec = p->precision;
+  if (prec == SMMD_PREC_AUTO) {
+    const bool big = (p->m + p->n) >= 1024 && p->d >= 32;
+    prec = (big && tc_mmd2_supported(p->d, want_grad)) ? SMMD_PREC_BF16 : SMMD_PREC_FP32;
+  }
+  return prec;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+}  // namespace
+
+extern "C" {
+
+int smmd_version(void) { return SMMD_VERSION; }
+
+const char* smmd_strerror(int status) {
+  switch (status) {
+    case SMMD_OK: return "ok";
+    case SMMD_EINVAL: return "invalid argument";
+    case SMMD_ESHAPE: return "invalid shape or stride";
+    case SMMD_EDTYPE: return "unsupported dtype";
+    case SMMD_EARCH: return "device is not sm_100 (B200): no fallback path exists";
+    case SMMD_EWORKSPACE: return "workspace missing, misaligned or too small";
+    case SMMD_ECUDA: return "CUDA call failed";
+    case SMMD_EUNSUPPORTED: return "combination not supported on the requested precision path";
+    default: return "unknown status";
+  }
+}
+
+const char* smmd_last_cuda_error(void) { return g_cuda_err; }
+int smmd_device_supported(void) { return device_ok(); }
+int smmd_last_launch_count(void) { return g_launches; }
+const char* smmd_last_path(void) { return g_path; }
+
+size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad) {
+  if (validate_problem(p) != SMMD_OK) return 0;
+  const int prec = resolve_precision(p, want_grad);
+  if (prec == SMMD_PREC_FP32) return simt_plan(p->m, p->n, p->d, 1).off_end;
+  return tc_mmd2_workspace_bytes(p->m, p->n, p->d, want_grad, prec);
+}
+
+int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars, float* dX, float* dY,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_path = "none";
+  int st = validate_problem(p);
+  if (st != SMMD_OK) return st;
+  if (!X || !Y || !scalars) return SMMD_EINVAL;
+  if ((dX == nullptr) != (dY == nullptr)) return SMMD_EINVAL;
+  if (p->kernel_id == SMMD_K_POLY && dX) return SMMD_EUNSUPPORTED;
+  if (!device_ok()) return SMMD_EARCH;
+  const int want_grad = dX != nullptr;
+  KernelFn kf;
+  st = build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  const size_t need = smmd_mmd2_workspace_bytes(p, want_grad);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Geometry g = make_geometry(p);
+  const Coefs c = make_coefs(g, kf);
+  const int prec = resolve_precision(p, want_grad);
+
+  if (prec == SMMD_PREC_FP32) {
+    g_path = "simt_fp32";
+    const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
+    char* ws = static_cast<char*>(workspace);
+    float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
+    float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
+    double* stats = reinterpret_cast<double*>(ws + pl.off_stats);
+    SMMD_CUDA(launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch,
+                              s));
+    SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, 1, stats, dX, dY, 0, s));
+    SMMD_CUDA(launch_finalize_mmd2(kf, g, stats, norms, scalars, s));
+    return SMMD_OK;
+  }
+  if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
+  if (!tc_mmd2_supported(p->d, want_grad)) return SMMD_EUNSUPPORTED;
+  int launches = 0;
+  cudaError_t e = tc_mmd2_run(kf, g, c, X, Y, p->dtype, p->ldx, p->ldy, prec, scalars, dX, dY, workspace,
+                              workspace_bytes, s, &launches, &g_path);
+  g_launches += launches;
+  if (e != cudaSuccess) return cuda_fail(e);
+  return SMMD_OK;
+}
+
+int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream) {
+  g_launches = 0;
+  int st = validate_problem(p);
+  if (st != SMMD_OK) return st;
+  if (!sums || !out) return SMMD_EINVAL;
+  if (!device_ok()) return SMMD_EARCH;
+  KernelFn kf;
+  st = build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  SMMD_CUDA(launch_combine_mmd2(kf, make_geometry(p), sums, out, static_cast<cudaStream_t>(stream)));
+  return SMMD_OK;
+}
+
+int smmd_mmd2_and_ratio(const smmd_problem* p, const void* X, const void* Y, double min_var_est, double* scalars,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_path = "none";
+  int st = validate_problem(p);
+  if (st != SMMD_OK) return st;
+  if (!X || !Y || !scalars) return SMMD_EINVAL;
+  if (p->m != p->n) return SMMD_ESHAPE;  // "Assumes X, Y are same shape" (mmd.py:237)
+  if (p->world != 1) return SMMD_EUNSUPPORTED;
+  if (!device_ok()) return SMMD_EARCH;
+  KernelFn kf;
+  st = build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  kf.true_distance = 1;  // second-order statistics see the real K entries
+  const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
+  if (!workspace || workspace_bytes < pl.off_end || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  g_path = "simt_fp32_stats";
+  char* ws = static_cast<char*>(workspace);
+  float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
+  float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
+  double* stats = reinterpret_cast<double*>(ws + pl.off_stats);
+  Geometry g = make_geometry(p);
+  const Coefs c = make_coefs(g, kf);
+  SMMD_CUDA(launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch, s));
+  SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, 1, stats, nullptr, nullptr, 1, s));
+  SMMD_CUDA(launch_finalize_ratio(kf, g, stats, min_var_est, scalars, s));
+  return SMMD_OK;
+}
+
+// K_XY_only needs Z/norms scratch: it is carved from a small internal cache-free scheme -- the caller
+// passes no workspace here, so these two entry points use stream-ordered allocation.
+static int witness_common(const smmd_problem* p, const void* X, const void* Y, KernelFn* kf, float** Z, float** norms,
+                          SimtPlan* pl, cudaStream_t s) {
+  int st = validate_problem(p);
+  if (st != SMMD_OK) return st;
+  if (!X || !Y) return SMMD_EINVAL;
+  if (!device_ok()) return SMMD_EARCH;
+  st = build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, kf);
+  if (st != SMMD_OK) return st;
+  kf->true_distance = 1;
+  *pl = simt_plan(p->m, p->n, p->d, 1);
+  void* buf = nullptr;
+  cudaError_t e = cudaMallocAsync(&buf, pl->off_stats, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  *Z = reinterpret_cast<float*>(static_cast<char*>(buf) + pl->off_Z);
+  *norms = reinterpret_cast<float*>(static_cast<char*>(buf) + pl->off_norm);
+  e = launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf->tanh_features, *Z, *norms, pl->dpitch, s);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(buf, s);
+    return cuda_fail(e);
+  }
+  ++g_launches;
+  return SMMD_OK;
+}
+
+int smmd_kernel_xy(const smmd_problem* p, const void* X, const void* Y, float* K, int64_t ldk, void* stream) {
+  g_launches = 0;
+  g_path = "simt_fp32_kxy";
+  if (!K || (p && ldk < p->n)) return SMMD_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KernelFn kf;
+  float *Z, *norms;
+  SimtPlan pl;
+  int st = witness_common(p, X, Y, &kf, &Z, &norms, &pl, s);
+  if (st != SMMD_OK) return st;
+  cudaError_t e = launch_kernel_xy(kf, Z, norms, pl.dpitch, p->m, p->n, p->d, K, ldk, s);
+  cudaFreeAsync(Z, s);  // Z is the base of the allocation (off_Z == 0)
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SMMD_OK;
+}
+
+int smmd_kernel_xy_bwd(const smmd_problem* p, const void* X, const void* Y, const float* dK, int64_t lddk, float* dX,
+                       float* dY, void* stream) {
+  g_launches = 0;
+  g_path = "simt_fp32_kxy_bwd";
+  if (!dK || !dX || !dY || (p && lddk < p->n)) return SMMD_EINVAL;
+  if (p && p->d > 2048) return SMMD_EUNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KernelFn kf;
+  float *Z, *norms;
+  SimtPlan pl;
+  int st = witness_common(p, X, Y, &kf, &Z, &norms, &pl, s);
+  if (st != SMMD_OK) return st;
+  cudaError_t e = launch_kernel_xy_bwd(kf, Z, norms, pl.dpitch, p->m, p->n, p->d, dK, lddk, dX, dY, s);
+  cudaFreeAsync(Z, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SMMD_OK;
+}
+
+// ---- KID -----------------------------------------------------------------------------------------
+static int validate_kid(const smmd_kid_problem* p) {
+  if (!p) return SMMD_EINVAL;
+  if (p->n_g < 1 || p->n_r < 1 || p->d < 1 || p->ldg < p->d || p->ldr < p->d) return SMMD_ESHAPE;
+  if (p->n_subsets < 1 || p->subset_size < 3) return SMMD_ESHAPE;
+  if (p->subset_size > p->n_g || p->subset_size > p->n_r) return SMMD_ESHAPE;  // replace=False (compute_scores.py:221)
+  if (p->dtype != SMMD_F32 && p->dtype != SMMD_BF16) return SMMD_EDTYPE;
+  if (p->degree < 1 || p->degree > 8) return SMMD_EINVAL;
+  if (p->mmd_est < SMMD_EST_UNBIASED || p->mmd_est > SMMD_EST_USTAT) return SMMD_EINVAL;
+  if (p->precision < SMMD_PREC_FP32 || p->precision > SMMD_PREC_AUTO) return SMMD_EINVAL;
+  if (p->first_subset < 0 || p->first_subset >= p->n_subsets) return SMMD_EINVAL;
+  if (p->n_local > 0 && p->first_subset + p->n_local > p->n_subsets) return SMMD_EINVAL;
+  return SMMD_OK;
+}
+static int kid_local(const smmd_kid_problem* p) { return p->n_local > 0 ? p->n_local : p->n_subsets - p->first_subset; }
+static int kid_precision(const smmd_kid_problem* p) {
+  int prec = p->precision;
+  if (prec == SMMD_PREC_AUTO) prec = tc_kid_supported(p->d) ? SMMD_PREC_BF16X3 : SMMD_PREC_FP32;
+  return prec;
+}
+
+size_t smmd_kid_workspace_bytes(const smmd_kid_problem* p) {
+  if (validate_kid(p) != SMMD_OK) return 0;
+  if (kid_precision(p) == SMMD_PREC_FP32) return simt_plan(p->subset_size, p->subset_size, p->d, kid_local(p)).off_end;
+  return tc_kid_workspace_bytes(p->subset_size, p->d, kid_local(p), kid_precision(p));
+}
+
+int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void* codes_r, const int32_t* idx_g,
+                     const int32_t* idx_r, double* mmd2_out, double* var_out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  g_launches = 0;
+  g_path = "none";
+  int st = validate_kid(p);
+  if (st != SMMD_OK) return st;
+  if (!codes_g || !codes_r || !idx_g || !idx_r || !mmd2_out) return SMMD_EINVAL;
+  if (p->ret_var && !var_out) return SMMD_EINVAL;
+  if (!device_ok()) return SMMD_EARCH;
+  const size_t need = smmd_kid_workspace_bytes(p);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KernelFn kf;
+  float prm[2] = {p->gamma, p->coef0};
+  st = build_kernel_fn(SMMD_K_POLY, 2, prm, prm, 0.f, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  const int64_t m = p->subset_size, nloc = kid_local(p);
+  const int64_t var_at_m = p->var_at_m > 0 ? p->var_at_m : m;
+  const int prec = kid_precision(p);
+  char* ws = static_cast<char*>(workspace);
+  double* stats = nullptr;
+  if (prec == SMMD_PREC_FP32) {
+    g_path = "simt_fp32_kid";
+    const SimtPlan pl = simt_plan(m, m, p->d, nloc);
+    float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
+    float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
+    stats = reinterpret_cast<double*>(ws + pl.off_stats);
+    SMMD_CUDA(launch_gather_f32(codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc, m,
+                                Z, norms, pl.dpitch, s));
+    Geometry g{m, m, p->d, 0, m, 0, m, 0};
+    Coefs c = make_coefs(g, kf);
+    SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, nloc, stats, nullptr, nullptr, 1, s));
+  } else {
+    if (!tc_kid_supported(p->d)) return SMMD_EUNSUPPORTED;
+    int launches = 0;
+    cudaError_t e = tc_kid_run(kf, codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc,
+                               m, prec, p->ret_var || p->mmd_est == SMMD_EST_USTAT, workspace, workspace_bytes, &stats,
+                               s, &launches, &g_path);
+    g_launches += launches;
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
+  SMMD_CUDA(launch_finalize_kid(stats, nloc, m, p->first_subset, p->mmd_est, p->ret_var, var_at_m, mmd2_out, var_out, s));
+  return SMMD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,660 @@
+// smmd_simt.cu -- exact-fp32 SIMT path (tolerance tier rel 1e-5) + the finalisation kernels shared with
+// the tensor-core path.
+//
+// Replaces, for small / exactness-critical problems, the whole chain of TF ops behind
+//   mmd2(kernel(X, Y))           gan/core/mmd.py:18-220   (+ autodiff, gan/core/model.py:446,452)
+//   mmd2_and_ratio(K)            gan/core/mmd.py:223-293
+//   kernel(X, Y, K_XY_only=True) gan/core/mmd.py:31-32,72-73,106-107,172-173
+//   polynomial_mmd(_averages)    gan/compute_scores.py:211-335 (exact variant)
+// with: one prep/gather pass (stack Z=[X;Y], tanh, squared norms), ONE row kernel that never
+// materialises an N x N matrix (warp = row, lanes = 32 columns; Gram entry, kernel transform, block
+// sums and the gradient row  g_i = sum_j 4 a_ij k'(D_ij)(z_i - z_j) + 2 a_ij dk/dG z_j  in one sweep),
+// and a tiny fp64 finalisation.
+#include <cuda_bf16.h>
+#include "smmd_kfun.cuh"
+
+namespace smmd {
+
+constexpr int kRowsPerCta = 8;
+constexpr int kChunk = 256;  // feature chunk staged in shared memory
+
+// ------------------------------------------------------------------------------------------------
+// prep / gather: Z[b][r][:] = f(src row), norms[b][r] = |z|^2 (fp32)
+// ------------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const void* A;  // X or codes_g
+  const void* B;  // Y or codes_r
+  int dtype;
+  int64_t lda, ldb, ma, mb, d, dpitch;
+  const int32_t* idxA;  // optional [batch][ma] row indices into A (KID subsets)
+  const int32_t* idxB;
+  int64_t first_batch;
+  int tanh_features;
+  float* Z;
+  float* norms;
+};
+
+__global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t M = a.ma + a.mb;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t b = blockIdx.y;
+  if (r >= M) return;
+  const bool inA = r < a.ma;
+  int64_t src = inA ? r : r - a.ma;
+  if (a.idxA) src = inA ? a.idxA[(a.first_batch + b) * a.ma + src] : a.idxB[(a.first_batch + b) * a.mb + src];
+  const int64_t ld = inA ? a.lda : a.ldb;
+  const void* base = inA ? a.A : a.B;
+  float* zrow = a.Z + (b * M + r) * a.dpitch;
+  float acc = 0.f;
+  for (int64_t c = lane; c < a.dpitch; c += 32) {
+    float v = 0.f;
+    if (c < a.d) {
+      v = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(base)[src * ld + c]
+                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[src * ld + c]);
+      if (a.tanh_features) v = tanhf(v);
+    }
+    zrow[c] = v;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) a.norms[b * M + r] = acc;
+}
+
+cudaError_t launch_prep_f32(const void* X, const void* Y, int dtype, int64_t ldx, int64_t ldy, int64_t m, int64_t n,
+                            int64_t d, int tanh_features, float* Z, float* norms, int64_t dpitch, cudaStream_t s) {
+  PrepArgs a{X, Y, dtype, ldx, ldy, m, n, d, dpitch, nullptr, nullptr, 0, tanh_features, Z, norms};
+  dim3 grid((unsigned)((m + n + 7) / 8), 1);
+  prep_rows_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_f32(const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
+                              const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,
+                              float* Z, float* norms, int64_t dpitch, cudaStream_t s) {
+  PrepArgs a{G, R, dtype, ldg, ldr, msub, msub, d, dpitch, idx_g, idx_r, first, 0, Z, norms};
+  dim3 grid((unsigned)((2 * msub + 7) / 8), (unsigned)nsub);
+  prep_rows_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+SimtPlan simt_plan(int64_t m, int64_t n, int64_t d, int64_t batch) {
+  SimtPlan p;
+  p.dpitch = (d + 7) / 8 * 8;
+  p.M = m + n;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t o = 0;
+  p.off_Z = o;
+  o = up(o + (size_t)batch * p.M * p.dpitch * sizeof(float));
+  p.off_norm = o;
+  o = up(o + (size_t)batch * p.M * sizeof(float));
+  p.off_stats = o;
+  o = up(o + (size_t)batch * p.M * RS_COUNT * sizeof(double));
+  p.off_end = o;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the row kernel
+// ------------------------------------------------------------------------------------------------
+struct SimtArgs {
+  KernelFn kf;
+  const float* Z;
+  const float* norms;
+  int64_t dpitch, d, m, n, M;
+  int64_t x0, ox, y0, oy;  // owned X rows [x0, x0+ox), owned Y rows [y0, y0+oy)
+  float a_xx, a_yy, a_xy;
+  int diag_in_sum;
+  double* stats;  // [batch][ox+oy][RS_COUNT] (may be null in witness mode)
+  float* dX;      // [ox][d]
+  float* dY;      // [oy][d]
+  // witness / VJP mode (K_XY_only backward): pair weight = dK[i][j] on cross pairs, 0 on same-set pairs
+  const float* dK;
+  int64_t lddk;
+};
+
+template <int NCH, bool GRAD>
+__global__ void __launch_bounds__(256) simt_rows_kernel(SimtArgs a) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dch = a.dpitch < kChunk ? (int)a.dpitch : kChunk;
+  const int cpitch = dch + 4;
+  float* colT = sm;                 // [32][cpitch]
+  float* rowT = sm + 32 * cpitch;   // [kRowsPerCta][dch]
+  const int nch = (int)((a.dpitch + kChunk - 1) / kChunk);
+
+  const int64_t b = blockIdx.y;
+  const float* Z = a.Z + b * a.M * a.dpitch;
+  const float* norms = a.norms + b * a.M;
+  const int64_t owned = a.ox + a.oy;
+  const int64_t lr = (int64_t)blockIdx.x * kRowsPerCta + warp;
+  const bool row_valid = lr < owned;
+  const int64_t ig = row_valid ? (lr < a.ox ? a.x0 + lr : a.m + a.y0 + (lr - a.ox)) : 0;
+  const bool rowX = ig < a.m;
+  const float ni = norms[ig];
+  const bool witness = a.dK != nullptr;
+
+  float4 zi[NCH][2], acc[NCH][2];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      acc[ch][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zi[ch][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (GRAD) {
+        int64_t c = (int64_t)ch * kChunk + 128 * t + lane * 4;
+        if (c < a.dpitch) zi[ch][t] = *reinterpret_cast<const float4*>(Z + ig * a.dpitch + c);
+      }
+    }
+
+  double s_same = 0, s_cross = 0, q_same = 0, q_cross = 0, pairv = 0, wsum = 0;
+  // column range: witness mode only visits the other set
+  int64_t jbeg = 0, jend = a.M;
+  if (witness) {
+    jbeg = rowX ? a.m : 0;
+    jend = rowX ? a.M : a.m;
+  }
+  // all warps of the CTA must walk the same tiles (shared colT): take the union over the CTA's rows.
+  // Rows of a CTA can straddle the X/Y boundary only in witness mode with mixed row types; handle by
+  // visiting [0, M) in that (rare) case.
+  {
+    __shared__ int mixed;
+    if (tid == 0) mixed = 0;
+    __syncthreads();
+    if (witness && row_valid) {
+      int64_t first_ig = ((int64_t)blockIdx.x * kRowsPerCta < a.ox) ? a.x0 : a.m;  // type of row 0 of this CTA
+      bool firstX = first_ig < a.m;
+      if (firstX != rowX) mixed = 1;
+    }
+    __syncthreads();
+    if (witness && mixed) {
+      jbeg = 0;
+      jend = a.M;
+    }
+    if (witness && !row_valid) {  // idle warps follow row 0 of the CTA
+      bool firstX = ((int64_t)blockIdx.x * kRowsPerCta < a.ox);
+      jbeg = mixed ? 0 : (firstX ? a.m : 0);
+      jend = mixed ? a.M : (firstX ? a.M : a.m);
+    }
+  }
+  const int64_t jt0 = jbeg / 32, jt1 = (jend + 31) / 32;
+
+  for (int64_t jt = jt0; jt < jt1; ++jt) {
+    float S = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+      __syncthreads();
+      const int q4 = dch >> 2;
+      for (int idx = tid; idx < 32 * q4; idx += 256) {
+        int r = idx / q4, c4 = idx - r * q4;
+        int64_t jg = jt * 32 + r, c = (int64_t)ch * kChunk + c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jg < a.M && c < a.dpitch) v = *reinterpret_cast<const float4*>(Z + jg * a.dpitch + c);
+        *reinterpret_cast<float4*>(colT + r * cpitch + c4 * 4) = v;
+      }
+      if (nch > 1 || jt == jt0) {
+        for (int idx = tid; idx < kRowsPerCta * q4; idx += 256) {
+          int r = idx / q4, c4 = idx - r * q4;
+          int64_t l2 = (int64_t)blockIdx.x * kRowsPerCta + r, c = (int64_t)ch * kChunk + c4 * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (l2 < owned && c < a.dpitch) {
+            int64_t g2 = l2 < a.ox ? a.x0 + l2 : a.m + a.y0 + (l2 - a.ox);
+            v = *reinterpret_cast<const float4*>(Z + g2 * a.dpitch + c);
+          }
+          *reinterpret_cast<float4*>(rowT + r * dch + c4 * 4) = v;
+        }
+      }
+      __syncthreads();
+      const float4* rp = reinterpret_cast<const float4*>(rowT + warp * dch);
+      const float4* cp = reinterpret_cast<const float4*>(colT + lane * cpitch);
+#pragma unroll 4
+      for (int c4 = 0; c4 < q4; ++c4) {
+        float4 x = rp[c4], y = cp[c4];
+        S = fmaf(x.x, y.x, S);
+        S = fmaf(x.y, y.y, S);
+        S = fmaf(x.z, y.z, S);
+        S = fmaf(x.w, y.w, S);
+      }
+    }
+    // ---- pair epilogue: lane <-> column jg ----
+    const int64_t jg = jt * 32 + lane;
+    const bool valid = row_valid && jg < a.M && jg >= jbeg && jg < jend;
+    float wd = 0.f, wg = 0.f;
+    if (valid) {
+      const float nj = norms[jg];
+      const bool colX = jg < a.m;
+      const bool same = (colX == rowX);
+      const bool isdiag = (jg == ig);
+      PairVal pv = eval_exact(a.kf, S, ni, nj);
+      if (witness) {
+        if (!same) {
+          float w = rowX ? a.dK[ig * a.lddk + (jg - a.m)] : a.dK[jg * a.lddk + (ig - a.m)];
+          wd = 2.f * w * pv.kd;
+          wg = w * pv.kg;
+          wsum += (double)w;
+        }
+      } else {
+        const float aco = same ? (rowX ? a.a_xx : a.a_yy) : a.a_xy;
+        if (isdiag) {
+          wg = a.diag_in_sum ? 2.f * aco * pv.kg : 0.f;
+        } else {
+          wd = 4.f * aco * pv.kd;
+          wg = 2.f * aco * pv.kg;
+          const double k = (double)pv.k;
+          if (same) {
+            s_same += k;
+            q_same += k * k;
+          } else {
+            s_cross += k;
+            q_cross += k * k;
+            if (rowX && (jg - a.m) == ig) pairv = k;
+          }
+        }
+      }
+    }
+    if (GRAD) {
+      for (int ch = 0; ch < nch; ++ch) {
+        if (nch > 1) {  // bring chunk `ch` of the column tile back
+          __syncthreads();
+          const int q4 = dch >> 2;
+          for (int idx = tid; idx < 32 * q4; idx += 256) {
+            int r = idx / q4, c4 = idx - r * q4;
+            int64_t j2 = jt * 32 + r, c = (int64_t)ch * kChunk + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j2 < a.M && c < a.dpitch) v = *reinterpret_cast<const float4*>(Z + j2 * a.dpitch + c);
+            *reinterpret_cast<float4*>(colT + r * cpitch + c4 * 4) = v;
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          if (cc != ch) continue;
+          for (int jj = 0; jj < 32; ++jj) {
+            const float wdj = __shfl_sync(0xffffffffu, wd, jj);
+            const float wgj = __shfl_sync(0xffffffffu, wg, jj);
+            if (wdj == 0.f && wgj == 0.f) continue;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int c = 128 * t + lane * 4;
+              if (c < dch) {
+                const float4 zj = *reinterpret_cast<const float4*>(colT + jj * cpitch + c);
+                float4& A = acc[cc][t];
+                const float4 z = zi[cc][t];
+                A.x = fmaf(wdj, z.x - zj.x, fmaf(wgj, zj.x, A.x));
+                A.y = fmaf(wdj, z.y - zj.y, fmaf(wgj, zj.y, A.y));
+                A.z = fmaf(wdj, z.z - zj.z, fmaf(wgj, zj.z, A.z));
+                A.w = fmaf(wdj, z.w - zj.w, fmaf(wgj, zj.w, A.w));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- per-row outputs ----
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_same += __shfl_xor_sync(0xffffffffu, s_same, o);
+    s_cross += __shfl_xor_sync(0xffffffffu, s_cross, o);
+    q_same += __shfl_xor_sync(0xffffffffu, q_same, o);
+    q_cross += __shfl_xor_sync(0xffffffffu, q_cross, o);
+    pairv += __shfl_xor_sync(0xffffffffu, pairv, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
+  if (!row_valid) return;
+  if (a.stats && lane == 0) {
+    double* st = a.stats + (b * owned + lr) * RS_COUNT;
+    st[RS_SAME] = s_same;
+    st[RS_CROSS] = s_cross;
+    st[RS_SQ_SAME] = q_same;
+    st[RS_SQ_CROSS] = q_cross;
+    double dg;
+    if (a.kf.family == FAM_RQ) dg = (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni;
+    else dg = (double)diag_value(a.kf, ni);
+    st[RS_DIAG] = dg;
+    st[RS_PAIR] = pairv;
+  }
+  if (GRAD) {
+    float* out = rowX ? a.dX + (ig - a.x0) * a.d : a.dY + (ig - a.m - a.y0) * a.d;
+    // distance kernel with its sqrt(|x|^2+eps) terms (witness mode only): d/dz_i sqrt(n_i+eps) = z_i/sqrt(n_i+eps)
+    float nterm = 0.f;
+    if (witness && a.kf.family == FAM_DISTANCE && a.kf.true_distance) nterm = (float)wsum * rsqrtf(ni + kEps);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t c = (int64_t)ch * kChunk + 128 * t + lane * 4;
+        const float g[4] = {acc[ch][t].x, acc[ch][t].y, acc[ch][t].z, acc[ch][t].w};
+        const float z[4] = {zi[ch][t].x, zi[ch][t].y, zi[ch][t].z, zi[ch][t].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < a.d && (128 * t + lane * 4) < dch) {
+            float v = g[e] + nterm * z[e];
+            if (a.kf.tanh_features) v *= (1.f - z[e] * z[e]);
+            out[c + e] = v;
+          }
+      }
+  }
+}
+
+template <bool GRAD>
+static cudaError_t launch_rows_t(const SimtArgs& a, int64_t batch, cudaStream_t s) {
+  const int dch = a.dpitch < kChunk ? (int)a.dpitch : kChunk;
+  const size_t smem = (size_t)(32 * (dch + 4) + kRowsPerCta * dch) * sizeof(float);
+  const int64_t owned = a.ox + a.oy;
+  dim3 grid((unsigned)((owned + kRowsPerCta - 1) / kRowsPerCta), (unsigned)batch);
+  const int nch = (int)((a.dpitch + kChunk - 1) / kChunk);
+  if (nch <= 1) simt_rows_kernel<1, GRAD><<<grid, 256, smem, s>>>(a);
+  else if (nch <= 2) simt_rows_kernel<2, GRAD><<<grid, 256, smem, s>>>(a);
+  else if (nch <= 4) simt_rows_kernel<4, GRAD><<<grid, 256, smem, s>>>(a);
+  else if (nch <= 8) simt_rows_kernel<(GRAD ? 8 : 1), GRAD><<<grid, 256, smem, s>>>(a);
+  else if (!GRAD) simt_rows_kernel<1, GRAD><<<grid, 256, smem, s>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_simt_rows(const KernelFn& kf, const Geometry& g, const Coefs& c, const float* Z,
+                             const float* norms, int64_t dpitch, int64_t batch, double* stats, float* dX, float* dY,
+                             int /*want_stats2*/, cudaStream_t s) {
+  SimtArgs a;
+  a.kf = kf;
+  a.Z = Z;
+  a.norms = norms;
+  a.dpitch = dpitch;
+  a.d = g.d;
+  a.m = g.m;
+  a.n = g.n;
+  a.M = g.m + g.n;
+  a.x0 = g.x0;
+  a.ox = g.x1 - g.x0;
+  a.y0 = g.y0;
+  a.oy = g.y1 - g.y0;
+  a.a_xx = (float)c.a_xx;
+  a.a_yy = (float)c.a_yy;
+  a.a_xy = (float)c.a_xy;
+  a.diag_in_sum = c.diag_in_sum;
+  a.stats = stats;
+  a.dX = dX;
+  a.dY = dY;
+  a.dK = nullptr;
+  a.lddk = 0;
+  if (dX != nullptr || dY != nullptr) return launch_rows_t<true>(a, batch, s);
+  return launch_rows_t<false>(a, batch, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block reduction helper for the finalisers (fixed order -> deterministic)
+// ------------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ void block_reduce(double (&q)[NQ], double* sh /* [NQ][256] */) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) sh[i * 256 + tid] = q[i];
+  __syncthreads();
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if (tid < stride) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) sh[i * 256 + tid] += sh[i * 256 + tid + stride];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) q[i] = sh[i * 256];
+}
+
+__device__ __forceinline__ double mmd2_from_sums(const KernelFn& kf, double m, double n, int biased, double sxx,
+                                                 double syy, double sxy, double syx, double dgx, double dgy) {
+  double a_xx, a_yy;
+  const double a_xy = -1.0 / (m * n);
+  if (biased) {
+    a_xx = 1.0 / (m * m);
+    a_yy = 1.0 / (n * n);
+    return a_xx * (sxx + dgx) + a_yy * (syy + dgy) + a_xy * (sxy + syx);
+  }
+  a_xx = 1.0 / (m * (m - 1.0));
+  a_yy = 1.0 / (n * (n - 1.0));
+  double ex = 0.0, ey = 0.0;
+  if (kf.has_const_diag) {  // trace := m * const_diagonal (mmd.py:209-212), whatever the true diagonal is
+    ex = dgx - m * (double)kf.const_diag;
+    ey = dgy - n * (double)kf.const_diag;
+  }
+  return a_xx * (sxx + ex) + a_yy * (syy + ey) + a_xy * (sxy + syx);
+}
+
+struct FinArgs {
+  KernelFn kf;
+  int64_t m, n, ox, oy;
+  int biased;
+  int full;  // world == 1: write the final MMD^2
+  const double* stats;
+  double* scalars;
+};
+
+__global__ void __launch_bounds__(256) finalize_mmd2_kernel(FinArgs a) {
+  __shared__ double sh[6 * 256];
+  double q[6] = {0, 0, 0, 0, 0, 0};  // sxx, syy, sxy, syx, dgx, dgy
+  for (int64_t r = threadIdx.x; r < a.ox + a.oy; r += 256) {
+    const double* st = a.stats + r * RS_COUNT;
+    if (r < a.ox) {
+      q[0] += st[RS_SAME];
+      q[2] += st[RS_CROSS];
+      q[4] += st[RS_DIAG];
+    } else {
+      q[1] += st[RS_SAME];
+      q[3] += st[RS_CROSS];
+      q[5] += st[RS_DIAG];
+    }
+  }
+  block_reduce<6>(q, sh);
+  if (threadIdx.x == 0) {
+    double* o = a.scalars;
+    for (int i = 0; i < SMMD_NUM_SCALARS; ++i) o[i] = 0.0;
+    o[SMMD_S_SUM_XX] = q[0];
+    o[SMMD_S_SUM_YY] = q[1];
+    o[SMMD_S_SUM_XY] = q[2];
+    o[SMMD_S_SUM_YX] = q[3];
+    o[SMMD_S_DIAG_X] = q[4];
+    o[SMMD_S_DIAG_Y] = q[5];
+    double v = mmd2_from_sums(a.kf, (double)a.m, (double)a.n, a.biased, q[0], q[1], q[2], q[3], q[4], q[5]);
+    o[SMMD_S_MMD2] = a.full ? v : 0.0;
+    bool bad = false;
+    for (int i = 0; i < 6; ++i) bad = bad || !isfinite(q[i]);
+    o[SMMD_S_NONFINITE] = bad ? 1.0 : 0.0;
+  }
+}
+
+cudaError_t launch_finalize_mmd2(const KernelFn& kf, const Geometry& g, const double* stats, const float*,
+                                 double* scalars, cudaStream_t s) {
+  FinArgs a{kf, g.m, g.n, g.x1 - g.x0, g.y1 - g.y0, g.biased,
+            (g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n) ? 1 : 0, stats, scalars};
+  finalize_mmd2_kernel<<<1, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void combine_mmd2_kernel(KernelFn kf, int64_t m, int64_t n, int biased, const double* sums, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    out[0] = mmd2_from_sums(kf, (double)m, (double)n, biased, sums[SMMD_S_SUM_XX], sums[SMMD_S_SUM_YY],
+                            sums[SMMD_S_SUM_XY], sums[SMMD_S_SUM_YX], sums[SMMD_S_DIAG_X], sums[SMMD_S_DIAG_Y]);
+}
+cudaError_t launch_combine_mmd2(const KernelFn& kf, const Geometry& g, const double* sums, double* out,
+                                cudaStream_t s) {
+  combine_mmd2_kernel<<<1, 32, 0, s>>>(kf, g.m, g.n, g.biased, sums, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// second-order statistics: the 18 sums both variance formulas are built from
+// ------------------------------------------------------------------------------------------------
+enum {
+  Q_SX, Q_SY, Q_CX, Q_CY, Q_DX, Q_DY, Q_D2X, Q_D2Y, Q_SX2, Q_SY2, Q_CX2, Q_CY2, Q_QX, Q_QY, Q_QXY, Q_DOTX, Q_DOTY,
+  Q_TRXY, Q_N
+};
+
+// stats: [2m][RS_COUNT] (X rows then Y rows).  excess_const > -1: const-diagonal kernels, where the
+// reference subtracts `const` instead of the true diagonal (quirk kept: mmd.py:239-243,256-257).
+__device__ void gather_second_order(const double* stats, int64_t m, bool const_diag, double cd, double (&q)[Q_N],
+                                    double* sh) {
+  for (int i = 0; i < Q_N; ++i) q[i] = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += 256) {
+    const double* sx = stats + i * RS_COUNT;
+    const double* sy = stats + (m + i) * RS_COUNT;
+    double rx = sx[RS_SAME], ry = sy[RS_SAME];
+    double qx = sx[RS_SQ_SAME], qy = sy[RS_SQ_SAME];
+    double dx = sx[RS_DIAG], dy = sy[RS_DIAG];
+    if (const_diag) {  // row sums keep (true diag - const); squares keep true_diag^2 - const^2
+      rx += dx - cd;
+      ry += dy - cd;
+      qx += dx * dx - cd * cd;
+      qy += dy * dy - cd * cd;
+      dx = cd;
+      dy = cd;
+    }
+    q[Q_SX] += rx;
+    q[Q_SY] += ry;
+    q[Q_CX] += sx[RS_CROSS];
+    q[Q_CY] += sy[RS_CROSS];
+    q[Q_DX] += dx;
+    q[Q_DY] += dy;
+    q[Q_D2X] += dx * dx;
+    q[Q_D2Y] += dy * dy;
+    q[Q_SX2] += rx * rx;
+    q[Q_SY2] += ry * ry;
+    q[Q_CX2] += sx[RS_CROSS] * sx[RS_CROSS];
+    q[Q_CY2] += sy[RS_CROSS] * sy[RS_CROSS];
+    q[Q_QX] += qx;
+    q[Q_QY] += qy;
+    q[Q_QXY] += sx[RS_SQ_CROSS];
+    q[Q_DOTX] += rx * sx[RS_CROSS];
+    q[Q_DOTY] += ry * sy[RS_CROSS];
+    q[Q_TRXY] += sx[RS_PAIR];
+  }
+  block_reduce<Q_N>(q, sh);
+}
+
+// gan/core/mmd.py:234-293
+__global__ void __launch_bounds__(256) finalize_ratio_kernel(KernelFn kf, int64_t mm, int biased, const double* stats,
+                                                             double min_var_est, double* scalars) {
+  extern __shared__ double shd[];
+  double q[Q_N];
+  gather_second_order(stats, mm, kf.has_const_diag != 0, (double)kf.const_diag, q, shd);
+  if (threadIdx.x != 0) return;
+  const double m = (double)mm;
+  const double sX = q[Q_SX], sY = q[Q_SY], sXY = q[Q_CX];
+  double val;
+  if (biased) val = (sX + q[Q_DX]) / (m * m) + (sY + q[Q_DY]) / (m * m) - 2 * sXY / (m * m);
+  else val = (sX + q[Q_DX]) / (m * (m - 1)) + (sY + q[Q_DY]) / (m * (m - 1)) - 2 * sXY / (m * m);
+  const double var = 2 / (m * m * (m - 1) * (m - 1)) * (2 * q[Q_SX2] - q[Q_QX] + 2 * q[Q_SY2] - q[Q_QY]) -
+                     (4 * m - 6) / (m * m * m * (m - 1) * (m - 1) * (m - 1)) * (sX * sX + sY * sY) +
+                     4 * (m - 2) / (m * m * m * (m - 1) * (m - 1)) * (q[Q_CX2] + q[Q_CY2]) -
+                     4 * (m - 3) / (m * m * m * (m - 1) * (m - 1)) * q[Q_QXY] -
+                     (8 * m - 12) / (m * m * m * m * m * (m - 1)) * sXY * sXY +
+                     8 / (m * m * m * (m - 1)) * (1 / m * (sX + sY) * sXY - q[Q_DOTX] - q[Q_DOTY]);
+  for (int i = 0; i < SMMD_NUM_SCALARS; ++i) scalars[i] = 0.0;
+  scalars[SMMD_S_MMD2] = val;
+  scalars[SMMD_S_VAR] = var;
+  scalars[SMMD_S_RATIO] = val / sqrt(fmax(var, min_var_est));
+  scalars[SMMD_S_NONFINITE] = (isfinite(val) && isfinite(var)) ? 0.0 : 1.0;
+}
+
+cudaError_t launch_finalize_ratio(const KernelFn& kf, const Geometry& g, const double* stats, double min_var_est,
+                                  double* scalars, cudaStream_t s) {
+  finalize_ratio_kernel<<<1, 256, Q_N * 256 * sizeof(double), s>>>(kf, g.m, g.biased, stats, min_var_est, scalars);
+  return cudaGetLastError();
+}
+
+// gan/compute_scores.py:252-335, one CTA per subset
+__global__ void __launch_bounds__(256) finalize_kid_kernel(const double* stats, int64_t msub, int64_t first, int est,
+                                                           int ret_var, int64_t var_at_m, double* mmd2_out,
+                                                           double* var_out) {
+  extern __shared__ double shd[];
+  const int64_t sub = blockIdx.x;
+  double q[Q_N];
+  gather_second_order(stats + sub * 2 * msub * RS_COUNT, msub, false, 0.0, q, shd);
+  if (threadIdx.x != 0) return;
+  const double m = (double)msub, m1 = m - 1, m2 = m - 2;
+  const double sX = q[Q_SX], sY = q[Q_SY], sXY = q[Q_CX];
+  double val;
+  if (est == SMMD_EST_BIASED) val = (sX + q[Q_DX]) / (m * m) + (sY + q[Q_DY]) / (m * m) - 2 * sXY / (m * m);
+  else {
+    val = (sX + sY) / (m * m1);
+    if (est == SMMD_EST_UNBIASED) val -= 2 * sXY / (m * m);
+    else val -= 2 * (sXY - q[Q_TRXY]) / (m * m1);
+  }
+  mmd2_out[first + sub] = val;
+  if (!ret_var || var_out == nullptr) return;
+  const double dots = q[Q_DOTX] + q[Q_DOTY];
+  const double zeta1 = 1 / (m * m1 * m2) * (q[Q_SX2] - q[Q_QX] + q[Q_SY2] - q[Q_QY]) -
+                       1 / ((m * m1) * (m * m1)) * (sX * sX + sY * sY) +
+                       1 / (m * m * m1) * (q[Q_CX2] + q[Q_CY2] - 2 * q[Q_QXY]) - 2 / (m * m * m * m) * sXY * sXY -
+                       2 / (m * m * m1) * dots + 2 / (m * m * m * m1) * (sX + sY) * sXY;
+  const double zeta2 = 1 / (m * m1) * (q[Q_QX] + q[Q_QY]) - 1 / ((m * m1) * (m * m1)) * (sX * sX + sY * sY) +
+                       2 / (m * m) * q[Q_QXY] - 2 / (m * m * m * m) * sXY * sXY - 4 / (m * m * m1) * dots +
+                       4 / (m * m * m * m1) * (sX + sY) * sXY;
+  const double vm = (double)var_at_m;
+  var_out[first + sub] = 4 * (vm - 2) / (vm * (vm - 1)) * zeta1 + 2 / (vm * (vm - 1)) * zeta2;
+}
+
+cudaError_t launch_finalize_kid(const double* stats, int64_t nsub, int64_t msub, int64_t first, int est,
+                                int ret_var, int64_t var_at_m, double* mmd2_out, double* var_out, cudaStream_t s) {
+  finalize_kid_kernel<<<(unsigned)nsub, 256, Q_N * 256 * sizeof(double), s>>>(stats, msub, first, est, ret_var,
+                                                                            var_at_m, mmd2_out, var_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_XY_only: dense witness block (the one place an m x n matrix is written, because the caller asks
+// for it) and its VJP through the row kernel in witness mode.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kernel_xy_kernel(KernelFn kf, const float* Z, const float* norms,
+                                                        int64_t dpitch, int64_t m, int64_t n, float* K, int64_t ldk) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.y * 8 + w, j = (int64_t)blockIdx.x * 32 + lane;
+  if (i >= m || j >= n) return;
+  const float4* a = reinterpret_cast<const float4*>(Z + i * dpitch);
+  const float4* b = reinterpret_cast<const float4*>(Z + (m + j) * dpitch);
+  float S = 0.f;
+  for (int64_t c = 0; c < dpitch / 4; ++c) {
+    float4 x = a[c], y = b[c];
+    S = fmaf(x.x, y.x, S);
+    S = fmaf(x.y, y.y, S);
+    S = fmaf(x.z, y.z, S);
+    S = fmaf(x.w, y.w, S);
+  }
+  K[i * ldk + j] = eval_exact(kf, S, norms[i], norms[m + j]).k;
+}
+
+cudaError_t launch_kernel_xy(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,
+                             int64_t n, int64_t, float* K, int64_t ldk, cudaStream_t s) {
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 7) / 8));
+  kernel_xy_kernel<<<grid, 256, 0, s>>>(kf, Z, norms, dpitch, m, n, K, ldk);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kernel_xy_bwd(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,
+                                 int64_t n, int64_t d, const float* dK, int64_t lddk, float* dX, float* dY,
+                                 cudaStream_t s) {
+  SimtArgs a;
+  a.kf = kf;
+  a.Z = Z;
+  a.norms = norms;
+  a.dpitch = dpitch;
+  a.d = d;
+  a.m = m;
+  a.n = n;
+  a.M = m + n;
+  a.x0 = 0;
+  a.ox = m;
+  a.y0 = 0;
+  a.oy = n;
+  a.a_xx = a.a_yy = a.a_xy = 0.f;
+  a.diag_in_sum = 0;
+  a.stats = nullptr;
+  a.dX = dX;
+  a.dY = dY;
+  a.dK = dK;
+  a.lddk = lddk;
+  return launch_rows_t<true>(a, 1, s);
+}
+
+}  // namespace smmd

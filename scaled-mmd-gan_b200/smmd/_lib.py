@@ -1,0 +1,117 @@
+"""ctypes binding of include/smmd.h (libsmmd.so).  No fallbacks: if the library is missing or the
+device is not a B200 the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SMMD_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libsmmd.so"))
+
+MAX_PARAMS = 8
+NUM_SCALARS = 16
+
+# enums (include/smmd.h)
+F32, BF16 = 0, 1
+K_DISTANCE, K_TANH_DISTANCE, K_DOT, K_RBF, K_MIX_RBF, K_MIX_RQ, K_TANH_MIX_RQ, K_POLY = range(8)
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_AUTO = range(4)
+EST_UNBIASED, EST_BIASED, EST_USTAT = range(3)
+S_MMD2, S_SUM_XX, S_SUM_YY, S_SUM_XY, S_SUM_YX, S_DIAG_X, S_DIAG_Y, S_NONFINITE, S_VAR, S_RATIO = range(10)
+
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "auto": PREC_AUTO}
+ESTIMATORS = {"unbiased": EST_UNBIASED, "biased": EST_BIASED, "u-statistic": EST_USTAT}
+
+EXPORTS = [
+    "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
+    "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_combine", "smmd_mmd2_and_ratio",
+    "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
+    "smmd_last_launch_count", "smmd_last_path",
+]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("m", C.c_int64), ("n", C.c_int64), ("d", C.c_int64),
+        ("ldx", C.c_int64), ("ldy", C.c_int64),
+        ("dtype", C.c_int32), ("kernel_id", C.c_int32), ("nparams", C.c_int32),
+        ("params", C.c_float * MAX_PARAMS), ("wts", C.c_float * MAX_PARAMS),
+        ("add_dot", C.c_float), ("degree", C.c_int32), ("biased", C.c_int32), ("precision", C.c_int32),
+        ("rank", C.c_int32), ("world", C.c_int32),
+    ]
+
+
+class KidProblem(C.Structure):
+    _fields_ = [
+        ("n_g", C.c_int64), ("n_r", C.c_int64), ("d", C.c_int64),
+        ("ldg", C.c_int64), ("ldr", C.c_int64),
+        ("dtype", C.c_int32), ("n_subsets", C.c_int32), ("subset_size", C.c_int32), ("degree", C.c_int32),
+        ("gamma", C.c_float), ("coef0", C.c_float),
+        ("var_at_m", C.c_int64),
+        ("mmd_est", C.c_int32), ("ret_var", C.c_int32), ("precision", C.c_int32),
+        ("first_subset", C.c_int32), ("n_local", C.c_int32),
+    ]
+
+
+class SmmdError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        super().__init__("%s failed: %s (status %d)%s" % (where, detail or "?", status, ""))
+
+
+_lib = None
+
+
+def load():
+    """Load libsmmd.so (built in-tree by `make -C scaled-mmd-gan_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "libsmmd.so not found at %s -- build it with `make -C scaled-mmd-gan_b200/csrc` "
+            "(there is no CPU/PyTorch fallback for this path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    lib.smmd_version.restype = C.c_int
+    lib.smmd_strerror.restype = C.c_char_p
+    lib.smmd_strerror.argtypes = [C.c_int]
+    lib.smmd_last_cuda_error.restype = C.c_char_p
+    lib.smmd_device_supported.restype = C.c_int
+    lib.smmd_last_launch_count.restype = C.c_int
+    lib.smmd_last_path.restype = C.c_char_p
+    lib.smmd_mmd2_workspace_bytes.restype = C.c_size_t
+    lib.smmd_mmd2_workspace_bytes.argtypes = [C.POINTER(Problem), C.c_int]
+    lib.smmd_mmd2_fwd_bwd.restype = C.c_int
+    lib.smmd_mmd2_fwd_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_mmd2_combine.restype = C.c_int
+    lib.smmd_mmd2_combine.argtypes = [C.POINTER(Problem), vp, vp, vp]
+    lib.smmd_mmd2_and_ratio.restype = C.c_int
+    lib.smmd_mmd2_and_ratio.argtypes = [C.POINTER(Problem), vp, vp, dbl, vp, vp, C.c_size_t, vp]
+    lib.smmd_kernel_xy.restype = C.c_int
+    lib.smmd_kernel_xy.argtypes = [C.POINTER(Problem), vp, vp, vp, i64, vp]
+    lib.smmd_kernel_xy_bwd.restype = C.c_int
+    lib.smmd_kernel_xy_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, i64, vp, vp, vp]
+    lib.smmd_kid_workspace_bytes.restype = C.c_size_t
+    lib.smmd_kid_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
+    lib.smmd_kid_subsets.restype = C.c_int
+    lib.smmd_kid_subsets.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    _lib = lib
+    return lib
+
+
+def check(status, where):
+    if status == 0:
+        return
+    lib = load()
+    detail = lib.smmd_strerror(status).decode()
+    if status == -6:
+        detail += " [" + lib.smmd_last_cuda_error().decode() + "]"
+    raise SmmdError(status, where, detail)
+
+
+def last_path():
+    return load().smmd_last_path().decode()
+
+
+def last_launch_count():
+    return int(load().smmd_last_launch_count())

@@ -1,0 +1,201 @@
+"""Drop-in for the KID part of the reference's ``gan/compute_scores.py`` (lines 211-335): same
+function names, kwargs and RNG draw order, backed by libsmmd.so.
+
+``polynomial_mmd_averages`` accepts numpy arrays (like the reference: host codes in, numpy float64
+arrays out -- the codes are copied to the GPU once per call) or torch CUDA tensors (device in, torch
+out, no host round trip).  Subset indices come from numpy's *global* RNG in the reference's call order
+(g first, then r, per subset; compute_scores.py:221-222) and are passed to the library explicitly.
+All subsets run as ONE batched pass: row gather, the three Gram blocks per subset on tensor cores,
+the cubic transform and every reduction of ``_mmd2_and_variance`` fused -- no m x m matrix is written.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from .mmd import _as_ptr, _stream_ptr
+
+_default_precision = "auto"
+
+
+def set_default_precision(name):
+    global _default_precision
+    if name not in _lib.PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+    _default_precision = name
+
+
+def _to_device_codes(a, device):
+    """numpy / CPU tensor -> CUDA tensor (pinned staging); CUDA tensor passes through."""
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = a
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.to(torch.float32)  # the reference's codes are float32 (compute_scores.py:131)
+    if not t.is_cuda:
+        t = t.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else t.to(device)
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def draw_subsets(len_g, len_r, n_subsets, subset_size):
+    """np.random.choice(..., replace=False) in the reference's order (compute_scores.py:219-222)."""
+    choice = np.random.choice
+    ig = np.empty((n_subsets, subset_size), dtype=np.int32)
+    ir = np.empty((n_subsets, subset_size), dtype=np.int32)
+    for i in range(n_subsets):
+        ig[i] = choice(len_g, subset_size, replace=False)
+        ir[i] = choice(len_r, subset_size, replace=False)
+    return ig, ir
+
+
+def kid_subsets(codes_g, codes_r, idx_g, idx_r, degree=3, gamma=None, coef0=1, var_at_m=None, ret_var=True,
+                mmd_est="unbiased", precision=None, first_subset=0, n_local=0):
+    """Thin wrapper of smmd_kid_subsets.  codes: CUDA [n, d]; idx: CUDA int32 [S, m].
+    Returns (mmd2[S] f64, var[S] f64 or None) device tensors (only the local shard is written)."""
+    lib = _lib.load()
+    if not (codes_g.is_cuda and codes_r.is_cuda and idx_g.is_cuda and idx_r.is_cuda):
+        raise RuntimeError("smmd: KID inputs must be CUDA tensors; there is no CPU fallback")
+    if codes_g.dim() != 2 or codes_r.dim() != 2 or codes_g.shape[1] != codes_r.shape[1]:
+        raise ValueError("codes must be 2-D with equal feature dim")
+    if idx_g.shape != idx_r.shape or idx_g.dim() != 2:
+        raise ValueError("idx_g / idx_r must both be [n_subsets, subset_size]")
+    S, m = idx_g.shape
+    p = _lib.KidProblem()
+    p.n_g, p.n_r, p.d = codes_g.shape[0], codes_r.shape[0], codes_g.shape[1]
+    p.ldg, p.ldr = codes_g.stride(0), codes_r.stride(0)
+    p.dtype = _lib.F32 if codes_g.dtype == torch.float32 else _lib.BF16
+    p.n_subsets, p.subset_size, p.degree = S, m, int(degree)
+    p.gamma = -1.0 if gamma is None else float(gamma)
+    p.coef0 = float(coef0)
+    p.var_at_m = int(var_at_m) if var_at_m is not None else 0
+    p.mmd_est = _lib.ESTIMATORS[mmd_est]
+    p.ret_var = 1 if ret_var else 0
+    p.precision = _lib.PRECISIONS[precision or _default_precision]
+    p.first_subset, p.n_local = int(first_subset), int(n_local)
+    dev = codes_g.device
+    idx_g = idx_g.to(torch.int32).contiguous()
+    idx_r = idx_r.to(torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        nbytes = lib.smmd_kid_workspace_bytes(C.byref(p))
+        if nbytes == 0:
+            raise _lib.SmmdError(-2, "smmd_kid_workspace_bytes", "problem rejected (shape/params)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        mm = torch.zeros(S, dtype=torch.float64, device=dev)
+        vv = torch.zeros(S, dtype=torch.float64, device=dev) if ret_var else None
+        st = lib.smmd_kid_subsets(C.byref(p), _as_ptr(codes_g), _as_ptr(codes_r), _as_ptr(idx_g), _as_ptr(idx_r),
+                                  _as_ptr(mm), _as_ptr(vv), _as_ptr(ws), nbytes, _stream_ptr(dev))
+        _lib.check(st, "smmd_kid_subsets")
+    return mm, vv
+
+
+def polynomial_mmd_averages(codes_g, codes_r, n_subsets=50, subset_size=1000, ret_var=True, output=sys.stdout,
+                            precision=None, **kernel_args):
+    """compute_scores.py:211-229.  `output` is accepted for signature compatibility (no progress bar)."""
+    host_in = isinstance(codes_g, np.ndarray) or (isinstance(codes_g, torch.Tensor) and not codes_g.is_cuda)
+    dev = codes_g.device if (isinstance(codes_g, torch.Tensor) and codes_g.is_cuda) else torch.device("cuda")
+    m = min(codes_g.shape[0], codes_r.shape[0])
+    ig, ir = draw_subsets(len(codes_g), len(codes_r), n_subsets, subset_size)
+    g = _to_device_codes(codes_g, dev)
+    r = _to_device_codes(codes_r, dev)
+    igd = torch.from_numpy(ig).to(dev, non_blocking=True)
+    ird = torch.from_numpy(ir).to(dev, non_blocking=True)
+    mm, vv = kid_subsets(g, r, igd, ird, var_at_m=m, ret_var=ret_var, precision=precision, **kernel_args)
+    if host_in:
+        mm = mm.cpu().numpy()
+        vv = vv.cpu().numpy() if ret_var else None
+    return (mm, vv) if ret_var else mm
+
+
+def polynomial_mmd(codes_g, codes_r, degree=3, gamma=None, coef0=1, var_at_m=None, ret_var=True,
+                   precision=None, mmd_est="unbiased"):
+    """compute_scores.py:232-244: one estimate on all rows of codes_g (X) vs codes_r (Y)."""
+    if codes_g.shape[0] != codes_r.shape[0]:
+        raise AssertionError("polynomial_mmd needs equally many rows in codes_g and codes_r "
+                             "(square kernel blocks are asserted at compute_scores.py:259-261)")
+    host_in = isinstance(codes_g, np.ndarray) or (isinstance(codes_g, torch.Tensor) and not codes_g.is_cuda)
+    dev = codes_g.device if (isinstance(codes_g, torch.Tensor) and codes_g.is_cuda) else torch.device("cuda")
+    g = _to_device_codes(codes_g, dev)
+    r = _to_device_codes(codes_r, dev)
+    m = g.shape[0]
+    ident = torch.arange(m, dtype=torch.int32, device=dev).unsqueeze(0)
+    mm, vv = kid_subsets(g, r, ident, ident, degree=degree, gamma=gamma, coef0=coef0, var_at_m=var_at_m,
+                         ret_var=ret_var, precision=precision, mmd_est=mmd_est)
+    if host_in:
+        return (float(mm[0].item()), float(vv[0].item())) if ret_var else float(mm[0].item())
+    return (mm[0], vv[0]) if ret_var else mm[0]
+
+
+def _sqn(arr):
+    """compute_scores.py:247-249."""
+    flat = arr.reshape(-1)
+    return flat.dot(flat)
+
+
+def _mmd2_and_variance(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est='unbiased', block_size=1024,
+                       var_at_m=None, ret_var=True):
+    """compute_scores.py:252-335 on caller-materialised dense m x m blocks (compatibility entry point:
+    plain fp64 reductions on the GPU; the fused path is polynomial_mmd / polynomial_mmd_averages)."""
+    host_in = isinstance(K_XX, np.ndarray)
+    dev = torch.device("cuda")
+    as_t = lambda a: (torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a).to(dev).double()
+    K_XX, K_XY, K_YY = as_t(K_XX), as_t(K_XY), as_t(K_YY)
+    m = K_XX.shape[0]
+    assert K_XX.shape == (m, m)
+    assert K_XY.shape == (m, m)
+    assert K_YY.shape == (m, m)
+    if var_at_m is None:
+        var_at_m = m
+    if unit_diagonal:
+        diag_X = diag_Y = torch.ones(m, dtype=torch.float64, device=dev)
+    else:
+        diag_X, diag_Y = torch.diagonal(K_XX), torch.diagonal(K_YY)
+    sum_diag_X, sum_diag_Y = diag_X.sum(), diag_Y.sum()
+    sum_diag2_X, sum_diag2_Y = _sqn(diag_X), _sqn(diag_Y)
+    Kt_XX_sums = K_XX.sum(dim=1) - diag_X
+    Kt_YY_sums = K_YY.sum(dim=1) - diag_Y
+    K_XY_sums_0 = K_XY.sum(dim=0)
+    K_XY_sums_1 = K_XY.sum(dim=1)
+    Kt_XX_sum, Kt_YY_sum, K_XY_sum = Kt_XX_sums.sum(), Kt_YY_sums.sum(), K_XY_sums_0.sum()
+    if mmd_est == 'biased':
+        mmd2 = ((Kt_XX_sum + sum_diag_X) / (m * m) + (Kt_YY_sum + sum_diag_Y) / (m * m)
+                - 2 * K_XY_sum / (m * m))
+    else:
+        assert mmd_est in {'unbiased', 'u-statistic'}
+        mmd2 = (Kt_XX_sum + Kt_YY_sum) / (m * (m - 1))
+        if mmd_est == 'unbiased':
+            mmd2 = mmd2 - 2 * K_XY_sum / (m * m)
+        else:
+            mmd2 = mmd2 - 2 * (K_XY_sum - torch.trace(K_XY)) / (m * (m - 1))
+    fin = (lambda t: float(t.item())) if host_in else (lambda t: t)
+    if not ret_var:
+        return fin(mmd2)
+    Kt_XX_2_sum = _sqn(K_XX) - sum_diag2_X
+    Kt_YY_2_sum = _sqn(K_YY) - sum_diag2_Y
+    K_XY_2_sum = _sqn(K_XY)
+    dot_XX_XY = Kt_XX_sums.dot(K_XY_sums_1)
+    dot_YY_YX = Kt_YY_sums.dot(K_XY_sums_0)
+    m1, m2 = m - 1, m - 2
+    zeta1_est = (
+        1 / (m * m1 * m2) * (_sqn(Kt_XX_sums) - Kt_XX_2_sum + _sqn(Kt_YY_sums) - Kt_YY_2_sum)
+        - 1 / (m * m1) ** 2 * (Kt_XX_sum ** 2 + Kt_YY_sum ** 2)
+        + 1 / (m * m * m1) * (_sqn(K_XY_sums_1) + _sqn(K_XY_sums_0) - 2 * K_XY_2_sum)
+        - 2 / m ** 4 * K_XY_sum ** 2
+        - 2 / (m * m * m1) * (dot_XX_XY + dot_YY_YX)
+        + 2 / (m ** 3 * m1) * (Kt_XX_sum + Kt_YY_sum) * K_XY_sum)
+    zeta2_est = (
+        1 / (m * m1) * (Kt_XX_2_sum + Kt_YY_2_sum)
+        - 1 / (m * m1) ** 2 * (Kt_XX_sum ** 2 + Kt_YY_sum ** 2)
+        + 2 / (m * m) * K_XY_2_sum
+        - 2 / m ** 4 * K_XY_sum ** 2
+        - 4 / (m * m * m1) * (dot_XX_XY + dot_YY_YX)
+        + 4 / (m ** 3 * m1) * (Kt_XX_sum + Kt_YY_sum) * K_XY_sum)
+    var_est = (4 * (var_at_m - 2) / (var_at_m * (var_at_m - 1)) * zeta1_est
+               + 2 / (var_at_m * (var_at_m - 1)) * zeta2_est)
+    return fin(mmd2), fin(var_est)

@@ -1,0 +1,320 @@
+"""Drop-in for the reference's ``gan/core/mmd.py`` (same function names, argument meaning and
+defaults), backed by libsmmd.so.  torch CUDA tensors in, torch tensors out, differentiable.
+
+    kernel = getattr(mmd, '_%s_kernel' % config.kernel)     # model.py:314 / smmd.py:11
+    loss = mmd.mmd2(kernel(G, images))                      # model.py:315-318
+
+``_<name>_kernel(X, Y, ...)`` returns a lazy :class:`KernelHandle` that unpacks like the reference's
+``(K_XX, K_XY, K_YY, const_diagonal)`` tuple (dense matrices are only built if it IS unpacked) and
+that ``mmd2`` / ``mmd2_and_ratio`` recognise so the whole loss -- Gram tiles, kernel transform,
+diagonal removal, block sums and both feature gradients -- runs as one fused pass in which no N x N
+matrix reaches HBM.  With ``K_XY_only=True`` a dense differentiable K_XY tensor is returned, as in
+the reference (model.py:336).
+
+There is deliberately no CPU / eager-PyTorch fallback: inputs must be CUDA tensors on a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_eps = 1.0e-5  # mmd.py:6
+
+_DEFAULT_SIGMAS = [2.0, 5.0, 10.0, 20.0, 40.0, 80.0]  # mmd.py:85
+_DEFAULT_ALPHAS = [0.1, 1.0, 10.0]  # mmd.py:143
+
+_default_precision = "auto"
+
+
+def set_default_precision(name):
+    """'auto' | 'fp32' (exact SIMT, rel 1e-5 tier) | 'bf16' (tcgen05, rel 1e-3 tier) | 'bf16x3'."""
+    global _default_precision
+    if name not in _lib.PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+    _default_precision = name
+
+
+def _as_ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_features(X, Y):
+    if not (isinstance(X, torch.Tensor) and isinstance(Y, torch.Tensor)):
+        raise TypeError("X and Y must be torch tensors")
+    if X.dim() != 2 or Y.dim() != 2 or X.shape[1] != Y.shape[1]:
+        raise ValueError("X and Y must be 2-D [rows, features] with equal feature dim (got %s, %s)"
+                         % (tuple(X.shape), tuple(Y.shape)))
+    if not (X.is_cuda and Y.is_cuda):
+        raise RuntimeError("smmd: features must be CUDA tensors on a B200; there is no CPU fallback")
+    if X.dtype not in (torch.float32, torch.bfloat16) or Y.dtype != X.dtype:
+        raise TypeError("smmd: features must both be float32 or both bfloat16")
+
+
+class KernelSpec:
+    """Kernel family + parameters, mirroring the reference's kernel constructors."""
+
+    def __init__(self, kernel_id, params=(), wts=(), add_dot=0.0, const_diagonal=False, degree=0, name=""):
+        self.kernel_id = kernel_id
+        self.params = [float(v) for v in params]
+        self.wts = [float(v) for v in wts]
+        self.add_dot = float(add_dot)
+        self.const_diagonal = const_diagonal
+        self.degree = int(degree)
+        self.name = name
+        if len(self.params) > _lib.MAX_PARAMS:
+            raise ValueError("at most %d sigmas/alphas are supported" % _lib.MAX_PARAMS)
+
+    def problem(self, m, n, d, ldx, ldy, dtype, biased=False, precision=None, rank=0, world=1):
+        p = _lib.Problem()
+        p.m, p.n, p.d, p.ldx, p.ldy = m, n, d, ldx, ldy
+        p.dtype = _lib.F32 if dtype == torch.float32 else _lib.BF16
+        p.kernel_id = self.kernel_id
+        p.nparams = len(self.params)
+        for i, v in enumerate(self.params):
+            p.params[i] = v
+        for i, v in enumerate(self.wts):
+            p.wts[i] = v
+        p.add_dot = self.add_dot
+        p.degree = self.degree
+        p.biased = 1 if biased else 0
+        p.precision = _lib.PRECISIONS[precision or _default_precision]
+        p.rank, p.world = rank, world
+        return p
+
+
+def _rows(t):
+    """Row-major view with unit inner stride (copy only if needed); returns (tensor, ld)."""
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, rank=0, world=1):
+    """One call of smmd_mmd2_fwd_bwd.  Returns (scalars[16] f64 device tensor, dX, dY) for the owned rows."""
+    _check_features(X, Y)
+    lib = _lib.load()
+    Xc, ldx = _rows(X.detach())
+    Yc, ldy = _rows(Y.detach())
+    m, d = Xc.shape
+    n = Yc.shape[0]
+    prob = spec.problem(m, n, d, ldx, ldy, Xc.dtype, biased, precision, rank, world)
+    dev = Xc.device
+    with torch.cuda.device(dev):
+        nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1 if want_grad else 0)
+        if nbytes == 0:
+            raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
+        dX = dY = None
+        if want_grad:
+            om = m * (rank + 1) // world - m * rank // world
+            on = n * (rank + 1) // world - n * rank // world
+            dX = torch.empty((om, d), dtype=torch.float32, device=dev)
+            dY = torch.empty((on, d), dtype=torch.float32, device=dev)
+        st = lib.smmd_mmd2_fwd_bwd(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(scalars), _as_ptr(dX),
+                                   _as_ptr(dY), _as_ptr(ws), nbytes, _stream_ptr(dev))
+        _lib.check(st, "smmd_mmd2_fwd_bwd")
+    return scalars, dX, dY
+
+
+class _FusedMMD2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, Y, spec, biased, precision):
+        need = X.requires_grad or Y.requires_grad
+        scalars, dX, dY = fused_mmd2_raw(spec, X, Y, biased, want_grad=need, precision=precision)
+        ctx.save_for_backward(dX, dY)
+        ctx.in_dtypes = (X.dtype, Y.dtype)
+        return scalars[_lib.S_MMD2].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dX, dY = ctx.saved_tensors
+        if dX is None:
+            return None, None, None, None, None
+        g = grad_out.to(torch.float32)
+        return (g * dX).to(ctx.in_dtypes[0]), (g * dY).to(ctx.in_dtypes[1]), None, None, None
+
+
+class KernelHandle:
+    """Lazy stand-in for the reference's ``(K_XX, K_XY, K_YY, const_diagonal)`` tuple."""
+
+    def __init__(self, spec, X, Y):
+        _check_features(X, Y)
+        self.spec, self.X, self.Y = spec, X, Y
+        self._dense = None
+
+    def dense(self):
+        if self._dense is None:
+            s, X, Y = self.spec, self.X, self.Y
+            self._dense = (kernel_xy(s, X, X), kernel_xy(s, X, Y), kernel_xy(s, Y, Y), s.const_diagonal)
+        return self._dense
+
+    def __iter__(self):
+        return iter(self.dense())
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        return self.dense()[i]
+
+
+# ---- K_XY_only: dense differentiable witness block ------------------------------------------------
+class _KernelXY(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, Y, spec):
+        _check_features(X, Y)
+        lib = _lib.load()
+        Xc, ldx = _rows(X.detach().float())
+        Yc, ldy = _rows(Y.detach().float())
+        m, d = Xc.shape
+        n = Yc.shape[0]
+        prob = spec.problem(m, n, d, ldx, ldy, torch.float32, precision="fp32")
+        K = torch.empty((m, n), dtype=torch.float32, device=Xc.device)
+        with torch.cuda.device(Xc.device):
+            st = lib.smmd_kernel_xy(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(K), n, _stream_ptr(Xc.device))
+        _lib.check(st, "smmd_kernel_xy")
+        ctx.save_for_backward(Xc, Yc)
+        ctx.spec = spec
+        ctx.in_dtypes = (X.dtype, Y.dtype)
+        return K
+
+    @staticmethod
+    def backward(ctx, dK):
+        Xc, Yc = ctx.saved_tensors
+        lib = _lib.load()
+        spec = ctx.spec
+        m, d = Xc.shape
+        n = Yc.shape[0]
+        dK = dK.contiguous().float()
+        prob = spec.problem(m, n, d, Xc.stride(0), Yc.stride(0), torch.float32, precision="fp32")
+        dX = torch.empty((m, d), dtype=torch.float32, device=Xc.device)
+        dY = torch.empty((n, d), dtype=torch.float32, device=Xc.device)
+        with torch.cuda.device(Xc.device):
+            st = lib.smmd_kernel_xy_bwd(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(dK), n, _as_ptr(dX),
+                                        _as_ptr(dY), _stream_ptr(Xc.device))
+        _lib.check(st, "smmd_kernel_xy_bwd")
+        return dX.to(ctx.in_dtypes[0]), dY.to(ctx.in_dtypes[1]), None
+
+
+def kernel_xy(spec, X, Y):
+    return _KernelXY.apply(X, Y, spec)
+
+
+def _make(spec, X, Y, K_XY_only):
+    if K_XY_only:
+        return kernel_xy(spec, X, Y)
+    return KernelHandle(spec, X, Y)
+
+
+# ---- the kernel zoo: names, defaults and argument order of gan/core/mmd.py:18-188 -------------------
+def _distance_kernel(X, Y, K_XY_only=False):
+    return _make(KernelSpec(_lib.K_DISTANCE, name="distance"), X, Y, K_XY_only)
+
+
+def _tanh_distance_kernel(X, Y, K_XY_only=False):
+    return _make(KernelSpec(_lib.K_TANH_DISTANCE, name="tanh_distance"), X, Y, K_XY_only)
+
+
+def _dot_kernel(X, Y, K_XY_only=False):
+    return _make(KernelSpec(_lib.K_DOT, name="dot"), X, Y, K_XY_only)
+
+
+def _rbf_kernel(X, Y, sigma=1., wt=1., K_XY_only=False):
+    spec = KernelSpec(_lib.K_RBF, [sigma], [wt], const_diagonal=float(wt), name="rbf")
+    return _make(spec, X, Y, K_XY_only)
+
+
+def _mix_rbf_kernel(X, Y, sigmas=None, wts=None, K_XY_only=False):
+    sigmas = _DEFAULT_SIGMAS if sigmas is None else list(sigmas)
+    wts = [1.0] * len(sigmas) if wts is None else list(wts)
+    spec = KernelSpec(_lib.K_MIX_RBF, sigmas, wts, const_diagonal=float(sum(wts)), name="mix_rbf")
+    return _make(spec, X, Y, K_XY_only)
+
+
+def _mix_rq_kernel(X, Y, alphas=None, wts=None, K_XY_only=False, add_dot=.0, _tanh=False):
+    alphas = _DEFAULT_ALPHAS if alphas is None else list(alphas)
+    wts = [1.0] * len(alphas) if wts is None else list(wts)
+    # const_diagonal is sum(wts) even when add_dot > 0 -- reference quirk kept (mmd.py:186-188)
+    spec = KernelSpec(_lib.K_TANH_MIX_RQ if _tanh else _lib.K_MIX_RQ, alphas, wts, add_dot=add_dot,
+                      const_diagonal=float(sum(wts)), name="tanh_mix_rq" if _tanh else "mix_rq")
+    return _make(spec, X, Y, K_XY_only)
+
+
+def _mix_rq_dot_kernel(X, Y, alphas=None, wts=None, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, alphas=alphas, wts=wts, K_XY_only=K_XY_only, add_dot=.1)
+
+
+def _mix_rq_1dot_kernel(X, Y, alphas=None, wts=None, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, alphas=alphas, wts=wts, K_XY_only=K_XY_only, add_dot=1.)
+
+
+def _mix_rq_10dot_kernel(X, Y, alphas=None, wts=None, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, alphas=alphas, wts=wts, K_XY_only=K_XY_only, add_dot=10.)
+
+
+def _mix_rq_01dot_kernel(X, Y, alphas=None, wts=None, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, alphas=alphas, wts=wts, K_XY_only=K_XY_only, add_dot=.1)
+
+
+def _mix_rq_001dot_kernel(X, Y, alphas=None, wts=None, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, alphas=alphas, wts=wts, K_XY_only=K_XY_only, add_dot=.01)
+
+
+def _tanh_mix_rq_kernel(X, Y, K_XY_only=False):
+    return _mix_rq_kernel(X, Y, K_XY_only=K_XY_only, _tanh=True)
+
+
+# ---- estimators -------------------------------------------------------------------------------------
+def mmd2(K, biased=False, precision=None):
+    """mmd.py:194-196.  ``K`` is a KernelHandle (fused path) or an explicit 4-tuple of dense blocks."""
+    if isinstance(K, KernelHandle):
+        return _FusedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision)
+    K_XX, K_XY, K_YY, const_diagonal = K
+    return _mmd2(K_XX, K_XY, K_YY, const_diagonal, biased)
+
+
+def _mmd2(K_XX, K_XY, K_YY, const_diagonal=False, biased=False):
+    """mmd.py:199-220 on caller-materialised dense blocks (compatibility path: plain reductions)."""
+    m = float(K_XX.shape[0])
+    n = float(K_YY.shape[0])
+    if biased:
+        return K_XX.sum() / (m * m) + K_YY.sum() / (n * n) - 2 * K_XY.sum() / (m * n)
+    if const_diagonal is not False:
+        trace_X, trace_Y = m * float(const_diagonal), n * float(const_diagonal)
+    else:
+        trace_X, trace_Y = torch.trace(K_XX), torch.trace(K_YY)
+    return ((K_XX.sum() - trace_X) / (m * (m - 1)) + (K_YY.sum() - trace_Y) / (n * (n - 1))
+            - 2 * K_XY.sum() / (m * n))
+
+
+def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
+    """mmd.py:223-232 -> (mmd2, ratio, var_est); fused statistics pass, not differentiable."""
+    if not isinstance(K, KernelHandle):
+        raise TypeError("mmd2_and_ratio expects the handle returned by a _<name>_kernel(X, Y) call")
+    X, Y, spec = K.X, K.Y, K.spec
+    lib = _lib.load()
+    Xc, ldx = _rows(X.detach())
+    Yc, ldy = _rows(Y.detach())
+    m, d = Xc.shape
+    n = Yc.shape[0]
+    if m != n:
+        raise ValueError("mmd2_and_ratio assumes X and Y have the same number of rows (mmd.py:237)")
+    prob = spec.problem(m, n, d, ldx, ldy, Xc.dtype, biased, "fp32")
+    dev = Xc.device
+    with torch.cuda.device(dev):
+        # statistics run on the exact path: same workspace formula as a forward-only fp32 problem
+        nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
+        st = lib.smmd_mmd2_and_ratio(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), float(min_var_est), _as_ptr(scalars),
+                                     _as_ptr(ws), nbytes, _stream_ptr(dev))
+        _lib.check(st, "smmd_mmd2_and_ratio")
+    return (scalars[_lib.S_MMD2].float(), scalars[_lib.S_RATIO].float(), scalars[_lib.S_VAR].float())

@@ -1,0 +1,87 @@
+"""CPU: the C-ABI library loads, exports every symbol include/smmd.h declares, validates arguments
+before touching the device, and refuses to run without a B200 (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from smmd import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "smmd.h")).read()
+    return sorted(set(re.findall(r"SMMD_API\s+[\w\s\*]+?\b(smmd_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    assert sorted(_lib.EXPORTS) == declared
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_version_and_strerror():
+    lib = _lib.load()
+    assert lib.smmd_version() == 100
+    assert lib.smmd_strerror(0) == b"ok"
+    assert b"sm_100" in lib.smmd_strerror(-4)
+
+
+def _problem(**kw):
+    p = _lib.Problem()
+    p.m, p.n, p.d, p.ldx, p.ldy = 64, 64, 16, 16, 16
+    p.dtype, p.kernel_id, p.nparams = _lib.F32, _lib.K_MIX_RBF, 2
+    p.params[0], p.params[1] = 1.0, 2.0
+    p.wts[0], p.wts[1] = 1.0, 1.0
+    p.precision, p.rank, p.world = _lib.PREC_FP32, 0, 1
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def test_validation_happens_before_device_access():
+    lib = _lib.load()
+    dummy = C.c_void_p(256)
+    call = lambda p: lib.smmd_mmd2_fwd_bwd(C.byref(p), dummy, dummy, dummy, None, None, dummy, 1 << 20, None)
+    assert call(_problem(m=0)) == -2            # SMMD_ESHAPE
+    assert call(_problem(ldx=8)) == -2
+    assert call(_problem(m=1)) == -2            # unbiased needs m >= 2
+    assert call(_problem(dtype=7)) == -3        # SMMD_EDTYPE
+    assert call(_problem(world=2, rank=2)) == -1
+    assert call(_problem(kernel_id=99)) == -1
+    assert lib.smmd_mmd2_workspace_bytes(C.byref(_problem(m=0)), 1) == 0
+    assert lib.smmd_mmd2_workspace_bytes(C.byref(_problem()), 1) > 0
+    # half-specified gradient outputs are rejected
+    assert lib.smmd_mmd2_fwd_bwd(C.byref(_problem()), dummy, dummy, dummy, dummy, None, dummy, 1 << 20, None) == -1
+
+
+def test_no_fallback_without_b200():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    assert lib.smmd_device_supported() == 0
+    dummy = C.c_void_p(256)
+    st = lib.smmd_mmd2_fwd_bwd(C.byref(_problem()), dummy, dummy, dummy, None, None, dummy, 1 << 20, None)
+    assert st == -4  # SMMD_EARCH: fails loudly, never computes on the CPU
+    from smmd import mmd
+
+    with pytest.raises(RuntimeError):
+        mmd.mmd2(mmd._rbf_kernel(torch.zeros(4, 2), torch.zeros(4, 2)))
+
+
+def test_kid_validation():
+    lib = _lib.load()
+    p = _lib.KidProblem()
+    p.n_g, p.n_r, p.d, p.ldg, p.ldr = 100, 100, 32, 32, 32
+    p.n_subsets, p.subset_size, p.degree, p.coef0 = 4, 50, 3, 1.0
+    p.precision = _lib.PREC_FP32
+    assert lib.smmd_kid_workspace_bytes(C.byref(p)) > 0
+    p.subset_size = 101  # replace=False cannot draw more rows than exist
+    assert lib.smmd_kid_workspace_bytes(C.byref(p)) == 0

@@ -1,0 +1,237 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the reference-shaped
+Python drop-in -> C-ABI -> kernels, against (a) the committed golden vectors minted from the
+reference itself and (b) the numpy oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): exact-fp32 path rel 1e-5 on MMD^2 / KID and element-wise on
+gradients, stated against the fp64 truth; bf16 tensor-core path rel 1e-3.  MMD^2 is a difference of
+three O(sum of weights) block means, so each assertion carries a cancellation floor
+`abs_floor = 2e-7 * kscale` (kscale = magnitude of the block means), i.e. ~2 fp32 ulps of the terms
+that are being subtracted -- the reference's own fp32 result sits 1e-5..4e-5 (relative) from the fp64
+truth on these inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import kid_codes, load_kid_golden, load_mmd_golden
+from oracle import kid_oracle, mmd_oracle
+
+pytestmark = pytest.mark.gpu
+
+Z, INDEX = load_mmd_golden()
+DEV = "cuda:0"
+
+
+def _kernel_fn(mmd, name):
+    return getattr(mmd, "_%s_kernel" % name)
+
+
+def _kscale(name, kw, X, Y):
+    Kxx, Kxy, Kyy, _ = mmd_oracle.kernel_matrices(name, X, Y, np.float64, **kw)
+    return max(abs(Kxx).mean(), abs(Kxy).mean(), abs(Kyy).mean(), 1e-30)
+
+
+@pytest.mark.parametrize("case", INDEX, ids=[c["key"] for c in INDEX])
+def test_fp32_path_matches_reference_golden(case):
+    from smmd import _lib, mmd
+
+    X, Y = Z["X_" + case["shape"]], Z["Y_" + case["shape"]]
+    key = case["key"]
+    Xt = torch.tensor(X, device=DEV, requires_grad=True)
+    Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+    K = _kernel_fn(mmd, case["kernel"])(Xt, Yt, **case["kwargs"])
+    loss = mmd.mmd2(K, biased=case["biased"], precision="fp32")
+    loss.backward()
+    assert _lib.last_path() == "simt_fp32"
+    v64 = float(Z[key + "|v64"])
+    floor = 2e-7 * _kscale(case["kernel"], case["kwargs"], X, Y)
+    assert abs(loss.item() - v64) <= 1e-5 * abs(v64) + floor, (loss.item(), v64)
+    for got, ref in ((Xt.grad, Z[key + "|gx64"]), (Yt.grad, Z[key + "|gy64"])):
+        ref = np.asarray(ref, dtype=np.float64)
+        err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
+        assert err <= 1e-5 * np.abs(ref).max() + 1e-9, (err, np.abs(ref).max())
+
+
+def test_fp32_scalars_are_float64_accurate():
+    """The raw fp64 scalar (before the fp32 cast of the autograd output) vs the fp64 oracle."""
+    from smmd import _lib, mmd
+
+    X, Y = Z["X_c1_64x16"], Z["Y_c1_64x16"]
+    spec = mmd._mix_rbf_kernel(torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV),
+                               sigmas=[1, 2, 4, 8, 16]).spec
+    sc, dX, dY = mmd.fused_mmd2_raw(spec, torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV),
+                                    precision="fp32")
+    v = mmd_oracle.mmd2("mix_rbf", X, Y, False, np.float64, sigmas=[1, 2, 4, 8, 16])
+    assert abs(sc[_lib.S_MMD2].item() - v) <= 1e-5 * abs(v)
+    assert sc[_lib.S_NONFINITE].item() == 0.0
+    Kxx, Kxy, Kyy, _ = mmd_oracle.kernel_matrices("mix_rbf", X, Y, np.float64, sigmas=[1, 2, 4, 8, 16])
+    assert abs(sc[_lib.S_SUM_XY].item() - Kxy.sum()) <= 1e-6 * Kxy.sum()
+    assert abs(sc[_lib.S_SUM_XX].item() - (Kxx.sum() - np.trace(Kxx))) <= 1e-6 * Kxx.sum()
+
+
+@pytest.mark.parametrize("m,n,d", [(2, 2, 1), (3, 5, 2), (33, 31, 9), (257, 129, 40), (64, 64, 300), (40, 40, 1030)])
+@pytest.mark.parametrize("name", ["mix_rq", "mix_rbf", "distance", "dot", "mix_rq_1dot", "tanh_mix_rq"])
+def test_fp32_ragged_shapes_vs_oracle(m, n, d, name):
+    from smmd import mmd
+
+    rng = np.random.RandomState(m * 1000 + n * 10 + d)
+    X = (rng.randn(m, d) / np.sqrt(d)).astype(np.float32)
+    Y = ((1.05 * rng.randn(n, d) + 0.1) / np.sqrt(d)).astype(np.float32)
+    for biased in (False, True):
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        loss = mmd.mmd2(_kernel_fn(mmd, name)(Xt, Yt), biased=biased, precision="fp32")
+        loss.backward()
+        v, gx, gy = mmd_oracle.mmd2_and_grads(name, X, Y, biased, np.float64)
+        floor = 2e-7 * _kscale(name, {}, X, Y)
+        assert abs(loss.item() - v) <= 1e-5 * abs(v) + floor, (name, biased, loss.item(), v)
+        assert np.abs(Xt.grad.cpu().numpy() - gx).max() <= 1e-5 * np.abs(gx).max() + 1e-9
+        assert np.abs(Yt.grad.cpu().numpy() - gy).max() <= 1e-5 * np.abs(gy).max() + 1e-9
+
+
+def test_noncontiguous_and_bf16_inputs():
+    from smmd import mmd
+
+    rng = np.random.RandomState(5)
+    big = torch.tensor(rng.randn(70, 40).astype(np.float32), device=DEV)
+    X, Y = big[:30, 3:19], big[30:, 3:19]          # row stride 40, unit inner stride
+    v = mmd_oracle.mmd2("mix_rq", X.cpu().numpy(), Y.cpu().numpy(), False, np.float64)
+    got = mmd.mmd2(mmd._mix_rq_kernel(X, Y), precision="fp32").item()
+    assert abs(got - v) <= 1e-5 * abs(v) + 2e-7
+    Xb, Yb = X.contiguous().bfloat16(), Y.contiguous().bfloat16()
+    vb = mmd_oracle.mmd2("mix_rq", Xb.float().cpu().numpy(), Yb.float().cpu().numpy(), False, np.float64)
+    gotb = mmd.mmd2(mmd._mix_rq_kernel(Xb, Yb), precision="fp32").item()
+    assert abs(gotb - vb) <= 1e-5 * abs(vb) + 2e-7
+
+
+def test_upstream_gradient_scaling_like_smmd():
+    """SMMD multiplies the loss by `scale` (smmd.py:21-23): autograd must chain through the fused op."""
+    from smmd import mmd
+
+    X, Y = Z["X_c1_64x16"], Z["Y_c1_64x16"]
+    Xt = torch.tensor(X, device=DEV, requires_grad=True)
+    Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+    scale = torch.tensor(0.37, device=DEV)
+    (mmd.mmd2(mmd._rbf_kernel(Xt, Yt), precision="fp32") * scale).backward()
+    _, gx, gy = mmd_oracle.mmd2_and_grads("rbf", X, Y, False, np.float64)
+    assert np.abs(Xt.grad.cpu().numpy() - 0.37 * gx).max() <= 1e-5 * np.abs(gx).max()
+
+
+def test_ratio_matches_reference_golden():
+    from smmd import mmd
+
+    n = 0
+    for k in Z.files:
+        if not k.startswith("ratio|"):
+            continue
+        _, shape, kname, biased = k.split("|")
+        kw = {"sigmas": [1.0, 2.0, 4.0, 8.0, 16.0]} if kname == "mix_rbf" else {}
+        X, Y = Z["X_" + shape], Z["Y_" + shape]
+        K = _kernel_fn(mmd, kname)(torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV), **kw)
+        v, r, var = [t.item() for t in mmd.mmd2_and_ratio(K, biased=bool(int(biased)))]
+        v6, r6, var6 = mmd_oracle.mmd2_and_ratio(kname, X, Y, bool(int(biased)), dtype=np.float64, **kw)
+        assert abs(v - v6) <= 1e-5 * max(abs(v6), 1.0), k
+        assert abs(var - var6) <= 1e-3 * abs(var6) + 1e-9, (k, var, var6)
+        assert abs(r - r6) <= 1e-3 * abs(r6) + 1e-6, k
+        n += 1
+    assert n >= 10
+
+
+def test_kxy_only_and_its_vjp():
+    from smmd import mmd
+
+    for k in Z.files:
+        if not k.startswith("kxy|"):
+            continue
+        _, shape, kname = k.split("|")
+        X, Y = Z["X_" + shape], Z["Y_" + shape]
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        K = _kernel_fn(mmd, kname)(Xt, Yt, K_XY_only=True)
+        assert np.allclose(K.detach().cpu().numpy(), Z[k], rtol=3e-5, atol=3e-5), k
+        # witness-style functional (model.py:336-338): mean over columns, weighted over rows
+        w = torch.linspace(-1, 1, K.shape[0], device=DEV)
+        (K.mean(dim=1) * w).sum().backward()
+        # torch fp64 reference of the same functional through the oracle formulas
+        Xr = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+        Yr = torch.tensor(Y, dtype=torch.float64, requires_grad=True)
+        Kr = _torch_kxy(kname, Xr, Yr)
+        (Kr.mean(dim=1) * w.cpu().double()).sum().backward()
+        assert np.abs(Xt.grad.cpu().numpy() - Xr.grad.numpy()).max() <= 2e-5 * Xr.grad.abs().max().item() + 1e-8, k
+        assert np.abs(Yt.grad.cpu().numpy() - Yr.grad.numpy()).max() <= 2e-5 * Yr.grad.abs().max().item() + 1e-8, k
+
+
+def _torch_kxy(name, X, Y):
+    """Plain torch fp64 restatement of K_XY for the witness VJP check (floating-point kernel -> torch ref)."""
+    G = X @ Y.T
+    nx, ny = (X * X).sum(1), (Y * Y).sum(1)
+    Draw = nx[:, None] + ny[None, :] - 2 * G
+    if name == "dot":
+        return G
+    if name == "distance":
+        return torch.sqrt(nx + 1e-5)[:, None] + torch.sqrt(ny + 1e-5)[None, :] - torch.sqrt(torch.clamp(Draw + 1e-5, min=0))
+    D = torch.clamp(Draw, min=0)
+    if name == "rbf":
+        return torch.exp(-0.5 * D)
+    K = sum((1 + D / (2 * a)) ** (-a) for a in (0.1, 1.0, 10.0))
+    if name == "mix_rq_1dot":
+        K = K + G
+    return K
+
+
+KZ = load_kid_golden()
+
+
+@pytest.mark.parametrize("tag", ["small", "mid"])
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_kid_matches_reference_golden(tag, precision):
+    from smmd import compute_scores
+
+    g, r = kid_codes(KZ, tag)
+    ng, nr, d, m, S = [int(v) for v in KZ["meta_" + tag]]
+    v, var = compute_scores.polynomial_mmd(g[:m], r[:m], precision=precision)
+    v64, var64 = KZ["pm64_" + tag]
+    assert abs(v - v64) <= 1e-5 * abs(v64) + 1e-8, (v, v64)
+    assert abs(var - var64) <= 1e-3 * abs(var64), (var, var64)
+    np.random.seed(0)
+    mmds, vrs = compute_scores.polynomial_mmd_averages(g, r, n_subsets=S, subset_size=m, ret_var=True,
+                                                       precision=precision)
+    assert np.allclose(mmds, KZ["avg_mmds64_" + tag], rtol=1e-5, atol=1e-8)
+    assert np.allclose(vrs, KZ["avg_vars64_" + tag], rtol=1e-3, atol=1e-12)
+    np.random.seed(0)
+    mm2 = compute_scores.polynomial_mmd_averages(g, r, n_subsets=S, subset_size=m, ret_var=False, precision=precision)
+    assert np.allclose(mm2, mmds, rtol=1e-12)
+    for est in ("biased", "unbiased", "u-statistic"):
+        vv, _ = compute_scores.polynomial_mmd(g[:m], r[:m], var_at_m=min(ng, nr), mmd_est=est, precision=precision)
+        ref = kid_oracle.polynomial_mmd(g[:m].astype(np.float64), r[:m].astype(np.float64), var_at_m=min(ng, nr),
+                                        mmd_est=est)[0]
+        assert abs(vv - ref) <= 1e-5 * abs(ref) + 1e-8, est
+
+
+def test_kid_dense_compat_entry_point():
+    from smmd import compute_scores
+
+    g, r = kid_codes(KZ, "small")
+    m = 100
+    Kxx = kid_oracle.poly_kernel(g[:m], g[:m])
+    Kyy = kid_oracle.poly_kernel(r[:m], r[:m])
+    Kxy = kid_oracle.poly_kernel(g[:m], r[:m])
+    v, var = compute_scores._mmd2_and_variance(Kxx, Kxy, Kyy)
+    rv, rvar = kid_oracle.mmd2_and_variance(Kxx.astype(np.float64), Kxy.astype(np.float64), Kyy.astype(np.float64))
+    assert abs(v - rv) <= 1e-9 * abs(rv) + 1e-12 and abs(var - rvar) <= 1e-7 * abs(rvar)
+    with pytest.raises(AssertionError):
+        compute_scores._mmd2_and_variance(Kxx, Kxy[:, :50], Kyy)
+
+
+def test_errors_are_loud():
+    from smmd import _lib, mmd
+
+    X = torch.zeros(8, 4, device=DEV)
+    with pytest.raises(_lib.SmmdError):
+        mmd.mmd2(mmd._mix_rbf_kernel(X, X, sigmas=[-1.0]), precision="fp32")
+    with pytest.raises(ValueError):
+        mmd._rbf_kernel(X, torch.zeros(8, 5, device=DEV))
+    with pytest.raises(RuntimeError):
+        mmd._rbf_kernel(X.cpu(), X.cpu())
+    with pytest.raises(ValueError):
+        mmd.mmd2_and_ratio(mmd._rbf_kernel(X, torch.zeros(9, 4, device=DEV)))
