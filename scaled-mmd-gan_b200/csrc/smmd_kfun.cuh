@@ -17,12 +17,14 @@ struct PairVal {
   float k, kd, kg;
 };
 
-__device__ __forceinline__ PairVal eval_exact(const KernelFn& f, float G, float ni, float nj) {
+// `Draw` is the squared distance.  The exact path evaluates it in difference form sum_c (a_c-b_c)^2,
+// which is >= 0 by construction and free of the cancellation the reference's fp32 Gram form
+// (-2*XY + |x|^2 + |y|^2, mmd.py:67) suffers for near-by points -- i.e. closer to the fp64 truth.
+__device__ __forceinline__ PairVal eval_exact(const KernelFn& f, float G, float Draw, float ni, float nj) {
   PairVal r;
   r.k = 0.f;
   r.kd = 0.f;
   r.kg = 0.f;
-  const float Draw = (-2.f * G + ni) + nj;  // same association as the reference: (-2*XY + c(n)) + r(n)
   switch (f.family) {
     case FAM_DOT:
       r.k = G;

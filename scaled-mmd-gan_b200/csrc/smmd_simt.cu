@@ -180,8 +180,12 @@ __global__ void __launch_bounds__(256) simt_rows_kernel(SimtArgs a) {
   }
   const int64_t jt0 = jbeg / 32, jt1 = (jend + 31) / 32;
 
+  // which pair quantities the family needs: G = <a,b> and/or D = |a-b|^2 (difference form)
+  const bool needG = a.kf.family == FAM_DOT || a.kf.family == FAM_POLY || a.kf.add_dot > 0.f;
+  const bool needD = a.kf.family == FAM_RBF || a.kf.family == FAM_RQ || a.kf.family == FAM_DISTANCE;
+
   for (int64_t jt = jt0; jt < jt1; ++jt) {
-    float S = 0.f;
+    float S = 0.f, Dd = 0.f;
     for (int ch = 0; ch < nch; ++ch) {
       __syncthreads();
       const int q4 = dch >> 2;
@@ -207,13 +211,26 @@ __global__ void __launch_bounds__(256) simt_rows_kernel(SimtArgs a) {
       __syncthreads();
       const float4* rp = reinterpret_cast<const float4*>(rowT + warp * dch);
       const float4* cp = reinterpret_cast<const float4*>(colT + lane * cpitch);
+      if (needG) {
 #pragma unroll 4
-      for (int c4 = 0; c4 < q4; ++c4) {
-        float4 x = rp[c4], y = cp[c4];
-        S = fmaf(x.x, y.x, S);
-        S = fmaf(x.y, y.y, S);
-        S = fmaf(x.z, y.z, S);
-        S = fmaf(x.w, y.w, S);
+        for (int c4 = 0; c4 < q4; ++c4) {
+          float4 x = rp[c4], y = cp[c4];
+          S = fmaf(x.x, y.x, S);
+          S = fmaf(x.y, y.y, S);
+          S = fmaf(x.z, y.z, S);
+          S = fmaf(x.w, y.w, S);
+        }
+      }
+      if (needD) {
+#pragma unroll 4
+        for (int c4 = 0; c4 < q4; ++c4) {
+          float4 x = rp[c4], y = cp[c4];
+          float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+          Dd = fmaf(e0, e0, Dd);
+          Dd = fmaf(e1, e1, Dd);
+          Dd = fmaf(e2, e2, Dd);
+          Dd = fmaf(e3, e3, Dd);
+        }
       }
     }
     // ---- pair epilogue: lane <-> column jg ----
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(256) simt_rows_kernel(SimtArgs a) {
       const bool colX = jg < a.m;
       const bool same = (colX == rowX);
       const bool isdiag = (jg == ig);
-      PairVal pv = eval_exact(a.kf, S, ni, nj);
+      PairVal pv = eval_exact(a.kf, S, Dd, ni, nj);
       if (witness) {
         if (!same) {
           float w = rowX ? a.dK[ig * a.lddk + (jg - a.m)] : a.dK[jg * a.lddk + (ig - a.m)];
@@ -613,15 +630,20 @@ __global__ void __launch_bounds__(256) kernel_xy_kernel(KernelFn kf, const float
   if (i >= m || j >= n) return;
   const float4* a = reinterpret_cast<const float4*>(Z + i * dpitch);
   const float4* b = reinterpret_cast<const float4*>(Z + (m + j) * dpitch);
-  float S = 0.f;
+  float S = 0.f, Dd = 0.f;
   for (int64_t c = 0; c < dpitch / 4; ++c) {
     float4 x = a[c], y = b[c];
     S = fmaf(x.x, y.x, S);
     S = fmaf(x.y, y.y, S);
     S = fmaf(x.z, y.z, S);
     S = fmaf(x.w, y.w, S);
+    float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+    Dd = fmaf(e0, e0, Dd);
+    Dd = fmaf(e1, e1, Dd);
+    Dd = fmaf(e2, e2, Dd);
+    Dd = fmaf(e3, e3, Dd);
   }
-  K[i * ldk + j] = eval_exact(kf, S, norms[i], norms[m + j]).k;
+  K[i * ldk + j] = eval_exact(kf, S, Dd, norms[i], norms[m + j]).k;
 }
 
 cudaError_t launch_kernel_xy(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,

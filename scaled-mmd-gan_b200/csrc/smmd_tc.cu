@@ -1,17 +1,1058 @@
-// placeholder until the tcgen05 kernels land
+// smmd_tc.cu -- tcgen05 (5th-gen tensor core) path, sm_100a only.
+//
+//  tc_fused_kernel   : MMD^2 forward AND backward in one sweep over Gram tiles (flash-attention shaped):
+//                        S  = Z_i Z_j^T          UMMA #1 (SS, bf16, fp32 accum in TMEM)
+//                        W  = 4 a k'(D(S))       epilogue warps: TMEM -> regs -> kernel transform; block sums,
+//                                                row sums; W written back to TMEM as bf16
+//                        O += W Z_j              UMMA #2 (A = W from TMEM, B = the SAME Z_j smem tile MN-major)
+//                      so neither the N x N kernel matrix nor its derivative ever reaches HBM.
+//                      Replaces gan/core/mmd.py:55-188 (kernels) + :194-220 (mmd2) + the TF autodiff graph
+//                      (gan/core/model.py:446,452) for d <= 256.
+//  tc_stream_kernel  : K-streaming Gram tiles + fused reduction epilogue (row stats), batched over problems;
+//                      used for KID (gan/compute_scores.py:232-335, all subsets in one launch) and for
+//                      value-only MMD^2.  bf16 or split-bf16 (hi*hi + lo*hi + hi*lo) operands.
+//
+// Work distribution is "stream-K" style: the flattened (row block, column tile) space is cut into equal
+// contiguous chunks, one per persistent CTA (grid = #SMs), partial results land in per-(CTA, slot)
+// workspace slabs and are reduced in a fixed order by the finalisation kernel (deterministic).
+#include <cuda_bf16.h>
+#include <algorithm>
+#include "sm100_ptx.cuh"
+#include "smmd_kfun.cuh"
 #include "smmd_tc.h"
+#include "tmap_host.h"
+
 namespace smmd {
-bool tc_mmd2_supported(int64_t, int) { return false; }
-size_t tc_mmd2_workspace_bytes(int64_t, int64_t, int64_t, int, int) { return 0; }
-cudaError_t tc_mmd2_run(const KernelFn&, const Geometry&, const Coefs&, const void*, const void*, int, int64_t, int64_t,
-                        int, double*, float*, float*, void*, size_t, cudaStream_t, int*, const char**) {
-  return cudaErrorNotSupported;
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;            // rows per row block (UMMA M)
+constexpr int BNF = 64;            // fused kernel: columns per tile
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue groups
+constexpr int kMaxSmem = 232448;   // 227 KB
+
+inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
-bool tc_kid_supported(int64_t) { return false; }
-size_t tc_kid_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }
-cudaError_t tc_kid_run(const KernelFn&, const void*, const void*, int, int64_t, int64_t, int64_t, const int32_t*,
-                       const int32_t*, int64_t, int64_t, int64_t, int, int, void*, size_t, double**, cudaStream_t, int*,
-                       const char**) {
-  return cudaErrorNotSupported;
+
+// ------------------------------------------------------------------------------------------------
+// prep: fp32/bf16 rows -> padded bf16 operand matrix (+ optional lo part), squared norms of exactly the
+// values the tensor core will see, optional gather (KID subsets), optional tanh, stats initialisation.
+// Layout per problem b: rows [0,mp) = X (valid < m), rows [mp, mp+np) = Y (valid < n); pad rows are zero.
+// ------------------------------------------------------------------------------------------------
+struct PrepTcArgs {
+  const void* A;
+  const void* B;
+  int dtype;
+  int64_t lda, ldb, m, n, mp, np, d, dp, dpz;
+  const int32_t* idxA;
+  const int32_t* idxB;
+  int64_t first_batch;
+  int tanh_features, split;
+  __nv_bfloat16* Z;
+  float* norms;
+  double* stats;  // optional [batch][m+n][RS_COUNT]: zeroed, RS_DIAG set analytically
+  KernelFn kf;
+};
+
+__global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t Mp = a.mp + a.np;
+  const int64_t p = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t b = blockIdx.y;
+  if (p >= Mp) return;
+  const bool inA = p < a.mp;
+  const int64_t loc = inA ? p : p - a.mp;
+  const bool valid = loc < (inA ? a.m : a.n);
+  int64_t src = loc;
+  if (valid && a.idxA) src = inA ? a.idxA[(a.first_batch + b) * a.m + loc] : a.idxB[(a.first_batch + b) * a.n + loc];
+  const int64_t ld = inA ? a.lda : a.ldb;
+  const void* base = inA ? a.A : a.B;
+  __nv_bfloat16* zrow = a.Z + (b * Mp + p) * a.dpz;
+  float acc = 0.f;
+  for (int64_t c = 2 * lane; c < a.dp; c += 64) {
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (valid && c + e < a.d) {
+        v[e] = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(base)[src * ld + c + e]
+                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[src * ld + c + e]);
+        if (a.tanh_features) v[e] = tanhf(v[e]);
+      }
+    }
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    const float f0 = __bfloat162float(h0), f1 = __bfloat162float(h1);
+    *reinterpret_cast<__nv_bfloat162*>(zrow + c) = __nv_bfloat162(h0, h1);
+    if (a.split) {
+      __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - f0), l1 = __float2bfloat16_rn(v[1] - f1);
+      *reinterpret_cast<__nv_bfloat162*>(zrow + a.dp + c) = __nv_bfloat162(l0, l1);
+      const float g0 = __bfloat162float(l0), g1 = __bfloat162float(l1);
+      // the 3-term Gram sees hi*hi + 2*hi*lo on the diagonal
+      acc = fmaf(f0, f0 + 2.f * g0, acc);
+      acc = fmaf(f1, f1 + 2.f * g1, acc);
+    } else {
+      acc = fmaf(f0, f0, acc);
+      acc = fmaf(f1, f1, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    a.norms[b * Mp + p] = acc;
+    if (a.stats && valid) {
+      double* st = a.stats + (b * (a.m + a.n) + (inA ? loc : a.m + loc)) * RS_COUNT;
+      for (int i = 0; i < RS_COUNT; ++i) st[i] = 0.0;
+      double dg;
+      if (a.kf.family == FAM_RQ) dg = (double)a.kf.const_diag + (double)a.kf.add_dot * (double)acc;
+      else if (a.kf.family == FAM_POLY) {
+        double bb = (double)a.kf.poly_gamma * (double)acc + (double)a.kf.poly_coef0;
+        dg = 1.0;
+        for (int i = 0; i < a.kf.degree; ++i) dg *= bb;
+      } else dg = (double)diag_value(a.kf, acc);
+      st[RS_DIAG] = dg;
+    }
+  }
 }
+
+// column sums of the X block and of the Y block (needed by the add_dot terms): csum[2][dp] double
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* Z, int64_t dpz, int64_t dp, int64_t m,
+                                                     int64_t mp, int64_t n, double* csum) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int which = blockIdx.y;  // 0 = X, 1 = Y
+  const int rl = threadIdx.x >> 5;
+  __shared__ double sh[8][33];
+  double s = 0.0;
+  const int64_t r0 = which ? mp : 0, cnt = which ? n : m;
+  if (c < dp)
+    for (int64_t r = rl; r < cnt; r += 8) s += (double)__bfloat162float(Z[(r0 + r) * dpz + c]);
+  sh[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < dp) {
+    for (int i = 1; i < 8; ++i) s += sh[i][threadIdx.x & 31];
+    csum[which * dp + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue element math shared by both kernels
+// ------------------------------------------------------------------------------------------------
+template <int FAM>
+__device__ __forceinline__ void pair_eval(const KernelFn& kf, float S, float nij, float& k, float& kd) {
+  if constexpr (FAM == FAM_POLY) {
+    const float bb = fmaf(kf.poly_gamma, S, kf.poly_coef0);
+    float p = bb;
+    for (int i = 1; i < kf.degree; ++i) p *= bb;
+    k = p;
+    kd = 0.f;
+  } else {
+    float D = fmaf(-2.f, S, nij);
+    if constexpr (FAM != FAM_DISTANCE) D = fmaxf(D, 0.f);
+    eval_fast<FAM>(kf, D, k, kd);
+  }
+}
+
+// ================================================================================================
+// fused forward + backward kernel
+// ================================================================================================
+struct FusedArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np;
+  float c_xx, c_yy, c_xy;      // 4 * a_xx etc. (folded into W)
+  const float* norms;          // [Mp]
+  int nrb_x, rb_x0, nrb_y, rb_y0;
+  int T;                       // column tiles of 64 over the padded stacked matrix
+  int64_t total_tiles, chunk;
+  int slots;
+  float* Opart;                // [grid][slots][128][DP]
+  float* rpart;                // [grid][slots][2][128]
+  double* spart;               // [grid][slots][2][128][2]
+};
+
+template <int DP>
+struct FusedCfg {
+  static constexpr int NPANEL = DP / 64;
+  static constexpr int ZI_BYTES = NPANEL * BM * 128;        // resident row block
+  static constexpr int ZJ_BYTES = NPANEL * BNF * 128;       // one column tile
+  static constexpr int STAGE_BYTES = ZJ_BYTES + 256;        // + 64 column norms
+  static constexpr int NST_RAW = (kMaxSmem - 2048 - ZI_BYTES) / (ZJ_BYTES + 1024);
+  static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+  static constexpr int SMEM = 1024 /*align slack*/ + ZI_BYTES + NST * ZJ_BYTES + NST * 256 + 512;
+  static constexpr uint32_t TM_O = 0, TM_S = 256, TM_W = 448;  // TMEM columns: O[DP] | S0..S2[64] | W0,W1[32]
+};
+
+template <int DP, int FAM>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj, FusedArgs a) {
+  using Cfg = FusedCfg<DP>;
+  constexpr int NPANEL = Cfg::NPANEL, NST = Cfg::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sZi = smem;
+  uint8_t* sZj = smem + Cfg::ZI_BYTES;
+  float* sN = reinterpret_cast<float*>(sZj + NST * Cfg::ZJ_BYTES);  // [NST][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sN) + NST * 256);
+  uint64_t* zj_full = bars;             // [NST]
+  uint64_t* zj_empty = bars + NST;      // [NST]
+  uint64_t* s_full = bars + 2 * NST;    // [3]
+  uint64_t* s_empty = s_full + 3;       // [3]
+  uint64_t* w_full = s_empty + 3;       // [2]
+  uint64_t* w_empty = w_full + 2;       // [2]
+  uint64_t* zi_full = w_empty + 2;
+  uint64_t* zi_empty = zi_full + 1;
+  uint64_t* o_full = zi_empty + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&zj_full[i], 1);
+      mbar_init(&zj_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&w_full[i], 128);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(zi_full, 1);
+    mbar_init(zi_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_zi);
+    prefetch_tmap(&tmap_zj);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
+  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  auto rb_of = [&](int64_t rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + (int)rbi : a.rb_y0 + (int)(rbi - a.nrb_x); };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t unit = 0;
+      uint64_t gt = 0;
+      for (int64_t pos = pos0; pos < pos1;) {
+        const int64_t rbi = pos / a.T;
+        const int t0 = (int)(pos - rbi * a.T);
+        const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
+        const int rb = rb_of(rbi);
+        mbar_wait(zi_empty, (unit & 1) ^ 1);
+        mbar_arrive_expect_tx(zi_full, Cfg::ZI_BYTES);
+#pragma unroll
+        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
+        for (int t = t0; t < t1; ++t, ++gt) {
+          const uint32_t st = (uint32_t)(gt % NST), ph = (uint32_t)((gt / NST) & 1);
+          mbar_wait(&zj_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&zj_full[st], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int p = 0; p < NPANEL; ++p)
+            tma_load_2d(sZj + st * Cfg::ZJ_BYTES + p * (BNF * 128), &tmap_zj, &zj_full[st], p * 64, t * BNF);
+          bulk_load_1d(sN + st * 64, a.norms + (int64_t)t * BNF, 256, &zj_full[st]);
+        }
+        pos += t1 - t0;
+        ++unit;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(BM, BNF, kFmtBF16, false, false);
+      constexpr uint32_t idesc2 = make_idesc(BM, DP, kFmtBF16, false, true);
+      uint32_t unit = 0;
+      uint64_t gbase = 0;
+      for (int64_t pos = pos0; pos < pos1;) {
+        const int64_t rbi = pos / a.T;
+        const int t0 = (int)(pos - rbi * a.T);
+        const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
+        const int TU = t1 - t0;
+        mbar_wait(zi_full, unit & 1);
+        for (int jj = 0; jj < TU + 3; ++jj) {
+          const int b2 = jj - 3;
+          if (b2 >= 0) {  // ---- UMMA #2 for local tile b2: O += W * Zj
+            const uint64_t gt = gbase + b2;
+            const uint32_t wb = (uint32_t)(gt & 1), st = (uint32_t)(gt % NST);
+            mbar_wait(&w_full[wb], (uint32_t)((gt >> 1) & 1));
+            if (b2 == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t zj = smem_u32(sZj + st * Cfg::ZJ_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BNF / 16; ++kk) {
+              const uint64_t db = make_smem_desc_sw128(zj + kk * 2048, BNF * 128, 1024);
+              umma_ts(tmem + Cfg::TM_O, tmem + Cfg::TM_W + wb * 32 + kk * 8, db, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&zj_empty[st]);
+            umma_commit(&w_empty[wb]);
+            if (b2 == TU - 1) umma_commit(o_full);
+          }
+          if (jj < TU) {  // ---- UMMA #1 for local tile jj: S = Zi * Zj^T
+            const uint64_t gt = gbase + jj;
+            const uint32_t sb = (uint32_t)(gt % 3), st = (uint32_t)(gt % NST);
+            mbar_wait(&zj_full[st], (uint32_t)((gt / NST) & 1));
+            mbar_wait(&s_empty[sb], (uint32_t)(((gt / 3) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t zi = smem_u32(sZi), zj = smem_u32(sZj + st * Cfg::ZJ_BYTES);
+#pragma unroll
+            for (int p = 0; p < NPANEL; ++p)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = make_smem_desc_sw128(zi + p * (BM * 128) + k * 32, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(zj + p * (BNF * 128) + k * 32, 16, 1024);
+                umma_ss(tmem + Cfg::TM_S + sb * 64, da, db, idesc1, (p | k) ? 1u : 0u);
+              }
+            umma_commit(&s_full[sb]);
+            if (jj == TU - 1) umma_commit(zi_empty);
+          }
+        }
+        gbase += TU;
+        pos += TU;
+        ++unit;
+      }
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int grp = (warp - 2) >> 2;          // 0 / 1
+    const int q = warp & 3;                   // TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane;              // row inside the row block
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t unit = 0;
+    uint64_t gbase = 0;
+    int slot = 0;
+    for (int64_t pos = pos0; pos < pos1; ++slot) {
+      const int64_t rbi = pos / a.T;
+      const int t0 = (int)(pos - rbi * a.T);
+      const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
+      const int TU = t1 - t0;
+      const int rb = rb_of(rbi);
+      const int64_t gi = (int64_t)rb * BM + r;
+      const bool rowX = gi < a.mp;
+      const float ni = a.norms[gi];
+      float rsum = 0.f;
+      double dsame = 0.0, dcross = 0.0;
+      for (int lt = 0; lt < TU; ++lt) {
+        const uint64_t gt = gbase + lt;
+        if ((int)(gt & 1) != grp) continue;
+        const int t = t0 + lt;
+        const uint32_t sb = (uint32_t)(gt % 3), st = (uint32_t)(gt % NST);
+        const int64_t c0 = (int64_t)t * BNF;
+        const bool colX = c0 < a.mp;
+        const bool same = (colX == rowX);
+        const float cw = same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy;
+        const int64_t lim = colX ? a.m : a.mp + a.n;               // first invalid column of this region
+        const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);  // pad columns or diagonal inside
+        mbar_wait(&zj_full[st], (uint32_t)((gt / NST) & 1));      // column norms ride with the Zj stage
+        mbar_wait(&s_full[sb], (uint32_t)((gt / 3) & 1));
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(tmem + Cfg::TM_S + sb * 64 + lane_base, v0);
+        tmem_ld_x32(tmem + Cfg::TM_S + sb * 64 + 32 + lane_base, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[sb]);
+        mbar_wait(&w_empty[grp], (uint32_t)(((gt >> 1) & 1) ^ 1));
+        const float* nj = sN + st * 64;
+        float tsum = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t wpk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float kk[2], ww[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cc = h * 32 + c + e;
+              const float S = __uint_as_float(h ? v1[c + e] : v0[c + e]);
+              float k, kd;
+              pair_eval<FAM>(a.kf, S, ni + nj[cc], k, kd);
+              if (special) {
+                const int64_t col = c0 + cc;
+                const bool ok = (col < lim) && (col != gi);
+                k = ok ? k : 0.f;
+                kd = ok ? kd : 0.f;
+              }
+              kk[e] = k;
+              ww[e] = cw * kd;
+            }
+            tsum += kk[0] + kk[1];
+            rsum += ww[0] + ww[1];
+            wpk[c >> 1] = pack_bf16x2(ww[0], ww[1]);
+          }
+          tmem_st_x16(tmem + Cfg::TM_W + grp * 32 + h * 16 + lane_base, wpk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&w_full[grp]);
+        if (same) dsame += (double)tsum;
+        else dcross += (double)tsum;
+      }
+      // ---- unit end: drain O (this group's half of the feature columns) ----
+      mbar_wait(o_full, unit & 1);
+      tc_fence_after();
+      {
+        const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
+        float* orow = a.Opart + (sl * BM + r) * DP + grp * (DP / 2);
+#pragma unroll
+        for (int c = 0; c < DP / 2; c += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + Cfg::TM_O + grp * (DP / 2) + c + lane_base, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+        a.rpart[(sl * 2 + grp) * BM + r] = rsum;
+        double* sp = a.spart + ((sl * 2 + grp) * BM + r) * 2;
+        sp[0] = dsame;
+        sp[1] = dcross;
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+      gbase += TU;
+      pos += TU;
+      ++unit;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ---- finalisation of the fused kernel: reduce slabs, form gradients and per-row stats ---------------
+struct FinRowsArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np, d;
+  int64_t x0, ox, y0, oy;
+  int dp;
+  int nrb_x, rb_x0, nrb_y, rb_y0, T;
+  int64_t chunk;
+  int slots;
+  double a_xx, a_yy, a_xy;
+  const __nv_bfloat16* Z;
+  int64_t dpz;
+  const float* norms;
+  const double* csum;  // [2][dp] or null
+  const float* Opart;
+  const float* rpart;
+  const double* spart;
+  float* dX;
+  float* dY;
+  double* stats;  // [ox+oy][RS_COUNT]
+};
+
+__global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t lr = (int64_t)blockIdx.x * 8 + warp;
+  if (lr >= a.ox + a.oy) return;
+  const bool rowX = lr < a.ox;
+  const int64_t li = rowX ? a.x0 + lr : a.y0 + (lr - a.ox);   // index inside X or Y
+  const int64_t gi = rowX ? li : a.mp + li;                   // padded stacked row
+  const int rb = (int)(gi / BM), r = (int)(gi % BM);
+  const int64_t rbi = rowX ? rb - a.rb_x0 : a.nrb_x + (rb - a.rb_y0);
+  const int64_t f0 = rbi * a.T, f1 = f0 + a.T - 1;
+  const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
+  float rs = 0.f;
+  double ssame = 0.0, scross = 0.0;
+  for (int64_t g = g0; g <= g1; ++g) {
+    const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
+    rs += a.rpart[(sl * 2 + 0) * BM + r] + a.rpart[(sl * 2 + 1) * BM + r];
+    const double* s0 = a.spart + ((sl * 2 + 0) * BM + r) * 2;
+    const double* s1 = a.spart + ((sl * 2 + 1) * BM + r) * 2;
+    ssame += s0[0] + s1[0];
+    scross += s0[1] + s1[1];
+  }
+  const __nv_bfloat16* zrow = a.Z + gi * a.dpz;
+  const double a_same = rowX ? a.a_xx : a.a_yy;
+  const bool dot = a.kf.family == FAM_RQ && a.kf.add_dot > 0.f && a.csum != nullptr;
+  double dsame = 0.0, dcross = 0.0;  // z_i . colsum(same set) / (other set)
+  float* out = nullptr;
+  if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
+  for (int64_t c = lane; c < a.d; c += 32) {
+    const float z = __bfloat162float(zrow[c]);
+    if (out) {
+      float o = 0.f;
+      for (int64_t g = g0; g <= g1; ++g) {
+        const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
+        o += a.Opart[(sl * BM + r) * a.dp + c];
+      }
+      float gv = rs * z - o;  // W already carries the factor 4 a_ij
+      if (dot) {
+        const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
+        gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
+      }
+      if (a.kf.tanh_features) gv *= (1.f - z * z);
+      out[c] = gv;
+    }
+    if (dot) {
+      dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
+      dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+    }
+  }
+  if (dot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dsame += __shfl_xor_sync(0xffffffffu, dsame, o);
+      dcross += __shfl_xor_sync(0xffffffffu, dcross, o);
+    }
+  }
+  if (lane == 0 && a.stats) {
+    const float ni = a.norms[gi];
+    double* st = a.stats + lr * RS_COUNT;
+    // dot part of the kernel handled in closed form: sum_{j != i} <z_i, z_j> = <z_i, colsum> - |z_i|^2
+    st[RS_SAME] = ssame + (dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0);
+    st[RS_CROSS] = scross + (dot ? (double)a.kf.add_dot * dcross : 0.0);
+    st[RS_SQ_SAME] = 0.0;
+    st[RS_SQ_CROSS] = 0.0;
+    st[RS_DIAG] = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                        : (double)diag_value(a.kf, ni);
+    st[RS_PAIR] = 0.0;
+  }
+}
+
+// ================================================================================================
+// K-streaming Gram + reduction epilogue (KID, value-only MMD^2)
+// ================================================================================================
+constexpr int BNS = 128;
+constexpr int kStreamStages = 6;
+constexpr int kStreamStageBytes = 2 * BM * 128;  // A panel + B panel
+constexpr int kStreamSmem = 1024 + kStreamStages * kStreamStageBytes + 512;
+
+struct StreamArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np;   // per problem
+  int RB, CT;             // row blocks / column tiles (128) per problem
+  int nkp;                // 64-wide k-panels of the operand (dp/64)
+  int ncombo;             // 1 (bf16) or 3 (split)
+  int64_t dp;
+  int64_t total_tiles, chunk;
+  const float* norms;     // [batch][Mp]
+  double* stats;          // [batch][m+n][RS_COUNT]
+  int want_sq;
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStreamStages;
+  uint64_t* acc_full = empty + kStreamStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kStreamStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t Mp = a.mp + a.np;
+  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
+  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  const int nk = a.nkp * a.ncombo;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint64_t it = 0;
+      for (int64_t pos = pos0; pos < pos1; ++pos) {
+        const int ct = (int)(pos % a.CT);
+        const int64_t brb = pos / a.CT;
+        const int rb = (int)(brb % a.RB);
+        const int64_t b = brb / a.RB;
+        const int32_t arow = (int32_t)(b * Mp + (int64_t)rb * BM), brow = (int32_t)(b * Mp + (int64_t)ct * BNS);
+        for (int kk = 0; kk < nk; ++kk, ++it) {
+          const int combo = kk / a.nkp, p = kk - combo * a.nkp;
+          const int32_t acol = (int32_t)(p * 64 + (combo == 1 ? a.dp : 0));
+          const int32_t bcol = (int32_t)(p * 64 + (combo == 2 ? a.dp : 0));
+          const uint32_t st = (uint32_t)(it % kStreamStages), ph = (uint32_t)((it / kStreamStages) & 1);
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
+          uint8_t* sa = smem + st * kStreamStageBytes;
+          tma_load_2d(sa, &tmap, &full[st], acol, arow);
+          tma_load_2d(sa + BM * 128, &tmap, &full[st], bcol, brow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BNS, kFmtBF16, false, false);
+      uint64_t it = 0, tc = 0;
+      for (int64_t pos = pos0; pos < pos1; ++pos, ++tc) {
+        const uint32_t ab = (uint32_t)(tc & 1);
+        mbar_wait(&acc_empty[ab], (uint32_t)(((tc >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int kk = 0; kk < nk; ++kk, ++it) {
+          const uint32_t st = (uint32_t)(it % kStreamStages), ph = (uint32_t)((it / kStreamStages) & 1);
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * kStreamStageBytes), sb = sa + BM * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_ss(tmem + ab * BNS, da, db, idesc, (kk | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // accumulators of the (problem, row block) currently being swept by this thread
+    int64_t cur_brb = -1;
+    double s_same = 0, s_cross = 0, q_same = 0, q_cross = 0, pairv = 0;
+    float ni = 0.f;
+    auto flush = [&]() {
+      if (cur_brb < 0) return;
+      const int rb = (int)(cur_brb % a.RB);
+      const int64_t b = cur_brb / a.RB;
+      const int64_t gi = (int64_t)rb * BM + r;
+      const bool rowX = gi < a.mp;
+      const int64_t loc = rowX ? gi : gi - a.mp;
+      if (loc < (rowX ? a.m : a.n)) {
+        double* st = a.stats + (b * (a.m + a.n) + (rowX ? loc : a.m + loc)) * RS_COUNT;
+        if (s_same != 0.0) atomicAdd(st + RS_SAME, s_same);
+        if (s_cross != 0.0) atomicAdd(st + RS_CROSS, s_cross);
+        if (a.want_sq) {
+          if (q_same != 0.0) atomicAdd(st + RS_SQ_SAME, q_same);
+          if (q_cross != 0.0) atomicAdd(st + RS_SQ_CROSS, q_cross);
+          if (pairv != 0.0) atomicAdd(st + RS_PAIR, pairv);
+        }
+      }
+      s_same = s_cross = q_same = q_cross = pairv = 0.0;
+    };
+    uint64_t tc = 0;
+    for (int64_t pos = pos0; pos < pos1; ++pos, ++tc) {
+      if ((int)(tc & 1) != grp) continue;
+      const int ct = (int)(pos % a.CT);
+      const int64_t brb = pos / a.CT;
+      const int rb = (int)(brb % a.RB);
+      const int64_t b = brb / a.RB;
+      if (brb != cur_brb) {
+        flush();
+        cur_brb = brb;
+        ni = a.norms[b * Mp + (int64_t)rb * BM + r];
+      }
+      const int64_t gi = (int64_t)rb * BM + r;
+      const bool rowX = gi < a.mp;
+      const int64_t c0 = (int64_t)ct * BNS;
+      const bool colX = c0 < a.mp;
+      const bool same = (colX == rowX);
+      const int64_t lim = colX ? a.m : a.mp + a.n;
+      const int64_t pair_col = rowX ? a.mp + gi : -1;  // the (x_i, y_i) element
+      const bool special = (c0 + BNS > lim) || (ct == rb) || (pair_col >= c0 && pair_col < c0 + BNS + BM);
+      mbar_wait(&acc_full[grp], (uint32_t)((tc >> 1) & 1));
+      tc_fence_after();
+      const float* nj = a.norms + b * Mp + c0;
+      float tsum = 0.f, tsq = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < BNS / 32; ++h) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem + grp * BNS + h * 32 + lane_base, v);
+        tmem_ld_wait();
+        if (h == BNS / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[grp]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nj + h * 32 + c));
+          const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float k, kd;
+            pair_eval<FAM>(a.kf, __uint_as_float(v[c + e]), ni + nn[e], k, kd);
+            if (special) {
+              const int64_t col = c0 + h * 32 + c + e;
+              const bool ok = (col < lim) && (col != gi);
+              k = ok ? k : 0.f;
+              if (col == pair_col) pairv = (double)k;
+            }
+            tsum += k;
+            tsq = fmaf(k, k, tsq);
+          }
+        }
+      }
+      if (same) {
+        s_same += (double)tsum;
+        q_same += (double)tsq;
+      } else {
+        s_cross += (double)tsum;
+        q_cross += (double)tsq;
+      }
+    }
+    flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct FusedPlan {
+  int64_t mp, np, Mp, dp;
+  int nrb_x, rb_x0, nrb_y, rb_y0, T, grid, slots;
+  int64_t total, chunk;
+  size_t off_Z, off_norm, off_csum, off_O, off_r, off_s, off_stats, off_end;
+};
+
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t y0, int64_t y1) {
+  FusedPlan p;
+  p.mp = round_up(m, BM);
+  p.np = round_up(n, BM);
+  p.Mp = p.mp + p.np;
+  p.dp = round_up(d, 64);
+  p.rb_x0 = (int)(x0 / BM);
+  p.nrb_x = x1 > x0 ? (int)((x1 - 1) / BM) - p.rb_x0 + 1 : 0;
+  p.rb_y0 = (int)((p.mp + y0) / BM);
+  p.nrb_y = y1 > y0 ? (int)((p.mp + y1 - 1) / BM) - p.rb_y0 + 1 : 0;
+  p.T = (int)(p.Mp / BNF);
+  p.total = (int64_t)(p.nrb_x + p.nrb_y) * p.T;
+  p.grid = (int)std::min<int64_t>(sm_count(), p.total);
+  if (p.grid < 1) p.grid = 1;
+  p.chunk = (p.total + p.grid - 1) / p.grid;
+  p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
+  p.slots = (int)((p.chunk + p.T - 1) / p.T) + 1;
+  size_t o = 0;
+  p.off_Z = o;
+  o = up256(o + (size_t)p.Mp * p.dp * 2);
+  p.off_norm = o;
+  o = up256(o + (size_t)p.Mp * 4);
+  p.off_csum = o;
+  o = up256(o + (size_t)2 * p.dp * 8);
+  p.off_O = o;
+  o = up256(o + (size_t)p.grid * p.slots * BM * p.dp * 4);
+  p.off_r = o;
+  o = up256(o + (size_t)p.grid * p.slots * 2 * BM * 4);
+  p.off_s = o;
+  o = up256(o + (size_t)p.grid * p.slots * 2 * BM * 2 * 8);
+  p.off_stats = o;
+  o = up256(o + (size_t)((x1 - x0) + (y1 - y0)) * RS_COUNT * 8);
+  p.off_end = o;
+  return p;
+}
+
+template <int DP, int FAM>
+cudaError_t launch_fused_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid, cudaStream_t s) {
+  using Cfg = FusedCfg<DP>;
+  static_assert(Cfg::NST >= 4, "need >= 4 Zj stages");
+  static_assert(Cfg::SMEM <= kMaxSmem, "smem budget");
+  auto kern = tc_fused_kernel<DP, FAM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, Cfg::SMEM, s>>>(tzi, tzj, a);
+  return cudaGetLastError();
+}
+
+template <int FAM>
+cudaError_t launch_fused_f(int dp, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
+                           cudaStream_t s) {
+  switch (dp) {
+    case 64: return launch_fused_t<64, FAM>(tzi, tzj, a, grid, s);
+    case 128: return launch_fused_t<128, FAM>(tzi, tzj, a, grid, s);
+    case 192: return launch_fused_t<192, FAM>(tzi, tzj, a, grid, s);
+    case 256: return launch_fused_t<256, FAM>(tzi, tzj, a, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+struct StreamPlan {
+  int64_t mp, np, Mp, dp, dpz;
+  int RB, CT, grid;
+  int64_t total, chunk;
+  size_t off_Z, off_norm, off_stats, off_end;
+};
+
+StreamPlan stream_plan(int64_t m, int64_t n, int64_t d, int64_t batch, int split) {
+  StreamPlan p;
+  p.mp = round_up(m, BM);
+  p.np = round_up(n, BM);
+  p.Mp = p.mp + p.np;
+  p.dp = round_up(d, 64);
+  p.dpz = split ? 2 * p.dp : p.dp;
+  p.RB = (int)(p.Mp / BM);
+  p.CT = (int)(p.Mp / BNS);
+  p.total = batch * p.RB * p.CT;
+  p.grid = (int)std::min<int64_t>(sm_count(), p.total);
+  p.chunk = (p.total + p.grid - 1) / p.grid;
+  p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
+  size_t o = 0;
+  p.off_Z = o;
+  o = up256(o + (size_t)batch * p.Mp * p.dpz * 2);
+  p.off_norm = o;
+  o = up256(o + (size_t)batch * p.Mp * 4);
+  p.off_stats = o;
+  o = up256(o + (size_t)batch * (m + n) * RS_COUNT * 8);
+  p.off_end = o;
+  return p;
+}
+
+template <int FAM>
+cudaError_t launch_stream_t(const CUtensorMap& tm, const StreamArgs& a, int grid, cudaStream_t s) {
+  auto kern = tc_stream_kernel<FAM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, kStreamSmem, s>>>(tm, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream(const KernelFn& kf, const CUtensorMap& tm, const StreamArgs& a, int grid, cudaStream_t s) {
+  switch (kf.family) {
+    case FAM_POLY: return launch_stream_t<FAM_POLY>(tm, a, grid, s);
+    case FAM_RBF: return launch_stream_t<FAM_RBF>(tm, a, grid, s);
+    case FAM_RQ: return launch_stream_t<FAM_RQ>(tm, a, grid, s);
+    case FAM_DISTANCE: return launch_stream_t<FAM_DISTANCE>(tm, a, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// public (library-internal) interface
+// ------------------------------------------------------------------------------------------------
+bool tc_mmd2_supported(int64_t d, int want_grad) { return want_grad ? d <= 256 : d <= 65536; }
+
+static bool tc_family_ok(const KernelFn& kf) {
+  return kf.family == FAM_RBF || kf.family == FAM_RQ || kf.family == FAM_DISTANCE;
+}
+
+size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision) {
+  // worst case over shards: a full-range plan bounds every rank's plan
+  const size_t fused = want_grad ? fused_plan(m, n, d, 0, m, 0, n).off_end : 0;
+  const size_t stream = stream_plan(m, n, d, 1, precision == SMMD_PREC_BF16X3).off_end + 4096;
+  return std::max(fused, stream);
+}
+
+cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, const void* X, const void* Y, int dtype,
+                        int64_t ldx, int64_t ldy, int precision, double* scalars, float* dX, float* dY, void* ws,
+                        size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
+  if (!tc_family_ok(kf)) return cudaErrorNotSupported;
+  char* w = static_cast<char*>(ws);
+  cudaError_t e;
+  const bool want_grad = dX != nullptr;
+  if (want_grad) {
+    *path = "tc_bf16_fused";
+    const FusedPlan p = fused_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1);
+    if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+    __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+    float* norms = reinterpret_cast<float*>(w + p.off_norm);
+    double* csum = reinterpret_cast<double*>(w + p.off_csum);
+    PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
+                  kf.tanh_features, 0, Z, norms, nullptr, kf};
+    prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+    const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
+    if (dot) {
+      colsum_kernel<<<dim3((unsigned)((p.dp + 31) / 32), 2), 256, 0, s>>>(Z, p.dp, p.dp, g.m, p.mp, g.n, csum);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      ++*launches;
+    }
+    CUtensorMap tzi, tzj;
+    if (!smmd_host::make_tmap_bf16_2d(&tzi, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
+    if (!smmd_host::make_tmap_bf16_2d(&tzj, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
+    FusedArgs fa;
+    fa.kf = kf;
+    fa.m = g.m;
+    fa.n = g.n;
+    fa.mp = p.mp;
+    fa.np = p.np;
+    fa.c_xx = (float)(4.0 * c.a_xx);
+    fa.c_yy = (float)(4.0 * c.a_yy);
+    fa.c_xy = (float)(4.0 * c.a_xy);
+    fa.norms = norms;
+    fa.nrb_x = p.nrb_x;
+    fa.rb_x0 = p.rb_x0;
+    fa.nrb_y = p.nrb_y;
+    fa.rb_y0 = p.rb_y0;
+    fa.T = p.T;
+    fa.total_tiles = p.total;
+    fa.chunk = p.chunk;
+    fa.slots = p.slots;
+    fa.Opart = reinterpret_cast<float*>(w + p.off_O);
+    fa.rpart = reinterpret_cast<float*>(w + p.off_r);
+    fa.spart = reinterpret_cast<double*>(w + p.off_s);
+    switch (kf.family) {
+      case FAM_RBF: e = launch_fused_f<FAM_RBF>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
+      case FAM_RQ: e = launch_fused_f<FAM_RQ>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
+      default: e = launch_fused_f<FAM_DISTANCE>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
+    }
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    FinRowsArgs fr;
+    fr.kf = kf;
+    fr.m = g.m;
+    fr.n = g.n;
+    fr.mp = p.mp;
+    fr.np = p.np;
+    fr.d = g.d;
+    fr.x0 = g.x0;
+    fr.ox = g.x1 - g.x0;
+    fr.y0 = g.y0;
+    fr.oy = g.y1 - g.y0;
+    fr.dp = (int)p.dp;
+    fr.nrb_x = p.nrb_x;
+    fr.rb_x0 = p.rb_x0;
+    fr.nrb_y = p.nrb_y;
+    fr.rb_y0 = p.rb_y0;
+    fr.T = p.T;
+    fr.chunk = p.chunk;
+    fr.slots = p.slots;
+    fr.a_xx = c.a_xx;
+    fr.a_yy = c.a_yy;
+    fr.a_xy = c.a_xy;
+    fr.Z = Z;
+    fr.dpz = p.dp;
+    fr.norms = norms;
+    fr.csum = dot ? csum : nullptr;
+    fr.Opart = fa.Opart;
+    fr.rpart = fa.rpart;
+    fr.spart = fa.spart;
+    fr.dX = dX;
+    fr.dY = dY;
+    fr.stats = reinterpret_cast<double*>(w + p.off_stats);
+    tc_finalize_rows_kernel<<<(unsigned)((fr.ox + fr.oy + 7) / 8), 256, 0, s>>>(fr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+    e = launch_finalize_mmd2(kf, g, fr.stats, norms, scalars, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    return cudaSuccess;
+  }
+  // ---- value only: streaming kernel over the whole stacked Gram (world == 1 only for now) ----
+  if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return cudaErrorNotSupported;
+  const int split = precision == SMMD_PREC_BF16X3;
+  *path = split ? "tc_bf16x3_stream" : "tc_bf16_stream";
+  const StreamPlan p = stream_plan(g.m, g.n, g.d, 1, split);
+  if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+  __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+  float* norms = reinterpret_cast<float*>(w + p.off_norm);
+  double* stats = reinterpret_cast<double*>(w + p.off_stats);
+  KernelFn kz = kf;
+  const float add_dot = kf.add_dot;
+  PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dpz, nullptr, nullptr, 0,
+                kf.tanh_features, split, Z, norms, stats, kz};
+  prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++*launches;
+  if (add_dot > 0.f) return cudaErrorNotSupported;  // value-only add_dot goes through the fused/SIMT paths
+  CUtensorMap tm;
+  if (!smmd_host::make_tmap_bf16_2d(&tm, Z, p.Mp, p.dpz, p.dpz, BM)) return cudaErrorUnknown;
+  StreamArgs sa;
+  sa.kf = kf;
+  sa.m = g.m;
+  sa.n = g.n;
+  sa.mp = p.mp;
+  sa.np = p.np;
+  sa.RB = p.RB;
+  sa.CT = p.CT;
+  sa.nkp = (int)(p.dp / 64);
+  sa.ncombo = split ? 3 : 1;
+  sa.dp = p.dp;
+  sa.total_tiles = p.total;
+  sa.chunk = p.chunk;
+  sa.norms = norms;
+  sa.stats = stats;
+  sa.want_sq = 0;
+  e = launch_stream(kf, tm, sa, p.grid, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  e = launch_finalize_mmd2(kf, g, stats, norms, scalars, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  return cudaSuccess;
+}
+
+bool tc_kid_supported(int64_t d) { return d >= 1 && d <= 65536; }
+
+size_t tc_kid_workspace_bytes(int64_t msub, int64_t d, int64_t nsub, int precision) {
+  return stream_plan(msub, msub, d, nsub, precision == SMMD_PREC_BF16X3).off_end;
+}
+
+cudaError_t tc_kid_run(const KernelFn& kf, const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
+                       const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,
+                       int precision, int want_second_order, void* ws, size_t ws_bytes, double** stats_out,
+                       cudaStream_t s, int* launches, const char** path) {
+  const int split = precision == SMMD_PREC_BF16X3;
+  *path = split ? "tc_bf16x3_kid" : "tc_bf16_kid";
+  const StreamPlan p = stream_plan(msub, msub, d, nsub, split);
+  if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+  if ((int64_t)nsub * p.Mp >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+  char* w = static_cast<char*>(ws);
+  __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+  float* norms = reinterpret_cast<float*>(w + p.off_norm);
+  double* stats = reinterpret_cast<double*>(w + p.off_stats);
+  cudaError_t e;
+  PrepTcArgs pa{G, R, dtype, ldg, ldr, msub, msub, p.mp, p.np, d, p.dp, p.dpz, idx_g, idx_r, first,
+                0, split, Z, norms, stats, kf};
+  prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), (unsigned)nsub), 256, 0, s>>>(pa);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++*launches;
+  CUtensorMap tm;
+  if (!smmd_host::make_tmap_bf16_2d(&tm, Z, (uint64_t)nsub * p.Mp, p.dpz, p.dpz, BM)) return cudaErrorUnknown;
+  StreamArgs sa;
+  sa.kf = kf;
+  sa.m = msub;
+  sa.n = msub;
+  sa.mp = p.mp;
+  sa.np = p.np;
+  sa.RB = p.RB;
+  sa.CT = p.CT;
+  sa.nkp = (int)(p.dp / 64);
+  sa.ncombo = split ? 3 : 1;
+  sa.dp = p.dp;
+  sa.total_tiles = p.total;
+  sa.chunk = p.chunk;
+  sa.norms = norms;
+  sa.stats = stats;
+  sa.want_sq = want_second_order;
+  e = launch_stream(kf, tm, sa, p.grid, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  *stats_out = stats;
+  return cudaSuccess;
+}
+
 }  // namespace smmd
