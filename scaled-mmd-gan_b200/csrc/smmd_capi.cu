@@ -121,12 +121,19 @@ Geometry make_geometry(const smmd_problem* p) {
   return g;
 }
 
-// AUTO: tensor cores only pay off once the Gram is big and the contraction deep enough.
+// AUTO: tensor cores only pay off once the Gram is big and the contraction deep enough; combinations the
+// tensor-core kernels do not cover stay on the exact path.  An explicit BF16/BF16X3 request is honoured or
+// refused (SMMD_EUNSUPPORTED), never silently downgraded.
 int resolve_precision(const smmd_problem* p, int want_grad) {
   int prec = p->precision;
   if (prec == SMMD_PREC_AUTO) {
+    KernelFn kf;
     const bool big = (p->m + p->n) >= 1024 && p->d >= 32;
-    prec = (big && tc_mmd2_supported(p->d, want_grad)) ? SMMD_PREC_BF16 : SMMD_PREC_FP32;
+    const bool ok = big &&
+                    build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf) ==
+                        SMMD_OK &&
+                    tc_mmd2_covers(kf, make_geometry(p), want_grad);
+    prec = ok ? SMMD_PREC_BF16 : SMMD_PREC_FP32;
   }
   return prec;
 }
@@ -199,7 +206,7 @@ int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, doubl
     return SMMD_OK;
   }
   if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
-  if (!tc_mmd2_supported(p->d, want_grad)) return SMMD_EUNSUPPORTED;
+  if (!tc_mmd2_covers(kf, g, want_grad)) return SMMD_EUNSUPPORTED;
   int launches = 0;
   cudaError_t e = tc_mmd2_run(kf, g, c, X, Y, p->dtype, p->ldx, p->ldy, prec, scalars, dX, dY, workspace,
                               workspace_bytes, s, &launches, &g_path);

@@ -420,6 +420,24 @@ __device__ void block_reduce(double (&q)[NQ], double* sh /* [NQ][256] */) {
   for (int i = 0; i < NQ; ++i) q[i] = sh[i * 256];
 }
 
+// same tree as block_reduce, for the first 256 threads of a larger block (named barrier 1)
+template <int NQ>
+__device__ void block_reduce256(double (&q)[NQ], double* sh /* [NQ][256] */) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) sh[i * 256 + tid] = q[i];
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if (tid < stride) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) sh[i * 256 + tid] += sh[i * 256 + tid + stride];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) q[i] = sh[i * 256];
+}
+
 __device__ __forceinline__ double mmd2_from_sums(const KernelFn& kf, double m, double n, int biased, double sxx,
                                                  double syy, double sxy, double syx, double dgx, double dgy) {
   double a_xx, a_yy;
@@ -448,22 +466,46 @@ struct FinArgs {
   double* scalars;
 };
 
-__global__ void __launch_bounds__(256) finalize_mmd2_kernel(FinArgs a) {
+__global__ void __launch_bounds__(512) finalize_mmd2_kernel(FinArgs a) {
   __shared__ double sh[6 * 256];
+  __shared__ double sh2[2][6 * 256];
   double q[6] = {0, 0, 0, 0, 0, 0};  // sxx, syy, sxy, syx, dgx, dgy
-  for (int64_t r = threadIdx.x; r < a.ox + a.oy; r += 256) {
-    const double* st = a.stats + r * RS_COUNT;
-    if (r < a.ox) {
-      q[0] += st[RS_SAME];
-      q[2] += st[RS_CROSS];
-      q[4] += st[RS_DIAG];
-    } else {
-      q[1] += st[RS_SAME];
-      q[3] += st[RS_CROSS];
-      q[5] += st[RS_DIAG];
+  // 512 threads, two row streams per reduction lane, 4 rows in flight per thread; partial sums are folded
+  // in a fixed order (deterministic).
+  const int lane256 = threadIdx.x & 255, stream = threadIdx.x >> 8;
+  const int64_t rows = a.ox + a.oy;
+  for (int64_t r0 = threadIdx.x; r0 < rows; r0 += 2048) {
+    double vs[4], vc[4], vd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + 512 * u;
+      const double* st = a.stats + (r < rows ? r : 0) * RS_COUNT;
+      const bool ok = r < rows;
+      vs[u] = ok ? st[RS_SAME] : 0.0;
+      vc[u] = ok ? st[RS_CROSS] : 0.0;
+      vd[u] = ok ? st[RS_DIAG] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + 512 * u;
+      if (r < a.ox) {
+        q[0] += vs[u];
+        q[2] += vc[u];
+        q[4] += vd[u];
+      } else {
+        q[1] += vs[u];
+        q[3] += vc[u];
+        q[5] += vd[u];
+      }
     }
   }
-  block_reduce<6>(q, sh);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sh2[stream][i * 256 + lane256] = q[i];
+  __syncthreads();
+  if (threadIdx.x >= 256) return;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) q[i] = sh2[0][i * 256 + lane256] + sh2[1][i * 256 + lane256];
+  block_reduce256<6>(q, sh);
   if (threadIdx.x == 0) {
     double* o = a.scalars;
     for (int i = 0; i < SMMD_NUM_SCALARS; ++i) o[i] = 0.0;
@@ -485,7 +527,7 @@ cudaError_t launch_finalize_mmd2(const KernelFn& kf, const Geometry& g, const do
                                  double* scalars, cudaStream_t s) {
   FinArgs a{kf, g.m, g.n, g.x1 - g.x0, g.y1 - g.y0, g.biased,
             (g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n) ? 1 : 0, stats, scalars};
-  finalize_mmd2_kernel<<<1, 256, 0, s>>>(a);
+  finalize_mmd2_kernel<<<1, 512, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -17,9 +17,11 @@
 // workspace slabs and are reduced in a fixed order by the finalisation kernel (deterministic).
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstdlib>
 #include "sm100_ptx.cuh"
 #include "smmd_kfun.cuh"
 #include "smmd_tc.h"
+#include "smmd_tc_math.cuh"
 #include "tmap_host.h"
 
 namespace smmd {
@@ -33,6 +35,20 @@ constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 two epi
 constexpr int kMaxSmem = 232448;   // 227 KB
 
 inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+// Developer tuning knobs (environment overrides are read once; defaults are the measured best).
+struct Tuning {
+  int fused_ksplit;
+};
+const Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning v;
+    v.fused_ksplit = 2;
+    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
+    return v;
+  }();
+  return t;
+}
 
 int sm_count() {
   static int n = 0;
@@ -143,21 +159,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* Z, int
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// epilogue element math shared by both kernels
-// ------------------------------------------------------------------------------------------------
-template <int FAM>
-__device__ __forceinline__ void pair_eval(const KernelFn& kf, float S, float nij, float& k, float& kd) {
-  if constexpr (FAM == FAM_POLY) {
-    const float bb = fmaf(kf.poly_gamma, S, kf.poly_coef0);
-    float p = bb;
-    for (int i = 1; i < kf.degree; ++i) p *= bb;
-    k = p;
-    kd = 0.f;
-  } else {
-    float D = fmaf(-2.f, S, nij);
-    if constexpr (FAM != FAM_DISTANCE) D = fmaxf(D, 0.f);
-    eval_fast<FAM>(kf, D, k, kd);
+// copy the mixture parameters to shared memory for the generic math variants: sp[0..7]=p0, [8..15]=p1, [16..23]=w
+__device__ __forceinline__ void stage_params(const KernelFn& kf, float* sp) {
+  if (threadIdx.x < 8) {
+    sp[threadIdx.x] = kf.p0[threadIdx.x];
+    sp[8 + threadIdx.x] = kf.p1[threadIdx.x];
+    sp[16 + threadIdx.x] = kf.w[threadIdx.x];
   }
 }
 
@@ -171,6 +178,8 @@ struct FusedArgs {
   const float* norms;          // [Mp]
   int nrb_x, rb_x0, nrb_y, rb_y0;
   int T;                       // column tiles of 64 over the padded stacked matrix
+  int dp, npanel, nst;         // padded feature dim, 64-wide panels, Zj ring depth
+  int ksplit;                  // epilogue column slices per tile (1 or 2)
   int64_t total_tiles, chunk;
   int slots;
   float* Opart;                // [grid][slots][128][DP]
@@ -178,28 +187,65 @@ struct FusedArgs {
   double* spart;               // [grid][slots][2][128][2]
 };
 
-template <int DP>
-struct FusedCfg {
-  static constexpr int NPANEL = DP / 64;
-  static constexpr int ZI_BYTES = NPANEL * BM * 128;        // resident row block
-  static constexpr int ZJ_BYTES = NPANEL * BNF * 128;       // one column tile
-  static constexpr int STAGE_BYTES = ZJ_BYTES + 256;        // + 64 column norms
-  static constexpr int NST_RAW = (kMaxSmem - 2048 - ZI_BYTES) / (ZJ_BYTES + 1024);
-  static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
-  static constexpr int SMEM = 1024 /*align slack*/ + ZI_BYTES + NST * ZJ_BYTES + NST * 256 + 512;
-  static constexpr uint32_t TM_O = 0, TM_S = 256, TM_W = 448;  // TMEM columns: O[DP] | S0..S2[64] | W0,W1[32]
-};
+// TMEM columns: O[dp <= 256] | S0..S2[64 each] | W0,W1[32 each]
+constexpr uint32_t TM_O = 0, TM_S = 256, TM_W = 448;
+constexpr int kZjRowBytes = BNF * 128;   // one 64-wide panel of a column tile
+constexpr int kZiRowBytes = BM * 128;    // one 64-wide panel of the row block
 
-template <int DP, int FAM>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj, FusedArgs a) {
-  using Cfg = FusedCfg<DP>;
-  constexpr int NPANEL = Cfg::NPANEL, NST = Cfg::NST;
+// smem = 1023 B alignment slack + Zi + nst * (Zj tile + 64 norms) + 512 B (barriers, tmem slot, staged params)
+inline int fused_stages(int npanel) {
+  int nst = (kMaxSmem - 1024 - 512 - npanel * kZiRowBytes) / (npanel * kZjRowBytes + 256);
+  return nst > 8 ? 8 : nst;
+}
+inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes + nst * (npanel * kZjRowBytes + 256) + 512; }
+
+// 16 columns of one row of a fused-epilogue tile: kernel transform, tile sum, row sum of W, and W packed to
+// bf16x2.  SPECIAL tiles (diagonal inside / padded columns) mask per element; interior tiles run the
+// unmasked instruction stream.  Kept small and called from a ROLLED loop: the whole hot loop must fit the
+// instruction caches (a fully unrolled 64-column epilogue stalled ~50% on instruction fetch).
+template <class Math, bool SPECIAL>
+__device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (&v)[16], const float* __restrict__ nj,
+                                              float ni, float cw, int col0, int lim, int gi, float& tsum,
+                                              float& rsum, uint32_t (&wpk)[8]) {
+#pragma unroll
+  for (int c = 0; c < 16; c += 4) {
+    const float4 n4 = *reinterpret_cast<const float4*>(nj + c);
+    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+    float ww[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float k, kd;
+      math.eval(__uint_as_float(v[c + e]), ni + nn[e], k, kd);
+      if (SPECIAL) {
+        const int col = col0 + c + e;
+        const bool ok = (col < lim) && (col != gi);
+        k = ok ? k : 0.f;
+        kd = ok ? kd : 0.f;
+      }
+      tsum += k;
+      ww[e] = cw * kd;
+      rsum += ww[e];
+    }
+    wpk[c >> 1] = pack_bf16x2(ww[0], ww[1]);
+    wpk[(c >> 1) + 1] = pack_bf16x2(ww[2], ww[3]);
+  }
+}
+
+// KSPLIT = column slices per tile: each of the two epilogue groups has 4*KSPLIT warps (TMEM lane quarter x
+// column slice), i.e. 8*KSPLIT epilogue warps per CTA.
+template <class Math, int KSPLIT>
+__global__ void __launch_bounds__(64 + 256 * KSPLIT, 1)
+tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
+                const __grid_constant__ FusedArgs a) {
+  constexpr int NPART = 2 * KSPLIT;           // partial-result slices per row (group x column slice)
+  constexpr int CH_PER = (BNF / 16) / KSPLIT; // 16-column chunks per thread per tile
+  const int NPANEL = a.npanel, NST = a.nst, DP = a.dp;
+  const int ZI_BYTES = NPANEL * kZiRowBytes, ZJ_BYTES = NPANEL * kZjRowBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sZi = smem;
-  uint8_t* sZj = smem + Cfg::ZI_BYTES;
-  float* sN = reinterpret_cast<float*>(sZj + NST * Cfg::ZJ_BYTES);  // [NST][64]
+  uint8_t* sZj = smem + ZI_BYTES;
+  float* sN = reinterpret_cast<float*>(sZj + NST * ZJ_BYTES);  // [NST][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sN) + NST * 256);
   uint64_t* zj_full = bars;             // [NST]
   uint64_t* zj_empty = bars + NST;      // [NST]
@@ -212,8 +258,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   uint64_t* o_full = zi_empty + 1;
   uint64_t* o_empty = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);  // [24]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(&zj_full[i], 1);
@@ -221,16 +269,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
+      mbar_init(&s_empty[i], 128 * KSPLIT);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&w_full[i], 128);
+      mbar_init(&w_full[i], 128 * KSPLIT);
       mbar_init(&w_empty[i], 1);
     }
     mbar_init(zi_full, 1);
     mbar_init(zi_empty, 1);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
+    mbar_init(o_empty, 256 * KSPLIT);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -249,188 +297,194 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (all ring bookkeeping is kept as running 32-bit counters: a single thread runs this loop)
     if (lane == 0) {
-      uint32_t unit = 0;
-      uint64_t gt = 0;
-      for (int64_t pos = pos0; pos < pos1;) {
-        const int64_t rbi = pos / a.T;
-        const int t0 = (int)(pos - rbi * a.T);
-        const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
+      uint32_t unit = 0, st = 0, ph = 0;
+      int rbi = (int)(pos0 / a.T);
+      int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+      for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+        const int TU = (int)std::min<int64_t>(a.T - t0, left);
         const int rb = rb_of(rbi);
         mbar_wait(zi_empty, (unit & 1) ^ 1);
-        mbar_arrive_expect_tx(zi_full, Cfg::ZI_BYTES);
-#pragma unroll
+        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
         for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
-        for (int t = t0; t < t1; ++t, ++gt) {
-          const uint32_t st = (uint32_t)(gt % NST), ph = (uint32_t)((gt / NST) & 1);
+        for (int t = t0; t < t0 + TU; ++t) {
           mbar_wait(&zj_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&zj_full[st], Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int p = 0; p < NPANEL; ++p)
-            tma_load_2d(sZj + st * Cfg::ZJ_BYTES + p * (BNF * 128), &tmap_zj, &zj_full[st], p * 64, t * BNF);
-          bulk_load_1d(sN + st * 64, a.norms + (int64_t)t * BNF, 256, &zj_full[st]);
+          mbar_arrive_expect_tx(&zj_full[st], (ZJ_BYTES + 256));
+          uint8_t* dst = sZj + st * ZJ_BYTES;
+          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * (BNF * 128), &tmap_zj, &zj_full[st], p * 64, t * BNF);
+          bulk_load_1d(sN + st * 64, a.norms + t * BNF, 256, &zj_full[st]);
+          if (++st == (uint32_t)NST) {
+            st = 0;
+            ph ^= 1;
+          }
         }
-        pos += t1 - t0;
-        ++unit;
+        left -= TU;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc(BM, BNF, kFmtBF16, false, false);
-      constexpr uint32_t idesc2 = make_idesc(BM, DP, kFmtBF16, false, true);
+      const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
+      const uint32_t hi = desc_hi_sw128(1024);
+      const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);                   // K-major A: LBO unused (16 B)
+      const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);                  // K-major B for UMMA #1
+      const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), BNF * 128);           // MN-major B for UMMA #2: LBO = panel stride
+      const uint32_t stage_step = (uint32_t)ZJ_BYTES >> 4;                 // descriptor address units are 16 B
       uint32_t unit = 0;
-      uint64_t gbase = 0;
-      for (int64_t pos = pos0; pos < pos1;) {
-        const int64_t rbi = pos / a.T;
-        const int t0 = (int)(pos - rbi * a.T);
-        const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
-        const int TU = t1 - t0;
+      // running state of the two MMA streams (UMMA #1 runs 3 tiles ahead of UMMA #2)
+      uint32_t st1 = 0, ph1 = 0, sb1 = 0, sph1 = 0;   // Zj stage / phase, S buffer / phase for UMMA #1
+      uint32_t st2 = 0, wb2 = 0, wph2 = 0;            // Zj stage, W buffer / phase for UMMA #2
+      int rbi = (int)(pos0 / a.T);
+      int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+      for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+        const int TU = (int)std::min<int64_t>(a.T - t0, left);
         mbar_wait(zi_full, unit & 1);
         for (int jj = 0; jj < TU + 3; ++jj) {
           const int b2 = jj - 3;
           if (b2 >= 0) {  // ---- UMMA #2 for local tile b2: O += W * Zj
-            const uint64_t gt = gbase + b2;
-            const uint32_t wb = (uint32_t)(gt & 1), st = (uint32_t)(gt % NST);
-            mbar_wait(&w_full[wb], (uint32_t)((gt >> 1) & 1));
+            mbar_wait(&w_full[wb2], wph2);
             if (b2 == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
             tc_fence_after();
-            const uint32_t zj = smem_u32(sZj + st * Cfg::ZJ_BYTES);
+            const uint32_t blo = zj_lo2 + st2 * stage_step;
+            const uint32_t wad = tmem + TM_W + wb2 * 32;
 #pragma unroll
-            for (int kk = 0; kk < BNF / 16; ++kk) {
-              const uint64_t db = make_smem_desc_sw128(zj + kk * 2048, BNF * 128, 1024);
-              umma_ts(tmem + Cfg::TM_O, tmem + Cfg::TM_W + wb * 32 + kk * 8, db, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&zj_empty[st]);
-            umma_commit(&w_empty[wb]);
+            for (int kk = 0; kk < BNF / 16; ++kk)
+              umma_ts2(tmem + TM_O, wad + kk * 8, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&zj_empty[st2]);
+            umma_commit(&w_empty[wb2]);
             if (b2 == TU - 1) umma_commit(o_full);
+            if (++st2 == (uint32_t)NST) st2 = 0;
+            wph2 ^= wb2;  // phase flips each time buffer index wraps 1 -> 0
+            wb2 ^= 1;
           }
           if (jj < TU) {  // ---- UMMA #1 for local tile jj: S = Zi * Zj^T
-            const uint64_t gt = gbase + jj;
-            const uint32_t sb = (uint32_t)(gt % 3), st = (uint32_t)(gt % NST);
-            mbar_wait(&zj_full[st], (uint32_t)((gt / NST) & 1));
-            mbar_wait(&s_empty[sb], (uint32_t)(((gt / 3) & 1) ^ 1));
+            mbar_wait(&zj_full[st1], ph1);
+            mbar_wait(&s_empty[sb1], sph1 ^ 1);
             tc_fence_after();
-            const uint32_t zi = smem_u32(sZi), zj = smem_u32(sZj + st * Cfg::ZJ_BYTES);
+            const uint32_t blo = zj_lo1 + st1 * stage_step;
+            const uint32_t sad = tmem + TM_S + sb1 * 64;
+            for (int p = 0; p < NPANEL; ++p) {
+              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * ((BNF * 128) >> 4);
 #pragma unroll
-            for (int p = 0; p < NPANEL; ++p)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc_sw128(zi + p * (BM * 128) + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc_sw128(zj + p * (BNF * 128) + k * 32, 16, 1024);
-                umma_ss(tmem + Cfg::TM_S + sb * 64, da, db, idesc1, (p | k) ? 1u : 0u);
-              }
-            umma_commit(&s_full[sb]);
+              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+            }
+            umma_commit(&s_full[sb1]);
             if (jj == TU - 1) umma_commit(zi_empty);
+            if (++st1 == (uint32_t)NST) {
+              st1 = 0;
+              ph1 ^= 1;
+            }
+            if (++sb1 == 3) {
+              sb1 = 0;
+              sph1 ^= 1;
+            }
           }
         }
-        gbase += TU;
-        pos += TU;
-        ++unit;
+        left -= TU;
       }
     }
   } else {
     // ===================== epilogue groups =====================
-    const int grp = (warp - 2) >> 2;          // 0 / 1
+    const int ew = warp - 2;
+    const int grp = ew / (4 * KSPLIT);        // 0 / 1
+    const int half = (ew % (4 * KSPLIT)) >> 2;  // column slice of the tile handled by this warp
+    const int part = grp * KSPLIT + half;
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // row inside the row block
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
     uint32_t unit = 0;
-    uint64_t gbase = 0;
     int slot = 0;
-    for (int64_t pos = pos0; pos < pos1; ++slot) {
-      const int64_t rbi = pos / a.T;
-      const int t0 = (int)(pos - rbi * a.T);
-      const int t1 = (int)std::min<int64_t>(a.T, t0 + (pos1 - pos));
-      const int TU = t1 - t0;
+    // running ring state for the tiles of THIS group (it handles every second tile of the CTA's stream)
+    uint32_t par = 0;                       // parity of the global tile counter
+    uint32_t st = 0, ph = 0;                // Zj stage / phase of the current tile
+    uint32_t sb = 0, sph = 0;               // S buffer / phase
+    uint32_t wph = 0;                       // phase of this group's W buffer
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit, ++slot) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
       const int rb = rb_of(rbi);
-      const int64_t gi = (int64_t)rb * BM + r;
-      const bool rowX = gi < a.mp;
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
       const float ni = a.norms[gi];
       float rsum = 0.f;
       double dsame = 0.0, dcross = 0.0;
       for (int lt = 0; lt < TU; ++lt) {
-        const uint64_t gt = gbase + lt;
-        if ((int)(gt & 1) != grp) continue;
-        const int t = t0 + lt;
-        const uint32_t sb = (uint32_t)(gt % 3), st = (uint32_t)(gt % NST);
-        const int64_t c0 = (int64_t)t * BNF;
-        const bool colX = c0 < a.mp;
-        const bool same = (colX == rowX);
-        const float cw = same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy;
-        const int64_t lim = colX ? a.m : a.mp + a.n;               // first invalid column of this region
-        const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);  // pad columns or diagonal inside
-        mbar_wait(&zj_full[st], (uint32_t)((gt / NST) & 1));      // column norms ride with the Zj stage
-        mbar_wait(&s_full[sb], (uint32_t)((gt / 3) & 1));
-        tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld_x32(tmem + Cfg::TM_S + sb * 64 + lane_base, v0);
-        tmem_ld_x32(tmem + Cfg::TM_S + sb * 64 + 32 + lane_base, v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_empty[sb]);
-        mbar_wait(&w_empty[grp], (uint32_t)(((gt >> 1) & 1) ^ 1));
-        const float* nj = sN + st * 64;
-        float tsum = 0.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t wpk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float kk[2], ww[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = h * 32 + c + e;
-              const float S = __uint_as_float(h ? v1[c + e] : v0[c + e]);
-              float k, kd;
-              pair_eval<FAM>(a.kf, S, ni + nj[cc], k, kd);
-              if (special) {
-                const int64_t col = c0 + cc;
-                const bool ok = (col < lim) && (col != gi);
-                k = ok ? k : 0.f;
-                kd = ok ? kd : 0.f;
-              }
-              kk[e] = k;
-              ww[e] = cw * kd;
+        if ((int)par == grp) {
+          const int c0 = (t0 + lt) * BNF;
+          const bool colX = c0 < mp;
+          const bool same = (colX == rowX);
+          const float cw = (same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale;
+          const int lim = colX ? mvalid : yvalid;                       // first invalid column of this region
+          const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);   // pad columns or diagonal inside
+          mbar_wait(&zj_full[st], ph);                                  // column norms ride with the Zj stage
+          mbar_wait(&s_full[sb], sph);
+          tc_fence_after();
+          mbar_wait(&w_empty[grp], wph ^ 1);
+          const float* nj = sN + st * 64;
+          float tsum = 0.f;
+          const uint32_t s_addr = tmem + TM_S + sb * 64 + lane_base;
+          const uint32_t w_addr = tmem + TM_W + grp * 32 + lane_base;
+#pragma unroll 1
+          for (int ch = half * CH_PER; ch < (half + 1) * CH_PER; ++ch) {
+            uint32_t v[16], wpk[8];
+            tmem_ld_x16(s_addr + ch * 16, v);
+            tmem_ld_wait();
+            if (ch == (half + 1) * CH_PER - 1) {  // this thread's slice of S is in registers: release it
+              tc_fence_before();
+              mbar_arrive(&s_empty[sb]);
             }
-            tsum += kk[0] + kk[1];
-            rsum += ww[0] + ww[1];
-            wpk[c >> 1] = pack_bf16x2(ww[0], ww[1]);
+            if (!special) fused_chunk16<Math, false>(math, v, nj + ch * 16, ni, cw, c0 + ch * 16, lim, gi, tsum, rsum, wpk);
+            else fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + ch * 16, lim, gi, tsum, rsum, wpk);
+            tmem_st_x8(w_addr + ch * 8, wpk);
           }
-          tmem_st_x16(tmem + Cfg::TM_W + grp * 32 + h * 16 + lane_base, wpk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&w_full[grp]);
+          wph ^= 1;
+          if (same) dsame += (double)(tsum * kscale);
+          else dcross += (double)(tsum * kscale);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&w_full[grp]);
-        if (same) dsame += (double)tsum;
-        else dcross += (double)tsum;
+        // advance the ring state by one tile of the CTA's stream
+        par ^= 1;
+        if (++st == (uint32_t)NST) {
+          st = 0;
+          ph ^= 1;
+        }
+        if (++sb == 3) {
+          sb = 0;
+          sph ^= 1;
+        }
       }
       // ---- unit end: drain O (this group's half of the feature columns) ----
       mbar_wait(o_full, unit & 1);
       tc_fence_after();
       {
         const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
-        float* orow = a.Opart + (sl * BM + r) * DP + grp * (DP / 2);
-#pragma unroll
-        for (int c = 0; c < DP / 2; c += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem + Cfg::TM_O + grp * (DP / 2) + c + lane_base, v);
+        const int seg = DP / NPART;  // feature columns drained by this thread (multiple of 16)
+        float* orow = a.Opart + (sl * BM + r) * DP + part * seg;
+        for (int c = 0; c < seg; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem + TM_O + part * seg + c + lane_base, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
+          for (int e = 0; e < 16; e += 4)
             *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
                                                                    __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
         }
-        a.rpart[(sl * 2 + grp) * BM + r] = rsum;
-        double* sp = a.spart + ((sl * 2 + grp) * BM + r) * 2;
+        a.rpart[(sl * NPART + part) * BM + r] = rsum;
+        double* sp = a.spart + ((sl * NPART + part) * BM + r) * 2;
         sp[0] = dsame;
         sp[1] = dcross;
       }
       tc_fence_before();
       mbar_arrive(o_empty);
-      gbase += TU;
-      pos += TU;
-      ++unit;
+      left -= TU;
     }
   }
   tc_fence_before();
@@ -446,10 +500,14 @@ struct FinRowsArgs {
   int dp;
   int nrb_x, rb_x0, nrb_y, rb_y0, T;
   int64_t chunk;
-  int slots;
+  int slots, npart;
   double a_xx, a_yy, a_xy;
   const __nv_bfloat16* Z;
   int64_t dpz;
+  const void* X;       // original features (fp32 or bf16): the r_i * z_i term uses the unrounded row
+  const void* Y;
+  int dtype;
+  int64_t ldx, ldy;
   const float* norms;
   const double* csum;  // [2][dp] or null
   const float* Opart;
@@ -475,27 +533,46 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
   double ssame = 0.0, scross = 0.0;
   for (int64_t g = g0; g <= g1; ++g) {
     const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
-    rs += a.rpart[(sl * 2 + 0) * BM + r] + a.rpart[(sl * 2 + 1) * BM + r];
-    const double* s0 = a.spart + ((sl * 2 + 0) * BM + r) * 2;
-    const double* s1 = a.spart + ((sl * 2 + 1) * BM + r) * 2;
-    ssame += s0[0] + s1[0];
-    scross += s0[1] + s1[1];
+    for (int pt = 0; pt < a.npart; ++pt) {
+      rs += a.rpart[(sl * a.npart + pt) * BM + r];
+      const double* sp = a.spart + ((sl * a.npart + pt) * BM + r) * 2;
+      ssame += sp[0];
+      scross += sp[1];
+    }
   }
-  const __nv_bfloat16* zrow = a.Z + gi * a.dpz;
   const double a_same = rowX ? a.a_xx : a.a_yy;
   const bool dot = a.kf.family == FAM_RQ && a.kf.add_dot > 0.f && a.csum != nullptr;
   double dsame = 0.0, dcross = 0.0;  // z_i . colsum(same set) / (other set)
   float* out = nullptr;
   if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
-  for (int64_t c = lane; c < a.d; c += 32) {
-    const float z = __bfloat162float(zrow[c]);
-    if (out) {
-      float o = 0.f;
-      for (int64_t g = g0; g <= g1; ++g) {
-        const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
-        o += a.Opart[(sl * BM + r) * a.dp + c];
+  // lane owns features lane, lane+32, ... (dp <= 256 -> at most 8); slabs are summed in fixed order
+  float oacc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) oacc[t] = 0.f;
+  if (out) {
+    for (int64_t g = g0; g <= g1; ++g) {
+      const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
+      const float* orow = a.Opart + (sl * BM + r) * a.dp;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = lane + 32 * t;
+        if (c < a.dp) oacc[t] += orow[c];
       }
-      float gv = rs * z - o;  // W already carries the factor 4 a_ij
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int c = lane + 32 * t;
+    if (c >= a.d) continue;
+    // z_i at full input precision: g_i = 4 sum_j W_ij (z_i - z_j) is dominated by r_i z_i, so rounding z_i
+    // to bf16 here would put a 2^-9 relative error straight into the gradient
+    const void* src = rowX ? a.X : a.Y;
+    const int64_t sidx = li * (rowX ? a.ldx : a.ldy) + c;
+    float z = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
+    if (a.kf.tanh_features) z = tanhf(z);
+    if (out) {
+      float gv = rs * z - oacc[t];  // W already carries the factor 4 a_ij
       if (dot) {
         const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
         gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
@@ -535,7 +612,7 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
 constexpr int BNS = 128;
 constexpr int kStreamStages = 6;
 constexpr int kStreamStageBytes = 2 * BM * 128;  // A panel + B panel
-constexpr int kStreamSmem = 1024 + kStreamStages * kStreamStageBytes + 512;
+constexpr int kStreamSmem = 1024 + kStreamStages * kStreamStageBytes + 1024;
 
 struct StreamArgs {
   KernelFn kf;
@@ -550,9 +627,9 @@ struct StreamArgs {
   int want_sq;
 };
 
-template <int FAM>
+template <class Math>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
+tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StreamArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes);
@@ -561,7 +638,9 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
   uint64_t* acc_full = empty + kStreamStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);  // [24]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
   if (tid == 0) {
     for (int i = 0; i < kStreamStages; ++i) {
       mbar_init(&full[i], 1);
@@ -586,48 +665,63 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
 
   if (warp == 0) {
     if (lane == 0) {
-      uint64_t it = 0;
+      uint32_t st = 0, ph = 0;
+      // decompose the first flattened tile index once, then step (ct, rb, b) incrementally
+      int ct = (int)(pos0 % a.CT);
+      int64_t brb = pos0 / a.CT;
+      int rb = (int)(brb % a.RB);
+      int64_t b = brb / a.RB;
+      const int dpi = (int)a.dp;
       for (int64_t pos = pos0; pos < pos1; ++pos) {
-        const int ct = (int)(pos % a.CT);
-        const int64_t brb = pos / a.CT;
-        const int rb = (int)(brb % a.RB);
-        const int64_t b = brb / a.RB;
-        const int32_t arow = (int32_t)(b * Mp + (int64_t)rb * BM), brow = (int32_t)(b * Mp + (int64_t)ct * BNS);
-        for (int kk = 0; kk < nk; ++kk, ++it) {
-          const int combo = kk / a.nkp, p = kk - combo * a.nkp;
-          const int32_t acol = (int32_t)(p * 64 + (combo == 1 ? a.dp : 0));
-          const int32_t bcol = (int32_t)(p * 64 + (combo == 2 ? a.dp : 0));
-          const uint32_t st = (uint32_t)(it % kStreamStages), ph = (uint32_t)((it / kStreamStages) & 1);
-          mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
-          uint8_t* sa = smem + st * kStreamStageBytes;
-          tma_load_2d(sa, &tmap, &full[st], acol, arow);
-          tma_load_2d(sa + BM * 128, &tmap, &full[st], bcol, brow);
+        const int32_t arow = (int32_t)(b * Mp) + rb * BM, brow = (int32_t)(b * Mp) + ct * BNS;
+        for (int combo = 0; combo < a.ncombo; ++combo) {
+          const int32_t aoff = combo == 1 ? dpi : 0, boff = combo == 2 ? dpi : 0;
+          for (int p = 0; p < a.nkp; ++p) {
+            mbar_wait(&empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
+            uint8_t* sa = smem + st * kStreamStageBytes;
+            tma_load_2d(sa, &tmap, &full[st], p * 64 + aoff, arow);
+            tma_load_2d(sa + BM * 128, &tmap, &full[st], p * 64 + boff, brow);
+            if (++st == kStreamStages) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        if (++ct == a.CT) {
+          ct = 0;
+          if (++rb == a.RB) {
+            rb = 0;
+            ++b;
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BNS, kFmtBF16, false, false);
-      uint64_t it = 0, tc = 0;
-      for (int64_t pos = pos0; pos < pos1; ++pos, ++tc) {
-        const uint32_t ab = (uint32_t)(tc & 1);
-        mbar_wait(&acc_empty[ab], (uint32_t)(((tc >> 1) & 1) ^ 1));
+      const uint32_t hi = desc_hi_sw128(1024);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+      uint32_t st = 0, ph = 0, ab = 0, aph = 0;
+      for (int64_t pos = pos0; pos < pos1; ++pos) {
+        mbar_wait(&acc_empty[ab], aph ^ 1);
         tc_fence_after();
-        for (int kk = 0; kk < nk; ++kk, ++it) {
-          const uint32_t st = (uint32_t)(it % kStreamStages), ph = (uint32_t)((it / kStreamStages) & 1);
+        const uint32_t dad = tmem + ab * BNS;
+        for (int kk = 0; kk < nk; ++kk) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * kStreamStageBytes), sb = sa + BM * 128;
+          const uint32_t alo = a_lo0 + st * (kStreamStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_ss(tmem + ab * BNS, da, db, idesc, (kk | k) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
           umma_commit(&empty[st]);
+          if (++st == kStreamStages) {
+            st = 0;
+            ph ^= 1;
+          }
         }
         umma_commit(&acc_full[ab]);
+        aph ^= ab;
+        ab ^= 1;
       }
     }
   } else {
@@ -635,6 +729,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale();
     // accumulators of the (problem, row block) currently being swept by this thread
     int64_t cur_brb = -1;
     double s_same = 0, s_cross = 0, q_same = 0, q_cross = 0, pairv = 0;
@@ -677,7 +773,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
       const bool same = (colX == rowX);
       const int64_t lim = colX ? a.m : a.mp + a.n;
       const int64_t pair_col = rowX ? a.mp + gi : -1;  // the (x_i, y_i) element
-      const bool special = (c0 + BNS > lim) || (ct == rb) || (pair_col >= c0 && pair_col < c0 + BNS + BM);
+      const bool special = (c0 + BNS > lim) || (ct == rb) || (rowX && ct == rb + (int)(a.mp / BNS));
       mbar_wait(&acc_full[grp], (uint32_t)((tc >> 1) & 1));
       tc_fence_after();
       const float* nj = a.norms + b * Mp + c0;
@@ -698,7 +794,8 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, StreamArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float k, kd;
-            pair_eval<FAM>(a.kf, __uint_as_float(v[c + e]), ni + nn[e], k, kd);
+            math.eval(__uint_as_float(v[c + e]), ni + nn[e], k, kd);
+            k *= kscale;
             if (special) {
               const int64_t col = c0 + h * 32 + c + e;
               const bool ok = (col < lim) && (col != gi);
@@ -764,37 +861,41 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.off_O = o;
   o = up256(o + (size_t)p.grid * p.slots * BM * p.dp * 4);
   p.off_r = o;
-  o = up256(o + (size_t)p.grid * p.slots * 2 * BM * 4);
+  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 4);
   p.off_s = o;
-  o = up256(o + (size_t)p.grid * p.slots * 2 * BM * 2 * 8);
+  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 2 * 8);
   p.off_stats = o;
   o = up256(o + (size_t)((x1 - x0) + (y1 - y0)) * RS_COUNT * 8);
   p.off_end = o;
   return p;
 }
 
-template <int DP, int FAM>
-cudaError_t launch_fused_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid, cudaStream_t s) {
-  using Cfg = FusedCfg<DP>;
-  static_assert(Cfg::NST >= 4, "need >= 4 Zj stages");
-  static_assert(Cfg::SMEM <= kMaxSmem, "smem budget");
-  auto kern = tc_fused_kernel<DP, FAM>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+template <class Math, int KSPLIT>
+cudaError_t launch_fused_k(const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid, cudaStream_t s) {
+  const int smem = fused_smem(a.npanel, a.nst);
+  if (a.nst < 4 || smem > kMaxSmem) return cudaErrorInvalidConfiguration;
+  auto kern = tc_fused_kernel<Math, KSPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, Cfg::SMEM, s>>>(tzi, tzj, a);
+  kern<<<grid, 64 + 256 * KSPLIT, smem, s>>>(tzi, tzj, a);
   return cudaGetLastError();
 }
+template <class Math>
+cudaError_t launch_fused_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid, cudaStream_t s) {
+  return a.ksplit == 2 ? launch_fused_k<Math, 2>(tzi, tzj, a, grid, s) : launch_fused_k<Math, 1>(tzi, tzj, a, grid, s);
+}
 
-template <int FAM>
-cudaError_t launch_fused_f(int dp, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
-                           cudaStream_t s) {
-  switch (dp) {
-    case 64: return launch_fused_t<64, FAM>(tzi, tzj, a, grid, s);
-    case 128: return launch_fused_t<128, FAM>(tzi, tzj, a, grid, s);
-    case 192: return launch_fused_t<192, FAM>(tzi, tzj, a, grid, s);
-    case 256: return launch_fused_t<256, FAM>(tzi, tzj, a, grid, s);
+cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
+                         cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_fused_t<MathRbf1>(tzi, tzj, a, grid, s);
+    case TV_RBF_LADDER5: return launch_fused_t<MathRbfLadder<5>>(tzi, tzj, a, grid, s);
+    case TV_RBF_GENERIC: return launch_fused_t<MathGeneric<FAM_RBF>>(tzi, tzj, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_fused_t<MathRq3Default>(tzi, tzj, a, grid, s);
+    case TV_RQ_GENERIC: return launch_fused_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, grid, s);
+    case TV_DISTANCE: return launch_fused_t<MathDistance>(tzi, tzj, a, grid, s);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaErrorInvalidValue;
 }
 
 struct StreamPlan {
@@ -828,23 +929,27 @@ StreamPlan stream_plan(int64_t m, int64_t n, int64_t d, int64_t batch, int split
   return p;
 }
 
-template <int FAM>
+template <class Math>
 cudaError_t launch_stream_t(const CUtensorMap& tm, const StreamArgs& a, int grid, cudaStream_t s) {
-  auto kern = tc_stream_kernel<FAM>;
+  auto kern = tc_stream_kernel<Math>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem);
   if (e != cudaSuccess) return e;
   kern<<<grid, kThreads, kStreamSmem, s>>>(tm, a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_stream(const KernelFn& kf, const CUtensorMap& tm, const StreamArgs& a, int grid, cudaStream_t s) {
-  switch (kf.family) {
-    case FAM_POLY: return launch_stream_t<FAM_POLY>(tm, a, grid, s);
-    case FAM_RBF: return launch_stream_t<FAM_RBF>(tm, a, grid, s);
-    case FAM_RQ: return launch_stream_t<FAM_RQ>(tm, a, grid, s);
-    case FAM_DISTANCE: return launch_stream_t<FAM_DISTANCE>(tm, a, grid, s);
+cudaError_t launch_stream(TcVariant v, const CUtensorMap& tm, const StreamArgs& a, int grid, cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_stream_t<MathRbf1>(tm, a, grid, s);
+    case TV_RBF_LADDER5: return launch_stream_t<MathRbfLadder<5>>(tm, a, grid, s);
+    case TV_RBF_GENERIC: return launch_stream_t<MathGeneric<FAM_RBF>>(tm, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_stream_t<MathRq3Default>(tm, a, grid, s);
+    case TV_RQ_GENERIC: return launch_stream_t<MathGeneric<FAM_RQ>>(tm, a, grid, s);
+    case TV_DISTANCE: return launch_stream_t<MathDistance>(tm, a, grid, s);
+    case TV_POLY3: return launch_stream_t<MathPoly3>(tm, a, grid, s);
+    case TV_POLY_GENERIC: return launch_stream_t<MathPolyN>(tm, a, grid, s);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -858,6 +963,17 @@ static bool tc_family_ok(const KernelFn& kf) {
   return kf.family == FAM_RBF || kf.family == FAM_RQ || kf.family == FAM_DISTANCE;
 }
 
+// Which (family, mode) combinations the tensor-core kernels cover.  dot is closed-form territory
+// (sum_ij <x_i,y_j> = <sum x, sum y>) and stays on the exact path.
+bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad) {
+  if (!tc_family_ok(kf) || !tc_mmd2_supported(g.d, want_grad)) return false;
+  if (!want_grad) {
+    if (kf.add_dot > 0.f) return false;
+    if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return false;
+  }
+  return true;
+}
+
 size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision) {
   // worst case over shards: a full-range plan bounds every rank's plan
   const size_t fused = want_grad ? fused_plan(m, n, d, 0, m, 0, n).off_end : 0;
@@ -865,10 +981,12 @@ size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, i
   return std::max(fused, stream);
 }
 
-cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, const void* X, const void* Y, int dtype,
-                        int64_t ldx, int64_t ldy, int precision, double* scalars, float* dX, float* dY, void* ws,
-                        size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
-  if (!tc_family_ok(kf)) return cudaErrorNotSupported;
+cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c, const void* X, const void* Y,
+                        int dtype, int64_t ldx, int64_t ldy, int precision, double* scalars, float* dX, float* dY,
+                        void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
+  if (!tc_family_ok(kf_in)) return cudaErrorNotSupported;
+  KernelFn kf = kf_in;
+  const TcVariant variant = select_tc_variant(kf);
   char* w = static_cast<char*>(ws);
   cudaError_t e;
   const bool want_grad = dX != nullptr;
@@ -908,17 +1026,17 @@ cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, c
     fa.nrb_y = p.nrb_y;
     fa.rb_y0 = p.rb_y0;
     fa.T = p.T;
+    fa.dp = (int)p.dp;
+    fa.npanel = (int)(p.dp / 64);
+    fa.nst = fused_stages(fa.npanel);
+    fa.ksplit = tuning().fused_ksplit;
     fa.total_tiles = p.total;
     fa.chunk = p.chunk;
     fa.slots = p.slots;
     fa.Opart = reinterpret_cast<float*>(w + p.off_O);
     fa.rpart = reinterpret_cast<float*>(w + p.off_r);
     fa.spart = reinterpret_cast<double*>(w + p.off_s);
-    switch (kf.family) {
-      case FAM_RBF: e = launch_fused_f<FAM_RBF>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
-      case FAM_RQ: e = launch_fused_f<FAM_RQ>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
-      default: e = launch_fused_f<FAM_DISTANCE>((int)p.dp, tzi, tzj, fa, p.grid, s); break;
-    }
+    e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
     if (e != cudaSuccess) return e;
     ++*launches;
     FinRowsArgs fr;
@@ -940,11 +1058,17 @@ cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, c
     fr.T = p.T;
     fr.chunk = p.chunk;
     fr.slots = p.slots;
+    fr.npart = 2 * fa.ksplit;
     fr.a_xx = c.a_xx;
     fr.a_yy = c.a_yy;
     fr.a_xy = c.a_xy;
     fr.Z = Z;
     fr.dpz = p.dp;
+    fr.X = X;
+    fr.Y = Y;
+    fr.dtype = dtype;
+    fr.ldx = ldx;
+    fr.ldy = ldy;
     fr.norms = norms;
     fr.csum = dot ? csum : nullptr;
     fr.Opart = fa.Opart;
@@ -970,14 +1094,12 @@ cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, c
   __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
   float* norms = reinterpret_cast<float*>(w + p.off_norm);
   double* stats = reinterpret_cast<double*>(w + p.off_stats);
-  KernelFn kz = kf;
-  const float add_dot = kf.add_dot;
+  if (kf.add_dot > 0.f) return cudaErrorNotSupported;  // value-only add_dot goes through the fused/SIMT paths
   PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dpz, nullptr, nullptr, 0,
-                kf.tanh_features, split, Z, norms, stats, kz};
+                kf.tanh_features, split, Z, norms, stats, kf};
   prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;
-  if (add_dot > 0.f) return cudaErrorNotSupported;  // value-only add_dot goes through the fused/SIMT paths
   CUtensorMap tm;
   if (!smmd_host::make_tmap_bf16_2d(&tm, Z, p.Mp, p.dpz, p.dpz, BM)) return cudaErrorUnknown;
   StreamArgs sa;
@@ -996,7 +1118,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, c
   sa.norms = norms;
   sa.stats = stats;
   sa.want_sq = 0;
-  e = launch_stream(kf, tm, sa, p.grid, s);
+  e = launch_stream(variant, tm, sa, p.grid, s);
   if (e != cudaSuccess) return e;
   ++*launches;
   e = launch_finalize_mmd2(kf, g, stats, norms, scalars, s);
@@ -1011,10 +1133,12 @@ size_t tc_kid_workspace_bytes(int64_t msub, int64_t d, int64_t nsub, int precisi
   return stream_plan(msub, msub, d, nsub, precision == SMMD_PREC_BF16X3).off_end;
 }
 
-cudaError_t tc_kid_run(const KernelFn& kf, const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
+cudaError_t tc_kid_run(const KernelFn& kf_in, const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
                        const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,
                        int precision, int want_second_order, void* ws, size_t ws_bytes, double** stats_out,
                        cudaStream_t s, int* launches, const char** path) {
+  KernelFn kf = kf_in;
+  const TcVariant variant = select_tc_variant(kf);
   const int split = precision == SMMD_PREC_BF16X3;
   *path = split ? "tc_bf16x3_kid" : "tc_bf16_kid";
   const StreamPlan p = stream_plan(msub, msub, d, nsub, split);
@@ -1048,7 +1172,7 @@ cudaError_t tc_kid_run(const KernelFn& kf, const void* G, const void* R, int dty
   sa.norms = norms;
   sa.stats = stats;
   sa.want_sq = want_second_order;
-  e = launch_stream(kf, tm, sa, p.grid, s);
+  e = launch_stream(variant, tm, sa, p.grid, s);
   if (e != cudaSuccess) return e;
   ++*launches;
   *stats_out = stats;

@@ -1,0 +1,122 @@
+"""Row-sharded MMD^2 and subset-sharded KID across the GPUs of one node (one process per GPU,
+``torch.distributed``; NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests of the host logic).
+
+The reference never computes the loss across its towers (each tower's loss sees only its own 64+64
+samples, gan/core/model.py:186-218,268-311; gradients are averaged on the CPU, :233-266).  BASELINE
+config 5 asks for the *global-batch* loss, so this is new capability whose parity target is the
+single-device oracle on the concatenated batch:
+
+  1. all_gather the local fake / real features  (rank r's rows land at rows [r*b, (r+1)*b))
+  2. each rank runs the fused kernel on ITS row block of the stacked Gram against all columns
+     (smmd_problem.rank/world): complete gradients for its own rows, partial block sums
+  3. all_reduce the 7 fp64 partial sums, then every rank forms the identical scalar (smmd_mmd2_combine)
+
+No gradient collective is needed: dMMD2/dz_i for an owned row only needs the columns, which every rank
+has after step 1.  KID shards the independent subsets across ranks and all_gathers S doubles.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_rows(total, rank, world):
+    """Rows [lo, hi) owned by `rank` -- the same split the C ABI uses (include/smmd.h smmd_problem)."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def _gather_rows(t, group):
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t.contiguous(), group=group)
+    return torch.cat(out, dim=0)
+
+
+def _default_local_compute(spec, X_all, Y_all, biased, precision, rank, world):
+    from .mmd import fused_mmd2_raw
+
+    return fused_mmd2_raw(spec, X_all, Y_all, biased, want_grad=True, precision=precision, rank=rank, world=world)
+
+
+def _default_combine(spec, sums, m, n, d, biased, dtype):
+    import ctypes as C
+
+    from .mmd import _as_ptr, _stream_ptr
+
+    lib = _lib.load()
+    prob = spec.problem(m, n, d, d, d, dtype, biased, "fp32")
+    out = torch.empty(1, dtype=torch.float64, device=sums.device)
+    with torch.cuda.device(sums.device):
+        st = lib.smmd_mmd2_combine(C.byref(prob), _as_ptr(sums), _as_ptr(out), _stream_ptr(sums.device))
+    _lib.check(st, "smmd_mmd2_combine")
+    return out[0]
+
+
+class _ShardedMMD2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X_local, Y_local, spec, biased, precision, group, local_compute, combine):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        X_all = _gather_rows(X_local.detach(), group)
+        Y_all = _gather_rows(Y_local.detach(), group)
+        m, n, d = X_all.shape[0], Y_all.shape[0], X_all.shape[1]
+        if m % world or n % world:
+            raise ValueError("every rank must contribute the same number of rows")
+        scalars, dX, dY = local_compute(spec, X_all, Y_all, biased, precision, rank, world)
+        sums = scalars.clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)   # 16 doubles; entries 1..7 are additive
+        value = combine(spec, sums, m, n, d, biased, X_all.dtype)
+        ctx.save_for_backward(dX, dY)
+        ctx.in_dtypes = (X_local.dtype, Y_local.dtype)
+        ctx.nonfinite = sums[_lib.S_NONFINITE]
+        return value.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dX, dY = ctx.saved_tensors
+        g = grad_out.to(dX.dtype)
+        return (g * dX).to(ctx.in_dtypes[0]), (g * dY).to(ctx.in_dtypes[1]), None, None, None, None, None, None
+
+
+def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=None, _combine=None):
+    """Global-batch ``mmd2(kernel(G, images))`` where ``K = mmd._<name>_kernel(G_local, images_local)`` holds
+    this rank's rows.  Returns the same scalar on every rank; backward yields gradients for the local rows.
+
+    ``_local_compute`` / ``_combine`` are injection points for the CPU tests of the host-side logic."""
+    from .mmd import KernelHandle
+
+    if not isinstance(K, KernelHandle):
+        raise TypeError("sharded_mmd2 expects the handle returned by a _<name>_kernel(X_local, Y_local) call")
+    return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group,
+                              _local_compute or _default_local_compute, _combine or _default_combine)
+
+
+def kid_shard(n_subsets, rank, world):
+    """Contiguous block of subsets owned by `rank`: (first, count)."""
+    lo, hi = shard_rows(n_subsets, rank, world)
+    return lo, hi - lo
+
+
+def sharded_polynomial_mmd_averages(codes_g, codes_r, idx_g, idx_r, ret_var=True, group=None, precision=None,
+                                    _local_kid=None, **kernel_args):
+    """KID over subsets split across ranks.  codes are replicated on every rank (device tensors), idx_* are
+    the [S, m] subset indices drawn ONCE (rank 0's numpy RNG, reference order) and broadcast by the caller.
+    Returns (mmd2[S], var[S] | None) identical on every rank."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    S = idx_g.shape[0]
+    first, count = kid_shard(S, rank, world)
+    m = min(codes_g.shape[0], codes_r.shape[0])
+    if _local_kid is None:
+        from .compute_scores import kid_subsets as _local_kid
+    if count > 0:
+        mm, vv = _local_kid(codes_g, codes_r, idx_g, idx_r, var_at_m=m, ret_var=ret_var, precision=precision,
+                            first_subset=first, n_local=count, **kernel_args)
+    else:
+        mm = torch.zeros(S, dtype=torch.float64, device=idx_g.device)
+        vv = torch.zeros(S, dtype=torch.float64, device=idx_g.device) if ret_var else None
+    # every rank wrote only its own entries (others are zero): a SUM all-reduce assembles the vector
+    dist.all_reduce(mm, op=dist.ReduceOp.SUM, group=group)
+    if ret_var:
+        dist.all_reduce(vv, op=dist.ReduceOp.SUM, group=group)
+    return mm, vv

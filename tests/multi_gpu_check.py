@@ -1,0 +1,59 @@
+"""Run under torchrun (one rank per GPU, NCCL): the row-sharded global-batch MMD^2 and the subset-sharded
+KID must equal the single-GPU result on the concatenated inputs.  Prints MULTI_GPU_OK from rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scaled-mmd-gan_b200"))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    from smmd import compute_scores, mmd
+    from smmd.distributed import sharded_mmd2, sharded_polynomial_mmd_averages
+
+    ok = True
+    for (b, d, precision, gtol) in ((64, 16, "fp32", 1e-5), (1024, 128, "bf16", 1e-5)):
+        rng = np.random.RandomState(100 + rank)
+        Xl = torch.tensor((rng.randn(b, d) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
+        Yl = torch.tensor(((1.05 * rng.randn(b, d) + 0.1) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
+        loss = sharded_mmd2(mmd._mix_rq_kernel(Xl, Yl), precision=precision)
+        loss.backward()
+        # single-GPU reference on the concatenated batch (same path, world = 1)
+        Xs = [torch.empty_like(Xl) for _ in range(world)]
+        Ys = [torch.empty_like(Yl) for _ in range(world)]
+        dist.all_gather(Xs, Xl.detach())
+        dist.all_gather(Ys, Yl.detach())
+        Xa = torch.cat(Xs).requires_grad_(True)
+        Ya = torch.cat(Ys).requires_grad_(True)
+        ref = mmd.mmd2(mmd._mix_rq_kernel(Xa, Ya), precision=precision)
+        ref.backward()
+        ok &= abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-12
+        ok &= torch.allclose(Xl.grad, Xa.grad[rank * b:(rank + 1) * b], rtol=gtol, atol=1e-12)
+        ok &= torch.allclose(Yl.grad, Ya.grad[rank * b:(rank + 1) * b], rtol=gtol, atol=1e-12)
+    # KID
+    gen = torch.Generator(device=dev).manual_seed(7)     # same seed on every rank -> replicated codes
+    g = torch.relu(torch.randn(4000, 256, device=dev, generator=gen))
+    r = torch.relu(torch.randn(4000, 256, device=dev, generator=gen) + 0.02)
+    idx = torch.stack([torch.randperm(4000, device=dev, generator=gen)[:500] for _ in range(10)]).to(torch.int32)
+    mm, vv = sharded_polynomial_mmd_averages(g, r, idx, idx, ret_var=True)
+    m1, v1 = compute_scores.kid_subsets(g, r, idx, idx, var_at_m=4000, ret_var=True)
+    ok &= torch.allclose(mm, m1, rtol=1e-9, atol=1e-14) and torch.allclose(vv, v1, rtol=1e-7, atol=1e-18)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_OK" if flag.item() == 1.0 else "MULTI_GPU_MISMATCH")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+"""CPU (gloo, world_size 2): host-side logic of the row-sharded MMD^2 and subset-sharded KID -- gather
+order, shard arithmetic, partial-sum all-reduce and the combine formula -- with the per-rank device
+compute replaced by an oracle-backed emulation of the C ABI's shard contract (include/smmd.h:
+smmd_problem.rank/world, scalars[] layout).  The sharded result must equal the single-device oracle on
+the concatenated global batch."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import kid_oracle, mmd_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _emulated_local_compute(spec, X_all, Y_all, biased, precision, rank, world):
+    """What smmd_mmd2_fwd_bwd returns for (rank, world), computed with the fp64 oracle."""
+    from smmd import _lib
+    from smmd.distributed import shard_rows
+
+    X, Y = X_all.numpy().astype(np.float64), Y_all.numpy().astype(np.float64)
+    m, n = len(X), len(Y)
+    x0, x1 = shard_rows(m, rank, world)
+    y0, y1 = shard_rows(n, rank, world)
+    kw = {"alphas": spec.params, "wts": spec.wts, "add_dot": spec.add_dot}
+    Kxx, Kxy, Kyy, cd = mmd_oracle.kernel_matrices("mix_rq", X, Y, np.float64, **kw)
+    sc = np.zeros(_lib.NUM_SCALARS)
+    off = lambda K, lo, hi: K[lo:hi].sum() - np.trace(K[lo:hi, lo:hi])
+    sc[_lib.S_SUM_XX] = off(Kxx, x0, x1)
+    sc[_lib.S_SUM_YY] = off(Kyy, y0, y1)
+    sc[_lib.S_SUM_XY] = Kxy[x0:x1].sum()
+    sc[_lib.S_SUM_YX] = Kxy[:, y0:y1].sum()
+    sc[_lib.S_DIAG_X] = np.diagonal(Kxx)[x0:x1].sum()
+    sc[_lib.S_DIAG_Y] = np.diagonal(Kyy)[y0:y1].sum()
+    _, gX, gY = mmd_oracle.mmd2_and_grads("mix_rq", X, Y, biased, np.float64, **kw)
+    return (torch.tensor(sc), torch.tensor(gX[x0:x1], dtype=torch.float32), torch.tensor(gY[y0:y1], dtype=torch.float32))
+
+
+def _emulated_combine(spec, sums, m, n, d, biased, dtype):
+    """Same arithmetic as mmd2_from_sums in csrc/smmd_simt.cu."""
+    from smmd import _lib
+
+    s = sums.numpy()
+    cross = s[_lib.S_SUM_XY] + s[_lib.S_SUM_YX]
+    if biased:
+        v = (s[_lib.S_SUM_XX] + s[_lib.S_DIAG_X]) / (m * m) + (s[_lib.S_SUM_YY] + s[_lib.S_DIAG_Y]) / (n * n) - cross / (m * n)
+    else:
+        cd = float(spec.const_diagonal)
+        v = ((s[_lib.S_SUM_XX] + s[_lib.S_DIAG_X] - m * cd) / (m * (m - 1))
+             + (s[_lib.S_SUM_YY] + s[_lib.S_DIAG_Y] - n * cd) / (n * (n - 1)) - cross / (m * n))
+    return torch.tensor(v, dtype=torch.float64)
+
+
+def _emulated_kid(codes_g, codes_r, idx_g, idx_r, var_at_m=None, ret_var=True, precision=None, first_subset=0,
+                  n_local=0, **kw):
+    S = idx_g.shape[0]
+    mm = torch.zeros(S, dtype=torch.float64)
+    vv = torch.zeros(S, dtype=torch.float64)
+    g, r = codes_g.numpy().astype(np.float64), codes_r.numpy().astype(np.float64)
+    for s in range(first_subset, first_subset + n_local):
+        out = kid_oracle.polynomial_mmd(g[idx_g[s].numpy()], r[idx_r[s].numpy()], var_at_m=var_at_m, ret_var=True)
+        mm[s], vv[s] = out
+    return mm, (vv if ret_var else None)
+
+
+def _worker(rank, world, port, biased, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "scaled-mmd-gan_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smmd import _lib, mmd
+        from smmd.distributed import sharded_mmd2, sharded_polynomial_mmd_averages
+
+        b, d = 12, 5
+        rng = np.random.RandomState(100 + rank)
+        Xl = torch.tensor(rng.randn(b, d).astype(np.float32), requires_grad=True)
+        Yl = torch.tensor((1.1 * rng.randn(b, d) + 0.1).astype(np.float32), requires_grad=True)
+        # build the handle without the CUDA-only checks (host-logic test)
+        spec = mmd.KernelSpec(_lib.K_MIX_RQ, [0.1, 1.0, 10.0], [1.0, 1.0, 1.0], add_dot=0.1, const_diagonal=3.0)
+        K = mmd.KernelHandle.__new__(mmd.KernelHandle)
+        K.spec, K.X, K.Y, K._dense = spec, Xl, Yl, None
+        loss = sharded_mmd2(K, biased=biased, _local_compute=_emulated_local_compute, _combine=_emulated_combine)
+        (loss * 2.0).backward()
+        # KID: subsets split across ranks
+        g = torch.tensor(np.maximum(np.random.RandomState(1).randn(60, 16), 0).astype(np.float32))
+        r = torch.tensor(np.maximum(np.random.RandomState(2).randn(70, 16) + 0.02, 0).astype(np.float32))
+        ig, ir = kid_oracle.draw_subset_indices(60, 70, 5, 20, np.random.RandomState(0))
+        mm, vv = sharded_polynomial_mmd_averages(g, r, torch.tensor(ig), torch.tensor(ir), ret_var=True,
+                                                 _local_kid=_emulated_kid)
+        q.put((rank, float(loss), Xl.grad.numpy(), Yl.grad.numpy(), Xl.detach().numpy(), Yl.detach().numpy(),
+               mm.numpy(), vv.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_sharded_mmd2_and_kid_world2(biased):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (1 if biased else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, biased, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = np.concatenate([r[4] for r in res])
+    Y = np.concatenate([r[5] for r in res])
+    v, gX, gY = mmd_oracle.mmd2_and_grads("mix_rq_dot", X, Y, biased, np.float64)
+    for rank, loss, gx, gy, *_ in res:
+        assert abs(loss - v) <= 1e-6 * abs(v)                       # same scalar on every rank
+        assert np.allclose(gx, 2.0 * gX[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
+        assert np.allclose(gy, 2.0 * gY[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
+    g = np.maximum(np.random.RandomState(1).randn(60, 16), 0).astype(np.float32).astype(np.float64)
+    r_ = np.maximum(np.random.RandomState(2).randn(70, 16) + 0.02, 0).astype(np.float32).astype(np.float64)
+    ig, ir = kid_oracle.draw_subset_indices(60, 70, 5, 20, np.random.RandomState(0))
+    ref_m, ref_v = kid_oracle.polynomial_mmd_averages(g, r_, n_subsets=5, subset_size=20, ret_var=True, idx_g=ig, idx_r=ir)
+    for rr in res:
+        assert np.allclose(rr[6], ref_m, rtol=1e-10) and np.allclose(rr[7], ref_v, rtol=1e-10)
+
+
+def test_shard_arithmetic_matches_c_abi_contract():
+    from smmd.distributed import kid_shard, shard_rows
+
+    for total in (1, 7, 64, 100, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_rows(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert sum(kid_shard(total, r, world)[1] for r in range(world)) == total

