@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native MMD^2 / KID hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU over NCCL)
+
+Workload (BASELINE.json configs[3], the one the metric "fused MMD^2 fwd+bwd kernel-pairs/s ... % tensor
+peak, target N >= 8192, d >= 256" is quoted on; configs[1] needs the conv critic, which stays in
+PyTorch/cuDNN and is out of scope): mixed-RQ MMD^2 loss forward + feature gradients between N fake and N
+real critic features, d = 256, synthetic data.  One "step" = one loss evaluation with both gradients.
+With several GPUs the Gram is row-sharded (all_gather of the local features, fused kernel on the owned
+row blocks against all columns, all_reduce of 7 partial sums): total N fixed -> "strong" scaling.
+
+JSON line (rank 0): the driver contract (metric/value/unit/...) plus
+  roofline      tensor-pipe roofline of the dominant kernel (algorithmic 14 N^2 d flop / its launch time,
+                timed with CUDA events inside the library on the launching stream)
+  cpu_baseline  the CPU port of the reference path on a bounded sample, on this box's host cores
+  e2e           the same metric through the public Python API with HOST buffers (H2D + D2H inside the timing)
+  kid           the second half of the headline metric: KID feature rows/s (configs[2])
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "scaled-mmd-gan_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_TOTAL = 32768        # fake rows = real rows (global)
+D_FEAT = 256
+CPU_SAMPLE_N = 4096    # the CPU port materialises ~12 N x N fp32 temporaries: 32768 would need > 50 GB
+KID = dict(n_codes=50000, d=2048, n_subsets=100, subset_size=1000)
+KID_CPU_SUBSETS = 4
+METRIC = "mmd2_fwd_bwd_kernel_pair_evals_per_s"
+UNIT = "N^2*d pair-dims/s"
+
+
+def synth_features(n, d, seed, shift):
+    # X = N(0,1)/sqrt(d), Y = (1.05 N(0,1) + 0.1)/sqrt(d)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g)
+    if shift:
+        x = 1.05 * x + 0.1
+    return (x / d ** 0.5).contiguous()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled through NVML (nvidia-smi's library) during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.gpu = gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self._stop.wait(0.005)
+        except Exception as e:  # NVML missing: fall back to one nvidia-smi sample
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                a, b = [float(p) for p in out.strip().split(",")]
+                self.samples.append(a)
+                self.max_mhz = b
+            except Exception:
+                pass
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: CPU port on a bounded sample
+# ----------------------------------------------------------------------------------------------------
+def cpu_step(n, d):
+    from oracle import cpu_port
+
+    X = synth_features(n, d, 1234, False).numpy()
+    Y = synth_features(n, d, 1235, True).numpy()
+    t0 = time.perf_counter()
+    cpu_port.mix_rq_fwd_bwd(X, Y)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, d = CPU_SAMPLE_N, D_FEAT
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_step(n, d)
+    steps = max(1, min(args.steps, 10))
+    ts = [cpu_step(n, d) for _ in range(steps)]
+    t = float(np.mean(ts))
+    value = n * n * d / t
+    sample = "mix_rq fwd+bwd on %d+%d x %d (N^2-scaling sample of the %d+%d workload; the port materialises N x N fp32 " \
+             "temporaries like the reference and cannot hold N=%d)" % (n, n, d, N_TOTAL, N_TOTAL, N_TOTAL)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 large-batch Gram: mix_rq MMD^2 fwd+bwd, N=%d fake + %d real, d=%d" % (N_TOTAL, N_TOTAL, D_FEAT),
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from smmd import _lib, compute_scores, mmd
+    from smmd.distributed import kid_shard, sharded_mmd2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    lib = _lib.load()
+
+    n, d = N_TOTAL, D_FEAT
+    nl = n // world
+    # each rank owns nl fake + nl real rows (rows [rank*nl, (rank+1)*nl) of the global batch)
+    Xh = synth_features(n, d, 1234, False)[rank * nl:(rank + 1) * nl].pin_memory()
+    Yh = synth_features(n, d, 1235, True)[rank * nl:(rank + 1) * nl].pin_memory()
+    Xd, Yd = Xh.to(dev), Yh.to(dev)
+    spec = mmd._mix_rq_kernel(Xd, Yd).spec
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(t):
+        if world == 1:
+            return t
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return torch.cat(out)
+
+    launches = [0]
+
+    def device_step():
+        """inputs resident in HBM: (all_gather) + fused kernel on the owned rows + (all_reduce, combine)."""
+        Xa, Ya = gather(Xd), gather(Yd)
+        sc, dX, dY = mmd.fused_mmd2_raw(spec, Xa, Ya, biased=False, want_grad=True, precision="bf16", rank=rank, world=world)
+        launches[0] += _lib.last_launch_count()
+        if world > 1:
+            sums = sc.clone()
+            dist.all_reduce(sums)
+            from smmd.distributed import _default_combine
+            val = _default_combine(spec, sums, n, n, d, False, torch.float32)
+            launches[0] += 1
+        else:
+            val = sc[_lib.S_MMD2]
+        return val, dX, dY
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        device_step()
+    barrier()
+
+    # ---- timed: K steps, device time per step (L2 flushed between iterations, flush outside the event pair) ----
+    lib.smmd_profile_enable(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    launches[0] = 0
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            val, dX, dY = device_step()
+            ev[i][1].record()
+            kern_ms.append(None)
+            # reading the in-library event pair synchronises on this step's dominant kernel only
+            kern_ms[-1] = lib.smmd_profile_last_ms()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    lib.smmd_profile_enable(0)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    value = float(n) * n * d / (ms_per_step * 1e-3)
+    n_launch = launches[0]
+    path = _lib.last_path()
+    mmd2_val = float(val.item())
+
+    # ---- roofline of the dominant kernel (this rank's share of the 14 N^2 d algorithmic flops) ----
+    peak, peak_src = measured_peak()
+    k_ms = float(np.mean([k for k in kern_ms if k is not None and k > 0]))
+    flops_rank = 14.0 * n * n * d / world
+    achieved = flops_rank / (k_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("tc_fused_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "tc_fused_kernel<MathRq3Default>", "kernel_ms": k_ms, "peak_source": peak_src,
+                "algorithmic_flops_per_launch": flops_rank}
+
+    # ---- e2e: public Python API, HOST buffers in, loss + gradients back on the host, every step ----
+    gXh = torch.empty((nl, d), dtype=torch.float32).pin_memory()
+    gYh = torch.empty((nl, d), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        X = Xh.to(dev, non_blocking=True).requires_grad_(True)
+        Y = Yh.to(dev, non_blocking=True).requires_grad_(True)
+        K = mmd._mix_rq_kernel(X, Y)
+        loss = sharded_mmd2(K, precision="bf16") if world > 1 else mmd.mmd2(K, precision="bf16")
+        loss.backward()
+        gXh.copy_(X.grad, non_blocking=True)
+        gYh.copy_(Y.grad, non_blocking=True)
+        return loss.item()          # device -> host read of the step's result (synchronises)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e2e_step()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = float(n) * n * d / (t_e2e.item() / args.steps)
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * nl * d * 4 * world,
+           "d2h_bytes_per_step": (2 * nl * d * 4 + 4) * world, "ms_per_step": t_e2e.item() / args.steps * 1e3,
+           "api": "smmd.mmd.mmd2(smmd.mmd._mix_rq_kernel(G, images)).backward() on tensors copied from pinned host memory"}
+
+    # ---- KID (configs[2]): 50k vs 50k x 2048, 100 subsets of 1000, subsets split across ranks ----
+    kid = run_kid(dev, rank, world, args, compute_scores, lib, dist, peak)
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_step(CPU_SAMPLE_N, d)
+        tc = min(cpu_step(CPU_SAMPLE_N, d) for _ in range(2))
+        cpu = {"value": CPU_SAMPLE_N * CPU_SAMPLE_N * d / tc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "oracle/cpu_port.py (torch-CPU fp32 restatement of mmd.py + autograd) on %d+%d x %d, best of 2; "
+                         "N^2-scaling sample -- the reference materialises N x N temporaries and cannot hold N=%d"
+                         % (CPU_SAMPLE_N, CPU_SAMPLE_N, d, n), "seconds_per_step_at_sample": tc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "C4 large-batch Gram: mix_rq MMD^2 fwd+bwd, N=%d fake + %d real, d=%d, alphas (.1,1,10), unbiased"
+                                   % (n, n, d),
+                       "parallelism": "row-sharded Gram x%d (all_gather features, all_reduce 7 fp64 sums)" % world,
+                       "l2": "flushed between timed iterations (256 MiB write, outside the per-step event pair)",
+                       "path": path, "mmd2": mmd2_val},
+            "clocks": clocks.summary(), "gpu_launches": n_launch, "roofline": roofline, "e2e": e2e, "kid": kid,
+            "tflops_algorithmic": 14.0 * n * n * d / (ms_per_step * 1e-3) / 1e12,
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
+    from smmd import _lib
+
+    nc, d, S, m = KID["n_codes"], KID["d"], KID["n_subsets"], KID["subset_size"]
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    # codes_g = relu(N(0,1)), codes_r = relu(N(0.02,1)); same seed on every rank = replicated codes
+    g = torch.relu(torch.randn(nc, d, device=dev, generator=gen))
+    r = torch.relu(torch.randn(nc, d, device=dev, generator=gen) + 0.02)
+    np.random.seed(0)
+    ig, ir = compute_scores.draw_subsets(nc, nc, S, m)      # reference draw order (g then r per subset)
+    igd, ird = torch.from_numpy(ig).to(dev), torch.from_numpy(ir).to(dev)
+    from smmd.distributed import kid_shard
+
+    first, count = kid_shard(S, rank, world)
+
+    def step():
+        mm, _ = compute_scores.kid_subsets(g, r, igd, ird, var_at_m=nc, ret_var=False, first_subset=first, n_local=count)
+        if world > 1:
+            dist.all_reduce(mm)
+        return mm
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    lib.smmd_profile_enable(1)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        mm = step()
+    e1.record()
+    torch.cuda.synchronize()
+    kms = lib.smmd_profile_last_ms()
+    lib.smmd_profile_enable(0)
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    rows = 2.0 * S * m
+    out = {"metric": "kid_feature_rows_per_s", "value": rows / (ms * 1e-3), "unit": "feature rows/s", "ms_per_call": ms,
+           "config": "polynomial_mmd_averages: %dk vs %dk x %d codes, %d subsets of %d, ret_var=False, codes resident in HBM"
+                     % (nc // 1000, nc // 1000, d, S, m),
+           "path": _lib.last_path(), "kid_mean": float(mm.mean().item()),
+           "tflops_algorithmic_6m2d": 6.0 * m * m * d * S / (ms * 1e-3) / 1e12,
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak,
+                        "achieved": 6.0 * m * m * d * count / (kms * 1e-3) / 1e12 if kms and kms > 0 else None,
+                        "kernel": "tc_stream_kernel<MathPoly3> (split-bf16: executes 3x the algorithmic flops)", "kernel_ms": kms}}
+    if out["roofline"]["achieved"]:
+        out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_port
+        gh, rh = g[:].cpu().numpy(), r[:].cpu().numpy()
+        t0 = time.perf_counter()
+        cpu_port.kid_subsets(gh, rh, ig[:KID_CPU_SUBSETS], ir[:KID_CPU_SUBSETS])
+        tc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2.0 * KID_CPU_SUBSETS * m / tc, "unit": "feature rows/s", "cores": os.cpu_count(),
+                               "kind": "port", "sample": "%d of the %d subsets (numpy/BLAS restatement of compute_scores.py:211-335)"
+                                                         % (KID_CPU_SUBSETS, S)}
+    del g, r
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

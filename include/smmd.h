@@ -177,6 +177,13 @@ SMMD_API int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, co
                      const int32_t* idx_g, const int32_t* idx_r, double* mmd2_out, double* var_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Roofline instrumentation (bench.py): when enabled on this thread, the library records a CUDA-event
+ * pair on the launching stream around the DOMINANT kernel of each call (the fused tcgen05 Gram kernel /
+ * the K-streaming KID kernel / the SIMT row kernel).  smmd_profile_last_ms() synchronises on the stop
+ * event and returns that launch's device time in milliseconds (< 0 if nothing was recorded). */
+SMMD_API void smmd_profile_enable(int on);
+SMMD_API float smmd_profile_last_ms(void);
+
 /* Introspection for tests/bench: number of kernels the last call on this thread launched, and the
  * name of the code path it took ("simt_fp32", "tc_bf16_fused", "tc_bf16_fwd", ...). */
 SMMD_API int smmd_last_launch_count(void);

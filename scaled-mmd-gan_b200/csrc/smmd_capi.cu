@@ -14,6 +14,10 @@ thread_local char g_cuda_err[256] = "";
 thread_local int g_launches = 0;
 thread_local const char* g_path = "none";
 
+thread_local int g_prof_on = 0;
+thread_local int g_prof_recorded = 0;
+thread_local cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+
 int cuda_fail(cudaError_t e) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
   return SMMD_ECUDA;
@@ -141,7 +145,35 @@ int resolve_precision(const smmd_problem* p, int want_grad) {
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 }  // namespace
 
+namespace smmd {
+void prof_begin(cudaStream_t s) {
+  if (!g_prof_on) return;
+  if (!g_prof_ev[0]) {
+    cudaEventCreate(&g_prof_ev[0]);
+    cudaEventCreate(&g_prof_ev[1]);
+  }
+  cudaEventRecord(g_prof_ev[0], s);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof_on || !g_prof_ev[0]) return;
+  cudaEventRecord(g_prof_ev[1], s);
+  g_prof_recorded = 1;
+}
+}  // namespace smmd
+
 extern "C" {
+
+void smmd_profile_enable(int on) {
+  g_prof_on = on ? 1 : 0;
+  g_prof_recorded = 0;
+}
+float smmd_profile_last_ms(void) {
+  if (!g_prof_recorded) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_prof_ev[1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_prof_ev[0], g_prof_ev[1]) != cudaSuccess) return -1.f;
+  return ms;
+}
 
 int smmd_version(void) { return SMMD_VERSION; }
 
@@ -201,7 +233,9 @@ int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, doubl
     double* stats = reinterpret_cast<double*>(ws + pl.off_stats);
     SMMD_CUDA(launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch,
                               s));
+    prof_begin(s);
     SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, 1, stats, dX, dY, 0, s));
+    prof_end(s);
     SMMD_CUDA(launch_finalize_mmd2(kf, g, stats, norms, scalars, s));
     return SMMD_OK;
   }
@@ -379,7 +413,9 @@ int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void*
                                 Z, norms, pl.dpitch, s));
     Geometry g{m, m, p->d, 0, m, 0, m, 0};
     Coefs c = make_coefs(g, kf);
+    prof_begin(s);
     SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, nloc, stats, nullptr, nullptr, 1, s));
+    prof_end(s);
   } else {
     if (!tc_kid_supported(p->d)) return SMMD_EUNSUPPORTED;
     int launches = 0;

@@ -66,6 +66,10 @@ enum RowStat : int {
   RS_COUNT = 6
 };
 
+// ---- roofline instrumentation (smmd_capi.cu): event pair around the dominant kernel of a call ----------
+void prof_begin(cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 // ---- launches implemented in smmd_simt.cu -------------------------------------------------------
 struct SimtPlan {
   int64_t dpitch;      // fp32 feature pitch (multiple of 8)

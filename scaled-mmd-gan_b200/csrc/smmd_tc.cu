@@ -1036,7 +1036,9 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fa.Opart = reinterpret_cast<float*>(w + p.off_O);
     fa.rpart = reinterpret_cast<float*>(w + p.off_r);
     fa.spart = reinterpret_cast<double*>(w + p.off_s);
+    prof_begin(s);
     e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
+    prof_end(s);
     if (e != cudaSuccess) return e;
     ++*launches;
     FinRowsArgs fr;
@@ -1118,7 +1120,9 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
   sa.norms = norms;
   sa.stats = stats;
   sa.want_sq = 0;
+  prof_begin(s);
   e = launch_stream(variant, tm, sa, p.grid, s);
+  prof_end(s);
   if (e != cudaSuccess) return e;
   ++*launches;
   e = launch_finalize_mmd2(kf, g, stats, norms, scalars, s);
@@ -1172,7 +1176,9 @@ cudaError_t tc_kid_run(const KernelFn& kf_in, const void* G, const void* R, int 
   sa.norms = norms;
   sa.stats = stats;
   sa.want_sq = want_second_order;
+  prof_begin(s);
   e = launch_stream(variant, tm, sa, p.grid, s);
+  prof_end(s);
   if (e != cudaSuccess) return e;
   ++*launches;
   *stats_out = stats;

@@ -25,7 +25,7 @@ EXPORTS = [
     "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_combine", "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
-    "smmd_last_launch_count", "smmd_last_path",
+    "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms",
 ]
 
 
@@ -79,6 +79,9 @@ def load():
     lib.smmd_device_supported.restype = C.c_int
     lib.smmd_last_launch_count.restype = C.c_int
     lib.smmd_last_path.restype = C.c_char_p
+    lib.smmd_profile_enable.restype = None
+    lib.smmd_profile_enable.argtypes = [C.c_int]
+    lib.smmd_profile_last_ms.restype = C.c_float
     lib.smmd_mmd2_workspace_bytes.restype = C.c_size_t
     lib.smmd_mmd2_workspace_bytes.argtypes = [C.POINTER(Problem), C.c_int]
     lib.smmd_mmd2_fwd_bwd.restype = C.c_int

@@ -37,8 +37,8 @@ def main():
         ref = mmd.mmd2(mmd._mix_rq_kernel(Xa, Ya), precision=precision)
         ref.backward()
         ok &= abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-12
-        ok &= torch.allclose(Xl.grad, Xa.grad[rank * b:(rank + 1) * b], rtol=gtol, atol=1e-12)
-        ok &= torch.allclose(Yl.grad, Ya.grad[rank * b:(rank + 1) * b], rtol=gtol, atol=1e-12)
+        ok &= bool((Xl.grad - Xa.grad[rank * b:(rank + 1) * b]).abs().max() <= gtol * Xa.grad.abs().max())
+        ok &= bool((Yl.grad - Ya.grad[rank * b:(rank + 1) * b]).abs().max() <= gtol * Ya.grad.abs().max())
     # KID
     gen = torch.Generator(device=dev).manual_seed(7)     # same seed on every rank -> replicated codes
     g = torch.relu(torch.randn(4000, 256, device=dev, generator=gen))
