@@ -43,8 +43,8 @@ struct Tuning {
 const Tuning& tuning() {
   static Tuning t = [] {
     Tuning v;
-    v.fused_ksplit = 2;
-    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
+    v.fused_ksplit = 1;
+    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 2 ? 2 : 1;
     return v;
   }();
   return t;
@@ -205,29 +205,29 @@ inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes 
 // instruction caches (a fully unrolled 64-column epilogue stalled ~50% on instruction fetch).
 template <class Math, bool SPECIAL>
 __device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (&v)[16], const float* __restrict__ nj,
-                                              float ni, float cw, int col0, int lim, int gi, float& tsum,
-                                              float& rsum, uint32_t (&wpk)[8]) {
+                                              float ni, float2 cw, int col0, int lim, int gi, float2& tsum,
+                                              float2& rsum, uint32_t (&wpk)[8]) {
+  const float2 ni2 = bc2(ni);
 #pragma unroll
   for (int c = 0; c < 16; c += 4) {
     const float4 n4 = *reinterpret_cast<const float4*>(nj + c);
-    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-    float ww[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float k, kd;
-      math.eval(__uint_as_float(v[c + e]), ni + nn[e], k, kd);
+    for (int e = 0; e < 4; e += 2) {
+      const float2 S = make_float2(__uint_as_float(v[c + e]), __uint_as_float(v[c + e + 1]));
+      const float2 nn = e == 0 ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w);
+      float2 k, kd;
+      math.eval2(S, add2(ni2, nn), k, kd);
       if (SPECIAL) {
         const int col = col0 + c + e;
-        const bool ok = (col < lim) && (col != gi);
-        k = ok ? k : 0.f;
-        kd = ok ? kd : 0.f;
+        const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
+        k = make_float2(ok0 ? k.x : 0.f, ok1 ? k.y : 0.f);
+        kd = make_float2(ok0 ? kd.x : 0.f, ok1 ? kd.y : 0.f);
       }
-      tsum += k;
-      ww[e] = cw * kd;
-      rsum += ww[e];
+      tsum = add2(tsum, k);
+      const float2 ww = mul2(kd, cw);
+      rsum = add2(rsum, ww);
+      wpk[(c + e) >> 1] = pack_bf16x2(ww.x, ww.y);
     }
-    wpk[c >> 1] = pack_bf16x2(ww[0], ww[1]);
-    wpk[(c >> 1) + 1] = pack_bf16x2(ww[2], ww[3]);
   }
 }
 
@@ -412,14 +412,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       const int gi = rb * BM + r;
       const bool rowX = gi < mp;
       const float ni = a.norms[gi];
-      float rsum = 0.f;
+      float2 rsum = make_float2(0.f, 0.f);
       double dsame = 0.0, dcross = 0.0;
       for (int lt = 0; lt < TU; ++lt) {
         if ((int)par == grp) {
           const int c0 = (t0 + lt) * BNF;
           const bool colX = c0 < mp;
           const bool same = (colX == rowX);
-          const float cw = (same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale;
+          const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
           const int lim = colX ? mvalid : yvalid;                       // first invalid column of this region
           const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);   // pad columns or diagonal inside
           mbar_wait(&zj_full[st], ph);                                  // column norms ride with the Zj stage
@@ -427,7 +427,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           tc_fence_after();
           mbar_wait(&w_empty[grp], wph ^ 1);
           const float* nj = sN + st * 64;
-          float tsum = 0.f;
+          float2 tsum = make_float2(0.f, 0.f);
           const uint32_t s_addr = tmem + TM_S + sb * 64 + lane_base;
           const uint32_t w_addr = tmem + TM_W + grp * 32 + lane_base;
 #pragma unroll 1
@@ -447,8 +447,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           tc_fence_before();
           mbar_arrive(&w_full[grp]);
           wph ^= 1;
-          if (same) dsame += (double)(tsum * kscale);
-          else dcross += (double)(tsum * kscale);
+          if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
+          else dcross += (double)((tsum.x + tsum.y) * kscale);
         }
         // advance the ring state by one tile of the CTA's stream
         par ^= 1;
@@ -477,7 +477,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
             *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
                                                                    __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
         }
-        a.rpart[(sl * NPART + part) * BM + r] = rsum;
+        a.rpart[(sl * NPART + part) * BM + r] = rsum.x + rsum.y;
         double* sp = a.spart + ((sl * NPART + part) * BM + r) * 2;
         sp[0] = dsame;
         sp[1] = dcross;
@@ -777,42 +777,45 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       mbar_wait(&acc_full[grp], (uint32_t)((tc >> 1) & 1));
       tc_fence_after();
       const float* nj = a.norms + b * Mp + c0;
-      float tsum = 0.f, tsq = 0.f;
+      float2 tsum = make_float2(0.f, 0.f), tsq = make_float2(0.f, 0.f);
+      const float2 ni2 = bc2(ni), ks2 = bc2(kscale);
 #pragma unroll 1
-      for (int h = 0; h < BNS / 32; ++h) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem + grp * BNS + h * 32 + lane_base, v);
+      for (int h = 0; h < BNS / 16; ++h) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem + grp * BNS + h * 16 + lane_base, v);
         tmem_ld_wait();
-        if (h == BNS / 32 - 1) {
+        if (h == BNS / 16 - 1) {
           tc_fence_before();
           mbar_arrive(&acc_empty[grp]);
         }
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nj + h * 32 + c));
-          const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+        for (int c = 0; c < 16; c += 4) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nj + h * 16 + c));
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float k, kd;
-            math.eval(__uint_as_float(v[c + e]), ni + nn[e], k, kd);
-            k *= kscale;
+          for (int e = 0; e < 4; e += 2) {
+            const float2 S = make_float2(__uint_as_float(v[c + e]), __uint_as_float(v[c + e + 1]));
+            const float2 nn = e == 0 ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w);
+            float2 k, kd;
+            math.eval2(S, add2(ni2, nn), k, kd);
+            k = mul2(k, ks2);
             if (special) {
-              const int64_t col = c0 + h * 32 + c + e;
-              const bool ok = (col < lim) && (col != gi);
-              k = ok ? k : 0.f;
-              if (col == pair_col) pairv = (double)k;
+              const int64_t col = c0 + h * 16 + c + e;
+              const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
+              k = make_float2(ok0 ? k.x : 0.f, ok1 ? k.y : 0.f);
+              if (col == pair_col) pairv = (double)k.x;
+              if (col + 1 == pair_col) pairv = (double)k.y;
             }
-            tsum += k;
-            tsq = fmaf(k, k, tsq);
+            tsum = add2(tsum, k);
+            tsq = fma2(k, k, tsq);
           }
         }
       }
       if (same) {
-        s_same += (double)tsum;
-        q_same += (double)tsq;
+        s_same += (double)(tsum.x + tsum.y);
+        q_same += (double)(tsq.x + tsq.y);
       } else {
-        s_cross += (double)tsum;
-        q_cross += (double)tsq;
+        s_cross += (double)(tsum.x + tsum.y);
+        q_cross += (double)(tsq.x + tsq.y);
       }
     }
     flush();

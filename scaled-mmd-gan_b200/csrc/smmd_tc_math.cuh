@@ -1,18 +1,22 @@
 // smmd_tc_math.cuh -- register-resident epilogue math for the tensor-core kernels.
 //
-// Every variant exposes
-//     eval(S, nij, k_raw, kd_raw)      S = <z_i,z_j> from TMEM, nij = |z_i|^2 + |z_j|^2
+// Every variant exposes, on PAIRS of adjacent Gram columns (packed fp32x2 -> FFMA2/FMUL2/FADD2, one issue
+// slot per two elements; MUFU ops per half),
+//     eval2(S, nij, k_raw, kd_raw)     S = <z_i,z_j> from TMEM, nij = |z_i|^2 + |z_j|^2
 //     k_scale(), kd_scale()            constants folded in once per tile / per coefficient
 // with  k = k_scale * k_raw  (kernel value, enters the block sums) and  dk/dD = kd_scale * kd_raw.
-// The epilogue is the limiter of the fused kernel at d = 256: per Gram element the
-// tensor pipe needs 1/8 cycle, so every FMA-pipe instruction and above all every MUFU op counts
-// (MUFU: 16/clk/SM = 8 FMA-pipe issue slots each).  Hence the specialisations:
+// The epilogue is the limiter of the fused kernel at d = 256: per Gram element the tensor pipe
+// needs 1/8 cycle, so every issue slot and above all every MUFU op counts (MUFU: 16/clk/SM = 8 FMA-pipe issue
+// slots each).  Hence the specialisations:
 //   MathRbf1        one sigma (the shipped yml kernel, mmd.py:55): 1 MUFU
 //   MathRbfLadder   gammas in ratio 4 (sigmas {1,2,4,8,16}, BASELINE config 1): 1 MUFU + 2 FMUL / step
 //   MathRq3Default  the reference's default alphas (.1, 1, 10), unit weights (mmd.py:143): ONE rcp of the
 //                   product of the three bases (instead of three), u^10 by a 4-multiply chain, and a single
 //                   lg2/ex2 pair for alpha = .1  -> 3 MUFU instead of 9
 //   MathGeneric     any sigmas / alphas / weights (parameters read from shared memory)
+// The lower clamp max(D,0) of the reference (mmd.py:67) is a no-op here up to fp32 rounding of D (the norms
+// are computed from the same bf16 operands the MMA sees), and a slightly negative D is harmless for every
+// transform below, so it is dropped; an upper cap keeps products of bases finite for absurd distances.
 #pragma once
 #include "smmd_kfun.cuh"
 
@@ -30,14 +34,19 @@ enum TcVariant : int {
   TV_NONE
 };
 
+__device__ __forceinline__ float2 dist2(float2 S, float2 nij) { return fma2(S, bc2(-2.f), nij); }
+__device__ __forceinline__ float2 ex2_2(float2 x) { return make_float2(fast_ex2(x.x), fast_ex2(x.y)); }
+__device__ __forceinline__ float2 lg2_2(float2 x) { return make_float2(fast_lg2(x.x), fast_lg2(x.y)); }
+__device__ __forceinline__ float2 rcp_2(float2 x) { return make_float2(fast_rcp(x.x), fast_rcp(x.y)); }
+
 struct MathRbf1 {
   float c1, w, g;
   __device__ explicit MathRbf1(const KernelFn& f, const float*) : c1(f.p1[0]), w(f.w[0]), g(-f.p0[0] * f.w[0]) {}
   __device__ __forceinline__ float k_scale() const { return w; }
   __device__ __forceinline__ float kd_scale() const { return g; }
-  __device__ __forceinline__ void eval(float S, float nij, float& k, float& kd) const {
-    const float D = fmaxf(fmaf(-2.f, S, nij), 0.f);
-    k = fast_ex2(c1 * D);
+  __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
+    // c1 * D folded into one FFMA2: c1*(nij - 2S) = (-2 c1) S + c1 nij
+    k = ex2_2(fma2(S, bc2(-2.f * c1), mul2(nij, bc2(c1))));
     kd = k;
   }
 };
@@ -55,17 +64,16 @@ struct MathRbfLadder {
   }
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 1.f; }
-  __device__ __forceinline__ void eval(float S, float nij, float& k, float& kd) const {
-    const float D = fmaxf(fmaf(-2.f, S, nij), 0.f);
-    float e = fast_ex2(c1 * D);
-    k = w[0] * e;
-    kd = g[0] * e;
+  __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
+    float2 e = ex2_2(fma2(S, bc2(-2.f * c1), mul2(nij, bc2(c1))));
+    k = mul2(e, bc2(w[0]));
+    kd = mul2(e, bc2(g[0]));
 #pragma unroll
     for (int i = 1; i < NP; ++i) {
-      e *= e;
-      e *= e;
-      k = fmaf(w[i], e, k);
-      kd = fmaf(g[i], e, kd);
+      e = mul2(e, e);
+      e = mul2(e, e);
+      k = fma2(e, bc2(w[i]), k);
+      kd = fma2(e, bc2(g[i]), kd);
     }
   }
 };
@@ -74,27 +82,27 @@ struct MathRq3Default {
   __device__ explicit MathRq3Default(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
-  __device__ __forceinline__ void eval(float S, float nij, float& k, float& kd) const {
-    // D is capped far above any realistic squared distance so the product of the bases stays finite
-    const float D = fminf(fmaxf(fmaf(-2.f, S, nij), 0.f), 1.0e10f);
-    const float b1 = fmaf(D, 5.f, 1.f);    // alpha = .1 : 1 + D / (2 * .1)
-    const float b2 = fmaf(D, .5f, 1.f);    // alpha = 1
-    const float b3 = fmaf(D, .05f, 1.f);   // alpha = 10
-    const float p23 = b2 * b3;
-    const float R = fast_rcp(b1 * p23);
-    const float r1 = R * p23;
-    const float t = R * b1;
-    const float r2 = t * b3;               // 1 / b2
-    const float r3 = t * b2;               // 1 / b3
-    const float e1 = fast_ex2(-0.1f * fast_lg2(b1));
-    const float q2 = r3 * r3, q4 = q2 * q2, q8 = q4 * q4;
-    const float e3 = q8 * q2;              // b3^-10
-    k = (e1 + r2) + e3;
-    kd = fmaf(e3, r3, fmaf(r2, r2, e1 * r1));   // sum_k e_k / b_k ; kd_scale = -1/2
+  __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
+    float2 D = dist2(S, nij);
+    D = make_float2(fminf(D.x, 1.0e10f), fminf(D.y, 1.0e10f));  // keeps b1*b2*b3 finite
+    const float2 b1 = fma2(D, bc2(5.f), bc2(1.f));     // alpha = .1 : 1 + D / (2 * .1)
+    const float2 b2 = fma2(D, bc2(.5f), bc2(1.f));     // alpha = 1
+    const float2 b3 = fma2(D, bc2(.05f), bc2(1.f));    // alpha = 10
+    const float2 p23 = mul2(b2, b3);
+    const float2 R = rcp_2(mul2(b1, p23));
+    const float2 r1 = mul2(R, p23);
+    const float2 t = mul2(R, b1);
+    const float2 r2 = mul2(t, b3);                     // 1 / b2
+    const float2 r3 = mul2(t, b2);                     // 1 / b3
+    const float2 e1 = ex2_2(mul2(lg2_2(b1), bc2(-0.1f)));
+    const float2 q2 = mul2(r3, r3), q4 = mul2(q2, q2), q8 = mul2(q4, q4);
+    const float2 e3 = mul2(q8, q2);                    // b3^-10
+    k = add2(add2(e1, r2), e3);
+    kd = fma2(e3, r3, fma2(r2, r2, mul2(e1, r1)));     // sum_k e_k / b_k ; kd_scale = -1/2
   }
 };
 
-// parameters in shared memory: sp[0][i] = p0, sp[1][i] = p1, sp[2][i] = w
+// parameters in shared memory: sp[0..7] = p0, sp[8..15] = p1, sp[16..23] = w
 template <int FAM>
 struct MathGeneric {
   const float* sp;
@@ -102,22 +110,23 @@ struct MathGeneric {
   __device__ explicit MathGeneric(const KernelFn& f, const float* smem_params) : sp(smem_params), np(f.np) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 1.f; }
-  __device__ __forceinline__ void eval(float S, float nij, float& k, float& kd) const {
-    const float D = fmaxf(fmaf(-2.f, S, nij), 0.f);
-    k = 0.f;
-    kd = 0.f;
+  __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
+    float2 D = dist2(S, nij);
+    D = make_float2(fminf(fmaxf(D.x, 0.f), 1.0e30f), fminf(fmaxf(D.y, 0.f), 1.0e30f));
+    k = bc2(0.f);
+    kd = bc2(0.f);
 #pragma unroll 1
     for (int i = 0; i < np; ++i) {
       const float p0 = sp[i], p1 = sp[8 + i], w = sp[16 + i];
       if constexpr (FAM == FAM_RBF) {
-        const float e = w * fast_ex2(p1 * D);
-        k += e;
-        kd = fmaf(-p0, e, kd);
+        const float2 e = mul2(ex2_2(mul2(D, bc2(p1))), bc2(w));
+        k = add2(k, e);
+        kd = fma2(e, bc2(-p0), kd);
       } else {
-        const float base = fmaf(D, p0, 1.f);
-        const float e = w * fast_ex2(-p1 * fast_lg2(base));
-        k += e;
-        kd = fmaf(-0.5f * e, fast_rcp(base), kd);
+        const float2 base = fma2(D, bc2(p0), bc2(1.f));
+        const float2 e = mul2(ex2_2(mul2(lg2_2(base), bc2(-p1))), bc2(w));
+        k = add2(k, e);
+        kd = fma2(mul2(e, bc2(-0.5f)), rcp_2(base), kd);
       }
     }
   }
@@ -127,11 +136,10 @@ struct MathDistance {
   __device__ explicit MathDistance(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return -1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
-  __device__ __forceinline__ void eval(float S, float nij, float& k, float& kd) const {
-    const float t = fmaf(-2.f, S, nij) + kEps;   // D not clamped before +eps (mmd.py:12,29)
-    const float rs = t > 0.f ? fast_rsqrt(t) : 0.f;
-    k = t * rs;                                   // sqrt(max(t,0))
-    kd = rs;
+  __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
+    const float2 t = add2(dist2(S, nij), bc2(kEps));   // D not clamped before +eps (mmd.py:12,29)
+    kd = make_float2(t.x > 0.f ? fast_rsqrt(t.x) : 0.f, t.y > 0.f ? fast_rsqrt(t.y) : 0.f);
+    k = mul2(t, kd);                                   // sqrt(max(t,0))
   }
 };
 
@@ -140,10 +148,10 @@ struct MathPoly3 {
   __device__ explicit MathPoly3(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 0.f; }
-  __device__ __forceinline__ void eval(float S, float, float& k, float& kd) const {
-    const float b = fmaf(gamma, S, c0);
-    k = b * b * b;
-    kd = 0.f;
+  __device__ __forceinline__ void eval2(float2 S, float2, float2& k, float2& kd) const {
+    const float2 b = fma2(S, bc2(gamma), bc2(c0));
+    k = mul2(mul2(b, b), b);
+    kd = bc2(0.f);
   }
 };
 
@@ -153,12 +161,12 @@ struct MathPolyN {
   __device__ explicit MathPolyN(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0), degree(f.degree) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 0.f; }
-  __device__ __forceinline__ void eval(float S, float, float& k, float& kd) const {
-    const float b = fmaf(gamma, S, c0);
-    float p = b;
-    for (int i = 1; i < degree; ++i) p *= b;
+  __device__ __forceinline__ void eval2(float2 S, float2, float2& k, float2& kd) const {
+    const float2 b = fma2(S, bc2(gamma), bc2(c0));
+    float2 p = b;
+    for (int i = 1; i < degree; ++i) p = mul2(p, b);
     k = p;
-    kd = 0.f;
+    kd = bc2(0.f);
   }
 };
 
