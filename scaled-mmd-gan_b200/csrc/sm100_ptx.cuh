@@ -59,6 +59,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking phase test (no suspend): used by the MMA issuer to poll several barriers
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a broken pipeline must turn into a CUDA error (trap), never into a hung GPU.
 #ifndef SMMD_WAIT_TIMEOUT_NS
 #define SMMD_WAIT_TIMEOUT_NS 4000000000ull /* 4 s */

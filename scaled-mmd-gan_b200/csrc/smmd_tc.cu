@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "sm100_ptx.cuh"
 #include "smmd_kfun.cuh"
 #include "smmd_tc.h"
@@ -39,12 +40,14 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 // Developer tuning knobs (environment overrides are read once; defaults are the measured best).
 struct Tuning {
   int fused_ksplit;
+  int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
 };
 const Tuning& tuning() {
   static Tuning t = [] {
     Tuning v;
-    v.fused_ksplit = 1;
-    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 2 ? 2 : 1;
+    v.fused_ksplit = 2;
+    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
+    v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
     return v;
   }();
   return t;
@@ -168,6 +171,20 @@ __device__ __forceinline__ void stage_params(const KernelFn& kf, float* sp) {
   }
 }
 
+// ---- optional pipeline timing (compile with -DSMMD_PIPE_TIMING; developer builds only) --------------------
+#ifdef SMMD_PIPE_TIMING
+__device__ unsigned long long g_pipe_dbg[32];
+#define PT_DECL(role) const bool pt_on = (blockIdx.x == 0) && (role); long long pt_t = 0
+#define PT_BEGIN() do { if (pt_on) pt_t = clock64(); } while (0)
+#define PT_END(slot) do { if (pt_on) { long long n_ = clock64(); atomicAdd(&g_pipe_dbg[slot], (unsigned long long)(n_ - pt_t)); pt_t = n_; } } while (0)
+#define PT_COUNT(slot) do { if (pt_on) atomicAdd(&g_pipe_dbg[slot], 1ull); } while (0)
+#else
+#define PT_DECL(role)
+#define PT_BEGIN()
+#define PT_END(slot)
+#define PT_COUNT(slot)
+#endif
+
 // ================================================================================================
 // fused forward + backward kernel
 // ================================================================================================
@@ -192,12 +209,12 @@ constexpr uint32_t TM_O = 0, TM_S = 256, TM_W = 448;
 constexpr int kZjRowBytes = BNF * 128;   // one 64-wide panel of a column tile
 constexpr int kZiRowBytes = BM * 128;    // one 64-wide panel of the row block
 
-// smem = 1023 B alignment slack + Zi + nst * (Zj tile + 64 norms) + 512 B (barriers, tmem slot, staged params)
+// smem = 1023 B alignment slack + Zi + nst * Zj tile + 512 B (barriers, tmem slot, staged params)
 inline int fused_stages(int npanel) {
-  int nst = (kMaxSmem - 1024 - 512 - npanel * kZiRowBytes) / (npanel * kZjRowBytes + 256);
+  int nst = (kMaxSmem - 1024 - 512 - npanel * kZiRowBytes) / (npanel * kZjRowBytes);
   return nst > 8 ? 8 : nst;
 }
-inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes + nst * (npanel * kZjRowBytes + 256) + 512; }
+inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes + nst * (npanel * kZjRowBytes) + 512; }
 
 // 16 columns of one row of a fused-epilogue tile: kernel transform, tile sum, row sum of W, and W packed to
 // bf16x2.  SPECIAL tiles (diagonal inside / padded columns) mask per element; interior tiles run the
@@ -209,51 +226,65 @@ __device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (
                                               float2& rsum, uint32_t (&wpk)[8]) {
   const float2 ni2 = bc2(ni);
 #pragma unroll
-  for (int c = 0; c < 16; c += 4) {
-    const float4 n4 = *reinterpret_cast<const float4*>(nj + c);
+  for (int c = 0; c < 16; c += 8) {   // 4 pairs (8 columns) evaluated in lock-step
+    const float4 na = *reinterpret_cast<const float4*>(nj + c);
+    const float4 nb = *reinterpret_cast<const float4*>(nj + c + 4);
+    float2 S[4], nij[4], k[4], kd[4];
 #pragma unroll
-    for (int e = 0; e < 4; e += 2) {
-      const float2 S = make_float2(__uint_as_float(v[c + e]), __uint_as_float(v[c + e + 1]));
-      const float2 nn = e == 0 ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w);
-      float2 k, kd;
-      math.eval2(S, add2(ni2, nn), k, kd);
+    for (int e = 0; e < 4; ++e) S[e] = make_float2(__uint_as_float(v[c + 2 * e]), __uint_as_float(v[c + 2 * e + 1]));
+    nij[0] = add2(ni2, make_float2(na.x, na.y));
+    nij[1] = add2(ni2, make_float2(na.z, na.w));
+    nij[2] = add2(ni2, make_float2(nb.x, nb.y));
+    nij[3] = add2(ni2, make_float2(nb.z, nb.w));
+    eval_pairs<Math, 4>(math, S, nij, k, kd);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
       if (SPECIAL) {
-        const int col = col0 + c + e;
+        const int col = col0 + c + 2 * e;
         const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
-        k = make_float2(ok0 ? k.x : 0.f, ok1 ? k.y : 0.f);
-        kd = make_float2(ok0 ? kd.x : 0.f, ok1 ? kd.y : 0.f);
+        k[e] = make_float2(ok0 ? k[e].x : 0.f, ok1 ? k[e].y : 0.f);
+        kd[e] = make_float2(ok0 ? kd[e].x : 0.f, ok1 ? kd[e].y : 0.f);
       }
-      tsum = add2(tsum, k);
-      const float2 ww = mul2(kd, cw);
+      tsum = add2(tsum, k[e]);
+      const float2 ww = mul2(kd[e], cw);
       rsum = add2(rsum, ww);
-      wpk[(c + e) >> 1] = pack_bf16x2(ww.x, ww.y);
+      wpk[(c >> 1) + e] = pack_bf16x2(ww.x, ww.y);
     }
   }
 }
 
 // KSPLIT = column slices per tile: each of the two epilogue groups has 4*KSPLIT warps (TMEM lane quarter x
-// column slice), i.e. 8*KSPLIT epilogue warps per CTA.
+// column slice).  Warp roles: warps [0, 8*KSPLIT) = epilogue, then the TMA producer, and LAST the UMMA issuer:
+// the warp scheduler favours the highest warp id on a sub-partition, and the single issuing thread is on the
+// critical path of the whole CTA (measured: as warp 1 it needed ~3100 cycles per tile, most of it waiting for
+// issue slots behind the epilogue warps and polling mbarriers at ~100-150 cycles per poll).
+//
+// mbarriers (all phases tracked with running counters, no div/mod):
+//   zj_full[nst]   TMA -> UMMA issuer                      (Zj tile landed)
+//   zj_empty[nst]  UMMA #2 commit -> TMA producer AND the epilogue group (its W buffer is drained)
+//   s_full[3]      UMMA #1 commit -> epilogue group
+//   w_full[2]      epilogue group -> UMMA issuer            (W published; also implies the S buffer is free,
+//                                                            because a thread loads S before it writes W)
+//   zi_full/zi_empty, o_full/o_empty  per row-block unit
 template <class Math, int KSPLIT>
 __global__ void __launch_bounds__(64 + 256 * KSPLIT, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
                 const __grid_constant__ FusedArgs a) {
   constexpr int NPART = 2 * KSPLIT;           // partial-result slices per row (group x column slice)
-  constexpr int CH_PER = (BNF / 16) / KSPLIT; // 16-column chunks per thread per tile
+  constexpr int CH_PER = (BNF / 16) / KSPLIT; // 16-column chunks per thread per tile (4 or 2)
+  constexpr int EPI_WARPS = 8 * KSPLIT;
   const int NPANEL = a.npanel, NST = a.nst, DP = a.dp;
   const int ZI_BYTES = NPANEL * kZiRowBytes, ZJ_BYTES = NPANEL * kZjRowBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sZi = smem;
   uint8_t* sZj = smem + ZI_BYTES;
-  float* sN = reinterpret_cast<float*>(sZj + NST * ZJ_BYTES);  // [NST][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sN) + NST * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sZj + NST * ZJ_BYTES);
   uint64_t* zj_full = bars;             // [NST]
   uint64_t* zj_empty = bars + NST;      // [NST]
   uint64_t* s_full = bars + 2 * NST;    // [3]
-  uint64_t* s_empty = s_full + 3;       // [3]
-  uint64_t* w_full = s_empty + 3;       // [2]
-  uint64_t* w_empty = w_full + 2;       // [2]
-  uint64_t* zi_full = w_empty + 2;
+  uint64_t* w_full = s_full + 3;        // [2]
+  uint64_t* zi_full = w_full + 2;
   uint64_t* zi_empty = zi_full + 1;
   uint64_t* o_full = zi_empty + 1;
   uint64_t* o_empty = o_full + 1;
@@ -267,22 +298,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       mbar_init(&zj_full[i], 1);
       mbar_init(&zj_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128 * KSPLIT);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&w_full[i], 128 * KSPLIT);
-      mbar_init(&w_empty[i], 1);
-    }
+    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&w_full[i], 128 * KSPLIT);
     mbar_init(zi_full, 1);
     mbar_init(zi_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 256 * KSPLIT);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  if (warp == 0 && lane == 0) {
+  if (warp == EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == EPI_WARPS && lane == 0) {
     prefetch_tmap(&tmap_zi);
     prefetch_tmap(&tmap_zj);
   }
@@ -295,10 +320,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
   auto rb_of = [&](int64_t rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + (int)rbi : a.rb_y0 + (int)(rbi - a.nrb_x); };
 
-  if (warp == 0) {
+  if (warp == EPI_WARPS) {
     // ===================== TMA producer =====================
-    // (all ring bookkeeping is kept as running 32-bit counters: a single thread runs this loop)
-    if (lane == 0) {
+    // The WHOLE warp runs this loop convergently and only the issue instructions are predicated on one
+    // elected lane: operands then live in uniform registers.  (Issuing from inside `if (lane == 0)` makes the
+    // compiler wrap every UTMALDG / UTCHMMA in an ELECT + R2UR "waterfall" loop, ~80 cycles per instruction.)
+    {
       uint32_t unit = 0, st = 0, ph = 0;
       int rbi = (int)(pos0 / a.T);
       int t0 = (int)(pos0 - (int64_t)rbi * a.T);
@@ -306,14 +333,19 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
         const int TU = (int)std::min<int64_t>(a.T - t0, left);
         const int rb = rb_of(rbi);
         mbar_wait(zi_empty, (unit & 1) ^ 1);
-        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
-        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(zi_full, ZI_BYTES);
+          for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
+        }
+        __syncwarp();
         for (int t = t0; t < t0 + TU; ++t) {
           mbar_wait(&zj_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&zj_full[st], (ZJ_BYTES + 256));
-          uint8_t* dst = sZj + st * ZJ_BYTES;
-          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * (BNF * 128), &tmap_zj, &zj_full[st], p * 64, t * BNF);
-          bulk_load_1d(sN + st * 64, a.norms + t * BNF, 256, &zj_full[st]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&zj_full[st], ZJ_BYTES);
+            uint8_t* dst = sZj + st * ZJ_BYTES;
+            for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * (BNF * 128), &tmap_zj, &zj_full[st], p * 64, t * BNF);
+          }
+          __syncwarp();
           if (++st == (uint32_t)NST) {
             st = 0;
             ph ^= 1;
@@ -322,9 +354,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
         left -= TU;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == EPI_WARPS + 1) {
+    // ===================== UMMA issuer (warp-convergent loop, one elected lane issues) ========================
+    {
       constexpr uint32_t idesc1 = make_idesc(BM, BNF, kFmtBF16, false, false);
       const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
       const uint32_t hi = desc_hi_sw128(1024);
@@ -333,53 +365,62 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), BNF * 128);           // MN-major B for UMMA #2: LBO = panel stride
       const uint32_t stage_step = (uint32_t)ZJ_BYTES >> 4;                 // descriptor address units are 16 B
       uint32_t unit = 0;
-      // running state of the two MMA streams (UMMA #1 runs 3 tiles ahead of UMMA #2)
-      uint32_t st1 = 0, ph1 = 0, sb1 = 0, sph1 = 0;   // Zj stage / phase, S buffer / phase for UMMA #1
-      uint32_t st2 = 0, wb2 = 0, wph2 = 0;            // Zj stage, W buffer / phase for UMMA #2
+      uint32_t st1 = 0, ph1 = 0, sb1 = 0;             // UMMA #1 stream: Zj stage / phase, S buffer
+      uint32_t st2 = 0, wb2 = 0, wph2 = 0;            // UMMA #2 stream: Zj stage, W buffer / phase
       int rbi = (int)(pos0 / a.T);
       int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+      PT_DECL(lane == 0);
       for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
         const int TU = (int)std::min<int64_t>(a.T - t0, left);
         mbar_wait(zi_full, unit & 1);
+        // static order, UMMA #1 three tiles ahead of UMMA #2; 2 waits + 2 commits per tile
         for (int jj = 0; jj < TU + 3; ++jj) {
           const int b2 = jj - 3;
           if (b2 >= 0) {  // ---- UMMA #2 for local tile b2: O += W * Zj
+            PT_BEGIN();
             mbar_wait(&w_full[wb2], wph2);
             if (b2 == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
             tc_fence_after();
+            PT_END(0);
             const uint32_t blo = zj_lo2 + st2 * stage_step;
             const uint32_t wad = tmem + TM_W + wb2 * 32;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BNF / 16; ++kk)
-              umma_ts2(tmem + TM_O, wad + kk * 8, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(&zj_empty[st2]);
-            umma_commit(&w_empty[wb2]);
-            if (b2 == TU - 1) umma_commit(o_full);
+              for (int kk = 0; kk < BNF / 16; ++kk)
+                umma_ts2(tmem + TM_O, wad + kk * 8, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&zj_empty[st2]);     // frees the Zj stage (producer) and this W buffer (epilogue group)
+              if (b2 == TU - 1) umma_commit(o_full);
+            }
+            __syncwarp();
             if (++st2 == (uint32_t)NST) st2 = 0;
-            wph2 ^= wb2;  // phase flips each time buffer index wraps 1 -> 0
+            wph2 ^= wb2;  // phase flips each time the buffer index wraps 1 -> 0
             wb2 ^= 1;
+            PT_END(1);
+            PT_COUNT(3);
           }
-          if (jj < TU) {  // ---- UMMA #1 for local tile jj: S = Zi * Zj^T
+          if (jj < TU) {  // ---- UMMA #1 for local tile jj: S = Zi * Zj^T  (S buffer is free: see w_full above)
+            PT_BEGIN();
             mbar_wait(&zj_full[st1], ph1);
-            mbar_wait(&s_empty[sb1], sph1 ^ 1);
             tc_fence_after();
+            PT_END(4);
             const uint32_t blo = zj_lo1 + st1 * stage_step;
             const uint32_t sad = tmem + TM_S + sb1 * 64;
-            for (int p = 0; p < NPANEL; ++p) {
-              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * ((BNF * 128) >> 4);
+            if (elect_one()) {
+              for (int p = 0; p < NPANEL; ++p) {
+                const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * ((BNF * 128) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+              }
+              umma_commit(&s_full[sb1]);
+              if (jj == TU - 1) umma_commit(zi_empty);
             }
-            umma_commit(&s_full[sb1]);
-            if (jj == TU - 1) umma_commit(zi_empty);
+            __syncwarp();
             if (++st1 == (uint32_t)NST) {
               st1 = 0;
               ph1 ^= 1;
             }
-            if (++sb1 == 3) {
-              sb1 = 0;
-              sph1 ^= 1;
-            }
+            if (++sb1 == 3) sb1 = 0;
+            PT_END(2);
           }
         }
         left -= TU;
@@ -387,9 +428,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     }
   } else {
     // ===================== epilogue groups =====================
-    const int ew = warp - 2;
-    const int grp = ew / (4 * KSPLIT);        // 0 / 1
-    const int half = (ew % (4 * KSPLIT)) >> 2;  // column slice of the tile handled by this warp
+    const int grp = warp / (4 * KSPLIT);      // 0 / 1
+    const int half = (warp % (4 * KSPLIT)) >> 2;  // column slice of the tile handled by this warp
     const int part = grp * KSPLIT + half;
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // row inside the row block
@@ -398,14 +438,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     const float kscale = math.k_scale(), kdscale = math.kd_scale();
     uint32_t unit = 0;
     int slot = 0;
-    // running ring state for the tiles of THIS group (it handles every second tile of the CTA's stream)
+    // running ring state (this group handles every second tile of the CTA's stream)
     uint32_t par = 0;                       // parity of the global tile counter
+    uint32_t sb = 0, sph = 0;               // S buffer / phase of the current tile
     uint32_t st = 0, ph = 0;                // Zj stage / phase of the current tile
-    uint32_t sb = 0, sph = 0;               // S buffer / phase
-    uint32_t wph = 0;                       // phase of this group's W buffer
+    uint32_t st_m2 = 0, ph_m2 = 0;          // ... and of the tile two back (whose UMMA #2 drains this group's W buffer)
+    uint32_t gcount = 0;                    // global tile counter (only its first two values matter)
     int rbi = (int)(pos0 / a.T);
     int t0 = (int)(pos0 - (int64_t)rbi * a.T);
     const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    PT_DECL(warp == 0 && lane == 0);
     for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit, ++slot) {
       const int TU = (int)std::min<int64_t>(a.T - t0, left);
       const int rb = rb_of(rbi);
@@ -416,42 +458,66 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       double dsame = 0.0, dcross = 0.0;
       for (int lt = 0; lt < TU; ++lt) {
         if ((int)par == grp) {
+          PT_BEGIN();
           const int c0 = (t0 + lt) * BNF;
           const bool colX = c0 < mp;
           const bool same = (colX == rowX);
           const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
           const int lim = colX ? mvalid : yvalid;                       // first invalid column of this region
           const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);   // pad columns or diagonal inside
-          mbar_wait(&zj_full[st], ph);                                  // column norms ride with the Zj stage
+          const float* nj = a.norms + c0 + half * (CH_PER * 16);        // column norms: tiny, L1/L2 resident
+          const uint32_t s_addr = tmem + TM_S + sb * 64 + half * (CH_PER * 16) + lane_base;
+          const uint32_t w_addr = tmem + TM_W + grp * 32 + half * (CH_PER * 8) + lane_base;
+          float2 tsum = make_float2(0.f, 0.f);
           mbar_wait(&s_full[sb], sph);
           tc_fence_after();
-          mbar_wait(&w_empty[grp], wph ^ 1);
-          const float* nj = sN + st * 64;
-          float2 tsum = make_float2(0.f, 0.f);
-          const uint32_t s_addr = tmem + TM_S + sb * 64 + lane_base;
-          const uint32_t w_addr = tmem + TM_W + grp * 32 + lane_base;
+          PT_END(9);
+          if (!special) {
+            // two 16-column chunks per iteration, the next tcgen05.ld in flight while the current chunk is computed
+            uint32_t va[16], vb[16], wpk[8];
+            tmem_ld_x16(s_addr, va);
 #pragma unroll 1
-          for (int ch = half * CH_PER; ch < (half + 1) * CH_PER; ++ch) {
-            uint32_t v[16], wpk[8];
-            tmem_ld_x16(s_addr + ch * 16, v);
-            tmem_ld_wait();
-            if (ch == (half + 1) * CH_PER - 1) {  // this thread's slice of S is in registers: release it
-              tc_fence_before();
-              mbar_arrive(&s_empty[sb]);
+            for (int it = 0; it < CH_PER / 2; ++it) {
+              tmem_ld_wait();
+              tmem_ld_x16(s_addr + (2 * it + 1) * 16, vb);
+              fused_chunk16<Math, false>(math, va, nj + (2 * it) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+              if (it == 0 && gcount >= 2) mbar_wait(&zj_empty[st_m2], ph_m2);   // W buffer drained by UMMA #2 of tile-2
+              tmem_st_x8(w_addr + (2 * it) * 8, wpk);
+              tmem_ld_wait();
+              if (2 * it + 2 < CH_PER) tmem_ld_x16(s_addr + (2 * it + 2) * 16, va);
+              fused_chunk16<Math, false>(math, vb, nj + (2 * it + 1) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+              tmem_st_x8(w_addr + (2 * it + 1) * 8, wpk);
             }
-            if (!special) fused_chunk16<Math, false>(math, v, nj + ch * 16, ni, cw, c0 + ch * 16, lim, gi, tsum, rsum, wpk);
-            else fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + ch * 16, lim, gi, tsum, rsum, wpk);
-            tmem_st_x8(w_addr + ch * 8, wpk);
+          } else {
+#pragma unroll 1
+            for (int ch = 0; ch < CH_PER; ++ch) {
+              uint32_t v[16], wpk[8];
+              tmem_ld_x16(s_addr + ch * 16, v);
+              tmem_ld_wait();
+              fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + half * (CH_PER * 16) + ch * 16, lim, gi, tsum,
+                                        rsum, wpk);
+              if (ch == 0 && gcount >= 2) mbar_wait(&zj_empty[st_m2], ph_m2);
+              tmem_st_x8(w_addr + ch * 8, wpk);
+            }
           }
+          PT_END(11);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&w_full[grp]);
-          wph ^= 1;
+          PT_END(13);
+          PT_COUNT(14);
           if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
           else dcross += (double)((tsum.x + tsum.y) * kscale);
         }
         // advance the ring state by one tile of the CTA's stream
         par ^= 1;
+        if (gcount >= 2) {
+          if (++st_m2 == (uint32_t)NST) {
+            st_m2 = 0;
+            ph_m2 ^= 1;
+          }
+        }
+        ++gcount;
         if (++st == (uint32_t)NST) {
           st = 0;
           ph ^= 1;
@@ -461,7 +527,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           sph ^= 1;
         }
       }
-      // ---- unit end: drain O (this group's half of the feature columns) ----
+      // ---- unit end: drain O (this thread's slice of the feature columns) ----
       mbar_wait(o_full, unit & 1);
       tc_fence_after();
       {
@@ -489,7 +555,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
 }
 
 // ---- finalisation of the fused kernel: reduce slabs, form gradients and per-row stats ---------------
@@ -664,7 +730,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   const int nk = a.nkp * a.ncombo;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp, elected lane issues (see tc_fused_kernel)
       uint32_t st = 0, ph = 0;
       // decompose the first flattened tile index once, then step (ct, rb, b) incrementally
       int ct = (int)(pos0 % a.CT);
@@ -678,10 +744,13 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           const int32_t aoff = combo == 1 ? dpi : 0, boff = combo == 2 ? dpi : 0;
           for (int p = 0; p < a.nkp; ++p) {
             mbar_wait(&empty[st], ph ^ 1);
-            mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
-            uint8_t* sa = smem + st * kStreamStageBytes;
-            tma_load_2d(sa, &tmap, &full[st], p * 64 + aoff, arow);
-            tma_load_2d(sa + BM * 128, &tmap, &full[st], p * 64 + boff, brow);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
+              uint8_t* sa = smem + st * kStreamStageBytes;
+              tma_load_2d(sa, &tmap, &full[st], p * 64 + aoff, arow);
+              tma_load_2d(sa + BM * 128, &tmap, &full[st], p * 64 + boff, brow);
+            }
+            __syncwarp();
             if (++st == kStreamStages) {
               st = 0;
               ph ^= 1;
@@ -698,7 +767,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(BM, BNS, kFmtBF16, false, false);
       const uint32_t hi = desc_hi_sw128(1024);
       const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
@@ -711,15 +780,19 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           mbar_wait(&full[st], ph);
           tc_fence_after();
           const uint32_t alo = a_lo0 + st * (kStreamStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
-          umma_commit(&empty[st]);
+            for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
+            umma_commit(&empty[st]);
+          }
+          __syncwarp();
           if (++st == kStreamStages) {
             st = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&acc_full[ab]);
+        if (elect_one()) umma_commit(&acc_full[ab]);
+        __syncwarp();
         aph ^= ab;
         ab ^= 1;
       }
@@ -897,6 +970,7 @@ cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap&
     case TV_RQ3_DEFAULT: return launch_fused_t<MathRq3Default>(tzi, tzj, a, grid, s);
     case TV_RQ_GENERIC: return launch_fused_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, grid, s);
     case TV_DISTANCE: return launch_fused_t<MathDistance>(tzi, tzj, a, grid, s);
+    case TV_NULL: return launch_fused_t<MathNull>(tzi, tzj, a, grid, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -957,6 +1031,23 @@ cudaError_t launch_stream(TcVariant v, const CUtensorMap& tm, const StreamArgs& 
 
 }  // namespace
 
+#ifdef SMMD_PIPE_TIMING
+void pipe_timing_dump(bool reset) {
+  unsigned long long h[32];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_pipe_dbg, sizeof(h));
+  const double nt2 = (double)(h[3] ? h[3] : 1), nt = (double)(h[14] ? h[14] : 1);
+  printf("[pipe timing CTA0] MMA thread per tile: wait_w %.0f  issue#2 %.0f  wait_zj %.0f  issue#1 %.0f   (tiles %llu)\n",
+         h[0] / nt2, h[1] / nt2, h[4] / nt2, h[2] / nt2, h[3]);
+  printf("[pipe timing CTA0] epilogue warp0 per OWN tile: wait_s %.0f  ld+math+st(+wait W drained) %.0f  st-drain+arrive %.0f"
+         "   (tiles %llu)\n", h[9] / nt, h[11] / nt, h[13] / nt, h[14]);
+  if (reset) {
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(g_pipe_dbg, h, sizeof(h));
+  }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) interface
 // ------------------------------------------------------------------------------------------------
@@ -989,7 +1080,8 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
                         void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
   if (!tc_family_ok(kf_in)) return cudaErrorNotSupported;
   KernelFn kf = kf_in;
-  const TcVariant variant = select_tc_variant(kf);
+  TcVariant variant = select_tc_variant(kf);
+  if (tuning().null_math) variant = TV_NULL;
   char* w = static_cast<char*>(ws);
   cudaError_t e;
   const bool want_grad = dX != nullptr;

@@ -31,6 +31,7 @@ enum TcVariant : int {
   TV_DISTANCE,
   TV_POLY3,
   TV_POLY_GENERIC,
+  TV_NULL,   // developer ablation: k = kd = S (no transform) -- measures the bare pipeline
   TV_NONE
 };
 
@@ -40,6 +41,7 @@ __device__ __forceinline__ float2 lg2_2(float2 x) { return make_float2(fast_lg2(
 __device__ __forceinline__ float2 rcp_2(float2 x) { return make_float2(fast_rcp(x.x), fast_rcp(x.y)); }
 
 struct MathRbf1 {
+  static constexpr bool kHasEvalN = false;
   float c1, w, g;
   __device__ explicit MathRbf1(const KernelFn& f, const float*) : c1(f.p1[0]), w(f.w[0]), g(-f.p0[0] * f.w[0]) {}
   __device__ __forceinline__ float k_scale() const { return w; }
@@ -54,6 +56,7 @@ struct MathRbf1 {
 // components sorted by increasing gamma with gamma[i+1] = 4 gamma[i]  ->  e[i+1] = e[i]^4
 template <int NP>
 struct MathRbfLadder {
+  static constexpr bool kHasEvalN = false;
   float c1, w[NP], g[NP];
   __device__ explicit MathRbfLadder(const KernelFn& f, const float*) : c1(f.p1[0]) {
 #pragma unroll
@@ -78,10 +81,63 @@ struct MathRbfLadder {
   }
 };
 
+// Default interleave helper: variants without a hand-interleaved evalN fall back to eval2 per pair.
+template <class Math, int NP>
+__device__ __forceinline__ void eval_pairs(const Math& m, const float2 (&S)[NP], const float2 (&nij)[NP],
+                                           float2 (&k)[NP], float2 (&kd)[NP]) {
+  if constexpr (Math::kHasEvalN) {
+    m.template evalN<NP>(S, nij, k, kd);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) m.eval2(S[i], nij[i], k[i], kd[i]);
+  }
+}
+
 struct MathRq3Default {
+  static constexpr bool kHasEvalN = true;
   __device__ explicit MathRq3Default(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
+  // NP pairs in lock-step: every stage is issued for all pairs before the next dependent stage, so the
+  // FMA pipe works on pair i+1..i+3 while the MUFU results of pair i are in flight (the per-pair chain is
+  // FMA -> rcp/lg2 -> FMA -> ex2 -> FMA, three MUFU latencies deep).
+  template <int NP>
+  __device__ __forceinline__ void evalN(const float2 (&S)[NP], const float2 (&nij)[NP], float2 (&k)[NP],
+                                        float2 (&kd)[NP]) const {
+    float2 b1[NP], b2[NP], b3[NP], p23[NP], R[NP], L[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float2 D = dist2(S[i], nij[i]);
+      D = make_float2(fminf(D.x, 1.0e10f), fminf(D.y, 1.0e10f));
+      b1[i] = fma2(D, bc2(5.f), bc2(1.f));
+      b2[i] = fma2(D, bc2(.5f), bc2(1.f));
+      b3[i] = fma2(D, bc2(.05f), bc2(1.f));
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = lg2_2(b1[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      p23[i] = mul2(b2[i], b3[i]);
+      R[i] = mul2(b1[i], p23[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) R[i] = rcp_2(R[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = mul2(L[i], bc2(-0.1f));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = ex2_2(L[i]);           // e1 = b1^-0.1
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float2 r1 = mul2(R[i], p23[i]);
+      const float2 t = mul2(R[i], b1[i]);
+      const float2 r2 = mul2(t, b3[i]);
+      const float2 r3 = mul2(t, b2[i]);
+      const float2 q2 = mul2(r3, r3), q4 = mul2(q2, q2), q8 = mul2(q4, q4);
+      const float2 e3 = mul2(q8, q2);
+      k[i] = add2(add2(L[i], r2), e3);
+      kd[i] = fma2(e3, r3, fma2(r2, r2, mul2(L[i], r1)));
+    }
+  }
   __device__ __forceinline__ void eval2(float2 S, float2 nij, float2& k, float2& kd) const {
     float2 D = dist2(S, nij);
     D = make_float2(fminf(D.x, 1.0e10f), fminf(D.y, 1.0e10f));  // keeps b1*b2*b3 finite
@@ -105,6 +161,7 @@ struct MathRq3Default {
 // parameters in shared memory: sp[0..7] = p0, sp[8..15] = p1, sp[16..23] = w
 template <int FAM>
 struct MathGeneric {
+  static constexpr bool kHasEvalN = false;
   const float* sp;
   int np;
   __device__ explicit MathGeneric(const KernelFn& f, const float* smem_params) : sp(smem_params), np(f.np) {}
@@ -133,6 +190,7 @@ struct MathGeneric {
 };
 
 struct MathDistance {
+  static constexpr bool kHasEvalN = false;
   __device__ explicit MathDistance(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return -1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
@@ -143,7 +201,19 @@ struct MathDistance {
   }
 };
 
+struct MathNull {
+  static constexpr bool kHasEvalN = false;
+  __device__ explicit MathNull(const KernelFn&, const float*) {}
+  __device__ __forceinline__ float k_scale() const { return 1.f; }
+  __device__ __forceinline__ float kd_scale() const { return 1.f; }
+  __device__ __forceinline__ void eval2(float2 S, float2, float2& k, float2& kd) const {
+    k = S;
+    kd = S;
+  }
+};
+
 struct MathPoly3 {
+  static constexpr bool kHasEvalN = false;
   float gamma, c0;
   __device__ explicit MathPoly3(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
@@ -156,6 +226,7 @@ struct MathPoly3 {
 };
 
 struct MathPolyN {
+  static constexpr bool kHasEvalN = false;
   float gamma, c0;
   int degree;
   __device__ explicit MathPolyN(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0), degree(f.degree) {}

@@ -12,6 +12,9 @@
 #include <cuda_runtime.h>
 #include "../../../include/smmd.h"
 
+#ifdef SMMD_PIPE_TIMING
+namespace smmd { void pipe_timing_dump(bool reset); }
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(2); } } while (0)
 #define SK(x) do { int st = (x); if (st != 0) { printf("smmd error %d (%s) [%s] at line %d\n", st, smmd_strerror(st), smmd_last_cuda_error(), __LINE__); exit(3); } } while (0)
 
@@ -114,6 +117,9 @@ int main(int argc, char** argv) {
     printf("[%s m=%lld n=%lld d=%lld] TC  path=%s launches=%d  %.3f ms  mmd2=%.9g  nonfinite=%g  -> %.3e pairs/s, %.1f TFLOP/s (14 N^2 d)\n",
            kname, (long long)m, (long long)n, (long long)d, tc.path, tc.launches, tc.ms, tc.sc[0], tc.sc[7],
            pairs / (tc.ms * 1e-3), 14.0 * pairs / (tc.ms * 1e-3) / 1e12);
+#ifdef SMMD_PIPE_TIMING
+    smmd::pipe_timing_dump(true);
+#endif
     Result tv = run_mmd(p, SMMD_PREC_BF16, dXin, dYin, reps, false);
     printf("   value-only TC path=%s %.3f ms mmd2=%.9g\n", tv.path, tv.ms, tv.sc[0]);
     if (ref) {

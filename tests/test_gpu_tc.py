@@ -170,7 +170,9 @@ def test_tc_kid_properties_at_scale():
     idx2[1] = idx[0][torch.randperm(1000, device=dev, generator=gen)]   # subset 1 := permutation of subset 0
     a, _ = compute_scores.kid_subsets(g, r, idx, idx, ret_var=False)
     b, _ = compute_scores.kid_subsets(g, r, idx2, idx2, ret_var=False)
-    assert abs(b[1].item() - b[0].item()) <= 1e-9 + 1e-6 * abs(b[0].item())
+    # same multiset of rows in another order: only the fp32 accumulation order inside the tiles changes
+    # (KID is a ~5e-4 difference of O(1) block means, so 1e-7-level reordering noise shows up at ~1e-4 relative)
+    assert abs(b[1].item() - b[0].item()) <= 1e-9 + 1e-3 * abs(b[0].item())
     assert torch.allclose(a[[0, 2, 3]], b[[0, 2, 3]], rtol=1e-9, atol=1e-12)
     c, _ = compute_scores.kid_subsets(r, g, idx, idx, ret_var=False)
     # swapping the roles reorders the three split-bf16 partial products inside the fp32 accumulation
