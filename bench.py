@@ -92,7 +92,7 @@ class ClockSampler:
                 for nm, b in bits.items():
                     if r & b:
                         self.reasons.add(nm)
-                self._stop.wait(0.005)
+                self._stop.wait(0.04)   # NVML calls take driver locks: polling faster than ~25 Hz slows kernel submission measurably
         except Exception as e:  # NVML missing: fall back to one nvidia-smi sample
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
             try:
@@ -222,10 +222,9 @@ def run_ours(args):
         device_step()
     barrier()
 
-    # ---- timed: K steps, device time per step (L2 flushed between iterations, flush outside the event pair) ----
-    lib.smmd_profile_enable(1)
+    # ---- timed: K steps back to back, device time per step (L2 flushed between iterations; the flush sits
+    #      outside the per-step event pair) ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
     launches[0] = 0
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -235,11 +234,18 @@ def run_ours(args):
             ev[i][0].record()
             val, dX, dY = device_step()
             ev[i][1].record()
-            kern_ms.append(None)
-            # reading the in-library event pair synchronises on this step's dominant kernel only
-            kern_ms[-1] = lib.smmd_profile_last_ms()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+    # ---- roofline: the dominant kernel alone, event pair recorded inside the library on the launching stream
+    #      (separate short loop: reading the pair back synchronises, which must not sit in the timed region) ----
+    lib.smmd_profile_enable(1)
+    kern_ms = []
+    saved_launches = launches[0]
+    for _ in range(5):
+        flush.zero_()
+        device_step()
+        kern_ms.append(lib.smmd_profile_last_ms())
+    launches[0] = saved_launches
     lib.smmd_profile_enable(0)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)

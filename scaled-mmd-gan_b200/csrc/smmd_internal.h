@@ -88,6 +88,9 @@ cudaError_t launch_simt_rows(const KernelFn& kf, const Geometry& g, const Coefs&
                              int want_stats2, cudaStream_t s);
 cudaError_t launch_finalize_mmd2(const KernelFn& kf, const Geometry& g, const double* stats, const float* norms,
                                  double* scalars, cudaStream_t s);
+// second-stage reduction: partials[nblocks][6] = (sxx, syy, sxy, syx, dgx, dgy) per CTA, summed in fixed order
+cudaError_t launch_finalize_partials(const KernelFn& kf, const Geometry& g, const double* partials, int64_t nblocks,
+                                     double* scalars, cudaStream_t s);
 cudaError_t launch_combine_mmd2(const KernelFn& kf, const Geometry& g, const double* sums, double* out,
                                 cudaStream_t s);
 cudaError_t launch_finalize_ratio(const KernelFn& kf, const Geometry& g, const double* stats, double min_var_est,

@@ -531,6 +531,39 @@ cudaError_t launch_finalize_mmd2(const KernelFn& kf, const Geometry& g, const do
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) finalize_partials_kernel(KernelFn kf, int64_t m, int64_t n, int biased, int full,
+                                                                const double* partials, int64_t nblocks,
+                                                                double* scalars) {
+  __shared__ double sh[6 * 256];
+  double q[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t b = threadIdx.x; b < nblocks; b += 256) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) q[i] += partials[b * 6 + i];
+  }
+  block_reduce<6>(q, sh);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SMMD_NUM_SCALARS; ++i) scalars[i] = 0.0;
+    scalars[SMMD_S_SUM_XX] = q[0];
+    scalars[SMMD_S_SUM_YY] = q[1];
+    scalars[SMMD_S_SUM_XY] = q[2];
+    scalars[SMMD_S_SUM_YX] = q[3];
+    scalars[SMMD_S_DIAG_X] = q[4];
+    scalars[SMMD_S_DIAG_Y] = q[5];
+    const double v = mmd2_from_sums(kf, (double)m, (double)n, biased, q[0], q[1], q[2], q[3], q[4], q[5]);
+    scalars[SMMD_S_MMD2] = full ? v : 0.0;
+    bool bad = false;
+    for (int i = 0; i < 6; ++i) bad = bad || !isfinite(q[i]);
+    scalars[SMMD_S_NONFINITE] = bad ? 1.0 : 0.0;
+  }
+}
+
+cudaError_t launch_finalize_partials(const KernelFn& kf, const Geometry& g, const double* partials, int64_t nblocks,
+                                     double* scalars, cudaStream_t s) {
+  const int full = (g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n) ? 1 : 0;
+  finalize_partials_kernel<<<1, 256, 0, s>>>(kf, g.m, g.n, g.biased, full, partials, nblocks, scalars);
+  return cudaGetLastError();
+}
+
 __global__ void combine_mmd2_kernel(KernelFn kf, int64_t m, int64_t n, int biased, const double* sums, double* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0)
     out[0] = mmd2_from_sums(kf, (double)m, (double)n, biased, sums[SMMD_S_SUM_XX], sums[SMMD_S_SUM_YY],

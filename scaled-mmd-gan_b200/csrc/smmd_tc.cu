@@ -99,6 +99,35 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
   const void* base = inA ? a.A : a.B;
   __nv_bfloat16* zrow = a.Z + (b * Mp + p) * a.dpz;
   float acc = 0.f;
+  // fast path: fp32 rows, 16-B aligned, no split/tanh tail handling needed per element: 8 features per lane
+  // per step (2 x LDG.128 -> 1 x STG.128), several independent loads in flight
+  const bool vec = a.dtype == SMMD_F32 && !a.split && (ld % 4 == 0) && (a.d % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  if (vec) {
+    const float* srow = reinterpret_cast<const float*>(base) + src * ld;
+    for (int64_t c = 8 * lane; c < a.dp; c += 256) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid && c < a.d) {
+        const float4 lo = *reinterpret_cast<const float4*>(srow + c), hi = *reinterpret_cast<const float4*>(srow + c + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        if (a.tanh_features) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+        }
+      }
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        const float f0 = __bfloat162float(h2.x), f1 = __bfloat162float(h2.y);
+        acc = fmaf(f0, f0, acc);
+        acc = fmaf(f1, f1, acc);
+      }
+      *reinterpret_cast<uint4*>(zrow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  } else
   for (int64_t c = 2 * lane; c < a.dp; c += 64) {
     float v[2] = {0.f, 0.f};
 #pragma unroll
@@ -581,94 +610,164 @@ struct FinRowsArgs {
   const double* spart;
   float* dX;
   float* dY;
-  double* stats;  // [ox+oy][RS_COUNT]
+  double* partials;  // [gridDim.x][6] per-CTA block sums (second stage: launch_finalize_partials)
 };
 
+constexpr int kFinRowsPerWarp = 4;
+constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
+
+// One warp per row (4 rows per warp): reduce the per-(CTA, slot) slabs in fixed order, form the gradient row
+// with the fp32 z_i, and fold the row's block sums into per-CTA partials (second stage: finalize_partials).
 __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t lr = (int64_t)blockIdx.x * 8 + warp;
-  if (lr >= a.ox + a.oy) return;
-  const bool rowX = lr < a.ox;
-  const int64_t li = rowX ? a.x0 + lr : a.y0 + (lr - a.ox);   // index inside X or Y
-  const int64_t gi = rowX ? li : a.mp + li;                   // padded stacked row
-  const int rb = (int)(gi / BM), r = (int)(gi % BM);
-  const int64_t rbi = rowX ? rb - a.rb_x0 : a.nrb_x + (rb - a.rb_y0);
-  const int64_t f0 = rbi * a.T, f1 = f0 + a.T - 1;
-  const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
-  float rs = 0.f;
-  double ssame = 0.0, scross = 0.0;
-  for (int64_t g = g0; g <= g1; ++g) {
-    const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
-    for (int pt = 0; pt < a.npart; ++pt) {
-      rs += a.rpart[(sl * a.npart + pt) * BM + r];
-      const double* sp = a.spart + ((sl * a.npart + pt) * BM + r) * 2;
-      ssame += sp[0];
-      scross += sp[1];
-    }
-  }
-  const double a_same = rowX ? a.a_xx : a.a_yy;
+  __shared__ double sh[8][6];
+  double q[6] = {0, 0, 0, 0, 0, 0};  // sxx, syy, sxy, syx, dgx, dgy of this warp's rows
+  const double a_xy = a.a_xy;
   const bool dot = a.kf.family == FAM_RQ && a.kf.add_dot > 0.f && a.csum != nullptr;
-  double dsame = 0.0, dcross = 0.0;  // z_i . colsum(same set) / (other set)
-  float* out = nullptr;
-  if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
-  // lane owns features lane, lane+32, ... (dp <= 256 -> at most 8); slabs are summed in fixed order
-  float oacc[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) oacc[t] = 0.f;
-  if (out) {
+  for (int rr = 0; rr < kFinRowsPerWarp; ++rr) {
+    const int64_t lr = ((int64_t)blockIdx.x * 8 + warp) * kFinRowsPerWarp + rr;
+    if (lr >= a.ox + a.oy) break;
+    const bool rowX = lr < a.ox;
+    const int64_t li = rowX ? a.x0 + lr : a.y0 + (lr - a.ox);   // index inside X or Y
+    const int64_t gi = rowX ? li : a.mp + li;                   // padded stacked row
+    const int rb = (int)(gi / BM), r = (int)(gi % BM);
+    const int64_t rbi = rowX ? rb - a.rb_x0 : a.nrb_x + (rb - a.rb_y0);
+    const int64_t f0 = rbi * a.T, f1 = f0 + a.T - 1;
+    const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
+    float rs = 0.f;
+    double ssame = 0.0, scross = 0.0;
     for (int64_t g = g0; g <= g1; ++g) {
       const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
-      const float* orow = a.Opart + (sl * BM + r) * a.dp;
+      for (int pt = 0; pt < a.npart; ++pt) {
+        rs += a.rpart[(sl * a.npart + pt) * BM + r];
+        const double* sp = a.spart + ((sl * a.npart + pt) * BM + r) * 2;
+        ssame += sp[0];
+        scross += sp[1];
+      }
+    }
+    const double a_same = rowX ? a.a_xx : a.a_yy;
+    double dsame = 0.0, dcross = 0.0;  // z_i . colsum(same set) / (other set)
+    float* out = nullptr;
+    if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
+    const void* src = rowX ? a.X : a.Y;
+    const int64_t ld = rowX ? a.ldx : a.ldy;
+    const bool vec = out != nullptr && !dot && a.dtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+      // lane owns features [4 lane + 128 t, +4), t = 0, 1 (dp <= 256)
+      float4 oacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      float4 z4[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      const float* zsrc = reinterpret_cast<const float*>(src) + li * ld;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = 4 * lane + 128 * t;
+        if (c < a.d) z4[t] = *reinterpret_cast<const float4*>(zsrc + c);
+      }
+      for (int64_t g = g0; g <= g1; ++g) {
+        const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
+        const float* orow = a.Opart + (sl * BM + r) * a.dp;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = 4 * lane + 128 * t;
+          if (c < a.dp) {
+            const float4 o = *reinterpret_cast<const float4*>(orow + c);
+            oacc[t].x += o.x;
+            oacc[t].y += o.y;
+            oacc[t].z += o.z;
+            oacc[t].w += o.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = 4 * lane + 128 * t;
+        if (c < a.d) {
+          float zz[4] = {z4[t].x, z4[t].y, z4[t].z, z4[t].w};
+          const float oo[4] = {oacc[t].x, oacc[t].y, oacc[t].z, oacc[t].w};
+          float gv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
+            gv[e] = rs * zz[e] - oo[e];                      // W already carries the factor 4 a_ij
+            if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
+          }
+          *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+      }
+    } else {
+      // general path: lane owns features lane, lane+32, ... (dp <= 256 -> at most 8)
+      float oacc[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) oacc[t] = 0.f;
+      if (out) {
+        for (int64_t g = g0; g <= g1; ++g) {
+          const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
+          const float* orow = a.Opart + (sl * BM + r) * a.dp;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int c = lane + 32 * t;
+            if (c < a.dp) oacc[t] += orow[c];
+          }
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int c = lane + 32 * t;
-        if (c < a.dp) oacc[t] += orow[c];
+        if (c >= a.d) continue;
+        // z_i at full input precision: g_i = 4 sum_j W_ij (z_i - z_j) is dominated by r_i z_i, so rounding
+        // z_i to bf16 here would put a 2^-9 relative error straight into the gradient
+        const int64_t sidx = li * ld + c;
+        float z = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+                                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
+        if (a.kf.tanh_features) z = tanhf(z);
+        if (out) {
+          float gv = rs * z - oacc[t];
+          if (dot) {
+            const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
+            gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a_xy * co));
+          }
+          if (a.kf.tanh_features) gv *= (1.f - z * z);
+          out[c] = gv;
+        }
+        if (dot) {
+          dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
+          dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+        }
       }
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int c = lane + 32 * t;
-    if (c >= a.d) continue;
-    // z_i at full input precision: g_i = 4 sum_j W_ij (z_i - z_j) is dominated by r_i z_i, so rounding z_i
-    // to bf16 here would put a 2^-9 relative error straight into the gradient
-    const void* src = rowX ? a.X : a.Y;
-    const int64_t sidx = li * (rowX ? a.ldx : a.ldy) + c;
-    float z = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
-                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
-    if (a.kf.tanh_features) z = tanhf(z);
-    if (out) {
-      float gv = rs * z - oacc[t];  // W already carries the factor 4 a_ij
       if (dot) {
-        const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
-        gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
-      }
-      if (a.kf.tanh_features) gv *= (1.f - z * z);
-      out[c] = gv;
-    }
-    if (dot) {
-      dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
-      dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
-    }
-  }
-  if (dot) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      dsame += __shfl_xor_sync(0xffffffffu, dsame, o);
-      dcross += __shfl_xor_sync(0xffffffffu, dcross, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          dsame += __shfl_xor_sync(0xffffffffu, dsame, o);
+          dcross += __shfl_xor_sync(0xffffffffu, dcross, o);
+        }
+      }
+    }
+    // row totals (lane-uniform values); the dot part of the kernel is closed form:
+    //   sum_{j != i} <z_i, z_j> = <z_i, colsum> - |z_i|^2
+    const float ni = a.norms[gi];
+    const double v_same = ssame + (dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0);
+    const double v_cross = scross + (dot ? (double)a.kf.add_dot * dcross : 0.0);
+    const double v_diag = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                                : (double)diag_value(a.kf, ni);
+    if (rowX) {
+      q[0] += v_same;
+      q[2] += v_cross;
+      q[4] += v_diag;
+    } else {
+      q[1] += v_same;
+      q[3] += v_cross;
+      q[5] += v_diag;
     }
   }
-  if (lane == 0 && a.stats) {
-    const float ni = a.norms[gi];
-    double* st = a.stats + lr * RS_COUNT;
-    // dot part of the kernel handled in closed form: sum_{j != i} <z_i, z_j> = <z_i, colsum> - |z_i|^2
-    st[RS_SAME] = ssame + (dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0);
-    st[RS_CROSS] = scross + (dot ? (double)a.kf.add_dot * dcross : 0.0);
-    st[RS_SQ_SAME] = 0.0;
-    st[RS_SQ_CROSS] = 0.0;
-    st[RS_DIAG] = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
-                                        : (double)diag_value(a.kf, ni);
-    st[RS_PAIR] = 0.0;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sh[warp][i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];   // fixed order
+    a.partials[(int64_t)blockIdx.x * 6 + threadIdx.x] = t;
   }
 }
 
@@ -1173,11 +1272,12 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.spart = fa.spart;
     fr.dX = dX;
     fr.dY = dY;
-    fr.stats = reinterpret_cast<double*>(w + p.off_stats);
-    tc_finalize_rows_kernel<<<(unsigned)((fr.ox + fr.oy + 7) / 8), 256, 0, s>>>(fr);
+    fr.partials = reinterpret_cast<double*>(w + p.off_stats);
+    const unsigned fin_blocks = (unsigned)((fr.ox + fr.oy + kFinRowsPerCta - 1) / kFinRowsPerCta);
+    tc_finalize_rows_kernel<<<fin_blocks, 256, 0, s>>>(fr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
-    e = launch_finalize_mmd2(kf, g, fr.stats, norms, scalars, s);
+    e = launch_finalize_partials(kf, g, fr.partials, fin_blocks, scalars, s);
     if (e != cudaSuccess) return e;
     ++*launches;
     return cudaSuccess;
