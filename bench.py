@@ -305,6 +305,9 @@ def run_ours(args):
     # ---- KID (configs[2]): 50k vs 50k x 2048, 100 subsets of 1000, subsets split across ranks ----
     kid = run_kid(dev, rank, world, args, compute_scores, lib, dist, peak)
 
+    # ---- latency-bound shapes (configs[0] and the shipped YAML shape): microseconds per loss fwd+bwd ----
+    small = run_small(dev, mmd, args) if (rank == 0 and world == 1) else None
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -332,9 +335,69 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if small is not None:
+            line["small_batch_latency"] = small
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_small(dev, mmd, args):
+    """C1 (64+64 x 16, mix_rbf sigmas {1,2,4,8,16}) and the shipped-YAML shape (64+64 x 1, rbf): these are
+    launch-latency bound (<= 1 MFLOP), reported as microseconds per fwd+bwd, exact fp32 path, CUDA-graph replay."""
+    from smmd import _lib
+
+    out = {}
+    for tag, d, mk in (("c1_mix_rbf_64x16", 16, lambda X, Y: mmd._mix_rbf_kernel(X, Y, sigmas=[1, 2, 4, 8, 16])),
+                       ("yml_rbf_64x1", 1, lambda X, Y: mmd._rbf_kernel(X, Y))):
+        X = torch.randn(64, d, generator=torch.Generator().manual_seed(1234)).to(dev)
+        Y = (1.1 * torch.randn(64, d, generator=torch.Generator().manual_seed(1235)) + 0.1).to(dev)
+        spec = mk(X, Y).spec
+        for _ in range(5):
+            mmd.fused_mmd2_raw(spec, X, Y, want_grad=True, precision="fp32")
+        torch.cuda.synchronize()
+        # plain stream launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 200
+        e0.record()
+        for _ in range(reps):
+            sc, dX, dY = mmd.fused_mmd2_raw(spec, X, Y, want_grad=True, precision="fp32")
+        e1.record()
+        torch.cuda.synchronize()
+        stream_us = e0.elapsed_time(e1) / reps * 1e3
+        # CUDA-graph replay of 20 calls (the training loop's steady state)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                mmd.fused_mmd2_raw(spec, X, Y, want_grad=True, precision="fp32")
+            s.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(20):
+                    sc, dX, dY = mmd.fused_mmd2_raw(spec, X, Y, want_grad=True, precision="fp32")
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_us = e0.elapsed_time(e1) / (20 * 20) * 1e3
+        entry = {"us_per_loss_stream": stream_us, "us_per_loss_cuda_graph": graph_us, "path": _lib.last_path(),
+                 "launches_per_loss": _lib.last_launch_count(), "mmd2": float(sc[0].item())}
+        if not args.no_cpu:
+            from oracle import mmd_oracle
+            import numpy as np
+            Xn, Yn = X.cpu().numpy(), Y.cpu().numpy()
+            name, kw = ("mix_rbf", {"sigmas": [1, 2, 4, 8, 16]}) if d == 16 else ("rbf", {})
+            t0 = time.perf_counter()
+            for _ in range(20):
+                v, _, _ = mmd_oracle.mmd2_and_grads(name, Xn, Yn, False, np.float32, **kw)
+            entry["cpu_port_us_per_loss"] = (time.perf_counter() - t0) / 20 * 1e6
+            entry["oracle_mmd2_f32"] = float(v)
+        out[tag] = entry
+    return out
 
 
 def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
@@ -386,7 +449,7 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
            "tflops_algorithmic_6m2d": 6.0 * m * m * d * S / (ms * 1e-3) / 1e12,
            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak,
                         "achieved": 6.0 * m * m * d * count / (kms * 1e-3) / 1e12 if kms and kms > 0 else None,
-                        "kernel": "tc_stream_kernel<MathPoly3> (split-bf16: executes 3x the algorithmic flops)", "kernel_ms": kms}}
+                        "kernel": "tc_macro_kernel<MathPoly3> 256x256 macro tiles (split-bf16: executes 3x the algorithmic flops; symmetric enumeration skips 25% of them)", "kernel_ms": kms}}
     if out["roofline"]["achieved"]:
         out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
     if rank == 0 and world == 1 and not args.no_cpu:
