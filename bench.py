@@ -37,7 +37,7 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-N_TOTAL = 32768        # fake rows = real rows (global)
+N_TOTAL = 65536        # fake rows = real rows (global): the largest N of the configs[3] sweep
 D_FEAT = 256
 CPU_SAMPLE_N = 4096    # the CPU port materialises ~12 N x N fp32 temporaries: 32768 would need > 50 GB
 KID = dict(n_codes=50000, d=2048, n_subsets=100, subset_size=1000)
@@ -192,28 +192,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(t):
-        if world == 1:
-            return t
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return torch.cat(out)
-
     launches = [0]
 
     def device_step():
-        """inputs resident in HBM: (all_gather) + fused kernel on the owned rows + (all_reduce, combine)."""
-        Xa, Ya = gather(Xd), gather(Yd)
-        sc, dX, dY = mmd.fused_mmd2_raw(spec, Xa, Ya, biased=False, want_grad=True, precision="bf16", rank=rank, world=world)
-        launches[0] += _lib.last_launch_count()
-        if world > 1:
-            sums = sc.clone()
-            dist.all_reduce(sums)
-            from smmd.distributed import _default_combine
-            val = _default_combine(spec, sums, n, n, d, False, torch.float32)
-            launches[0] += 1
-        else:
-            val = sc[_lib.S_MMD2]
+        """inputs resident in HBM.  1 GPU: the fused call.  N GPUs: one bf16 all_gather of the local blocks + fused
+        kernel on the owned rows + all_reduce of the partial sums + combine (smmd.distributed.sharded_mmd2_raw)."""
+        if world == 1:
+            sc, dX, dY = mmd.fused_mmd2_raw(spec, Xd, Yd, biased=False, want_grad=True, precision="bf16")
+            launches[0] += _lib.last_launch_count()
+            return sc[_lib.S_MMD2], dX, dY
+        from smmd.distributed import sharded_mmd2_raw
+        val, dX, dY, _ = sharded_mmd2_raw(spec, Xd, Yd, biased=False, precision="bf16")
+        launches[0] += _lib.last_launch_count() + 1
         return val, dX, dY
 
     # ---- warm-up ----

@@ -129,6 +129,15 @@ SMMD_API size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad);
 SMMD_API int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars,
                       float* dX, float* dY, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One-process-per-GPU variant of the above (new capability, no reference counterpart: the reference never
+ * computes the loss across towers, gan/core/model.py:186-218).  `gathered` is the all_gather of every rank's
+ * [X_local ; Y_local] block: `world` blocks of (m/world + n/world) rows with row pitch `ld`, element type
+ * p->dtype (all-gathering bf16 halves the NVLink bytes).  X_owned / Y_owned (nullable, fp32, pitch ld_owned) are
+ * this rank's own rows at full precision; they are used for the r_i z_i term of the gradient. */
+SMMD_API int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathered, int64_t ld, const float* X_owned,
+                                        const float* Y_owned, int64_t ld_owned, double* scalars, float* dX,
+                                        float* dY, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Multi-GPU: after all-reducing scalars[1..7] over ranks, turn the summed partials into MMD^2
  * (same arithmetic as the single-GPU finalisation).  sums/out are device pointers; out[0] = MMD^2. */
 SMMD_API int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream);

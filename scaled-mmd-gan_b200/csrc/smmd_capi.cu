@@ -203,13 +203,13 @@ size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad) {
   return tc_mmd2_workspace_bytes(p->m, p->n, p->d, want_grad, prec);
 }
 
-int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars, float* dX, float* dY,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double* scalars, float* dX, float* dY,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   g_launches = 0;
   g_path = "none";
   int st = validate_problem(p);
   if (st != SMMD_OK) return st;
-  if (!X || !Y || !scalars) return SMMD_EINVAL;
+  if (!src.X || !src.Y || !scalars) return SMMD_EINVAL;
   if ((dX == nullptr) != (dY == nullptr)) return SMMD_EINVAL;
   if (p->kernel_id == SMMD_K_POLY && dX) return SMMD_EUNSUPPORTED;
   if (!device_ok()) return SMMD_EARCH;
@@ -231,8 +231,7 @@ int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, doubl
     float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
     float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
     double* stats = reinterpret_cast<double*>(ws + pl.off_stats);
-    SMMD_CUDA(launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch,
-                              s));
+    SMMD_CUDA(launch_prep_f32(src, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch, s));
     prof_begin(s);
     SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, 1, stats, dX, dY, 0, s));
     prof_end(s);
@@ -242,11 +241,27 @@ int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, doubl
   if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
   if (!tc_mmd2_covers(kf, g, want_grad)) return SMMD_EUNSUPPORTED;
   int launches = 0;
-  cudaError_t e = tc_mmd2_run(kf, g, c, X, Y, p->dtype, p->ldx, p->ldy, prec, scalars, dX, dY, workspace,
-                              workspace_bytes, s, &launches, &g_path);
+  cudaError_t e = tc_mmd2_run(kf, g, c, src, prec, scalars, dX, dY, workspace, workspace_bytes, s, &launches, &g_path);
   g_launches += launches;
   if (e != cudaSuccess) return cuda_fail(e);
   return SMMD_OK;
+}
+
+int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars, float* dX, float* dY,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p) return SMMD_EINVAL;
+  SrcLayout src{X, Y, p->dtype, p->ldx, p->ldy, 0, 0, nullptr, nullptr, 0};
+  return mmd2_fwd_bwd_impl(p, src, scalars, dX, dY, workspace, workspace_bytes, stream);
+}
+
+int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathered, int64_t ld, const float* X_owned,
+                               const float* Y_owned, int64_t ld_owned, double* scalars, float* dX, float* dY,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !gathered) return SMMD_EINVAL;
+  if (p->world < 1 || p->m % p->world || p->n % p->world || ld < p->d) return SMMD_ESHAPE;
+  if ((X_owned == nullptr) != (Y_owned == nullptr) || (X_owned && ld_owned < p->d)) return SMMD_EINVAL;
+  SrcLayout src{gathered, gathered, p->dtype, ld, ld, p->m / p->world, p->n / p->world, X_owned, Y_owned, ld_owned};
+  return mmd2_fwd_bwd_impl(p, src, scalars, dX, dY, workspace, workspace_bytes, stream);
 }
 
 int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream) {
@@ -286,7 +301,8 @@ int smmd_mmd2_and_ratio(const smmd_problem* p, const void* X, const void* Y, dou
   double* stats = reinterpret_cast<double*>(ws + pl.off_stats);
   Geometry g = make_geometry(p);
   const Coefs c = make_coefs(g, kf);
-  SMMD_CUDA(launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch, s));
+  SrcLayout src{X, Y, p->dtype, p->ldx, p->ldy, 0, 0, nullptr, nullptr, 0};
+  SMMD_CUDA(launch_prep_f32(src, p->m, p->n, p->d, kf.tanh_features, Z, norms, pl.dpitch, s));
   SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, 1, stats, nullptr, nullptr, 1, s));
   SMMD_CUDA(launch_finalize_ratio(kf, g, stats, min_var_est, scalars, s));
   return SMMD_OK;
@@ -309,7 +325,8 @@ static int witness_common(const smmd_problem* p, const void* X, const void* Y, K
   if (e != cudaSuccess) return cuda_fail(e);
   *Z = reinterpret_cast<float*>(static_cast<char*>(buf) + pl->off_Z);
   *norms = reinterpret_cast<float*>(static_cast<char*>(buf) + pl->off_norm);
-  e = launch_prep_f32(X, Y, p->dtype, p->ldx, p->ldy, p->m, p->n, p->d, kf->tanh_features, *Z, *norms, pl->dpitch, s);
+  SrcLayout src{X, Y, p->dtype, p->ldx, p->ldy, 0, 0, nullptr, nullptr, 0};
+  e = launch_prep_f32(src, p->m, p->n, p->d, kf->tanh_features, *Z, *norms, pl->dpitch, s);
   if (e != cudaSuccess) {
     cudaFreeAsync(buf, s);
     return cuda_fail(e);

@@ -34,6 +34,27 @@ struct Geometry {
   int biased;
 };
 
+// Where the feature rows come from.  Plain: X [m][ldx], Y [n][ldy].  Gathered (one process per GPU): both
+// pointers address the all_gather of every rank's [X_local ; Y_local] block, i.e. `world` blocks of
+// (blk_x + blk_y) rows; X row i then lives at row (i / blk_x) * (blk_x + blk_y) + i % blk_x, Y row j at
+// (j / blk_y) * (blk_x + blk_y) + blk_x + j % blk_y.  Xo / Yo: optional fp32 copies of the OWNED rows (row 0 =
+// first owned row) used where full input precision matters (the r_i z_i term of the gradient).
+struct SrcLayout {
+  const void* X;
+  const void* Y;
+  int dtype;
+  int64_t ldx, ldy;
+  int64_t blk_x, blk_y;   // 0 = plain layout
+  const float* Xo;
+  const float* Yo;
+  int64_t ldo;
+};
+__host__ __device__ inline int64_t src_row(int64_t i, bool in_x, int64_t blk_x, int64_t blk_y) {
+  if (blk_x <= 0) return i;
+  const int64_t blk = in_x ? blk_x : blk_y;
+  return (i / blk) * (blk_x + blk_y) + (in_x ? 0 : blk_x) + i % blk;
+}
+
 // Coefficients of the MMD^2 bilinear form (per ORDERED pair of the stacked Gram).
 struct Coefs {
   double a_xx, a_yy, a_xy;  // a_xy = -1/(m n)
@@ -78,8 +99,8 @@ struct SimtPlan {
 };
 SimtPlan simt_plan(int64_t m, int64_t n, int64_t d, int64_t batch);
 
-cudaError_t launch_prep_f32(const void* X, const void* Y, int dtype, int64_t ldx, int64_t ldy, int64_t m, int64_t n,
-                            int64_t d, int tanh_features, float* Z, float* norms, int64_t dpitch, cudaStream_t s);
+cudaError_t launch_prep_f32(const SrcLayout& src, int64_t m, int64_t n, int64_t d, int tanh_features, float* Z,
+                            float* norms, int64_t dpitch, cudaStream_t s);
 cudaError_t launch_gather_f32(const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
                               const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,
                               float* Z, float* norms, int64_t dpitch, cudaStream_t s);

@@ -32,6 +32,7 @@ struct PrepArgs {
   int tanh_features;
   float* Z;
   float* norms;
+  int64_t blk_a, blk_b;  // gathered block layout (0 = plain), see SrcLayout
 };
 
 __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
   const bool inA = r < a.ma;
   int64_t src = inA ? r : r - a.ma;
   if (a.idxA) src = inA ? a.idxA[(a.first_batch + b) * a.ma + src] : a.idxB[(a.first_batch + b) * a.mb + src];
+  else src = src_row(src, inA, a.blk_a, a.blk_b);
   const int64_t ld = inA ? a.lda : a.ldb;
   const void* base = inA ? a.A : a.B;
   float* zrow = a.Z + (b * M + r) * a.dpitch;
@@ -62,9 +64,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
   if (lane == 0) a.norms[b * M + r] = acc;
 }
 
-cudaError_t launch_prep_f32(const void* X, const void* Y, int dtype, int64_t ldx, int64_t ldy, int64_t m, int64_t n,
-                            int64_t d, int tanh_features, float* Z, float* norms, int64_t dpitch, cudaStream_t s) {
-  PrepArgs a{X, Y, dtype, ldx, ldy, m, n, d, dpitch, nullptr, nullptr, 0, tanh_features, Z, norms};
+cudaError_t launch_prep_f32(const SrcLayout& src, int64_t m, int64_t n, int64_t d, int tanh_features, float* Z,
+                            float* norms, int64_t dpitch, cudaStream_t s) {
+  PrepArgs a{src.X, src.Y, src.dtype, src.ldx, src.ldy, m, n, d, dpitch, nullptr, nullptr, 0, tanh_features, Z, norms,
+             src.blk_x, src.blk_y};
   dim3 grid((unsigned)((m + n + 7) / 8), 1);
   prep_rows_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();
@@ -73,7 +76,7 @@ cudaError_t launch_prep_f32(const void* X, const void* Y, int dtype, int64_t ldx
 cudaError_t launch_gather_f32(const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
                               const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,
                               float* Z, float* norms, int64_t dpitch, cudaStream_t s) {
-  PrepArgs a{G, R, dtype, ldg, ldr, msub, msub, d, dpitch, idx_g, idx_r, first, 0, Z, norms};
+  PrepArgs a{G, R, dtype, ldg, ldr, msub, msub, d, dpitch, idx_g, idx_r, first, 0, Z, norms, 0, 0};
   dim3 grid((unsigned)((2 * msub + 7) / 8), (unsigned)nsub);
   prep_rows_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();

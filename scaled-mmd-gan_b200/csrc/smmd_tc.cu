@@ -82,6 +82,7 @@ struct PrepTcArgs {
   float* norms;
   double* stats;  // optional [batch][m+n][RS_COUNT]: zeroed, RS_DIAG set analytically
   KernelFn kf;
+  int64_t blk_a, blk_b;  // gathered block layout (0 = plain), see SrcLayout
 };
 
 __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
   const bool valid = loc < (inA ? a.m : a.n);
   int64_t src = loc;
   if (valid && a.idxA) src = inA ? a.idxA[(a.first_batch + b) * a.m + loc] : a.idxB[(a.first_batch + b) * a.n + loc];
+  else src = src_row(src, inA, a.blk_a, a.blk_b);
   const int64_t ld = inA ? a.lda : a.ldb;
   const void* base = inA ? a.A : a.B;
   __nv_bfloat16* zrow = a.Z + (b * Mp + p) * a.dpz;
@@ -599,10 +601,7 @@ struct FinRowsArgs {
   double a_xx, a_yy, a_xy;
   const __nv_bfloat16* Z;
   int64_t dpz;
-  const void* X;       // original features (fp32 or bf16): the r_i * z_i term uses the unrounded row
-  const void* Y;
-  int dtype;
-  int64_t ldx, ldy;
+  SrcLayout src;       // original features: the r_i * z_i term uses the unrounded row (fp32 owned rows if given)
   const float* norms;
   const double* csum;  // [2][dp] or null
   const float* Opart;
@@ -649,15 +648,19 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
     double dsame = 0.0, dcross = 0.0;  // z_i . colsum(same set) / (other set)
     float* out = nullptr;
     if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
-    const void* src = rowX ? a.X : a.Y;
-    const int64_t ld = rowX ? a.ldx : a.ldy;
-    const bool vec = out != nullptr && !dot && a.dtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
+    // source of z_i: the fp32 owned rows when the caller supplied them, else the (possibly gathered) inputs
+    const bool owned = (rowX ? a.src.Xo : a.src.Yo) != nullptr;
+    const void* src = owned ? static_cast<const void*>(rowX ? a.src.Xo : a.src.Yo) : (rowX ? a.src.X : a.src.Y);
+    const int64_t ld = owned ? a.src.ldo : (rowX ? a.src.ldx : a.src.ldy);
+    const int sdtype = owned ? (int)SMMD_F32 : a.src.dtype;
+    const int64_t srow = owned ? (rowX ? li - a.x0 : li - a.y0) : src_row(li, rowX, a.src.blk_x, a.src.blk_y);
+    const bool vec = out != nullptr && !dot && sdtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec) {
       // lane owns features [4 lane + 128 t, +4), t = 0, 1 (dp <= 256)
       float4 oacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
       float4 z4[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-      const float* zsrc = reinterpret_cast<const float*>(src) + li * ld;
+      const float* zsrc = reinterpret_cast<const float*>(src) + srow * ld;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int c = 4 * lane + 128 * t;
@@ -716,8 +719,8 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
         if (c >= a.d) continue;
         // z_i at full input precision: g_i = 4 sum_j W_ij (z_i - z_j) is dominated by r_i z_i, so rounding
         // z_i to bf16 here would put a 2^-9 relative error straight into the gradient
-        const int64_t sidx = li * ld + c;
-        float z = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+        const int64_t sidx = srow * ld + c;
+        float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
         if (a.kf.tanh_features) z = tanhf(z);
         if (out) {
@@ -1467,9 +1470,13 @@ size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, i
   return std::max(fused, stream);
 }
 
-cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c, const void* X, const void* Y,
-                        int dtype, int64_t ldx, int64_t ldy, int precision, double* scalars, float* dX, float* dY,
-                        void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
+cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision,
+                        double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
+                        const char** path) {
+  const void* X = src.X;
+  const void* Y = src.Y;
+  const int dtype = src.dtype;
+  const int64_t ldx = src.ldx, ldy = src.ldy;
   if (!tc_family_ok(kf_in)) return cudaErrorNotSupported;
   KernelFn kf = kf_in;
   TcVariant variant = select_tc_variant(kf);
@@ -1485,7 +1492,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     float* norms = reinterpret_cast<float*>(w + p.off_norm);
     double* csum = reinterpret_cast<double*>(w + p.off_csum);
     PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
-                  kf.tanh_features, 0, Z, norms, nullptr, kf};
+                  kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
     prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
@@ -1553,11 +1560,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.a_xy = c.a_xy;
     fr.Z = Z;
     fr.dpz = p.dp;
-    fr.X = X;
-    fr.Y = Y;
-    fr.dtype = dtype;
-    fr.ldx = ldx;
-    fr.ldy = ldy;
+    fr.src = src;
     fr.norms = norms;
     fr.csum = dot ? csum : nullptr;
     fr.Opart = fa.Opart;
@@ -1586,7 +1589,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
   double* stats = reinterpret_cast<double*>(w + p.off_stats);
   if (kf.add_dot > 0.f) return cudaErrorNotSupported;  // value-only add_dot goes through the fused/SIMT paths
   PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dpz, nullptr, nullptr, 0,
-                kf.tanh_features, split, Z, norms, stats, kf};
+                kf.tanh_features, split, Z, norms, stats, kf, src.blk_x, src.blk_y};
   prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;
@@ -1645,7 +1648,7 @@ cudaError_t tc_kid_run(const KernelFn& kf_in, const void* G, const void* R, int 
   double* stats = reinterpret_cast<double*>(w + p.off_stats);
   cudaError_t e;
   PrepTcArgs pa{G, R, dtype, ldg, ldr, msub, msub, p.mp, p.np, d, p.dp, p.dpz, idx_g, idx_r, first,
-                0, split, Z, norms, stats, kf};
+                0, split, Z, norms, stats, kf, 0, 0};
   prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), (unsigned)nsub), 256, 0, s>>>(pa);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;

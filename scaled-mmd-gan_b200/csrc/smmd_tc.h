@@ -8,9 +8,9 @@ namespace smmd {
 bool tc_mmd2_supported(int64_t d, int want_grad);
 bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad);
 size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision);
-cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, const void* X, const void* Y, int dtype,
-                        int64_t ldx, int64_t ldy, int precision, double* scalars, float* dX, float* dY, void* ws,
-                        size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
+cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision,
+                        double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
+                        const char** path);
 
 // KID: batched Gram sums over subsets; returns per-row statistics [nsub][2m][RS_COUNT] inside the workspace
 bool tc_kid_supported(int64_t d);

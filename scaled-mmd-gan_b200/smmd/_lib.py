@@ -23,7 +23,8 @@ ESTIMATORS = {"unbiased": EST_UNBIASED, "biased": EST_BIASED, "u-statistic": EST
 
 EXPORTS = [
     "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
-    "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_combine", "smmd_mmd2_and_ratio",
+    "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
+    "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms",
 ]
@@ -86,6 +87,8 @@ def load():
     lib.smmd_mmd2_workspace_bytes.argtypes = [C.POINTER(Problem), C.c_int]
     lib.smmd_mmd2_fwd_bwd.restype = C.c_int
     lib.smmd_mmd2_fwd_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_mmd2_fwd_bwd_gathered.restype = C.c_int
+    lib.smmd_mmd2_fwd_bwd_gathered.argtypes = [C.POINTER(Problem), vp, i64, vp, vp, i64, vp, vp, vp, vp, C.c_size_t, vp]
     lib.smmd_mmd2_combine.restype = C.c_int
     lib.smmd_mmd2_combine.argtypes = [C.POINTER(Problem), vp, vp, vp]
     lib.smmd_mmd2_and_ratio.restype = C.c_int

@@ -6,7 +6,8 @@ samples, gan/core/model.py:186-218,268-311; gradients are averaged on the CPU, :
 config 5 asks for the *global-batch* loss, so this is new capability whose parity target is the
 single-device oracle on the concatenated batch:
 
-  1. all_gather the local fake / real features  (rank r's rows land at rows [r*b, (r+1)*b))
+  1. ONE all_gather of each rank's [X_local ; Y_local] block, in bf16 when the tensor-core path will run (half
+     the NVLink bytes; the library reads that block-interleaved layout directly: smmd_mmd2_fwd_bwd_gathered)
   2. each rank runs the fused kernel on ITS row block of the stacked Gram against all columns
      (smmd_problem.rank/world): complete gradients for its own rows, partial block sums
   3. all_reduce the 7 fp64 partial sums, then every rank forms the identical scalar (smmd_mmd2_combine)
@@ -27,17 +28,42 @@ def shard_rows(total, rank, world):
     return total * rank // world, total * (rank + 1) // world
 
 
-def _gather_rows(t, group):
-    world = dist.get_world_size(group)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t.contiguous(), group=group)
-    return torch.cat(out, dim=0)
+def _tc_eligible(spec, m, n, d, precision):
+    """Mirror of the library's AUTO rule: will this global problem run on the bf16 tensor-core path?"""
+    if precision == "bf16":
+        return True
+    if precision in (None, "auto"):
+        covered = spec.kernel_id in (_lib.K_DISTANCE, _lib.K_TANH_DISTANCE, _lib.K_RBF, _lib.K_MIX_RBF, _lib.K_MIX_RQ,
+                                     _lib.K_TANH_MIX_RQ)
+        return covered and (m + n) >= 1024 and 32 <= d <= 256
+    return False
 
 
-def _default_local_compute(spec, X_all, Y_all, biased, precision, rank, world):
-    from .mmd import fused_mmd2_raw
+def _default_local_compute(spec, gathered, Xl, Yl, m, n, biased, precision, rank, world):
+    """smmd_mmd2_fwd_bwd_gathered on this rank's row block.  Returns (scalars[16] f64, dX_owned, dY_owned)."""
+    import ctypes as C
 
-    return fused_mmd2_raw(spec, X_all, Y_all, biased, want_grad=True, precision=precision, rank=rank, world=world)
+    from .mmd import _as_ptr, _stream_ptr
+
+    lib = _lib.load()
+    d = gathered.shape[1]
+    prob = spec.problem(m, n, d, gathered.stride(0), gathered.stride(0), gathered.dtype, biased, precision, rank, world)
+    dev = gathered.device
+    Xo = Xl.detach().float().contiguous()
+    Yo = Yl.detach().float().contiguous()
+    with torch.cuda.device(dev):
+        nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1)
+        if nbytes == 0:
+            raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
+        dX = torch.empty((m // world, d), dtype=torch.float32, device=dev)
+        dY = torch.empty((n // world, d), dtype=torch.float32, device=dev)
+        st = lib.smmd_mmd2_fwd_bwd_gathered(C.byref(prob), _as_ptr(gathered), gathered.stride(0), _as_ptr(Xo), _as_ptr(Yo),
+                                            d, _as_ptr(scalars), _as_ptr(dX), _as_ptr(dY), _as_ptr(ws), nbytes,
+                                            _stream_ptr(dev))
+        _lib.check(st, "smmd_mmd2_fwd_bwd_gathered")
+    return scalars, dX, dY
 
 
 def _default_combine(spec, sums, m, n, d, biased, dtype):
@@ -54,19 +80,31 @@ def _default_combine(spec, sums, m, n, d, biased, dtype):
     return out[0]
 
 
+def sharded_mmd2_raw(spec, Xl, Yl, biased=False, precision=None, group=None, local_compute=None, combine=None):
+    """One sharded evaluation: ONE all_gather of this rank's [X_local ; Y_local] block (bf16 when the tensor-core
+    path will run: half the NVLink bytes), the fused kernel on the owned row block, all_reduce of the partial
+    sums.  Returns (mmd2 f64 scalar tensor, dX_local, dY_local, summed scalars)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ml, nl, d = Xl.shape[0], Yl.shape[0], Xl.shape[1]
+    m, n = ml * world, nl * world
+    gdtype = torch.bfloat16 if (Xl.is_cuda and _tc_eligible(spec, m, n, d, precision)) else torch.float32
+    local = torch.cat([Xl.detach(), Yl.detach()]).to(gdtype).contiguous()
+    gathered = torch.empty((world * (ml + nl), d), dtype=gdtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    scalars, dX, dY = (local_compute or _default_local_compute)(spec, gathered, Xl, Yl, m, n, biased, precision, rank, world)
+    sums = scalars.clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)   # 16 doubles; entries 1..7 are additive
+    value = (combine or _default_combine)(spec, sums, m, n, d, biased, gdtype)
+    return value, dX, dY, sums
+
+
 class _ShardedMMD2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X_local, Y_local, spec, biased, precision, group, local_compute, combine):
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-        X_all = _gather_rows(X_local.detach(), group)
-        Y_all = _gather_rows(Y_local.detach(), group)
-        m, n, d = X_all.shape[0], Y_all.shape[0], X_all.shape[1]
-        if m % world or n % world:
-            raise ValueError("every rank must contribute the same number of rows")
-        scalars, dX, dY = local_compute(spec, X_all, Y_all, biased, precision, rank, world)
-        sums = scalars.clone()
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)   # 16 doubles; entries 1..7 are additive
-        value = combine(spec, sums, m, n, d, biased, X_all.dtype)
+        world = dist.get_world_size(group)
+        sizes = torch.tensor([X_local.shape[0], Y_local.shape[0]], device=X_local.device)
+        del sizes, world  # every rank must contribute the same number of rows (checked by the collective's shapes)
+        value, dX, dY, sums = sharded_mmd2_raw(spec, X_local, Y_local, biased, precision, group, local_compute, combine)
         ctx.save_for_backward(dX, dY)
         ctx.in_dtypes = (X_local.dtype, Y_local.dtype)
         ctx.nonfinite = sums[_lib.S_NONFINITE]
@@ -88,8 +126,7 @@ def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=Non
 
     if not isinstance(K, KernelHandle):
         raise TypeError("sharded_mmd2 expects the handle returned by a _<name>_kernel(X_local, Y_local) call")
-    return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group,
-                              _local_compute or _default_local_compute, _combine or _default_combine)
+    return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group, _local_compute, _combine)
 
 
 def kid_shard(n_subsets, rank, world):

@@ -21,7 +21,9 @@ def main():
     from smmd.distributed import sharded_mmd2, sharded_polynomial_mmd_averages
 
     ok = True
-    for (b, d, precision, gtol) in ((64, 16, "fp32", 1e-5), (1024, 128, "bf16", 1e-5)):
+    # bf16 path: shards cut the tile stream elsewhere -> fp32 accumulation order differs, amplified by the
+    # cancellation in r*z - O (measured 3-5e-5 of max|g|; the bf16 tier itself is 4e-3)
+    for (b, d, precision, gtol) in ((64, 16, "fp32", 1e-5), (1024, 128, "bf16", 2e-4)):
         rng = np.random.RandomState(100 + rank)
         Xl = torch.tensor((rng.randn(b, d) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
         Yl = torch.tensor(((1.05 * rng.randn(b, d) + 0.1) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
@@ -36,9 +38,13 @@ def main():
         Ya = torch.cat(Ys).requires_grad_(True)
         ref = mmd.mmd2(mmd._mix_rq_kernel(Xa, Ya), precision=precision)
         ref.backward()
-        ok &= abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-12
-        ok &= bool((Xl.grad - Xa.grad[rank * b:(rank + 1) * b]).abs().max() <= gtol * Xa.grad.abs().max())
-        ok &= bool((Yl.grad - Ya.grad[rank * b:(rank + 1) * b]).abs().max() <= gtol * Ya.grad.abs().max())
+        c1 = abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-12
+        ex = (Xl.grad - Xa.grad[rank * b:(rank + 1) * b]).abs().max().item() / Xa.grad.abs().max().item()
+        ey = (Yl.grad - Ya.grad[rank * b:(rank + 1) * b]).abs().max().item() / Ya.grad.abs().max().item()
+        if not (c1 and ex <= gtol and ey <= gtol):
+            print("rank %d MISMATCH mmd2 b=%d d=%d %s: loss %.10g ref %.10g  grad rel err %.3e %.3e" %
+                  (rank, b, d, precision, loss.item(), ref.item(), ex, ey), flush=True)
+        ok &= c1 and ex <= gtol and ey <= gtol
     # KID
     gen = torch.Generator(device=dev).manual_seed(7)     # same seed on every rank -> replicated codes
     g = torch.relu(torch.randn(4000, 256, device=dev, generator=gen))
@@ -46,7 +52,10 @@ def main():
     idx = torch.stack([torch.randperm(4000, device=dev, generator=gen)[:500] for _ in range(10)]).to(torch.int32)
     mm, vv = sharded_polynomial_mmd_averages(g, r, idx, idx, ret_var=True)
     m1, v1 = compute_scores.kid_subsets(g, r, idx, idx, var_at_m=4000, ret_var=True)
-    ok &= torch.allclose(mm, m1, rtol=1e-9, atol=1e-14) and torch.allclose(vv, v1, rtol=1e-7, atol=1e-18)
+    ck = torch.allclose(mm, m1, rtol=1e-9, atol=1e-14) and torch.allclose(vv, v1, rtol=1e-7, atol=1e-18)
+    if not ck:
+        print("rank %d MISMATCH kid: %s vs %s ; var %s vs %s" % (rank, mm.tolist(), m1.tolist(), vv.tolist(), v1.tolist()), flush=True)
+    ok &= ck
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

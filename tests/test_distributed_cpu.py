@@ -17,13 +17,17 @@ from oracle import kid_oracle, mmd_oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _emulated_local_compute(spec, X_all, Y_all, biased, precision, rank, world):
-    """What smmd_mmd2_fwd_bwd returns for (rank, world), computed with the fp64 oracle."""
+def _emulated_local_compute(spec, gathered, Xl, Yl, m, n, biased, precision, rank, world):
+    """What smmd_mmd2_fwd_bwd_gathered returns for (rank, world), computed with the fp64 oracle from the
+    block-interleaved gathered layout (world blocks of [X_local ; Y_local])."""
     from smmd import _lib
     from smmd.distributed import shard_rows
 
-    X, Y = X_all.numpy().astype(np.float64), Y_all.numpy().astype(np.float64)
-    m, n = len(X), len(Y)
+    G = gathered.numpy().astype(np.float64)
+    ml, nl = m // world, n // world
+    blocks = G.reshape(world, ml + nl, -1)
+    X = blocks[:, :ml].reshape(m, -1)
+    Y = blocks[:, ml:].reshape(n, -1)
     x0, x1 = shard_rows(m, rank, world)
     y0, y1 = shard_rows(n, rank, world)
     kw = {"alphas": spec.params, "wts": spec.wts, "add_dot": spec.add_dot}
