@@ -589,6 +589,366 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
 }
 
+// ================================================================================================
+// cluster variant of the fused kernel: 256 < d <= 1024
+// ================================================================================================
+// O (128 x d fp32) no longer fits one SM's TMEM next to S, so CS = 2 or 4 CTAs of a thread-block cluster share
+// one row block.  CTA c holds the feature slice [c*FW, (c+1)*FW) of Z_i (resident), of the Z_j ring and of O.
+// Per 64-column tile:
+//   1. UMMA #1 (every CTA): partial S_c = Z_i[:, slice c] Z_j[:, slice c]^T                     (TMEM)
+//   2. reduce-scatter over DSMEM: CTA c owns columns [c*64/CS, (c+1)*64/CS) of the tile; every epilogue thread
+//      (= one row) sends the other CTAs' column ranges of its partial row into their receive buffers
+//      (st.shared::cluster, lane-contiguous [col][row] layout) and signals their mbarrier;
+//   3. the owner adds the partials, runs the kernel transform on ITS columns only (1/CS of the epilogue math per
+//      CTA -- this is what makes large d tensor-bound), accumulates tile / row sums for those columns, and
+//   4. all-gathers its W slice (bf16) into EVERY CTA's W panel (K-major SW128 shared-memory tile);
+//   5. UMMA #2 (every CTA, SS form): O[:, slice c] += W Z_j[:, slice c].
+// Buffer reuse across tiles is guarded by one cluster-wide "W buffer free" barrier per epilogue group.
+struct ClusterArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np;
+  float c_xx, c_yy, c_xy;
+  const float* norms;
+  int nrb_x, rb_x0, nrb_y, rb_y0;
+  int T;
+  int dp, fw, npanel, nst, la;   // fw = feature slice per CTA, npanel = fw/64, la = UMMA #1 look-ahead (tiles)
+  int64_t total_tiles, chunk;    // per cluster
+  int slots;
+  float* Opart;                  // [ncluster][slots][128][dp]
+  float* rpart;                  // [ncluster][slots][2*CS][128]
+  double* spart;                 // [ncluster][slots][2*CS][128][2]
+};
+
+template <int CS>
+struct ClusterSmem {
+  static constexpr int OC = BNF / CS;                              // tile columns owned by one CTA
+  static constexpr int W_BYTES = BM * 128;                         // one K-major SW128 panel: 128 rows x 64 bf16
+  static constexpr int RECV_BYTES = (CS - 1) * OC * BM * 4;        // [peer slot][col][row] fp32
+};
+
+inline int cluster_stages(int npanel, int cs) {
+  const int recv = (cs - 1) * (BNF / cs) * BM * 4;
+  int nst = (kMaxSmem - 1024 - 1024 - npanel * kZiRowBytes - 2 * BM * 128 - 2 * recv) / (npanel * kZjRowBytes);
+  return nst > 6 ? 6 : nst;
+}
+inline int cluster_smem(int npanel, int nst, int cs) {
+  const int recv = (cs - 1) * (BNF / cs) * BM * 4;
+  return 1024 + npanel * kZiRowBytes + nst * npanel * kZjRowBytes + 2 * BM * 128 + 2 * recv + 1024;
+}
+
+template <class Math, int CS>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fused_cluster_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
+                        const __grid_constant__ ClusterArgs a) {
+  using SM = ClusterSmem<CS>;
+  constexpr int OC = SM::OC;
+  constexpr int EPI_WARPS = 8;
+  const int NPANEL = a.npanel, NST = a.nst, FW = a.fw, LA = a.la;
+  const int ZI_BYTES = NPANEL * kZiRowBytes, ZJ_BYTES = NPANEL * kZjRowBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sZi = smem;
+  uint8_t* sZj = sZi + ZI_BYTES;
+  uint8_t* sW = sZj + NST * ZJ_BYTES;                         // [2][W_BYTES]
+  float* sRecv = reinterpret_cast<float*>(sW + 2 * SM::W_BYTES);  // [2][CS-1][OC][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRecv) + 2 * SM::RECV_BYTES);
+  uint64_t* zj_full = bars;             // [NST]
+  uint64_t* zj_empty = bars + NST;      // [NST]
+  uint64_t* s_full = bars + 2 * NST;    // [3]
+  uint64_t* w_full = s_full + 3;        // [2]  cluster: CS * 4 warp arrivals (all CTAs' W slices landed here)
+  uint64_t* sx_full = w_full + 2;       // [2]  cluster: (CS-1) * 4 warp arrivals (peers' partial S landed here)
+  uint64_t* w_free = sx_full + 2;       // [2]  cluster: CS * 4 warp arrivals (every CTA's UMMA #2 of tile-2 is done)
+  uint64_t* zi_full = w_free + 2;
+  uint64_t* zi_empty = zi_full + 1;
+  uint64_t* o_full = zi_empty + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t me = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x / CS;
+  stage_params(a.kf, sParams);
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&zj_full[i], 1);
+      mbar_init(&zj_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&w_full[i], CS * 4);
+      mbar_init(&sx_full[i], (CS - 1) * 4);
+      mbar_init(&w_free[i], CS * 4);
+    }
+    mbar_init(zi_full, 1);
+    mbar_init(zi_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 256);
+    fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tmap_zi);
+    prefetch_tmap(&tmap_zj);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // every CTA's barriers are initialised before anyone signals remotely
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t pos0 = cluster_id * a.chunk;
+  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  auto rb_of = [&](int64_t rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + (int)rbi : a.rb_y0 + (int)(rbi - a.nrb_x); };
+  const int fcol0 = (int)me * FW;   // first feature column of this CTA's slice
+
+  if (warp == EPI_WARPS) {
+    // ===================== TMA producer =====================
+    uint32_t unit = 0, st = 0, ph = 0;
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      const int rb = rb_of(rbi);
+      mbar_wait(zi_empty, (unit & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
+        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, fcol0 + p * 64, rb * BM);
+      }
+      __syncwarp();
+      for (int t = t0; t < t0 + TU; ++t) {
+        mbar_wait(&zj_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&zj_full[st], ZJ_BYTES);
+          uint8_t* dst = sZj + st * ZJ_BYTES;
+          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * (BNF * 128), &tmap_zj, &zj_full[st], fcol0 + p * 64, t * BNF);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)NST) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      left -= TU;
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ===================== UMMA issuer =====================
+    constexpr uint32_t idesc1 = make_idesc(BM, BNF, kFmtBF16, false, false);
+    const uint32_t idesc2 = make_idesc(BM, (uint32_t)FW, kFmtBF16, false, true);
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
+    const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);
+    const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), BNF * 128);
+    const uint32_t w_lo = desc_lo(smem_u32(sW), 16);               // K-major A operand of UMMA #2
+    const uint32_t stage_step = (uint32_t)ZJ_BYTES >> 4;
+    uint32_t unit = 0;
+    uint32_t st1 = 0, ph1 = 0, sb1 = 0;
+    uint32_t st2 = 0, wb2 = 0, wph2 = 0;
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      mbar_wait(zi_full, unit & 1);
+      for (int jj = 0; jj < TU + LA; ++jj) {
+        const int b2 = jj - LA;
+        if (b2 >= 0) {  // ---- UMMA #2: O[:, slice] += W * Zj[:, slice]   (A = W from shared memory)
+          mbar_wait_cluster(&w_full[wb2], wph2);
+          if (b2 == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
+          fence_proxy_async_all();   // W was written through the generic proxy (partly by peer CTAs)
+          tc_fence_after();
+          const uint32_t blo = zj_lo2 + st2 * stage_step;
+          const uint32_t alo = w_lo + wb2 * (SM::W_BYTES >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < BNF / 16; ++kk)
+              umma_ss2(tmem + TM_O, alo + kk * 2, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&zj_empty[st2]);
+            if (b2 == TU - 1) umma_commit(o_full);
+          }
+          __syncwarp();
+          if (++st2 == (uint32_t)NST) st2 = 0;
+          wph2 ^= wb2;
+          wb2 ^= 1;
+        }
+        if (jj < TU) {  // ---- UMMA #1: partial S over this CTA's feature slice
+          mbar_wait(&zj_full[st1], ph1);
+          tc_fence_after();
+          const uint32_t blo = zj_lo1 + st1 * stage_step;
+          const uint32_t sad = tmem + TM_S + sb1 * 64;
+          if (elect_one()) {
+            for (int p = 0; p < NPANEL; ++p) {
+              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * ((BNF * 128) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+            }
+            umma_commit(&s_full[sb1]);
+            if (jj == TU - 1) umma_commit(zi_empty);
+          }
+          __syncwarp();
+          if (++st1 == (uint32_t)NST) {
+            st1 = 0;
+            ph1 ^= 1;
+          }
+          if (++sb1 == 3) sb1 = 0;
+        }
+      }
+      left -= TU;
+    }
+  } else {
+    // ===================== epilogue groups (8 warps: group = warp / 4, TMEM lane quarter = warp % 4) ==========
+    const int grp = warp >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
+    // shared::cluster addresses of every CTA's buffers of THIS group
+    const uint32_t lW = smem_u32(sW + grp * SM::W_BYTES), lRecv = smem_u32(sRecv) + grp * SM::RECV_BYTES;
+    const uint32_t lWfull = smem_u32(&w_full[grp]), lSx = smem_u32(&sx_full[grp]), lWfree = smem_u32(&w_free[grp]);
+    const float* myRecv = sRecv + grp * (SM::RECV_BYTES / 4);
+    uint32_t unit = 0;
+    int slot = 0;
+    uint32_t par = 0, sb = 0, sph = 0;
+    uint32_t st_m2 = 0, ph_m2 = 0, gcount = 0;
+    uint32_t xph = 0, fph = 0;            // phases of sx_full[grp] / w_free[grp]
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit, ++slot) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      const int rb = rb_of(rbi);
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
+      const float ni = a.norms[gi];
+      float2 rsum = make_float2(0.f, 0.f);
+      double dsame = 0.0, dcross = 0.0;
+      for (int lt = 0; lt < TU; ++lt) {
+        if ((int)par == grp) {
+          const int c0 = (t0 + lt) * BNF;
+          const bool colX = c0 < mp;
+          const bool same = (colX == rowX);
+          const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
+          const int lim = colX ? mvalid : yvalid;
+          const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);
+          const uint32_t s_addr = tmem + TM_S + sb * 64 + lane_base;
+          // (a) this group's buffers of tile-2 are free everywhere: every CTA's UMMA #2 of that tile is done
+          if (gcount >= 2) {
+            mbar_wait(&zj_empty[st_m2], ph_m2);
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int o = 0; o < CS; ++o) mbar_arrive_cluster(map_to_cta(lWfree, o));
+            }
+            mbar_wait_cluster(&w_free[grp], fph);
+            fph ^= 1;
+          }
+          mbar_wait(&s_full[sb], sph);
+          tc_fence_after();
+          // (b) reduce-scatter: send the other CTAs' column ranges of my partial row
+#pragma unroll
+          for (int oo = 1; oo < CS; ++oo) {
+            const int o = (int)((me + oo) % CS);             // destination CTA
+            const int slot_at_o = CS - 1 - oo;                // = (me - o - 1 + CS) % CS
+            const uint32_t dst = map_to_cta(lRecv, o) + (uint32_t)(slot_at_o * OC * BM + r) * 4;
+#pragma unroll
+            for (int c = 0; c < OC; c += 16) {
+              uint32_t v[16];
+              tmem_ld_x16(s_addr + o * OC + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) st_cluster_f32(dst + (uint32_t)((c + e) * BM) * 4, __uint_as_float(v[e]));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int oo = 1; oo < CS; ++oo) mbar_arrive_cluster(map_to_cta(lSx, (me + oo) % CS));
+          }
+          // (c) my columns: own partial + peers' partials -> kernel transform -> W slice
+          mbar_wait_cluster(&sx_full[grp], xph);
+          xph ^= 1;
+          float2 tsum = make_float2(0.f, 0.f);
+          const float* nj = a.norms + c0 + (int)me * OC;
+#pragma unroll
+          for (int c = 0; c < OC; c += 16) {
+            uint32_t v[16], wpk[8];
+            tmem_ld_x16(s_addr + (int)me * OC + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int sl = 0; sl < CS - 1; ++sl) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                v[e] = __float_as_uint(__uint_as_float(v[e]) + myRecv[(sl * OC + c + e) * BM + r]);
+            }
+            if (!special) fused_chunk16<Math, false>(math, v, nj + c, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+            else fused_chunk16<Math, true>(math, v, nj + c, ni, cw, c0 + (int)me * OC + c, lim, gi, tsum, rsum, wpk);
+            // (d) all-gather: 16 bf16 of this row = two 16-B chunks of the K-major SW128 W panel, into every CTA
+            const int j0 = ((int)me * OC + c) >> 3;
+            const uint32_t off0 = (uint32_t)(r * 128 + (((j0) ^ (r & 7)) << 4));
+            const uint32_t off1 = (uint32_t)(r * 128 + (((j0 + 1) ^ (r & 7)) << 4));
+#pragma unroll
+            for (int o = 0; o < CS; ++o) {
+              const uint32_t wb = map_to_cta(lW, o);
+              st_cluster_v4(wb + off0, wpk[0], wpk[1], wpk[2], wpk[3]);
+              st_cluster_v4(wb + off1, wpk[4], wpk[5], wpk[6], wpk[7]);
+            }
+          }
+          fence_proxy_async_all();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int o = 0; o < CS; ++o) mbar_arrive_cluster(map_to_cta(lWfull, o));
+          }
+          if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
+          else dcross += (double)((tsum.x + tsum.y) * kscale);
+        }
+        par ^= 1;
+        if (gcount >= 2) {
+          if (++st_m2 == (uint32_t)NST) {
+            st_m2 = 0;
+            ph_m2 ^= 1;
+          }
+        }
+        ++gcount;
+        if (++sb == 3) {
+          sb = 0;
+          sph ^= 1;
+        }
+      }
+      // ---- unit end: drain this CTA's feature slice of O ----
+      mbar_wait(o_full, unit & 1);
+      tc_fence_after();
+      {
+        const int64_t sl = cluster_id * a.slots + slot;
+        const int seg = FW / 2;   // two groups share the slice (multiple of 32)
+        float* orow = a.Opart + (sl * BM + r) * a.dp + fcol0 + grp * seg;
+        for (int c = 0; c < seg; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem + TM_O + grp * seg + c + lane_base, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+        const int part = (int)me * 2 + grp;
+        a.rpart[(sl * (2 * CS) + part) * BM + r] = rsum.x + rsum.y;
+        double* sp = a.spart + ((sl * (2 * CS) + part) * BM + r) * 2;
+        sp[0] = dsame;
+        sp[1] = dcross;
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+      left -= TU;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // nobody leaves while a peer may still write into its shared memory
+  if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
+}
+
 // ---- finalisation of the fused kernel: reduce slabs, form gradients and per-row stats ---------------
 struct FinRowsArgs {
   KernelFn kf;
@@ -617,6 +977,8 @@ constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
 
 // One warp per row (4 rows per warp): reduce the per-(CTA, slot) slabs in fixed order, form the gradient row
 // with the fp32 z_i, and fold the row's block sums into per-CTA partials (second stage: finalize_partials).
+// NT = 128-feature groups per row: 2 covers dp <= 256 (single-CTA fused kernel), 8 covers the cluster kernel (dp <= 1024).
+template <int NT>
 __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ double sh[8][6];
@@ -657,12 +1019,13 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
     const bool vec = out != nullptr && !dot && sdtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec) {
-      // lane owns features [4 lane + 128 t, +4), t = 0, 1 (dp <= 256)
-      float4 oacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-      float4 z4[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      // lane owns features [4 lane + 128 t, +4), t < NT
+      float4 oacc[NT], z4[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) oacc[t] = z4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* zsrc = reinterpret_cast<const float*>(src) + srow * ld;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const int c = 4 * lane + 128 * t;
         if (c < a.d) z4[t] = *reinterpret_cast<const float4*>(zsrc + c);
       }
@@ -670,7 +1033,7 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
         const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
         const float* orow = a.Opart + (sl * BM + r) * a.dp;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const int c = 4 * lane + 128 * t;
           if (c < a.dp) {
             const float4 o = *reinterpret_cast<const float4*>(orow + c);
@@ -682,7 +1045,7 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
         }
       }
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const int c = 4 * lane + 128 * t;
         if (c < a.d) {
           float zz[4] = {z4[t].x, z4[t].y, z4[t].z, z4[t].w};
@@ -698,23 +1061,23 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
         }
       }
     } else {
-      // general path: lane owns features lane, lane+32, ... (dp <= 256 -> at most 8)
-      float oacc[8];
+      // general path: lane owns features lane, lane+32, ... (at most 4 NT)
+      float oacc[4 * NT];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) oacc[t] = 0.f;
+      for (int t = 0; t < 4 * NT; ++t) oacc[t] = 0.f;
       if (out) {
         for (int64_t g = g0; g <= g1; ++g) {
           const int64_t sl = g * a.slots + (rbi - (g * a.chunk) / a.T);
           const float* orow = a.Opart + (sl * BM + r) * a.dp;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 4 * NT; ++t) {
             const int c = lane + 32 * t;
             if (c < a.dp) oacc[t] += orow[c];
           }
         }
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < 4 * NT; ++t) {
         const int c = lane + 32 * t;
         if (c >= a.d) continue;
         // z_i at full input precision: g_i = 4 sum_j W_ij (z_i - z_j) is dominated by r_i z_i, so rounding
@@ -1257,7 +1620,9 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 struct FusedPlan {
   int64_t mp, np, Mp, dp;
-  int nrb_x, rb_x0, nrb_y, rb_y0, T, grid, slots;
+  int cs;      // CTAs per cluster sharing a row block: 1 (d <= 256), 2 (d <= 512), 4 (d <= 1024)
+  int npart;   // partial row-sum slices per (unit, row)
+  int nrb_x, rb_x0, nrb_y, rb_y0, T, grid, slots;   // grid counts work units = CTAs (cs == 1) or clusters
   int64_t total, chunk;
   size_t off_Z, off_norm, off_csum, off_O, off_r, off_s, off_stats, off_end;
 };
@@ -1269,14 +1634,16 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.mp = round_up(m, BM);
   p.np = round_up(n, BM);
   p.Mp = p.mp + p.np;
-  p.dp = round_up(d, 64);
+  p.cs = d <= 256 ? 1 : (d <= 512 ? 2 : 4);
+  p.dp = round_up(d, 64 * p.cs);
+  p.npart = p.cs == 1 ? 4 : 2 * p.cs;
   p.rb_x0 = (int)(x0 / BM);
   p.nrb_x = x1 > x0 ? (int)((x1 - 1) / BM) - p.rb_x0 + 1 : 0;
   p.rb_y0 = (int)((p.mp + y0) / BM);
   p.nrb_y = y1 > y0 ? (int)((p.mp + y1 - 1) / BM) - p.rb_y0 + 1 : 0;
   p.T = (int)(p.Mp / BNF);
   p.total = (int64_t)(p.nrb_x + p.nrb_y) * p.T;
-  p.grid = (int)std::min<int64_t>(sm_count(), p.total);
+  p.grid = (int)std::min<int64_t>(sm_count() / p.cs, p.total);
   if (p.grid < 1) p.grid = 1;
   p.chunk = (p.total + p.grid - 1) / p.grid;
   p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
@@ -1291,9 +1658,9 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.off_O = o;
   o = up256(o + (size_t)p.grid * p.slots * BM * p.dp * 4);
   p.off_r = o;
-  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 4);
+  o = up256(o + (size_t)p.grid * p.slots * p.npart * BM * 4);
   p.off_s = o;
-  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 2 * 8);
+  o = up256(o + (size_t)p.grid * p.slots * p.npart * BM * 2 * 8);
   p.off_stats = o;
   o = up256(o + (size_t)((x1 - x0) + (y1 - y0)) * RS_COUNT * 8);
   p.off_end = o;
@@ -1325,6 +1692,47 @@ cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap&
     case TV_RQ_GENERIC: return launch_fused_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, grid, s);
     case TV_DISTANCE: return launch_fused_t<MathDistance>(tzi, tzj, a, grid, s);
     case TV_NULL: return launch_fused_t<MathNull>(tzi, tzj, a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <class Math, int CS>
+cudaError_t launch_cluster_k(const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int nclusters,
+                             cudaStream_t s) {
+  const int smem = cluster_smem(a.npanel, a.nst, CS);
+  if (a.nst < 2 || smem > kMaxSmem) return cudaErrorInvalidConfiguration;
+  auto kern = tc_fused_cluster_kernel<Math, CS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nclusters * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tzi, tzj, a);
+}
+template <class Math>
+cudaError_t launch_cluster_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int cs, int nclusters,
+                             cudaStream_t s) {
+  return cs == 2 ? launch_cluster_k<Math, 2>(tzi, tzj, a, nclusters, s) : launch_cluster_k<Math, 4>(tzi, tzj, a, nclusters, s);
+}
+cudaError_t launch_cluster(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int cs,
+                           int nclusters, cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_cluster_t<MathRbf1>(tzi, tzj, a, cs, nclusters, s);
+    case TV_RBF_LADDER5: return launch_cluster_t<MathRbfLadder<5>>(tzi, tzj, a, cs, nclusters, s);
+    case TV_RBF_GENERIC: return launch_cluster_t<MathGeneric<FAM_RBF>>(tzi, tzj, a, cs, nclusters, s);
+    case TV_RQ3_DEFAULT: return launch_cluster_t<MathRq3Default>(tzi, tzj, a, cs, nclusters, s);
+    case TV_RQ_GENERIC: return launch_cluster_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, cs, nclusters, s);
+    case TV_DISTANCE: return launch_cluster_t<MathDistance>(tzi, tzj, a, cs, nclusters, s);
+    case TV_NULL: return launch_cluster_t<MathNull>(tzi, tzj, a, cs, nclusters, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1446,7 +1854,7 @@ void pipe_timing_dump(bool reset) {
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) interface
 // ------------------------------------------------------------------------------------------------
-bool tc_mmd2_supported(int64_t d, int want_grad) { return want_grad ? d <= 256 : d <= 65536; }
+bool tc_mmd2_supported(int64_t d, int want_grad) { return want_grad ? d <= 1024 : d <= 65536; }
 
 static bool tc_family_ok(const KernelFn& kf) {
   return kf.family == FAM_RBF || kf.family == FAM_RQ || kf.family == FAM_DISTANCE;
@@ -1485,9 +1893,9 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
   cudaError_t e;
   const bool want_grad = dX != nullptr;
   if (want_grad) {
-    *path = "tc_bf16_fused";
     const FusedPlan p = fused_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1);
     if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+    *path = p.cs == 1 ? "tc_bf16_fused" : (p.cs == 2 ? "tc_bf16_fused_cluster2" : "tc_bf16_fused_cluster4");
     __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
     float* norms = reinterpret_cast<float*>(w + p.off_norm);
     double* csum = reinterpret_cast<double*>(w + p.off_csum);
@@ -1531,7 +1939,37 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fa.rpart = reinterpret_cast<float*>(w + p.off_r);
     fa.spart = reinterpret_cast<double*>(w + p.off_s);
     prof_begin(s);
-    e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
+    if (p.cs == 1) {
+      e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
+    } else {
+      ClusterArgs ca;
+      ca.kf = kf;
+      ca.m = g.m;
+      ca.n = g.n;
+      ca.mp = p.mp;
+      ca.np = p.np;
+      ca.c_xx = fa.c_xx;
+      ca.c_yy = fa.c_yy;
+      ca.c_xy = fa.c_xy;
+      ca.norms = norms;
+      ca.nrb_x = p.nrb_x;
+      ca.rb_x0 = p.rb_x0;
+      ca.nrb_y = p.nrb_y;
+      ca.rb_y0 = p.rb_y0;
+      ca.T = p.T;
+      ca.dp = (int)p.dp;
+      ca.fw = (int)(p.dp / p.cs);
+      ca.npanel = ca.fw / 64;
+      ca.nst = cluster_stages(ca.npanel, p.cs);
+      ca.la = std::min(3, ca.nst - 1);
+      ca.total_tiles = p.total;
+      ca.chunk = p.chunk;
+      ca.slots = p.slots;
+      ca.Opart = fa.Opart;
+      ca.rpart = fa.rpart;
+      ca.spart = fa.spart;
+      e = launch_cluster(variant, tzi, tzj, ca, p.cs, p.grid, s);
+    }
     prof_end(s);
     if (e != cudaSuccess) return e;
     ++*launches;
@@ -1554,7 +1992,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.T = p.T;
     fr.chunk = p.chunk;
     fr.slots = p.slots;
-    fr.npart = 2 * fa.ksplit;
+    fr.npart = p.cs == 1 ? 2 * fa.ksplit : p.npart;
     fr.a_xx = c.a_xx;
     fr.a_yy = c.a_yy;
     fr.a_xy = c.a_xy;
@@ -1570,7 +2008,8 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.dY = dY;
     fr.partials = reinterpret_cast<double*>(w + p.off_stats);
     const unsigned fin_blocks = (unsigned)((fr.ox + fr.oy + kFinRowsPerCta - 1) / kFinRowsPerCta);
-    tc_finalize_rows_kernel<<<fin_blocks, 256, 0, s>>>(fr);
+    if (p.dp <= 256) tc_finalize_rows_kernel<2><<<fin_blocks, 256, 0, s>>>(fr);
+    else tc_finalize_rows_kernel<8><<<fin_blocks, 256, 0, s>>>(fr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
     e = launch_finalize_partials(kf, g, fr.partials, fin_blocks, scalars, s);

@@ -39,6 +39,11 @@ def _data(m, n, d, seed):
     return X, Y
 
 
+def _fused_path(d):
+    """d <= 256: one CTA per row block; above, 2 or 4 CTAs of a cluster share it."""
+    return "tc_bf16_fused" if d <= 256 else ("tc_bf16_fused_cluster2" if d <= 512 else "tc_bf16_fused_cluster4")
+
+
 def _kscale(name, kw, X, Y):
     n = min(len(X), 256)
     Kxx, Kxy, Kyy, _ = mmd_oracle.kernel_matrices(name, X[:n], Y[:n], np.float64, **kw)
@@ -58,13 +63,70 @@ def test_tc_fused_fwd_bwd_vs_oracle(case, shape):
         Yt = torch.tensor(Y, device=DEV, requires_grad=True)
         loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), biased=biased, precision="bf16")
         loss.backward()
-        assert _lib.last_path() == "tc_bf16_fused"
+        assert _lib.last_path() == _fused_path(d)
         v, gx, gy = mmd_oracle.mmd2_and_grads(name, X, Y, biased, np.float64, **kw)
         floor = 2e-6 * _kscale(name, kw, X, Y)
         assert abs(loss.item() - v) <= 1e-3 * abs(v) + floor, (name, biased, loss.item(), v)
         for got, ref in ((Xt.grad, gx), (Yt.grad, gy)):
             err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
             assert err <= 4e-3 * np.abs(ref).max(), (name, biased, err, np.abs(ref).max())
+
+
+# BASELINE config 4 sweeps d = 256..1024: the cluster kernel (feature-sliced row blocks, partial Gram tiles
+# reduced over distributed shared memory) against the fp64 oracle, ragged sizes included
+WIDE_SHAPES = [(700, 900, 512), (513, 640, 384), (300, 200, 300), (640, 520, 1024), (1100, 1000, 768), (257, 255, 600)]
+WIDE_CASES = [("mix_rq", {}), ("rbf", {}), ("mix_rbf", {"sigmas": [1.0, 2.0, 4.0, 8.0, 16.0]}), ("mix_rq_dot", {}),
+              ("tanh_mix_rq", {}), ("distance", {})]
+
+
+@pytest.mark.parametrize("shape", WIDE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: c[0] + ("+" if c[1] else ""))
+def test_tc_cluster_fwd_bwd_vs_oracle(case, shape):
+    from smmd import _lib, mmd
+
+    name, kw = case
+    m, n, d = shape
+    X, Y = _data(m, n, d, m + n + d)
+    for biased in (False, True):
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), biased=biased, precision="bf16")
+        loss.backward()
+        assert _lib.last_path() == _fused_path(d)
+        v, gx, gy = mmd_oracle.mmd2_and_grads(name, X, Y, biased, np.float64, **kw)
+        floor = 2e-6 * _kscale(name, kw, X, Y)
+        assert abs(loss.item() - v) <= 1e-3 * abs(v) + floor, (name, biased, loss.item(), v)   # bf16 TC tolerance
+        for got, ref in ((Xt.grad, gx), (Yt.grad, gy)):
+            err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
+            assert err <= 4e-3 * np.abs(ref).max(), (name, biased, err, np.abs(ref).max())
+
+
+def test_tc_cluster_long_stream_and_shards():
+    """Several row-block units per cluster (ring phases wrap many times) and rank/world row shards at d = 512."""
+    from smmd import _lib, mmd
+
+    X, Y = _data(5000, 4600, 512, 77)
+    Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+    spec = mmd._mix_rq_kernel(Xt, Yt).spec
+    full, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert _lib.last_path() == "tc_bf16_fused_cluster2"
+    ref, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
+    assert abs(full[_lib.S_MMD2].item() - ref[_lib.S_MMD2].item()) <= 1e-3 * abs(ref[_lib.S_MMD2].item())
+    assert (gX - rX).abs().max() <= 4e-3 * rX.abs().max()
+    assert (gY - rY).abs().max() <= 4e-3 * rY.abs().max()
+    full2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert torch.equal(gX, gX2) and torch.equal(gY, gY2) and torch.equal(full, full2)   # deterministic
+    world = 3
+    acc = torch.zeros_like(full)
+    for rank in range(world):
+        sc, dX, dY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16", rank=rank, world=world)
+        acc += sc
+        x0, x1 = 5000 * rank // world, 5000 * (rank + 1) // world
+        y0, y1 = 4600 * rank // world, 4600 * (rank + 1) // world
+        assert (dX - gX[x0:x1]).abs().max() <= 1e-5 * gX.abs().max()
+        assert (dY - gY[y0:y1]).abs().max() <= 1e-5 * gY.abs().max()
+    for i in (_lib.S_SUM_XX, _lib.S_SUM_YY, _lib.S_SUM_XY, _lib.S_SUM_YX):
+        assert abs(acc[i].item() - full[i].item()) <= 1e-9 * abs(full[i].item())
 
 
 @pytest.mark.parametrize("name,kw", [("rbf", {}), ("mix_rq", {}), ("distance", {}),
@@ -97,12 +159,16 @@ def test_auto_precision_dispatch_and_refusals():
     assert _lib.last_path() == "simt_fp32"
     with pytest.raises(_lib.SmmdError):                             # explicit request that cannot be honoured
         mmd.mmd2(mmd._dot_kernel(Xt, Yt), precision="bf16")
-    Xw, Yw = _data(512, 512, 300, 3)
+    Xw, Yw = _data(512, 512, 1100, 3)
     Xt, Yt = torch.tensor(Xw, device=DEV, requires_grad=True), torch.tensor(Yw, device=DEV, requires_grad=True)
-    with pytest.raises(_lib.SmmdError):                             # fused backward needs d <= 256
+    with pytest.raises(_lib.SmmdError):                             # fused backward needs d <= 1024
         mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt), precision="bf16").backward()
     mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # AUTO falls back to the exact path
     assert _lib.last_path() == "simt_fp32"
+    Xw, Yw = _data(512, 512, 300, 3)
+    Xt, Yt = torch.tensor(Xw, device=DEV, requires_grad=True), torch.tensor(Yw, device=DEV, requires_grad=True)
+    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # AUTO: 256 < d <= 1024 -> cluster kernel
+    assert _lib.last_path() == "tc_bf16_fused_cluster2"
 
 
 def test_row_shards_compose_to_single_gpu_result():
