@@ -41,6 +41,8 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 struct Tuning {
   int fused_ksplit;
   int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
+  int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
+  int64_t wz_panel_bytes;   // byte budget of one W row panel
 };
 const Tuning& tuning() {
   static Tuning t = [] {
@@ -48,6 +50,10 @@ const Tuning& tuning() {
     v.fused_ksplit = 2;
     if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
     v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
+    v.wz_min_d = 256;
+    if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
+    v.wz_panel_bytes = (int64_t)4 << 30;
+    if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
     return v;
   }();
   return t;
@@ -589,366 +595,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
 }
 
-// ================================================================================================
-// cluster variant of the fused kernel: 256 < d <= 1024
-// ================================================================================================
-// O (128 x d fp32) no longer fits one SM's TMEM next to S, so CS = 2 or 4 CTAs of a thread-block cluster share
-// one row block.  CTA c holds the feature slice [c*FW, (c+1)*FW) of Z_i (resident), of the Z_j ring and of O.
-// Per 64-column tile:
-//   1. UMMA #1 (every CTA): partial S_c = Z_i[:, slice c] Z_j[:, slice c]^T                     (TMEM)
-//   2. reduce-scatter over DSMEM: CTA c owns columns [c*64/CS, (c+1)*64/CS) of the tile; every epilogue thread
-//      (= one row) sends the other CTAs' column ranges of its partial row into their receive buffers
-//      (st.shared::cluster, lane-contiguous [col][row] layout) and signals their mbarrier;
-//   3. the owner adds the partials, runs the kernel transform on ITS columns only (1/CS of the epilogue math per
-//      CTA -- this is what makes large d tensor-bound), accumulates tile / row sums for those columns, and
-//   4. all-gathers its W slice (bf16) into EVERY CTA's W panel (K-major SW128 shared-memory tile);
-//   5. UMMA #2 (every CTA, SS form): O[:, slice c] += W Z_j[:, slice c].
-// Buffer reuse across tiles is guarded by one cluster-wide "W buffer free" barrier per epilogue group.
-struct ClusterArgs {
-  KernelFn kf;
-  int64_t m, n, mp, np;
-  float c_xx, c_yy, c_xy;
-  const float* norms;
-  int nrb_x, rb_x0, nrb_y, rb_y0;
-  int T;
-  int dp, fw, npanel, nst, la;   // fw = feature slice per CTA, npanel = fw/64, la = UMMA #1 look-ahead (tiles)
-  int64_t total_tiles, chunk;    // per cluster
-  int slots;
-  float* Opart;                  // [ncluster][slots][128][dp]
-  float* rpart;                  // [ncluster][slots][2*CS][128]
-  double* spart;                 // [ncluster][slots][2*CS][128][2]
-};
-
-template <int CS>
-struct ClusterSmem {
-  static constexpr int OC = BNF / CS;                              // tile columns owned by one CTA
-  static constexpr int W_BYTES = BM * 128;                         // one K-major SW128 panel: 128 rows x 64 bf16
-  static constexpr int RECV_BYTES = (CS - 1) * OC * BM * 4;        // [peer slot][col][row] fp32
-};
-
-inline int cluster_stages(int npanel, int cs) {
-  const int recv = (cs - 1) * (BNF / cs) * BM * 4;
-  int nst = (kMaxSmem - 1024 - 1024 - npanel * kZiRowBytes - 2 * BM * 128 - 2 * recv) / (npanel * kZjRowBytes);
-  return nst > 6 ? 6 : nst;
-}
-inline int cluster_smem(int npanel, int nst, int cs) {
-  const int recv = (cs - 1) * (BNF / cs) * BM * 4;
-  return 1024 + npanel * kZiRowBytes + nst * npanel * kZjRowBytes + 2 * BM * 128 + 2 * recv + 1024;
-}
-
-template <class Math, int CS>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_fused_cluster_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
-                        const __grid_constant__ ClusterArgs a) {
-  using SM = ClusterSmem<CS>;
-  constexpr int OC = SM::OC;
-  constexpr int EPI_WARPS = 8;
-  const int NPANEL = a.npanel, NST = a.nst, FW = a.fw, LA = a.la;
-  const int ZI_BYTES = NPANEL * kZiRowBytes, ZJ_BYTES = NPANEL * kZjRowBytes;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sZi = smem;
-  uint8_t* sZj = sZi + ZI_BYTES;
-  uint8_t* sW = sZj + NST * ZJ_BYTES;                         // [2][W_BYTES]
-  float* sRecv = reinterpret_cast<float*>(sW + 2 * SM::W_BYTES);  // [2][CS-1][OC][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRecv) + 2 * SM::RECV_BYTES);
-  uint64_t* zj_full = bars;             // [NST]
-  uint64_t* zj_empty = bars + NST;      // [NST]
-  uint64_t* s_full = bars + 2 * NST;    // [3]
-  uint64_t* w_full = s_full + 3;        // [2]  cluster: CS * 4 warp arrivals (all CTAs' W slices landed here)
-  uint64_t* sx_full = w_full + 2;       // [2]  cluster: (CS-1) * 4 warp arrivals (peers' partial S landed here)
-  uint64_t* w_free = sx_full + 2;       // [2]  cluster: CS * 4 warp arrivals (every CTA's UMMA #2 of tile-2 is done)
-  uint64_t* zi_full = w_free + 2;
-  uint64_t* zi_empty = zi_full + 1;
-  uint64_t* o_full = zi_empty + 1;
-  uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
-  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t me = cluster_ctarank();
-  const int64_t cluster_id = blockIdx.x / CS;
-  stage_params(a.kf, sParams);
-  if (tid == 0) {
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(&zj_full[i], 1);
-      mbar_init(&zj_empty[i], 1);
-    }
-    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&w_full[i], CS * 4);
-      mbar_init(&sx_full[i], (CS - 1) * 4);
-      mbar_init(&w_free[i], CS * 4);
-    }
-    mbar_init(zi_full, 1);
-    mbar_init(zi_empty, 1);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
-    fence_mbar_init();
-  }
-  if (warp == EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
-  if (warp == EPI_WARPS && lane == 0) {
-    prefetch_tmap(&tmap_zi);
-    prefetch_tmap(&tmap_zj);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();   // every CTA's barriers are initialised before anyone signals remotely
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  const int64_t pos0 = cluster_id * a.chunk;
-  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
-  auto rb_of = [&](int64_t rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + (int)rbi : a.rb_y0 + (int)(rbi - a.nrb_x); };
-  const int fcol0 = (int)me * FW;   // first feature column of this CTA's slice
-
-  if (warp == EPI_WARPS) {
-    // ===================== TMA producer =====================
-    uint32_t unit = 0, st = 0, ph = 0;
-    int rbi = (int)(pos0 / a.T);
-    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
-    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
-      const int TU = (int)std::min<int64_t>(a.T - t0, left);
-      const int rb = rb_of(rbi);
-      mbar_wait(zi_empty, (unit & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
-        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, fcol0 + p * 64, rb * BM);
-      }
-      __syncwarp();
-      for (int t = t0; t < t0 + TU; ++t) {
-        mbar_wait(&zj_empty[st], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&zj_full[st], ZJ_BYTES);
-          uint8_t* dst = sZj + st * ZJ_BYTES;
-          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * (BNF * 128), &tmap_zj, &zj_full[st], fcol0 + p * 64, t * BNF);
-        }
-        __syncwarp();
-        if (++st == (uint32_t)NST) {
-          st = 0;
-          ph ^= 1;
-        }
-      }
-      left -= TU;
-    }
-  } else if (warp == EPI_WARPS + 1) {
-    // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc(BM, BNF, kFmtBF16, false, false);
-    const uint32_t idesc2 = make_idesc(BM, (uint32_t)FW, kFmtBF16, false, true);
-    const uint32_t hi = desc_hi_sw128(1024);
-    const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
-    const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);
-    const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), BNF * 128);
-    const uint32_t w_lo = desc_lo(smem_u32(sW), 16);               // K-major A operand of UMMA #2
-    const uint32_t stage_step = (uint32_t)ZJ_BYTES >> 4;
-    uint32_t unit = 0;
-    uint32_t st1 = 0, ph1 = 0, sb1 = 0;
-    uint32_t st2 = 0, wb2 = 0, wph2 = 0;
-    int rbi = (int)(pos0 / a.T);
-    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
-    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
-      const int TU = (int)std::min<int64_t>(a.T - t0, left);
-      mbar_wait(zi_full, unit & 1);
-      for (int jj = 0; jj < TU + LA; ++jj) {
-        const int b2 = jj - LA;
-        if (b2 >= 0) {  // ---- UMMA #2: O[:, slice] += W * Zj[:, slice]   (A = W from shared memory)
-          mbar_wait_cluster(&w_full[wb2], wph2);
-          if (b2 == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
-          fence_proxy_async_all();   // W was written through the generic proxy (partly by peer CTAs)
-          tc_fence_after();
-          const uint32_t blo = zj_lo2 + st2 * stage_step;
-          const uint32_t alo = w_lo + wb2 * (SM::W_BYTES >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < BNF / 16; ++kk)
-              umma_ss2(tmem + TM_O, alo + kk * 2, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(&zj_empty[st2]);
-            if (b2 == TU - 1) umma_commit(o_full);
-          }
-          __syncwarp();
-          if (++st2 == (uint32_t)NST) st2 = 0;
-          wph2 ^= wb2;
-          wb2 ^= 1;
-        }
-        if (jj < TU) {  // ---- UMMA #1: partial S over this CTA's feature slice
-          mbar_wait(&zj_full[st1], ph1);
-          tc_fence_after();
-          const uint32_t blo = zj_lo1 + st1 * stage_step;
-          const uint32_t sad = tmem + TM_S + sb1 * 64;
-          if (elect_one()) {
-            for (int p = 0; p < NPANEL; ++p) {
-              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * ((BNF * 128) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
-            }
-            umma_commit(&s_full[sb1]);
-            if (jj == TU - 1) umma_commit(zi_empty);
-          }
-          __syncwarp();
-          if (++st1 == (uint32_t)NST) {
-            st1 = 0;
-            ph1 ^= 1;
-          }
-          if (++sb1 == 3) sb1 = 0;
-        }
-      }
-      left -= TU;
-    }
-  } else {
-    // ===================== epilogue groups (8 warps: group = warp / 4, TMEM lane quarter = warp % 4) ==========
-    const int grp = warp >> 2;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const Math math(a.kf, sParams);
-    const float kscale = math.k_scale(), kdscale = math.kd_scale();
-    // shared::cluster addresses of every CTA's buffers of THIS group
-    const uint32_t lW = smem_u32(sW + grp * SM::W_BYTES), lRecv = smem_u32(sRecv) + grp * SM::RECV_BYTES;
-    const uint32_t lWfull = smem_u32(&w_full[grp]), lSx = smem_u32(&sx_full[grp]), lWfree = smem_u32(&w_free[grp]);
-    const float* myRecv = sRecv + grp * (SM::RECV_BYTES / 4);
-    uint32_t unit = 0;
-    int slot = 0;
-    uint32_t par = 0, sb = 0, sph = 0;
-    uint32_t st_m2 = 0, ph_m2 = 0, gcount = 0;
-    uint32_t xph = 0, fph = 0;            // phases of sx_full[grp] / w_free[grp]
-    int rbi = (int)(pos0 / a.T);
-    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
-    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
-    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit, ++slot) {
-      const int TU = (int)std::min<int64_t>(a.T - t0, left);
-      const int rb = rb_of(rbi);
-      const int gi = rb * BM + r;
-      const bool rowX = gi < mp;
-      const float ni = a.norms[gi];
-      float2 rsum = make_float2(0.f, 0.f);
-      double dsame = 0.0, dcross = 0.0;
-      for (int lt = 0; lt < TU; ++lt) {
-        if ((int)par == grp) {
-          const int c0 = (t0 + lt) * BNF;
-          const bool colX = c0 < mp;
-          const bool same = (colX == rowX);
-          const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
-          const int lim = colX ? mvalid : yvalid;
-          const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);
-          const uint32_t s_addr = tmem + TM_S + sb * 64 + lane_base;
-          // (a) this group's buffers of tile-2 are free everywhere: every CTA's UMMA #2 of that tile is done
-          if (gcount >= 2) {
-            mbar_wait(&zj_empty[st_m2], ph_m2);
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-              for (int o = 0; o < CS; ++o) mbar_arrive_cluster(map_to_cta(lWfree, o));
-            }
-            mbar_wait_cluster(&w_free[grp], fph);
-            fph ^= 1;
-          }
-          mbar_wait(&s_full[sb], sph);
-          tc_fence_after();
-          // (b) reduce-scatter: send the other CTAs' column ranges of my partial row
-#pragma unroll
-          for (int oo = 1; oo < CS; ++oo) {
-            const int o = (int)((me + oo) % CS);             // destination CTA
-            const int slot_at_o = CS - 1 - oo;                // = (me - o - 1 + CS) % CS
-            const uint32_t dst = map_to_cta(lRecv, o) + (uint32_t)(slot_at_o * OC * BM + r) * 4;
-#pragma unroll
-            for (int c = 0; c < OC; c += 16) {
-              uint32_t v[16];
-              tmem_ld_x16(s_addr + o * OC + c, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 16; ++e) st_cluster_f32(dst + (uint32_t)((c + e) * BM) * 4, __uint_as_float(v[e]));
-            }
-          }
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int oo = 1; oo < CS; ++oo) mbar_arrive_cluster(map_to_cta(lSx, (me + oo) % CS));
-          }
-          // (c) my columns: own partial + peers' partials -> kernel transform -> W slice
-          mbar_wait_cluster(&sx_full[grp], xph);
-          xph ^= 1;
-          float2 tsum = make_float2(0.f, 0.f);
-          const float* nj = a.norms + c0 + (int)me * OC;
-#pragma unroll
-          for (int c = 0; c < OC; c += 16) {
-            uint32_t v[16], wpk[8];
-            tmem_ld_x16(s_addr + (int)me * OC + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int sl = 0; sl < CS - 1; ++sl) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                v[e] = __float_as_uint(__uint_as_float(v[e]) + myRecv[(sl * OC + c + e) * BM + r]);
-            }
-            if (!special) fused_chunk16<Math, false>(math, v, nj + c, ni, cw, 0, 0, 0, tsum, rsum, wpk);
-            else fused_chunk16<Math, true>(math, v, nj + c, ni, cw, c0 + (int)me * OC + c, lim, gi, tsum, rsum, wpk);
-            // (d) all-gather: 16 bf16 of this row = two 16-B chunks of the K-major SW128 W panel, into every CTA
-            const int j0 = ((int)me * OC + c) >> 3;
-            const uint32_t off0 = (uint32_t)(r * 128 + (((j0) ^ (r & 7)) << 4));
-            const uint32_t off1 = (uint32_t)(r * 128 + (((j0 + 1) ^ (r & 7)) << 4));
-#pragma unroll
-            for (int o = 0; o < CS; ++o) {
-              const uint32_t wb = map_to_cta(lW, o);
-              st_cluster_v4(wb + off0, wpk[0], wpk[1], wpk[2], wpk[3]);
-              st_cluster_v4(wb + off1, wpk[4], wpk[5], wpk[6], wpk[7]);
-            }
-          }
-          fence_proxy_async_all();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int o = 0; o < CS; ++o) mbar_arrive_cluster(map_to_cta(lWfull, o));
-          }
-          if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
-          else dcross += (double)((tsum.x + tsum.y) * kscale);
-        }
-        par ^= 1;
-        if (gcount >= 2) {
-          if (++st_m2 == (uint32_t)NST) {
-            st_m2 = 0;
-            ph_m2 ^= 1;
-          }
-        }
-        ++gcount;
-        if (++sb == 3) {
-          sb = 0;
-          sph ^= 1;
-        }
-      }
-      // ---- unit end: drain this CTA's feature slice of O ----
-      mbar_wait(o_full, unit & 1);
-      tc_fence_after();
-      {
-        const int64_t sl = cluster_id * a.slots + slot;
-        const int seg = FW / 2;   // two groups share the slice (multiple of 32)
-        float* orow = a.Opart + (sl * BM + r) * a.dp + fcol0 + grp * seg;
-        for (int c = 0; c < seg; c += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(tmem + TM_O + grp * seg + c + lane_base, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        }
-        const int part = (int)me * 2 + grp;
-        a.rpart[(sl * (2 * CS) + part) * BM + r] = rsum.x + rsum.y;
-        double* sp = a.spart + ((sl * (2 * CS) + part) * BM + r) * 2;
-        sp[0] = dsame;
-        sp[1] = dcross;
-      }
-      tc_fence_before();
-      mbar_arrive(o_empty);
-      left -= TU;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();   // nobody leaves while a peer may still write into its shared memory
-  if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
-}
-
 // ---- finalisation of the fused kernel: reduce slabs, form gradients and per-row stats ---------------
 struct FinRowsArgs {
   KernelFn kf;
@@ -977,9 +623,8 @@ constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
 
 // One warp per row (4 rows per warp): reduce the per-(CTA, slot) slabs in fixed order, form the gradient row
 // with the fp32 z_i, and fold the row's block sums into per-CTA partials (second stage: finalize_partials).
-// NT = 128-feature groups per row: 2 covers dp <= 256 (single-CTA fused kernel), 8 covers the cluster kernel (dp <= 1024).
-template <int NT>
 __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
+  constexpr int NT = 2;   // 128-feature groups per row: dp <= 256
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ double sh[8][6];
   double q[6] = {0, 0, 0, 0, 0, 0};  // sxx, syy, sxy, syx, dgx, dgy of this warp's rows
@@ -1618,11 +1263,448 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// ================================================================================================
+// two-pass path for wide features (d > 256): W = A o k'(D) materialised per row panel, then O = W Z as a GEMM
+// ================================================================================================
+// The fused kernel keeps O (128 x d fp32) in tensor memory, which caps it at d = 256.  A thread-block-cluster
+// variant (feature-sliced O, partial Gram tiles reduce-scattered and W all-gathered over distributed shared
+// memory) was built and measured first: correct, but shared memory left only a 2-3 stage TMA ring next to the
+// exchange buffers and it reached 23% (d = 512) / 6% (d = 1024) of peak (profiles/r01_cluster_*.log).
+// The two-pass path below reaches 42% / 51% and has no upper limit on d:
+//   pass 1 (tc_wgen_kernel):  128 x 128 tiles of S = Z_i Z_j^T with K streamed through a 6-stage TMA ring (both
+//          operands), epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
+//          buffer W[panel rows][Mp] (K-major for pass 2).  The panel is sized by a byte budget (default 4 GB), so
+//          the N x N matrix never exists as a whole; panels run back to back on the stream.
+//   pass 2 (tc_wz_kernel):    O[256 rows x 256 features] = W[256 x Mp] Z[Mp x 256]: 2 x 128-row A panels and one
+//          64-row MN-major Z tile per 64-deep K step (64 KB / 1024 tensor cycles, the macro-tile ratio), all 512
+//          TMEM columns as accumulators, K split S ways per unit so that units * S fills the SMs; partial tiles go
+//          to slabs and are reduced in fixed order by the finalize kernel (deterministic).
+//   finalize (wz_finalize_rows_kernel): g_i = r_i z_i - O_i (+ closed-form dot term), block sums.
+struct WgenArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np;
+  float c_xx, c_yy, c_xy;
+  const float* norms;
+  int nrb_x, rb_x0, nrb_y, rb_y0;   // owned row blocks (as FusedArgs)
+  int rbi0;                         // first owned row block (flat index) of this panel
+  int CT;                           // 128-column tiles per row block
+  int nkp;                          // 64-feature panels
+  int64_t total_tiles, chunk;
+  int slots;
+  __nv_bfloat16* W;                 // [panel row blocks * 128][ldw]
+  int64_t ldw;
+  float* rpart;                     // [grid][slots][2][128]
+  double* spart;                    // [grid][slots][2][128][2]
+};
+
+template <class Math>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WgenArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStreamStages;
+  uint64_t* acc_full = empty + kStreamStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
+  if (tid == 0) {
+    for (int i = 0; i < kStreamStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<256>(tmem_slot);
+  if (warp == 8 && lane == 0) prefetch_tmap(&tmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
+  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  auto rb_of = [&](int rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + rbi : a.rb_y0 + (rbi - a.nrb_x); };
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    uint32_t st = 0, ph = 0;
+    int rbl = (int)(pos0 / a.CT);
+    int ct = (int)(pos0 - (int64_t)rbl * a.CT);
+    for (int64_t pos = pos0; pos < pos1; ++pos) {
+      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = ct * BNS;
+      for (int p = 0; p < a.nkp; ++p) {
+        mbar_wait(&empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
+          uint8_t* sa = smem + st * kStreamStageBytes;
+          tma_load_2d(sa, &tmap, &full[st], p * 64, arow);
+          tma_load_2d(sa + BM * 128, &tmap, &full[st], p * 64, brow);
+        }
+        __syncwarp();
+        if (++st == kStreamStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      if (++ct == a.CT) {
+        ct = 0;
+        ++rbl;
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== UMMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BM, BNS, kFmtBF16, false, false);
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+    uint32_t st = 0, ph = 0, ab = 0, aph = 0;
+    for (int64_t pos = pos0; pos < pos1; ++pos) {
+      mbar_wait(&acc_empty[ab], aph ^ 1);
+      tc_fence_after();
+      const uint32_t dad = tmem + ab * BNS;
+      for (int kk = 0; kk < a.nkp; ++kk) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t alo = a_lo0 + st * (kStreamStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
+          umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        if (++st == kStreamStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&acc_full[ab]);
+      __syncwarp();
+      aph ^= ab;
+      ab ^= 1;
+    }
+  } else {
+    // ===================== epilogue groups: tile parity = group =====================
+    const int grp = warp >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
+    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    int rbl = (int)(pos0 / a.CT);
+    int ct0 = (int)(pos0 - (int64_t)rbl * a.CT);
+    uint32_t tc = 0;   // tiles of this CTA so far (parity = accumulator buffer = group)
+    int slot = 0;
+    for (int64_t left = pos1 - pos0; left > 0; ++rbl, ct0 = 0, ++slot) {
+      const int TU = (int)std::min<int64_t>(a.CT - ct0, left);
+      const int rb = rb_of(a.rbi0 + rbl);
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
+      const float ni = a.norms[gi];
+      float2 rsum = make_float2(0.f, 0.f);
+      double dsame = 0.0, dcross = 0.0;
+      __nv_bfloat16* wrow = a.W + ((int64_t)rbl * BM + r) * a.ldw;
+      for (int lt = 0; lt < TU; ++lt, ++tc) {
+        if ((int)(tc & 1) != grp) continue;
+        const int ct = ct0 + lt;
+        const int c0 = ct * BNS;
+        const bool colX = c0 < mp;
+        const bool same = (colX == rowX);
+        const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
+        const int lim = colX ? mvalid : yvalid;
+        const bool special = (c0 + BNS > lim) || (ct == rb);
+        mbar_wait(&acc_full[grp], (tc >> 1) & 1);
+        tc_fence_after();
+        const float* nj = a.norms + c0;
+        float2 tsum = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int h = 0; h < BNS / 16; ++h) {
+          uint32_t v[16], wpk[8];
+          tmem_ld_x16(tmem + grp * BNS + h * 16 + lane_base, v);
+          tmem_ld_wait();
+          if (h == BNS / 16 - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[grp]);
+          }
+          if (!special) fused_chunk16<Math, false>(math, v, nj + h * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+          else fused_chunk16<Math, true>(math, v, nj + h * 16, ni, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
+          uint4* dst = reinterpret_cast<uint4*>(wrow + c0 + h * 16);
+          dst[0] = make_uint4(wpk[0], wpk[1], wpk[2], wpk[3]);
+          dst[1] = make_uint4(wpk[4], wpk[5], wpk[6], wpk[7]);
+        }
+        if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
+        else dcross += (double)((tsum.x + tsum.y) * kscale);
+      }
+      const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
+      a.rpart[(sl * 2 + grp) * BM + r] = rsum.x + rsum.y;
+      double* sp = a.spart + ((sl * 2 + grp) * BM + r) * 2;
+      sp[0] = dsame;
+      sp[1] = dcross;
+      left -= TU;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<256>(tmem);
+}
+
+// ---- pass 2: O = W Z ----
+constexpr int kWzStages = 3;
+constexpr int kWzStageBytes = 2 * BM * 128 + 4 * BNF * 128;   // two 128-row W panels + four 64-feature Z panels = 64 KB
+constexpr int kWzSmem = 1024 + kWzStages * kWzStageBytes + 1024;
+
+struct WzArgs {
+  int nmb;        // 256-row macro blocks of the panel
+  int FB;         // 256-feature blocks
+  int dp;         // padded feature count (multiple of 64)
+  int KT;         // K steps of 64 (= Mp / 64)
+  int S;          // K splits per unit
+  int ksteps;     // K steps per piece
+  float* Opart;   // [unit = mb * FB + fb][S][256][256]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wz_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_z,
+             const __grid_constant__ WzArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWzStages * kWzStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWzStages;
+  uint64_t* acc_full = empty + kWzStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kWzStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_z);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // piece = (split s, unit u), s-major so that one wave of CTAs walks the same rows of Z (L2 reuse)
+  const int units = a.nmb * a.FB;
+  const int s = (int)blockIdx.x / units;
+  const int u = (int)blockIdx.x - s * units;
+  const int mb = u / a.FB, fb = u - mb * a.FB;
+  const int k0 = s * a.ksteps;
+  const int k1 = k0 + a.ksteps < a.KT ? k0 + a.ksteps : a.KT;
+  const int nf = a.dp - fb * 256 < 256 ? a.dp - fb * 256 : 256;   // features of this block (multiple of 64)
+  const int npan = nf / 64;
+
+  if (warp == 8) {
+    uint32_t st = 0, ph = 0;
+    for (int ks = k0; ks < k1; ++ks) {
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[st], 2 * BM * 128 + npan * BNF * 128);
+        uint8_t* sa = smem + st * kWzStageBytes;
+        tma_load_2d(sa, &tmap_w, &full[st], ks * 64, mb * 256);
+        tma_load_2d(sa + BM * 128, &tmap_w, &full[st], ks * 64, mb * 256 + BM);
+        uint8_t* sb = sa + 2 * BM * 128;
+        for (int p = 0; p < npan; ++p) tma_load_2d(sb + p * (BNF * 128), &tmap_z, &full[st], fb * 256 + p * 64, ks * 64);
+      }
+      __syncwarp();
+      if (++st == kWzStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 9) {
+    const uint32_t idesc = make_idesc(BM, (uint32_t)nf, kFmtBF16, false, true);   // B = Z tile, MN-major
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem + 2 * BM * 128), BNF * 128);
+    uint32_t st = 0, ph = 0;
+    for (int ks = k0; ks < k1; ++ks) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t alo = a_lo0 + st * (kWzStageBytes >> 4), blo = b_lo0 + st * (kWzStageBytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss2(tmem + h * 256, alo + h * ((BM * 128) >> 4) + k * 2, blo + k * (2048 >> 4), hi, idesc,
+                     (ks > k0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+        if (ks == k1 - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++st == kWzStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // drain: warp -> (row half, TMEM lane quarter); each thread stores its row of the partial tile
+    const int half = warp >> 2, q = warp & 3;
+    const int row = half * BM + q * 32 + lane;
+    float* orow = a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
+    if (k1 > k0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t base = tmem + half * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < nf; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(base + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+    } else {
+      for (int c = 0; c < nf; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// ---- finalize of the two-pass path (one panel): warp per row, lanes over features ----
+struct WzFinArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np, d;
+  int64_t x0, ox, y0, oy;
+  int dp;
+  int nrb_x, rb_x0, nrb_y, rb_y0;
+  int rbi0, nrb_p;           // panel: first owned row block (flat) / count
+  int CT;                    // pass-1 tiles per row block
+  int64_t chunk;             // pass-1 tiles per CTA
+  int slots;
+  int FB, S;                 // pass-2 feature blocks / K splits
+  double a_xx, a_yy, a_xy;
+  SrcLayout src;
+  const float* norms;
+  const double* csum;
+  const float* Opart;
+  const float* rpart;
+  const double* spart;
+  float* dX;
+  float* dY;
+  double* partials;          // [gridDim.x][6] of this panel
+};
+
+__global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double sh[8][6];
+  double q[6] = {0, 0, 0, 0, 0, 0};
+  const bool dot = a.kf.family == FAM_RQ && a.kf.add_dot > 0.f && a.csum != nullptr;
+  for (int rr = 0; rr < kFinRowsPerWarp; ++rr) {
+    const int64_t lr = ((int64_t)blockIdx.x * 8 + warp) * kFinRowsPerWarp + rr;   // row of the panel
+    if (lr >= (int64_t)a.nrb_p * BM) break;
+    const int rbl = (int)(lr / BM), r = (int)(lr % BM);
+    const int rbi = a.rbi0 + rbl;
+    const int rb = rbi < a.nrb_x ? a.rb_x0 + rbi : a.rb_y0 + (rbi - a.nrb_x);
+    const int64_t gi = (int64_t)rb * BM + r;
+    const bool rowX = gi < a.mp;
+    const int64_t li = rowX ? gi : gi - a.mp;
+    if (rowX ? (li < a.x0 || li >= a.x0 + a.ox) : (li < a.y0 || li >= a.y0 + a.oy)) continue;   // not owned / padding
+    // pass-1 slabs of this row block
+    const int64_t f0 = (int64_t)rbl * a.CT, f1 = f0 + a.CT - 1;
+    const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
+    float rs = 0.f;
+    double ssame = 0.0, scross = 0.0;
+    for (int64_t g = g0; g <= g1; ++g) {
+      const int64_t sl = g * a.slots + (rbl - (g * a.chunk) / a.CT);
+      for (int pt = 0; pt < 2; ++pt) {
+        rs += a.rpart[(sl * 2 + pt) * BM + r];
+        const double* sp = a.spart + ((sl * 2 + pt) * BM + r) * 2;
+        ssame += sp[0];
+        scross += sp[1];
+      }
+    }
+    const double a_same = rowX ? a.a_xx : a.a_yy;
+    double dsame = 0.0, dcross = 0.0;
+    float* out = nullptr;
+    if (a.dX) out = rowX ? a.dX + (li - a.x0) * a.d : a.dY + (li - a.y0) * a.d;
+    const bool owned = (rowX ? a.src.Xo : a.src.Yo) != nullptr;
+    const void* src = owned ? static_cast<const void*>(rowX ? a.src.Xo : a.src.Yo) : (rowX ? a.src.X : a.src.Y);
+    const int64_t ld = owned ? a.src.ldo : (rowX ? a.src.ldx : a.src.ldy);
+    const int sdtype = owned ? (int)SMMD_F32 : a.src.dtype;
+    const int64_t srow = owned ? (rowX ? li - a.x0 : li - a.y0) : src_row(li, rowX, a.src.blk_x, a.src.blk_y);
+    const int mbl = rbl >> 1;                 // macro block of the panel, row inside it
+    const int row256 = (rbl & 1) * BM + r;
+    for (int c = lane; c < a.d; c += 32) {
+      const int fb = c >> 8, cc = c & 255;
+      float o = 0.f;
+      if (out) {
+        const float* op = a.Opart + ((((int64_t)mbl * a.FB + fb) * a.S) * 256 + row256) * 256 + cc;
+        for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 256 * 256];   // fixed order
+      }
+      const int64_t sidx = srow * ld + c;
+      float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+                                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
+      if (a.kf.tanh_features) z = tanhf(z);
+      if (out) {
+        float gv = rs * z - o;
+        if (dot) {
+          const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
+          gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
+        }
+        if (a.kf.tanh_features) gv *= (1.f - z * z);
+        out[c] = gv;
+      }
+      if (dot) {
+        dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
+        dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+      }
+    }
+    if (dot) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsame += __shfl_xor_sync(0xffffffffu, dsame, o);
+        dcross += __shfl_xor_sync(0xffffffffu, dcross, o);
+      }
+    }
+    const float ni = a.norms[gi];
+    const double v_same = ssame + (dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0);
+    const double v_cross = scross + (dot ? (double)a.kf.add_dot * dcross : 0.0);
+    const double v_diag = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                                : (double)diag_value(a.kf, ni);
+    if (rowX) {
+      q[0] += v_same;
+      q[2] += v_cross;
+      q[4] += v_diag;
+    } else {
+      q[1] += v_same;
+      q[3] += v_cross;
+      q[5] += v_diag;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sh[warp][i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    a.partials[(int64_t)blockIdx.x * 6 + threadIdx.x] = t;
+  }
+}
+
 struct FusedPlan {
   int64_t mp, np, Mp, dp;
-  int cs;      // CTAs per cluster sharing a row block: 1 (d <= 256), 2 (d <= 512), 4 (d <= 1024)
-  int npart;   // partial row-sum slices per (unit, row)
-  int nrb_x, rb_x0, nrb_y, rb_y0, T, grid, slots;   // grid counts work units = CTAs (cs == 1) or clusters
+  int nrb_x, rb_x0, nrb_y, rb_y0, T, grid, slots;
   int64_t total, chunk;
   size_t off_Z, off_norm, off_csum, off_O, off_r, off_s, off_stats, off_end;
 };
@@ -1634,16 +1716,14 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.mp = round_up(m, BM);
   p.np = round_up(n, BM);
   p.Mp = p.mp + p.np;
-  p.cs = d <= 256 ? 1 : (d <= 512 ? 2 : 4);
-  p.dp = round_up(d, 64 * p.cs);
-  p.npart = p.cs == 1 ? 4 : 2 * p.cs;
+  p.dp = round_up(d, 64);
   p.rb_x0 = (int)(x0 / BM);
   p.nrb_x = x1 > x0 ? (int)((x1 - 1) / BM) - p.rb_x0 + 1 : 0;
   p.rb_y0 = (int)((p.mp + y0) / BM);
   p.nrb_y = y1 > y0 ? (int)((p.mp + y1 - 1) / BM) - p.rb_y0 + 1 : 0;
   p.T = (int)(p.Mp / BNF);
   p.total = (int64_t)(p.nrb_x + p.nrb_y) * p.T;
-  p.grid = (int)std::min<int64_t>(sm_count() / p.cs, p.total);
+  p.grid = (int)std::min<int64_t>(sm_count(), p.total);
   if (p.grid < 1) p.grid = 1;
   p.chunk = (p.total + p.grid - 1) / p.grid;
   p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
@@ -1658,9 +1738,9 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.off_O = o;
   o = up256(o + (size_t)p.grid * p.slots * BM * p.dp * 4);
   p.off_r = o;
-  o = up256(o + (size_t)p.grid * p.slots * p.npart * BM * 4);
+  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 4);
   p.off_s = o;
-  o = up256(o + (size_t)p.grid * p.slots * p.npart * BM * 2 * 8);
+  o = up256(o + (size_t)p.grid * p.slots * 4 * BM * 2 * 8);
   p.off_stats = o;
   o = up256(o + (size_t)((x1 - x0) + (y1 - y0)) * RS_COUNT * 8);
   p.off_end = o;
@@ -1696,45 +1776,139 @@ cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap&
   }
 }
 
-template <class Math, int CS>
-cudaError_t launch_cluster_k(const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int nclusters,
-                             cudaStream_t s) {
-  const int smem = cluster_smem(a.npanel, a.nst, CS);
-  if (a.nst < 2 || smem > kMaxSmem) return cudaErrorInvalidConfiguration;
-  auto kern = tc_fused_cluster_kernel<Math, CS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(nclusters * CS));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = (size_t)smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tzi, tzj, a);
+// ---- two-pass path: plan ----
+struct WzPlan {
+  int64_t mp, np, Mp, dp;
+  int nrb_x, rb_x0, nrb_y, rb_y0, nrb;
+  int CT, KT, FB;
+  int P, npanels;   // row blocks per panel (even) / panels
+  size_t off_Z, off_norm, off_csum, off_W, off_r, off_s, off_O, off_stats, off_end;
+  int fin_blocks_total;
+};
+struct WzPanel {
+  int rbi0, nrb_p;
+  int grid1, slots1;
+  int64_t tiles1, chunk1;
+  int nmb, units, S, ksteps, grid2;
+  int fin_blocks, fin_block0;
+};
+
+// K splits per unit so that units * S fills whole waves of SMs (>= 8 K steps per piece, <= 16 splits)
+int wz_choose_split(int units, int KT) {
+  const int sm = sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= 16 && KT / S >= 8; ++S) {
+    const int64_t pieces = (int64_t)units * S;
+    const int64_t waves = (pieces + sm - 1) / sm;
+    const double eff = (double)pieces / (double)(waves * sm);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = S;
+    }
+    if (eff >= 0.92) return S;
+  }
+  return best;
 }
+
+WzPanel wz_panel(const WzPlan& p, int idx) {
+  WzPanel q;
+  q.rbi0 = idx * p.P;
+  q.nrb_p = std::min(p.P, p.nrb - q.rbi0);
+  q.tiles1 = (int64_t)q.nrb_p * p.CT;
+  q.grid1 = (int)std::min<int64_t>(sm_count(), q.tiles1);
+  if (q.grid1 < 1) q.grid1 = 1;
+  q.chunk1 = (q.tiles1 + q.grid1 - 1) / q.grid1;
+  q.grid1 = (int)((q.tiles1 + q.chunk1 - 1) / q.chunk1);
+  q.slots1 = (int)((q.chunk1 + p.CT - 1) / p.CT) + 1;
+  q.nmb = (q.nrb_p + 1) / 2;
+  q.units = q.nmb * p.FB;
+  q.S = wz_choose_split(q.units, p.KT);
+  q.ksteps = (p.KT + q.S - 1) / q.S;
+  q.grid2 = q.units * q.S;
+  q.fin_blocks = (q.nrb_p * BM + kFinRowsPerCta - 1) / kFinRowsPerCta;
+  q.fin_block0 = idx * ((p.P * BM + kFinRowsPerCta - 1) / kFinRowsPerCta);
+  return q;
+}
+
+WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t y0, int64_t y1) {
+  WzPlan p;
+  p.mp = round_up(m, BM);
+  p.np = round_up(n, BM);
+  p.Mp = p.mp + p.np;
+  p.dp = round_up(d, 64);
+  p.rb_x0 = (int)(x0 / BM);
+  p.nrb_x = x1 > x0 ? (int)((x1 - 1) / BM) - p.rb_x0 + 1 : 0;
+  p.rb_y0 = (int)((p.mp + y0) / BM);
+  p.nrb_y = y1 > y0 ? (int)((p.mp + y1 - 1) / BM) - p.rb_y0 + 1 : 0;
+  p.nrb = p.nrb_x + p.nrb_y;
+  p.CT = (int)(p.Mp / BNS);
+  p.KT = (int)(p.Mp / 64);
+  p.FB = (int)((p.dp + 255) / 256);
+  int64_t P = tuning().wz_panel_bytes / (BM * p.Mp * 2);
+  P = std::max<int64_t>(2, P & ~int64_t(1));
+  P = std::min<int64_t>(P, (p.nrb + 1) & ~1);
+  p.P = (int)std::max<int64_t>(2, P);
+  p.npanels = std::max(1, (p.nrb + p.P - 1) / p.P);
+  size_t need_r = 0, need_O = 0;
+  int fin_total = 0;
+  for (int i = 0; i < p.npanels; i += std::max(1, p.npanels - 1)) {   // first (full) and last panel bound all others
+    const WzPanel q = wz_panel(p, i);
+    need_r = std::max(need_r, (size_t)q.grid1 * q.slots1 * 2 * BM);
+    need_O = std::max(need_O, (size_t)q.units * q.S * 256 * 256 * 4);
+    if (p.npanels == 1) break;
+  }
+  {
+    const WzPanel last = wz_panel(p, p.npanels - 1);
+    fin_total = last.fin_block0 + last.fin_blocks;
+  }
+  p.fin_blocks_total = fin_total;
+  size_t o = 0;
+  p.off_Z = o;
+  o = up256(o + (size_t)p.Mp * p.dp * 2);
+  p.off_norm = o;
+  o = up256(o + (size_t)p.Mp * 4);
+  p.off_csum = o;
+  o = up256(o + (size_t)2 * p.dp * 8);
+  p.off_W = o;
+  o = up256(o + (size_t)p.P * BM * p.Mp * 2);
+  p.off_r = o;
+  o = up256(o + need_r * 4);
+  p.off_s = o;
+  o = up256(o + need_r * 2 * 8);
+  p.off_O = o;
+  o = up256(o + need_O);
+  p.off_stats = o;
+  o = up256(o + (size_t)std::max(1, fin_total) * 6 * 8);
+  p.off_end = o;
+  return p;
+}
+
 template <class Math>
-cudaError_t launch_cluster_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int cs, int nclusters,
-                             cudaStream_t s) {
-  return cs == 2 ? launch_cluster_k<Math, 2>(tzi, tzj, a, nclusters, s) : launch_cluster_k<Math, 4>(tzi, tzj, a, nclusters, s);
+cudaError_t launch_wgen_t(const CUtensorMap& tm, const WgenArgs& a, int grid, cudaStream_t s) {
+  auto kern = tc_wgen_kernel<Math>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, kStreamSmem, s>>>(tm, a);
+  return cudaGetLastError();
 }
-cudaError_t launch_cluster(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const ClusterArgs& a, int cs,
-                           int nclusters, cudaStream_t s) {
+cudaError_t launch_wgen(TcVariant v, const CUtensorMap& tm, const WgenArgs& a, int grid, cudaStream_t s) {
   switch (v) {
-    case TV_RBF1: return launch_cluster_t<MathRbf1>(tzi, tzj, a, cs, nclusters, s);
-    case TV_RBF_LADDER5: return launch_cluster_t<MathRbfLadder<5>>(tzi, tzj, a, cs, nclusters, s);
-    case TV_RBF_GENERIC: return launch_cluster_t<MathGeneric<FAM_RBF>>(tzi, tzj, a, cs, nclusters, s);
-    case TV_RQ3_DEFAULT: return launch_cluster_t<MathRq3Default>(tzi, tzj, a, cs, nclusters, s);
-    case TV_RQ_GENERIC: return launch_cluster_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, cs, nclusters, s);
-    case TV_DISTANCE: return launch_cluster_t<MathDistance>(tzi, tzj, a, cs, nclusters, s);
-    case TV_NULL: return launch_cluster_t<MathNull>(tzi, tzj, a, cs, nclusters, s);
+    case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, a, grid, s);
+    case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, a, grid, s);
+    case TV_RBF_GENERIC: return launch_wgen_t<MathGeneric<FAM_RBF>>(tm, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_wgen_t<MathRq3Default>(tm, a, grid, s);
+    case TV_RQ_GENERIC: return launch_wgen_t<MathGeneric<FAM_RQ>>(tm, a, grid, s);
+    case TV_DISTANCE: return launch_wgen_t<MathDistance>(tm, a, grid, s);
+    case TV_NULL: return launch_wgen_t<MathNull>(tm, a, grid, s);
     default: return cudaErrorInvalidValue;
   }
+}
+cudaError_t launch_wz(const CUtensorMap& tw, const CUtensorMap& tz, const WzArgs& a, int grid, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(tc_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWzSmem);
+  if (e != cudaSuccess) return e;
+  tc_wz_kernel<<<grid, kThreads, kWzSmem, s>>>(tw, tz, a);
+  return cudaGetLastError();
 }
 
 struct StreamPlan {
@@ -1854,7 +2028,9 @@ void pipe_timing_dump(bool reset) {
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) interface
 // ------------------------------------------------------------------------------------------------
-bool tc_mmd2_supported(int64_t d, int want_grad) { return want_grad ? d <= 1024 : d <= 65536; }
+bool tc_mmd2_supported(int64_t d, int want_grad) { return d >= 1 && d <= 65536; }
+
+static bool use_two_pass(int64_t d) { return d > tuning().wz_min_d; }
 
 static bool tc_family_ok(const KernelFn& kf) {
   return kf.family == FAM_RBF || kf.family == FAM_RQ || kf.family == FAM_DISTANCE;
@@ -1873,7 +2049,8 @@ bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad) {
 
 size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision) {
   // worst case over shards: a full-range plan bounds every rank's plan
-  const size_t fused = want_grad ? fused_plan(m, n, d, 0, m, 0, n).off_end : 0;
+  const size_t fused = !want_grad ? 0 : (use_two_pass(d) ? wz_plan(m, n, d, 0, m, 0, n).off_end
+                                                          : fused_plan(m, n, d, 0, m, 0, n).off_end);
   const size_t stream = stream_plan(m, n, d, 1, precision == SMMD_PREC_BF16X3).off_end + 4096;
   return std::max(fused, stream);
 }
@@ -1892,10 +2069,118 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
   char* w = static_cast<char*>(ws);
   cudaError_t e;
   const bool want_grad = dX != nullptr;
+  if (want_grad && use_two_pass(g.d)) {
+    *path = "tc_bf16_wz";
+    const WzPlan p = wz_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1);
+    if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+    __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+    float* norms = reinterpret_cast<float*>(w + p.off_norm);
+    double* csum = reinterpret_cast<double*>(w + p.off_csum);
+    __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(w + p.off_W);
+    PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
+                  kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+    prep_tc_kernel<<<dim3((unsigned)((p.Mp + 7) / 8), 1), 256, 0, s>>>(pa);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+    const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
+    if (dot) {
+      colsum_kernel<<<dim3((unsigned)((p.dp + 31) / 32), 2), 256, 0, s>>>(Z, p.dp, p.dp, g.m, p.mp, g.n, csum);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      ++*launches;
+    }
+    CUtensorMap t1, tz, tw;
+    if (!smmd_host::make_tmap_bf16_2d(&t1, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
+    if (!smmd_host::make_tmap_bf16_2d(&tz, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
+    if (!smmd_host::make_tmap_bf16_2d(&tw, Wb, (int64_t)p.P * BM, p.Mp, p.Mp, BM)) return cudaErrorUnknown;
+    double* partials = reinterpret_cast<double*>(w + p.off_stats);
+    prof_begin(s);
+    for (int ip = 0; ip < p.npanels; ++ip) {
+      const WzPanel q = wz_panel(p, ip);
+      WgenArgs ga;
+      ga.kf = kf;
+      ga.m = g.m;
+      ga.n = g.n;
+      ga.mp = p.mp;
+      ga.np = p.np;
+      ga.c_xx = (float)(4.0 * c.a_xx);
+      ga.c_yy = (float)(4.0 * c.a_yy);
+      ga.c_xy = (float)(4.0 * c.a_xy);
+      ga.norms = norms;
+      ga.nrb_x = p.nrb_x;
+      ga.rb_x0 = p.rb_x0;
+      ga.nrb_y = p.nrb_y;
+      ga.rb_y0 = p.rb_y0;
+      ga.rbi0 = q.rbi0;
+      ga.CT = p.CT;
+      ga.nkp = (int)(p.dp / 64);
+      ga.total_tiles = q.tiles1;
+      ga.chunk = q.chunk1;
+      ga.slots = q.slots1;
+      ga.W = Wb;
+      ga.ldw = p.Mp;
+      ga.rpart = reinterpret_cast<float*>(w + p.off_r);
+      ga.spart = reinterpret_cast<double*>(w + p.off_s);
+      if ((e = launch_wgen(variant, t1, ga, q.grid1, s)) != cudaSuccess) return e;
+      ++*launches;
+      WzArgs za;
+      za.nmb = q.nmb;
+      za.FB = p.FB;
+      za.dp = (int)p.dp;
+      za.KT = p.KT;
+      za.S = q.S;
+      za.ksteps = q.ksteps;
+      za.Opart = reinterpret_cast<float*>(w + p.off_O);
+      if ((e = launch_wz(tw, tz, za, q.grid2, s)) != cudaSuccess) return e;
+      ++*launches;
+      WzFinArgs fr;
+      fr.kf = kf;
+      fr.m = g.m;
+      fr.n = g.n;
+      fr.mp = p.mp;
+      fr.np = p.np;
+      fr.d = g.d;
+      fr.x0 = g.x0;
+      fr.ox = g.x1 - g.x0;
+      fr.y0 = g.y0;
+      fr.oy = g.y1 - g.y0;
+      fr.dp = (int)p.dp;
+      fr.nrb_x = p.nrb_x;
+      fr.rb_x0 = p.rb_x0;
+      fr.nrb_y = p.nrb_y;
+      fr.rb_y0 = p.rb_y0;
+      fr.rbi0 = q.rbi0;
+      fr.nrb_p = q.nrb_p;
+      fr.CT = p.CT;
+      fr.chunk = q.chunk1;
+      fr.slots = q.slots1;
+      fr.FB = p.FB;
+      fr.S = q.S;
+      fr.a_xx = c.a_xx;
+      fr.a_yy = c.a_yy;
+      fr.a_xy = c.a_xy;
+      fr.src = src;
+      fr.norms = norms;
+      fr.csum = dot ? csum : nullptr;
+      fr.Opart = za.Opart;
+      fr.rpart = ga.rpart;
+      fr.spart = ga.spart;
+      fr.dX = dX;
+      fr.dY = dY;
+      fr.partials = partials + (int64_t)q.fin_block0 * 6;
+      wz_finalize_rows_kernel<<<(unsigned)q.fin_blocks, 256, 0, s>>>(fr);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      ++*launches;
+    }
+    prof_end(s);
+    e = launch_finalize_partials(kf, g, partials, (unsigned)p.fin_blocks_total, scalars, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    return cudaSuccess;
+  }
   if (want_grad) {
     const FusedPlan p = fused_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1);
     if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
-    *path = p.cs == 1 ? "tc_bf16_fused" : (p.cs == 2 ? "tc_bf16_fused_cluster2" : "tc_bf16_fused_cluster4");
+    *path = "tc_bf16_fused";
     __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
     float* norms = reinterpret_cast<float*>(w + p.off_norm);
     double* csum = reinterpret_cast<double*>(w + p.off_csum);
@@ -1939,37 +2224,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fa.rpart = reinterpret_cast<float*>(w + p.off_r);
     fa.spart = reinterpret_cast<double*>(w + p.off_s);
     prof_begin(s);
-    if (p.cs == 1) {
-      e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
-    } else {
-      ClusterArgs ca;
-      ca.kf = kf;
-      ca.m = g.m;
-      ca.n = g.n;
-      ca.mp = p.mp;
-      ca.np = p.np;
-      ca.c_xx = fa.c_xx;
-      ca.c_yy = fa.c_yy;
-      ca.c_xy = fa.c_xy;
-      ca.norms = norms;
-      ca.nrb_x = p.nrb_x;
-      ca.rb_x0 = p.rb_x0;
-      ca.nrb_y = p.nrb_y;
-      ca.rb_y0 = p.rb_y0;
-      ca.T = p.T;
-      ca.dp = (int)p.dp;
-      ca.fw = (int)(p.dp / p.cs);
-      ca.npanel = ca.fw / 64;
-      ca.nst = cluster_stages(ca.npanel, p.cs);
-      ca.la = std::min(3, ca.nst - 1);
-      ca.total_tiles = p.total;
-      ca.chunk = p.chunk;
-      ca.slots = p.slots;
-      ca.Opart = fa.Opart;
-      ca.rpart = fa.rpart;
-      ca.spart = fa.spart;
-      e = launch_cluster(variant, tzi, tzj, ca, p.cs, p.grid, s);
-    }
+    e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
     prof_end(s);
     if (e != cudaSuccess) return e;
     ++*launches;
@@ -1992,7 +2247,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.T = p.T;
     fr.chunk = p.chunk;
     fr.slots = p.slots;
-    fr.npart = p.cs == 1 ? 2 * fa.ksplit : p.npart;
+    fr.npart = 2 * fa.ksplit;
     fr.a_xx = c.a_xx;
     fr.a_yy = c.a_yy;
     fr.a_xy = c.a_xy;
@@ -2008,8 +2263,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
     fr.dY = dY;
     fr.partials = reinterpret_cast<double*>(w + p.off_stats);
     const unsigned fin_blocks = (unsigned)((fr.ox + fr.oy + kFinRowsPerCta - 1) / kFinRowsPerCta);
-    if (p.dp <= 256) tc_finalize_rows_kernel<2><<<fin_blocks, 256, 0, s>>>(fr);
-    else tc_finalize_rows_kernel<8><<<fin_blocks, 256, 0, s>>>(fr);
+    tc_finalize_rows_kernel<<<fin_blocks, 256, 0, s>>>(fr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
     e = launch_finalize_partials(kf, g, fr.partials, fin_blocks, scalars, s);
