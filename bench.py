@@ -455,6 +455,75 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
     return out
 
 
+def run_sweep(args):
+    """N in {4096..65536} x d in {256,512,1024}, mix_rq fwd+bwd, inputs resident in HBM.
+    One JSON line per cell (rank 0): ms per evaluation (CUDA events, max over ranks, L2 flushed between iterations),
+    algorithmic TFLOP/s (14 N^2 d) and its fraction of the measured bf16 peak.  Not the driver's headline line."""
+    import torch.distributed as dist
+
+    from smmd import _lib, mmd
+    from smmd.distributed import sharded_mmd2_raw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    _lib.load()
+    peak, _ = measured_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ns = [int(v) for v in args.sweep_n.split(",")]
+    ds = [int(v) for v in args.sweep_d.split(",")]
+    for d in ds:
+        for n in ns:
+            nl = n // world
+            Xd = synth_features(n, d, 1234, False)[rank * nl:(rank + 1) * nl].to(dev)
+            Yd = synth_features(n, d, 1235, True)[rank * nl:(rank + 1) * nl].to(dev)
+            spec = mmd._mix_rq_kernel(Xd, Yd).spec
+
+            def step():
+                if world == 1:
+                    sc, dX, dY = mmd.fused_mmd2_raw(spec, Xd, Yd, biased=False, want_grad=True, precision="bf16")
+                    return sc[_lib.S_MMD2]
+                return sharded_mmd2_raw(spec, Xd, Yd, biased=False, precision="bf16")[0]
+
+            steps = max(3, min(args.steps, int(2e15 / (14.0 * n * n * d / world)) + 1))
+            for _ in range(3):
+                flush.zero_()
+                val = step()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i in range(steps):
+                flush.zero_()
+                ev[i][0].record()
+                val = step()
+                ev[i][1].record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            ms = tot.item() / steps
+            if rank == 0:
+                tf = 14.0 * n * n * d / (ms * 1e-3) / 1e12
+                print(json.dumps({"sweep": "C4", "n": n, "d": d, "n_gpus": world, "ms": ms, "steps": steps,
+                                  "pairs_per_s": float(n) * n * d / (ms * 1e-3), "tflops_algorithmic": tf,
+                                  "frac_of_peak": tf / (peak * world), "path": _lib.last_path(), "mmd2": float(val.item())}),
+                      flush=True)
+            del Xd, Yd
+            torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,8 +531,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
+    ap.add_argument("--sweep", action="store_true", help="C4 grid (N x d) instead of the headline line")
+    ap.add_argument("--sweep-n", default="4096,8192,16384,32768,65536")
+    ap.add_argument("--sweep-d", default="256,512,1024")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

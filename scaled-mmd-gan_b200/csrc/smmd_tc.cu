@@ -1271,8 +1271,9 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // memory) was built and measured first: correct, but shared memory left only a 2-3 stage TMA ring next to the
 // exchange buffers and it reached 23% (d = 512) / 6% (d = 1024) of peak (profiles/r01_cluster_*.log).
 // The two-pass path below reaches 42% / 51% and has no upper limit on d:
-//   pass 1 (tc_wgen_kernel):  128 x 128 tiles of S = Z_i Z_j^T with K streamed through a 6-stage TMA ring (both
-//          operands), epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
+//   pass 1 (tc_wgen_kernel):  128 x 256 tiles of S = Z_i Z_j^T with K streamed through a 4-stage TMA ring (both
+//          operands, 48 KB per 64-deep step: 25% less L2 traffic per flop than 128 x 128), two 256-column TMEM
+//          accumulators alternate between the two epilogue groups; epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
 //          buffer W[panel rows][Mp] (K-major for pass 2).  The panel is sized by a byte budget (default 4 GB), so
 //          the N x N matrix never exists as a whole; panels run back to back on the stream.
 //   pass 2 (tc_wz_kernel):    O[256 rows x 256 features] = W[256 x Mp] Z[Mp x 256]: 2 x 128-row A panels and one
@@ -1287,43 +1288,55 @@ struct WgenArgs {
   const float* norms;
   int nrb_x, rb_x0, nrb_y, rb_y0;   // owned row blocks (as FusedArgs)
   int rbi0;                         // first owned row block (flat index) of this panel
-  int CT;                           // 128-column tiles per row block
+  int TX, CT;                       // 256-column tiles of the X columns / per row block (X tiles, then Y tiles)
   int nkp;                          // 64-feature panels
   int64_t total_tiles, chunk;
   int slots;
   __nv_bfloat16* W;                 // [panel row blocks * 128][ldw]
   int64_t ldw;
-  float* rpart;                     // [grid][slots][2][128]
-  double* spart;                    // [grid][slots][2][128][2]
+  float* rpart;                     // [grid][slots][4][128]   (part = epilogue group * 2 + column half)
+  double* spart;                    // [grid][slots][4][128][2]
 };
 
+constexpr int BNW = 256;                                  // tile width of pass 1
+constexpr int kWgStages = 4;
+constexpr int kWgStageBytes = BM * 128 + BNW * 128;       // one 128-row A panel + one 256-row B panel = 48 KB
+constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 1024;
+
+constexpr int kWgEpiWarps = 16;                           // 2 groups x (4 TMEM lane quarters x 2 column halves)
+constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
+
 template <class Math>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WgenArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 1)
+tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ WgenArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kStreamStages;
-  uint64_t* acc_full = empty + kStreamStages;   // [2]
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* acc_full = empty + kWgStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sParams = reinterpret_cast<float*>(tmem_slot + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   stage_params(a.kf, sParams);
   if (tid == 0) {
-    for (int i = 0; i < kStreamStages; ++i) {
+    for (int i = 0; i < kWgStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 256);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<256>(tmem_slot);
-  if (warp == 8 && lane == 0) prefetch_tmap(&tmap);
+  if (warp == kWgEpiWarps + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kWgEpiWarps && lane == 0) {
+    prefetch_tmap(&tmap);
+    prefetch_tmap(&tmap_b);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1331,24 +1344,26 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
   const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
   auto rb_of = [&](int rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + rbi : a.rb_y0 + (rbi - a.nrb_x); };
+  // tile ct of a row block: first column / end of its column set (X tiles never run into the Y columns)
+  auto col0_of = [&](int ct) -> int { return ct < a.TX ? ct * BNW : (int)a.mp + (ct - a.TX) * BNW; };
 
-  if (warp == 8) {
+  if (warp == kWgEpiWarps) {
     // ===================== TMA producer =====================
     uint32_t st = 0, ph = 0;
     int rbl = (int)(pos0 / a.CT);
     int ct = (int)(pos0 - (int64_t)rbl * a.CT);
     for (int64_t pos = pos0; pos < pos1; ++pos) {
-      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = ct * BNS;
+      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = col0_of(ct);
       for (int p = 0; p < a.nkp; ++p) {
         mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[st], kStreamStageBytes);
-          uint8_t* sa = smem + st * kStreamStageBytes;
+          mbar_arrive_expect_tx(&full[st], kWgStageBytes);
+          uint8_t* sa = smem + st * kWgStageBytes;
           tma_load_2d(sa, &tmap, &full[st], p * 64, arow);
-          tma_load_2d(sa + BM * 128, &tmap, &full[st], p * 64, brow);
+          tma_load_2d(sa + BM * 128, &tmap_b, &full[st], p * 64, brow);
         }
         __syncwarp();
-        if (++st == kStreamStages) {
+        if (++st == kWgStages) {
           st = 0;
           ph ^= 1;
         }
@@ -1358,27 +1373,27 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         ++rbl;
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWgEpiWarps + 1) {
     // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BM, BNS, kFmtBF16, false, false);
+    constexpr uint32_t idesc = make_idesc(BM, BNW, kFmtBF16, false, false);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
     for (int64_t pos = pos0; pos < pos1; ++pos) {
       mbar_wait(&acc_empty[ab], aph ^ 1);
       tc_fence_after();
-      const uint32_t dad = tmem + ab * BNS;
+      const uint32_t dad = tmem + ab * BNW;
       for (int kk = 0; kk < a.nkp; ++kk) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t alo = a_lo0 + st * (kStreamStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
+        const uint32_t alo = a_lo0 + st * (kWgStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
           umma_commit(&empty[st]);
         }
         __syncwarp();
-        if (++st == kStreamStages) {
+        if (++st == kWgStages) {
           st = 0;
           ph ^= 1;
         }
@@ -1389,8 +1404,10 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       ab ^= 1;
     }
   } else {
-    // ===================== epilogue groups: tile parity = group =====================
-    const int grp = warp >> 2;
+    // ===================== epilogue groups: tile parity = group; 8 warps per group =====================
+    const int grp = warp >> 3;
+    const int half = (warp >> 2) & 1;   // columns [half * 128, +128) of the tile
+    const int part = grp * 2 + half;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -1413,22 +1430,30 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int lt = 0; lt < TU; ++lt, ++tc) {
         if ((int)(tc & 1) != grp) continue;
         const int ct = ct0 + lt;
-        const int c0 = ct * BNS;
-        const bool colX = c0 < mp;
+        const int c0 = col0_of(ct);
+        const bool colX = ct < a.TX;
         const bool same = (colX == rowX);
         const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
         const int lim = colX ? mvalid : yvalid;
-        const bool special = (c0 + BNS > lim) || (ct == rb);
+        const int cend = colX ? mp : (int)(a.mp + a.np);               // end of this column set
+        const int nch = (cend - c0 < BNW ? cend - c0 : BNW) / 16;      // chunks that belong to this tile
+        const bool special = (c0 + BNW > lim) || (rb * BM >= c0 && rb * BM < c0 + BNW);
         mbar_wait(&acc_full[grp], (tc >> 1) & 1);
         tc_fence_after();
         const float* nj = a.norms + c0;
         float2 tsum = make_float2(0.f, 0.f);
+        const int h0 = half * (BNW / 32);
+        const int h1 = nch < h0 + BNW / 32 ? nch : h0 + BNW / 32;
+        if (h1 <= h0) {   // nothing of this tile in my column half: only release the accumulator
+          tc_fence_before();
+          mbar_arrive(&acc_empty[grp]);
+        }
 #pragma unroll 1
-        for (int h = 0; h < BNS / 16; ++h) {
+        for (int h = h0; h < h1; ++h) {
           uint32_t v[16], wpk[8];
-          tmem_ld_x16(tmem + grp * BNS + h * 16 + lane_base, v);
+          tmem_ld_x16(tmem + grp * BNW + h * 16 + lane_base, v);
           tmem_ld_wait();
-          if (h == BNS / 16 - 1) {
+          if (h == h1 - 1) {
             tc_fence_before();
             mbar_arrive(&acc_empty[grp]);
           }
@@ -1442,8 +1467,8 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         else dcross += (double)((tsum.x + tsum.y) * kscale);
       }
       const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
-      a.rpart[(sl * 2 + grp) * BM + r] = rsum.x + rsum.y;
-      double* sp = a.spart + ((sl * 2 + grp) * BM + r) * 2;
+      a.rpart[(sl * 4 + part) * BM + r] = rsum.x + rsum.y;
+      double* sp = a.spart + ((sl * 4 + part) * BM + r) * 2;
       sp[0] = dsame;
       sp[1] = dcross;
       left -= TU;
@@ -1451,7 +1476,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<256>(tmem);
+  if (warp == kWgEpiWarps + 1) tmem_dealloc<512>(tmem);
 }
 
 // ---- pass 2: O = W Z ----
@@ -1625,9 +1650,9 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
     double ssame = 0.0, scross = 0.0;
     for (int64_t g = g0; g <= g1; ++g) {
       const int64_t sl = g * a.slots + (rbl - (g * a.chunk) / a.CT);
-      for (int pt = 0; pt < 2; ++pt) {
-        rs += a.rpart[(sl * 2 + pt) * BM + r];
-        const double* sp = a.spart + ((sl * 2 + pt) * BM + r) * 2;
+      for (int pt = 0; pt < 4; ++pt) {
+        rs += a.rpart[(sl * 4 + pt) * BM + r];
+        const double* sp = a.spart + ((sl * 4 + pt) * BM + r) * 2;
         ssame += sp[0];
         scross += sp[1];
       }
@@ -1643,29 +1668,57 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
     const int64_t srow = owned ? (rowX ? li - a.x0 : li - a.y0) : src_row(li, rowX, a.src.blk_x, a.src.blk_y);
     const int mbl = rbl >> 1;                 // macro block of the panel, row inside it
     const int row256 = (rbl & 1) * BM + r;
-    for (int c = lane; c < a.d; c += 32) {
-      const int fb = c >> 8, cc = c & 255;
-      float o = 0.f;
-      if (out) {
-        const float* op = a.Opart + ((((int64_t)mbl * a.FB + fb) * a.S) * 256 + row256) * 256 + cc;
-        for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 256 * 256];   // fixed order
-      }
-      const int64_t sidx = srow * ld + c;
-      float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
-                                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
-      if (a.kf.tanh_features) z = tanhf(z);
-      if (out) {
-        float gv = rs * z - o;
-        if (dot) {
-          const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
-          gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
+    const float* obase = a.Opart + (((int64_t)mbl * a.FB) * a.S * 256 + row256) * 256;   // + (fb * S + s) * 65536 + cc
+    const bool vec = out != nullptr && !dot && sdtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+      const float* zsrc = reinterpret_cast<const float*>(src) + srow * ld;
+      for (int c = 4 * lane; c < a.d; c += 128) {   // 4 consecutive features per lane (never straddle a 256 block)
+        const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.S; ++s) {   // fixed order
+          const float4 t = *reinterpret_cast<const float4*>(op + (int64_t)s * 65536);
+          o.x += t.x;
+          o.y += t.y;
+          o.z += t.z;
+          o.w += t.w;
         }
-        if (a.kf.tanh_features) gv *= (1.f - z * z);
-        out[c] = gv;
+        const float4 z4 = *reinterpret_cast<const float4*>(zsrc + c);
+        float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+        const float oo[4] = {o.x, o.y, o.z, o.w};
+        float gv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
+          gv[e] = rs * zz[e] - oo[e];
+          if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
+        }
+        *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
       }
-      if (dot) {
-        dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
-        dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+    } else {
+      for (int c = lane; c < a.d; c += 32) {
+        float o = 0.f;
+        if (out) {
+          const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
+          for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 65536];   // fixed order
+        }
+        const int64_t sidx = srow * ld + c;
+        float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+                                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
+        if (a.kf.tanh_features) z = tanhf(z);
+        if (out) {
+          float gv = rs * z - o;
+          if (dot) {
+            const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
+            gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
+          }
+          if (a.kf.tanh_features) gv *= (1.f - z * z);
+          out[c] = gv;
+        }
+        if (dot) {
+          dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
+          dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+        }
       }
     }
     if (dot) {
@@ -1780,7 +1833,7 @@ cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap&
 struct WzPlan {
   int64_t mp, np, Mp, dp;
   int nrb_x, rb_x0, nrb_y, rb_y0, nrb;
-  int CT, KT, FB;
+  int TX, CT, KT, FB;   // pass-1 tiles (256 columns) over the X columns / per row block
   int P, npanels;   // row blocks per panel (even) / panels
   size_t off_Z, off_norm, off_csum, off_W, off_r, off_s, off_O, off_stats, off_end;
   int fin_blocks_total;
@@ -1842,7 +1895,8 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
   p.rb_y0 = (int)((p.mp + y0) / BM);
   p.nrb_y = y1 > y0 ? (int)((p.mp + y1 - 1) / BM) - p.rb_y0 + 1 : 0;
   p.nrb = p.nrb_x + p.nrb_y;
-  p.CT = (int)(p.Mp / BNS);
+  p.TX = (int)((p.mp + BNW - 1) / BNW);
+  p.CT = p.TX + (int)((p.np + BNW - 1) / BNW);
   p.KT = (int)(p.Mp / 64);
   p.FB = (int)((p.dp + 255) / 256);
   int64_t P = tuning().wz_panel_bytes / (BM * p.Mp * 2);
@@ -1854,7 +1908,7 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
   int fin_total = 0;
   for (int i = 0; i < p.npanels; i += std::max(1, p.npanels - 1)) {   // first (full) and last panel bound all others
     const WzPanel q = wz_panel(p, i);
-    need_r = std::max(need_r, (size_t)q.grid1 * q.slots1 * 2 * BM);
+    need_r = std::max(need_r, (size_t)q.grid1 * q.slots1 * 4 * BM);
     need_O = std::max(need_O, (size_t)q.units * q.S * 256 * 256 * 4);
     if (p.npanels == 1) break;
   }
@@ -1885,22 +1939,23 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
 }
 
 template <class Math>
-cudaError_t launch_wgen_t(const CUtensorMap& tm, const WgenArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_wgen_t(const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid, cudaStream_t s) {
   auto kern = tc_wgen_kernel<Math>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, kStreamSmem, s>>>(tm, a);
+  kern<<<grid, kWgThreads, kWgSmem, s>>>(tm, tb, a);
   return cudaGetLastError();
 }
-cudaError_t launch_wgen(TcVariant v, const CUtensorMap& tm, const WgenArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_wgen(TcVariant v, const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid,
+                        cudaStream_t s) {
   switch (v) {
-    case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, a, grid, s);
-    case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, a, grid, s);
-    case TV_RBF_GENERIC: return launch_wgen_t<MathGeneric<FAM_RBF>>(tm, a, grid, s);
-    case TV_RQ3_DEFAULT: return launch_wgen_t<MathRq3Default>(tm, a, grid, s);
-    case TV_RQ_GENERIC: return launch_wgen_t<MathGeneric<FAM_RQ>>(tm, a, grid, s);
-    case TV_DISTANCE: return launch_wgen_t<MathDistance>(tm, a, grid, s);
-    case TV_NULL: return launch_wgen_t<MathNull>(tm, a, grid, s);
+    case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, tb, a, grid, s);
+    case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, tb, a, grid, s);
+    case TV_RBF_GENERIC: return launch_wgen_t<MathGeneric<FAM_RBF>>(tm, tb, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_wgen_t<MathRq3Default>(tm, tb, a, grid, s);
+    case TV_RQ_GENERIC: return launch_wgen_t<MathGeneric<FAM_RQ>>(tm, tb, a, grid, s);
+    case TV_DISTANCE: return launch_wgen_t<MathDistance>(tm, tb, a, grid, s);
+    case TV_NULL: return launch_wgen_t<MathNull>(tm, tb, a, grid, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -2088,8 +2143,9 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       ++*launches;
     }
-    CUtensorMap t1, tz, tw;
+    CUtensorMap t1, t1b, tz, tw;
     if (!smmd_host::make_tmap_bf16_2d(&t1, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
+    if (!smmd_host::make_tmap_bf16_2d(&t1b, Z, p.Mp, p.dp, p.dp, BNW)) return cudaErrorUnknown;
     if (!smmd_host::make_tmap_bf16_2d(&tz, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
     if (!smmd_host::make_tmap_bf16_2d(&tw, Wb, (int64_t)p.P * BM, p.Mp, p.Mp, BM)) return cudaErrorUnknown;
     double* partials = reinterpret_cast<double*>(w + p.off_stats);
@@ -2111,6 +2167,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       ga.nrb_y = p.nrb_y;
       ga.rb_y0 = p.rb_y0;
       ga.rbi0 = q.rbi0;
+      ga.TX = p.TX;
       ga.CT = p.CT;
       ga.nkp = (int)(p.dp / 64);
       ga.total_tiles = q.tiles1;
@@ -2120,7 +2177,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       ga.ldw = p.Mp;
       ga.rpart = reinterpret_cast<float*>(w + p.off_r);
       ga.spart = reinterpret_cast<double*>(w + p.off_s);
-      if ((e = launch_wgen(variant, t1, ga, q.grid1, s)) != cudaSuccess) return e;
+      if ((e = launch_wgen(variant, t1, t1b, ga, q.grid1, s)) != cudaSuccess) return e;
       ++*launches;
       WzArgs za;
       za.nmb = q.nmb;
