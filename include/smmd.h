@@ -186,6 +186,22 @@ SMMD_API int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, co
                      const int32_t* idx_g, const int32_t* idx_r, double* mmd2_out, double* var_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* 3-sample test of the scorer (gan/utils/scorer.py:119-163): the "Y related sums" that
+ * np_diff_polynomial_mmd2_and_ratio_with_saving (gan/core/mmd.py:429-444) builds with _np_get_sums
+ * (gan/core/mmd.py:515-539) from K_XY = (X Y^T / d + 1)^3 and K_YY, without materialising either block.
+ * X, Y: device [m, d] (equal sizes, mmd.py:516); the problem struct is smmd_kid_problem with
+ * n_subsets = 1 and n_g = n_r = subset_size = m (degree / gamma / coef0 / precision as for KID).
+ * sums_out: device double[3 m + 2] =
+ *   [0, m)    Kt_YY_sums    row sums of K_YY without the diagonal
+ *   [m, 2m)   K_XY_sums_0   sum over x of K(x, y_j)       (K_XY.sum(axis=0))
+ *   [2m, 3m)  K_XY_sums_1   sum over y of K(x_i, y)       (K_XY.sum(axis=1))
+ *   [3m]      Kt_YY_2_sum   sum of K_YY^2 without the diagonal
+ *   [3m + 1]  K_XY_2_sum    sum of K_XY^2
+ * The estimator arithmetic on these vectors (mmd.py:447-512) is host-side in smmd/mmd.py. */
+SMMD_API size_t smmd_poly_sums_workspace_bytes(const smmd_kid_problem* p);
+SMMD_API int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void* Y, double* sums_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Roofline instrumentation (bench.py): when enabled on this thread, the library records a CUDA-event
  * pair on the launching stream around the DOMINANT kernel of each call (the fused tcgen05 Gram kernel /
  * the K-streaming KID kernel / the SIMT row kernel).  smmd_profile_last_ms() synchronises on the stop

@@ -145,11 +145,38 @@ def make_kid_golden(path):
     np.savez_compressed(path, **out)
 
 
+def make_three_sample_golden(path):
+    """Reference numpy 3-sample test (mmd.py:429-539) on seeded synthetic codes; fp32 (as the scorer feeds it) and
+    fp64.  Inputs are regenerated from the seeds by the tests (tests/golden_util.py:three_sample_codes)."""
+    ref = ref_loader.load_reference_mmd("float64")
+    out = {}
+    for tag, m, d in (("small", 96, 40), ("mid", 320, 192)):
+        rng = np.random.RandomState(4321)
+        X = np.maximum(rng.randn(m, d), 0)
+        Y = np.maximum(rng.randn(m, d) + 0.05, 0)
+        Z = np.maximum(rng.randn(m, d) + 0.15, 0)
+        out["meta_%s" % tag] = np.array([4321, m, d], dtype=np.int64)
+        for dt, dn in ((np.float32, "f32"), (np.float64, "f64")):
+            x, y, z = X.astype(dt), Y.astype(dt), Z.astype(dt)
+            zs = ref.np_diff_polynomial_mmd2_and_ratio_with_saving(x, z, None)
+            diff, ratio, ys = ref.np_diff_polynomial_mmd2_and_ratio_with_saving(x, y, zs)
+            for name, sums in (("ys", ys), ("zs", zs)):
+                out["%s_%s_%s_vec" % (name, dn, tag)] = np.stack([sums[0], sums[2], sums[3]]).astype(np.float64)
+                out["%s_%s_%s_sc" % (name, dn, tag)] = np.array([sums[1], sums[4]], dtype=np.float64)
+            out["res_%s_%s" % (dn, tag)] = np.array([diff, ratio], dtype=np.float64)
+    np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         sys.exit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
+    if "--three-sample" in sys.argv:   # only the 3-sample fixture (leaves the committed mmd/kid files untouched)
+        make_three_sample_golden(os.path.join(gdir, "three_sample_golden.npz"))
+        print("wrote 3-sample fixtures to %s" % gdir)
+        sys.exit(0)
     n = make_mmd_golden(os.path.join(gdir, "mmd_golden.npz"))
     make_kid_golden(os.path.join(gdir, "kid_golden.npz"))
+    make_three_sample_golden(os.path.join(gdir, "three_sample_golden.npz"))
     print("wrote %d mmd cases + kid fixtures to %s" % (n, gdir))

@@ -398,6 +398,41 @@ size_t smmd_kid_workspace_bytes(const smmd_kid_problem* p) {
   return tc_kid_workspace_bytes(p->subset_size, p->d, kid_local(p), kid_precision(p));
 }
 
+// Gram row statistics of the local subsets: stats[nloc][2m][RS_COUNT] inside the workspace.
+static int kid_row_stats(const smmd_kid_problem* p, const void* codes_g, const void* codes_r, const int32_t* idx_g,
+                         const int32_t* idx_r, int want_second_order, void* workspace, size_t workspace_bytes,
+                         cudaStream_t s, double** stats_out) {
+  KernelFn kf;
+  float prm[2] = {p->gamma, p->coef0};
+  int st = build_kernel_fn(SMMD_K_POLY, 2, prm, prm, 0.f, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  const int64_t m = p->subset_size, nloc = kid_local(p);
+  const int prec = kid_precision(p);
+  char* ws = static_cast<char*>(workspace);
+  if (prec == SMMD_PREC_FP32) {
+    g_path = "simt_fp32_kid";
+    const SimtPlan pl = simt_plan(m, m, p->d, nloc);
+    float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
+    float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
+    *stats_out = reinterpret_cast<double*>(ws + pl.off_stats);
+    SMMD_CUDA(launch_gather_f32(codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc, m,
+                                Z, norms, pl.dpitch, s));
+    Geometry g{m, m, p->d, 0, m, 0, m, 0};
+    Coefs c = make_coefs(g, kf);
+    prof_begin(s);
+    SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, nloc, *stats_out, nullptr, nullptr, 1, s));
+    prof_end(s);
+  } else {
+    if (!tc_kid_supported(p->d)) return SMMD_EUNSUPPORTED;
+    int launches = 0;
+    cudaError_t e = tc_kid_run(kf, codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc,
+                               m, prec, want_second_order, workspace, workspace_bytes, stats_out, s, &launches, &g_path);
+    g_launches += launches;
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
+  return SMMD_OK;
+}
+
 int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void* codes_r, const int32_t* idx_g,
                      const int32_t* idx_r, double* mmd2_out, double* var_out, void* workspace, size_t workspace_bytes,
                      void* stream) {
@@ -411,38 +446,46 @@ int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void*
   const size_t need = smmd_kid_workspace_bytes(p);
   if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  KernelFn kf;
-  float prm[2] = {p->gamma, p->coef0};
-  st = build_kernel_fn(SMMD_K_POLY, 2, prm, prm, 0.f, p->degree, p->d, &kf);
-  if (st != SMMD_OK) return st;
   const int64_t m = p->subset_size, nloc = kid_local(p);
   const int64_t var_at_m = p->var_at_m > 0 ? p->var_at_m : m;
-  const int prec = kid_precision(p);
-  char* ws = static_cast<char*>(workspace);
   double* stats = nullptr;
-  if (prec == SMMD_PREC_FP32) {
-    g_path = "simt_fp32_kid";
-    const SimtPlan pl = simt_plan(m, m, p->d, nloc);
-    float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
-    float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
-    stats = reinterpret_cast<double*>(ws + pl.off_stats);
-    SMMD_CUDA(launch_gather_f32(codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc, m,
-                                Z, norms, pl.dpitch, s));
-    Geometry g{m, m, p->d, 0, m, 0, m, 0};
-    Coefs c = make_coefs(g, kf);
-    prof_begin(s);
-    SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, nloc, stats, nullptr, nullptr, 1, s));
-    prof_end(s);
-  } else {
-    if (!tc_kid_supported(p->d)) return SMMD_EUNSUPPORTED;
-    int launches = 0;
-    cudaError_t e = tc_kid_run(kf, codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc,
-                               m, prec, p->ret_var || p->mmd_est == SMMD_EST_USTAT, workspace, workspace_bytes, &stats,
-                               s, &launches, &g_path);
-    g_launches += launches;
-    if (e != cudaSuccess) return cuda_fail(e);
-  }
+  st = kid_row_stats(p, codes_g, codes_r, idx_g, idx_r, p->ret_var || p->mmd_est == SMMD_EST_USTAT, workspace,
+                     workspace_bytes, s, &stats);
+  if (st != SMMD_OK) return st;
   SMMD_CUDA(launch_finalize_kid(stats, nloc, m, p->first_subset, p->mmd_est, p->ret_var, var_at_m, mmd2_out, var_out, s));
+  return SMMD_OK;
+}
+
+// ---- 3-sample test sums (gan/core/mmd.py:429-444, 515-539) -----------------------------------------
+static int validate_poly_sums(const smmd_kid_problem* p) {
+  int st = validate_kid(p);
+  if (st != SMMD_OK) return st;
+  // X, Y (and the saved Z) are equally sized samples (mmd.py:516 "Assumes X, Y, Z are same shape")
+  if (p->n_subsets != 1 || p->n_g != p->subset_size || p->n_r != p->subset_size) return SMMD_ESHAPE;
+  if (p->first_subset != 0 || p->n_local > 1) return SMMD_EINVAL;
+  return SMMD_OK;
+}
+
+size_t smmd_poly_sums_workspace_bytes(const smmd_kid_problem* p) {
+  if (validate_poly_sums(p) != SMMD_OK) return 0;
+  return smmd_kid_workspace_bytes(p);
+}
+
+int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void* Y, double* sums_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_path = "none";
+  int st = validate_poly_sums(p);
+  if (st != SMMD_OK) return st;
+  if (!X || !Y || !sums_out) return SMMD_EINVAL;
+  if (!device_ok()) return SMMD_EARCH;
+  const size_t need = smmd_poly_sums_workspace_bytes(p);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* stats = nullptr;
+  st = kid_row_stats(p, X, Y, nullptr, nullptr, 1, workspace, workspace_bytes, s, &stats);
+  if (st != SMMD_OK) return st;
+  SMMD_CUDA(launch_poly_sums(stats, p->subset_size, sums_out, s));
   return SMMD_OK;
 }
 

@@ -116,6 +116,7 @@ cudaError_t launch_combine_mmd2(const KernelFn& kf, const Geometry& g, const dou
                                 cudaStream_t s);
 cudaError_t launch_finalize_ratio(const KernelFn& kf, const Geometry& g, const double* stats, double min_var_est,
                                   double* scalars, cudaStream_t s);
+cudaError_t launch_poly_sums(const double* stats, int64_t m, double* out, cudaStream_t s);
 cudaError_t launch_finalize_kid(const double* stats, int64_t nsub, int64_t msub, int64_t first, int est,
                                 int ret_var, int64_t var_at_m, double* mmd2_out, double* var_out, cudaStream_t s);
 cudaError_t launch_kernel_xy(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,

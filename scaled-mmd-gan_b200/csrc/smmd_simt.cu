@@ -697,6 +697,33 @@ cudaError_t launch_finalize_kid(const double* stats, int64_t nsub, int64_t msub,
   return cudaGetLastError();
 }
 
+// gan/core/mmd.py:515-539 (_np_get_sums): per-row statistics -> the five "Y related sums" of the 3-sample test.
+// stats: [2m][RS_COUNT] (X rows then Y rows); out: [0,m) Kt_YY_sums, [m,2m) K_XY_sums_0 (per y_j), [2m,3m)
+// K_XY_sums_1 (per x_i), [3m] Kt_YY_2_sum, [3m+1] K_XY_2_sum.  One CTA, fixed reduction order.
+__global__ void __launch_bounds__(256) poly_sums_kernel(const double* stats, int64_t m, double* out) {
+  extern __shared__ double shd[];
+  double q[2] = {0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < m; i += 256) {
+    const double* sx = stats + i * RS_COUNT;
+    const double* sy = stats + (m + i) * RS_COUNT;
+    out[i] = sy[RS_SAME];            // off-diagonal row sum of K_YY
+    out[m + i] = sy[RS_CROSS];       // sum_x K(x, y_i)
+    out[2 * m + i] = sx[RS_CROSS];   // sum_y K(x_i, y)
+    q[0] += sy[RS_SQ_SAME];
+    q[1] += sx[RS_SQ_CROSS];
+  }
+  block_reduce<2>(q, shd);
+  if (threadIdx.x == 0) {
+    out[3 * m] = q[0];
+    out[3 * m + 1] = q[1];
+  }
+}
+
+cudaError_t launch_poly_sums(const double* stats, int64_t m, double* out, cudaStream_t s) {
+  poly_sums_kernel<<<1, 256, 2 * 256 * sizeof(double), s>>>(stats, m, out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_XY_only: dense witness block (the one place an m x n matrix is written, because the caller asks
 // for it) and its VJP through the row kernel in witness mode.

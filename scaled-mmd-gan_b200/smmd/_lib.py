@@ -26,6 +26,7 @@ EXPORTS = [
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
+    "smmd_poly_sums_workspace_bytes", "smmd_poly_sums",
     "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms",
 ]
 
@@ -101,6 +102,10 @@ def load():
     lib.smmd_kid_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
     lib.smmd_kid_subsets.restype = C.c_int
     lib.smmd_kid_subsets.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_poly_sums_workspace_bytes.restype = C.c_size_t
+    lib.smmd_poly_sums_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
+    lib.smmd_poly_sums.restype = C.c_int
+    lib.smmd_poly_sums.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, C.c_size_t, vp]
     _lib = lib
     return lib
 

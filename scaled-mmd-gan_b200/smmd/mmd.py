@@ -318,3 +318,136 @@ def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
                                      _as_ptr(ws), nbytes, _stream_ptr(dev))
         _lib.check(st, "smmd_mmd2_and_ratio")
     return (scalars[_lib.S_MMD2].float(), scalars[_lib.S_RATIO].float(), scalars[_lib.S_VAR].float())
+
+
+# ---------------------------------------------------------------------------------------------------
+# 3-sample test of the scorer (reference gan/core/mmd.py:296-539, caller gan/utils/scorer.py:119-163)
+# ---------------------------------------------------------------------------------------------------
+def polynomial_related_sums(X, Y, precision=None):
+    """The five sums of `_get_sums` / `_np_get_sums` (mmd.py:405-426, 515-539) for the cubic kernel
+    K = (A B^T / d + 1)^3, computed on the GPU without materialising K_XY / K_YY (smmd_poly_sums).
+    X, Y: CUDA [m, d] of equal shape.  Returns (Kt_YY_sums[m], Kt_YY_2_sum, K_XY_sums_0[m], K_XY_sums_1[m],
+    K_XY_2_sum) as float64 device tensors."""
+    lib = _lib.load()
+    if not (isinstance(X, torch.Tensor) and isinstance(Y, torch.Tensor) and X.is_cuda and Y.is_cuda):
+        raise RuntimeError("smmd: the 3-sample sums need CUDA tensors; there is no CPU fallback")
+    if X.dim() != 2 or X.shape != Y.shape:
+        raise ValueError("X and Y must be 2-D with the same shape (mmd.py:516)")
+    Xc, ldx = _rows(X.detach())
+    Yc, ldy = _rows(Y.detach())
+    if Yc.dtype != Xc.dtype:
+        Yc = Yc.to(Xc.dtype)
+    m, d = Xc.shape
+    p = _lib.KidProblem()
+    p.n_g = p.n_r = m
+    p.d = d
+    p.ldg, p.ldr = ldx, ldy
+    p.dtype = _lib.F32 if Xc.dtype == torch.float32 else _lib.BF16
+    p.n_subsets, p.subset_size, p.degree = 1, m, 3
+    p.gamma, p.coef0 = -1.0, 1.0
+    p.var_at_m, p.mmd_est, p.ret_var = 0, _lib.ESTIMATORS["unbiased"], 1
+    p.precision = _lib.PRECISIONS[precision or "auto"]
+    p.first_subset, p.n_local = 0, 0
+    dev = Xc.device
+    with torch.cuda.device(dev):
+        nbytes = lib.smmd_poly_sums_workspace_bytes(C.byref(p))
+        if nbytes == 0:
+            raise _lib.SmmdError(-2, "smmd_poly_sums_workspace_bytes", "problem rejected (shape/params)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(3 * m + 2, dtype=torch.float64, device=dev)
+        st = lib.smmd_poly_sums(C.byref(p), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(out), _as_ptr(ws), nbytes, _stream_ptr(dev))
+        _lib.check(st, "smmd_poly_sums")
+    return out[:m], out[3 * m], out[m:2 * m], out[2 * m:3 * m], out[3 * m + 1]
+
+
+def _diff_mmd2_and_ratio_from_sums(Y_related_sums, Z_related_sums, m, const_diagonal=False):
+    """mmd.py:339-402 / 447-512: MMD^2(X,Y) - MMD^2(X,Z), and its ratio to the estimated standard deviation.
+    Works on torch tensors or numpy arrays (vectors of length m and scalars); `const_diagonal` is accepted for
+    signature compatibility (the reference ignores it here as well)."""
+    yy_r, yy_q, xy_c, xy_r, xy_q = Y_related_sums
+    zz_r, zz_q, xz_c, xz_r, xz_q = Z_related_sums
+    m = float(m)
+    mm1, mm = m * (m - 1), m * m
+    mu_yy, mu_zz = yy_r.sum() / mm1, zz_r.sum() / mm1
+    mu_xy, mu_xz = xy_c.sum() / mm, xz_c.sum() / mm
+    t3, t2 = mm1 * (m - 2), mm * (m - 1)
+    e_y_yy, e_z_zz = ((yy_r * yy_r).sum() - yy_q) / t3, ((zz_r * zz_r).sum() - zz_q) / t3
+    e_x_xy, e_x_xz = ((xy_r * xy_r).sum() - xy_q) / t2, ((xz_r * xz_r).sum() - xz_q) / t2
+    e_y_xy, e_z_xz = ((xy_c * xy_c).sum() - xy_q) / t2, ((xz_c * xz_c).sum() - xz_q) / t2
+    c_y, c_z = (yy_r * xy_c).sum() / t2, (zz_r * xz_c).sum() / t2
+    c_x = (xy_r * xz_r).sum() / (mm * m)
+    cross = (-2 * c_y + 2 * mu_yy * mu_xy - 2 * c_x + 2 * mu_xy * mu_xz - 2 * c_z + 2 * mu_zz * mu_xz)
+    mmd2_diff = mu_yy - 2 * mu_xy - mu_zz + 2 * mu_xz
+    first_order = 4 * (m - 2) / mm1 * (e_y_yy - mu_yy ** 2 + e_x_xy - mu_xy ** 2 + e_y_xy - mu_xy ** 2
+                                       + e_z_zz - mu_zz ** 2 + e_x_xz - mu_xz ** 2 + e_z_xz - mu_xz ** 2 + cross)
+    second_order = 2 / mm1 * (yy_q / mm1 - mu_yy ** 2 + 2 * xy_q / mm - 2 * mu_xy ** 2
+                              + zz_q / mm1 - mu_zz ** 2 + 2 * xz_q / mm - 2 * mu_xz ** 2 + 2 * cross)
+    var_est = first_order + second_order
+    if isinstance(var_est, torch.Tensor):
+        ratio = mmd2_diff / torch.sqrt(torch.clamp(var_est, min=_eps))
+    else:
+        ratio = mmd2_diff / max(float(var_est), _eps) ** 0.5
+    return mmd2_diff, ratio
+
+
+_np_diff_mmd2_and_ratio_from_sums = _diff_mmd2_and_ratio_from_sums   # mmd.py:447 (same arithmetic on numpy)
+
+
+def _sums_like(sums, like):
+    """Hand the sums back in the caller's world: numpy in -> numpy (float64) out."""
+    if isinstance(like, torch.Tensor):
+        return sums
+    return tuple(s.cpu().numpy() if s.dim() else float(s.item()) for s in sums)
+
+
+def _codes_to_device(a):
+    if isinstance(a, torch.Tensor):
+        return a if a.is_cuda else a.cuda()
+    import numpy as np
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def np_diff_polynomial_mmd2_and_ratio_with_saving(X, Y, saved_sums_for_Z, precision=None):
+    """mmd.py:429-444 (scorer.py:129,157): numpy (or torch) codes X = real, Y = new fake sample, and the sums
+    saved from an earlier call for the older sample Z.  Returns the sums of (X, Y) when `saved_sums_for_Z` is
+    None, else (mmd2_diff, ratio, Y_related_sums)."""
+    sums = polynomial_related_sums(_codes_to_device(X), _codes_to_device(Y), precision=precision)
+    if saved_sums_for_Z is None:
+        return _sums_like(sums, X)
+    m = float(Y.shape[0])
+    if isinstance(X, torch.Tensor):
+        saved = tuple(torch.as_tensor(s, dtype=torch.float64, device=sums[0].device) for s in saved_sums_for_Z)
+        diff, ratio = _diff_mmd2_and_ratio_from_sums(sums, saved, m)
+        return diff, ratio, sums
+    host = _sums_like(sums, X)
+    diff, ratio = _diff_mmd2_and_ratio_from_sums(host, saved_sums_for_Z, m)
+    return float(diff), float(ratio), host
+
+
+def diff_polynomial_mmd2_and_ratio_with_saving(X, Y, saved_sums_for_Z, precision=None):
+    """mmd.py:307-319 (graph version of the above): torch tensors in, torch scalars out."""
+    sums = polynomial_related_sums(X, Y, precision=precision)
+    diff, ratio = _diff_mmd2_and_ratio_from_sums(sums, saved_sums_for_Z, float(Y.shape[0]))
+    return diff, ratio, sums
+
+
+def diff_polynomial_mmd2_and_ratio(X, Y, Z, precision=None):
+    """mmd.py:296-304: MMD^2(X,Y) - MMD^2(X,Z) with the cubic kernel, and its test statistic."""
+    ys = polynomial_related_sums(X, Y, precision=precision)
+    zs = polynomial_related_sums(X, Z, precision=precision)
+    return _diff_mmd2_and_ratio_from_sums(ys, zs, float(Y.shape[0]))
+
+
+def _np_get_sums(K_XY, K_YY, const_diagonal=False):
+    """mmd.py:515-539 on dense blocks (numpy or torch), for callers that already hold the matrices."""
+    m = float(K_YY.shape[0])
+    if const_diagonal is not False:
+        diag = float(const_diagonal)
+        diag2 = m * diag ** 2
+    else:
+        diag = K_YY.diagonal()
+        diag2 = (diag * diag).sum()
+    return (K_YY.sum(1) - diag, (K_YY * K_YY).sum() - diag2, K_XY.sum(0), K_XY.sum(1), (K_XY * K_XY).sum())
+
+
+_get_sums = _np_get_sums   # mmd.py:405-426
