@@ -156,6 +156,16 @@ SMMD_API int smmd_kernel_xy(const smmd_problem* p, const void* X, const void* Y,
 SMMD_API int smmd_kernel_xy_bwd(const smmd_problem* p, const void* X, const void* Y, const float* dK,
                        int64_t lddk, float* dX, float* dY, void* stream);
 
+/* Second-order VJP of the witness block: the backward of smmd_kernel_xy_bwd, needed because the gradient
+ * penalty differentiates |d witness / d x_hat| again w.r.t. the critic (gan/core/model.py:336-341,
+ * `tf.gradients(witness, [x_hat_data])` inside the loss that `tf.gradients(d_loss, d_vars)` then differentiates).
+ * Inputs: X [m,d], Y [n,d], dK [m,n] as in smmd_kernel_xy_bwd; VX [m,d] / VY [n,d] fp32 contiguous cotangents of
+ * that call's (dX, dY) (either may be NULL = zero).  Outputs (fp32, contiguous): ddK [m,n] = dL/d(dK),
+ * gX [m,d] = dL/dX, gY [n,d] = dL/dY.  Not available for the poly / tanh_* kernel ids (SMMD_EUNSUPPORTED): tanh
+ * is applied to the features by the caller. */
+SMMD_API int smmd_kernel_xy_bwd2(const smmd_problem* p, const void* X, const void* Y, const float* dK, int64_t lddk,
+                        const float* VX, const float* VY, float* ddK, float* gX, float* gY, void* stream);
+
 /* KID: polynomial_mmd_averages over subsets given by explicit row indices.
  *   Replaces gan/compute_scores.py:211-229 (subset loop + fancy-index gather), :232-244
  *   (polynomial_mmd = 3x sklearn polynomial_kernel) and :252-335 (_mmd2_and_variance), as called

@@ -371,6 +371,34 @@ int smmd_kernel_xy_bwd(const smmd_problem* p, const void* X, const void* Y, cons
   return SMMD_OK;
 }
 
+int smmd_kernel_xy_bwd2(const smmd_problem* p, const void* X, const void* Y, const float* dK, int64_t lddk,
+                        const float* VX, const float* VY, float* ddK, float* gX, float* gY, void* stream) {
+  g_launches = 0;
+  g_path = "simt_fp32_kxy_bwd2";
+  if (!dK || !ddK || !gX || !gY || (p && lddk < p->n)) return SMMD_EINVAL;
+  if (p && (p->kernel_id == SMMD_K_POLY || p->kernel_id == SMMD_K_TANH_DISTANCE || p->kernel_id == SMMD_K_TANH_MIX_RQ))
+    return SMMD_EUNSUPPORTED;   // tanh kernels: the caller applies tanh to the features (smmd/mmd.py kernel_xy)
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KernelFn kf;
+  float *Z, *norms;
+  SimtPlan pl;
+  int st = witness_common(p, X, Y, &kf, &Z, &norms, &pl, s);
+  if (st != SMMD_OK) return st;
+  float* AB = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&AB), (size_t)2 * p->m * p->n * sizeof(float), s);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(Z, s);
+    return cuda_fail(e);
+  }
+  e = launch_kernel_xy_bwd2(kf, Z, norms, pl.dpitch, p->m, p->n, p->d, dK, lddk, VX, VY, ddK, AB, AB + p->m * p->n, gX,
+                            gY, s);
+  cudaFreeAsync(AB, s);
+  cudaFreeAsync(Z, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 3;
+  return SMMD_OK;
+}
+
 // ---- KID -----------------------------------------------------------------------------------------
 static int validate_kid(const smmd_kid_problem* p) {
   if (!p) return SMMD_EINVAL;

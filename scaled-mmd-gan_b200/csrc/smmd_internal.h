@@ -124,5 +124,8 @@ cudaError_t launch_kernel_xy(const KernelFn& kf, const float* Z, const float* no
 cudaError_t launch_kernel_xy_bwd(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,
                                  int64_t n, int64_t d, const float* dK, int64_t lddk, float* dX, float* dY,
                                  cudaStream_t s);
+cudaError_t launch_kernel_xy_bwd2(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,
+                                  int64_t n, int64_t d, const float* dK, int64_t lddk, const float* VX, const float* VY,
+                                  float* ddK, float* A, float* B, float* gX, float* gY, cudaStream_t s);
 
 }  // namespace smmd

@@ -80,6 +80,52 @@ __device__ __forceinline__ PairVal eval_exact(const KernelFn& f, float G, float 
   return r;
 }
 
+// First and second derivative of the distance part g(D) of a kernel (k = g(D) + kg*G + f(|a|^2) + f(|b|^2)),
+// for the double backward of the witness (gradient penalty, gan/core/model.py:327-350).  Same clamping
+// conventions as eval_exact: the reference's max(D, 0) has zero derivative on the clamped side.
+struct PairD2 {
+  float kd, kdd;
+};
+__device__ __forceinline__ PairD2 eval_second(const KernelFn& f, float Draw) {
+  PairD2 r;
+  r.kd = 0.f;
+  r.kdd = 0.f;
+  switch (f.family) {
+    case FAM_DISTANCE: {
+      float t = Draw + kEps;
+      if (t > 0.f) {
+        float root = sqrtf(t);
+        r.kd = -0.5f / root;
+        r.kdd = 0.25f / (root * t);
+      }
+      break;
+    }
+    case FAM_RBF: {
+      if (Draw > 0.f) {
+        for (int i = 0; i < f.np; ++i) {
+          float e = f.w[i] * expf(-f.p0[i] * Draw);
+          r.kd -= f.p0[i] * e;
+          r.kdd += f.p0[i] * f.p0[i] * e;
+        }
+      }
+      break;
+    }
+    case FAM_RQ: {
+      if (Draw > 0.f) {
+        for (int i = 0; i < f.np; ++i) {
+          float base = 1.f + Draw * f.p0[i];   // 1 + D/(2 alpha), p0 = 1/(2 alpha), p1 = alpha
+          float e = f.w[i] * expf(-f.p1[i] * logf(base));
+          r.kd -= 0.5f * e / base;
+          r.kdd += 0.5f * f.p0[i] * (f.p1[i] + 1.f) * e / (base * base);
+        }
+      }
+      break;
+    }
+    default: break;   // dot: no distance part
+  }
+  return r;
+}
+
 // Analytic diagonal value k(a, a) (D = 0 exactly in the reference because the norms ARE the Gram diagonal).
 __device__ __forceinline__ float diag_value(const KernelFn& f, float ni) {
   switch (f.family) {

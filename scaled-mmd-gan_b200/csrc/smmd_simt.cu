@@ -784,4 +784,146 @@ cudaError_t launch_kernel_xy_bwd(const KernelFn& kf, const float* Z, const float
   return launch_rows_t<true>(a, 1, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// second-order VJP of the witness block (gradient penalty: the gradient of |d witness / d x_hat| flows back
+// into the critic through K_XY's first backward, gan/core/model.py:336-341).
+// First backward:  gX_i = sum_j dK_ij [2 k'(D_ij)(x_i - y_j) + kg y_j + 2 f'(|x_i|^2) x_i]   (gY_j alike).
+// With cotangents VX, VY of (gX, gY):  L = sum_ij dK_ij [2 k' u_ij + kg p_ij + 2 f'(n_i) s_i + 2 f'(n_j) t_j],
+//   u_ij = <VX_i - VY_j, x_i - y_j>,  p_ij = <VX_i, y_j> + <VY_j, x_i>,  s_i = <VX_i, x_i>,  t_j = <VY_j, y_j>.
+// Kernel 1 (per pair): dL/ddK_ij and the pair weights A_ij = 4 dK_ij k'' u_ij, B_ij = 2 dK_ij k'.
+// Kernel 2 (per row):  dL/dx_i = sum_j [A_ij (x_i - y_j) + B_ij (VX_i - VY_j) + kg dK_ij VY_j]
+//                                + r_i [4 f''(n_i) s_i x_i + 2 f'(n_i) VX_i],   r_i = sum_j dK_ij   (dL/dy_j alike).
+// f(n) = sqrt(n + eps) only for the distance kernel (mmd.py:29); zero otherwise.
+// ------------------------------------------------------------------------------------------------
+struct Kxy2Args {
+  KernelFn kf;
+  const float* Z;       // [m + n][dpitch] stacked fp32 rows (prep output)
+  const float* norms;
+  int64_t dpitch, m, n, d;
+  const float* dK;
+  int64_t lddk;
+  const float* VX;      // [m][d] or null
+  const float* VY;      // [n][d] or null
+  float* ddK;           // [m][n]
+  float* A;             // [m][n] scratch
+  float* B;             // [m][n] scratch
+  float* gX;            // [m][d]
+  float* gY;            // [n][d]
+  float kg;             // coefficient of the Gram (dot) part of the kernel
+};
+
+__device__ __forceinline__ float dist_f1(float n) { return 0.5f * rsqrtf(n + kEps); }              // f'
+__device__ __forceinline__ float dist_f2(float n) { return -0.25f * rsqrtf(n + kEps) / (n + kEps); }  // f''
+
+__global__ void __launch_bounds__(256) kxy_bwd2_pair_kernel(Kxy2Args a) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.y * 8 + w, j = (int64_t)blockIdx.x * 32 + lane;
+  if (i >= a.m || j >= a.n) return;
+  const float* x = a.Z + i * a.dpitch;
+  const float* y = a.Z + (a.m + j) * a.dpitch;
+  const float* vx = a.VX ? a.VX + i * a.d : nullptr;
+  const float* vy = a.VY ? a.VY + j * a.d : nullptr;
+  float Dd = 0.f, u = 0.f, pd = 0.f, sx = 0.f, ty = 0.f;
+  for (int64_t c = 0; c < a.d; ++c) {
+    const float xc = x[c], yc = y[c];
+    const float vxc = vx ? vx[c] : 0.f, vyc = vy ? vy[c] : 0.f;
+    const float e = xc - yc;
+    Dd = fmaf(e, e, Dd);
+    u = fmaf(vxc - vyc, e, u);
+    pd = fmaf(vxc, yc, pd);
+    pd = fmaf(vyc, xc, pd);
+    sx = fmaf(vxc, xc, sx);
+    ty = fmaf(vyc, yc, ty);
+  }
+  const PairD2 dd = eval_second(a.kf, Dd);
+  float g = 2.f * dd.kd * u + a.kg * pd;
+  if (a.kf.family == FAM_DISTANCE && a.kf.true_distance)
+    g += 2.f * dist_f1(a.norms[i]) * sx + 2.f * dist_f1(a.norms[a.m + j]) * ty;
+  const float dk = a.dK[i * a.lddk + j];
+  a.ddK[i * a.n + j] = g;
+  a.A[i * a.n + j] = 4.f * dk * dd.kdd * u;
+  a.B[i * a.n + j] = 2.f * dk * dd.kd;
+}
+
+template <bool ROWS_X>
+__global__ void __launch_bounds__(128) kxy_bwd2_rows_kernel(Kxy2Args a) {
+  __shared__ float red[2][4];
+  const int64_t row = blockIdx.x;                        // i (X rows) or j (Y rows)
+  const int64_t cnt = ROWS_X ? a.n : a.m;                // partners
+  const float* self = a.Z + (ROWS_X ? row : a.m + row) * a.dpitch;
+  const float* vself = ROWS_X ? (a.VX ? a.VX + row * a.d : nullptr) : (a.VY ? a.VY + row * a.d : nullptr);
+  const float* vother_base = ROWS_X ? a.VY : a.VX;
+  float* out = (ROWS_X ? a.gX : a.gY) + row * a.d;
+  const bool dist = a.kf.family == FAM_DISTANCE && a.kf.true_distance;
+  // r = sum of dK over partners, s = <V_row, z_row> (distance kernel only)
+  float r = 0.f, sdot = 0.f;
+  if (dist) {
+    for (int64_t k = threadIdx.x; k < cnt; k += 128) r += ROWS_X ? a.dK[row * a.lddk + k] : a.dK[k * a.lddk + row];
+    if (vself)
+      for (int64_t c = threadIdx.x; c < a.d; c += 128) sdot = fmaf(vself[c], self[c], sdot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r += __shfl_xor_sync(0xffffffffu, r, o);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = r;
+      red[1][threadIdx.x >> 5] = sdot;
+    }
+    __syncthreads();
+    r = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    sdot = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
+  const float nself = a.norms[ROWS_X ? row : a.m + row];
+  for (int64_t c = threadIdx.x; c < a.d; c += 128) {
+    const float zc = self[c];
+    const float vc = vself ? vself[c] : 0.f;
+    float acc = 0.f;
+    for (int64_t k = 0; k < cnt; ++k) {
+      const int64_t ij = ROWS_X ? row * a.n + k : k * a.n + row;
+      const float Aij = a.A[ij], Bij = a.B[ij];
+      const float oc = a.Z[(ROWS_X ? a.m + k : k) * a.dpitch + c];          // partner feature
+      const float voc = vother_base ? vother_base[k * a.d + c] : 0.f;      // partner cotangent
+      // X rows:  A (x - y) + B (vx - vy) + kg dK vy      Y rows: -A (x - y) - B (vx - vy) + kg dK vx
+      //          = A (z - o) + B (v - vo) + ...                  = A (z - o) + B (v - vo) + ...   (sign folds in)
+      acc = fmaf(Aij, zc - oc, acc);
+      acc = fmaf(Bij, vc - voc, acc);
+      if (a.kg != 0.f) acc = fmaf(a.kg * (ROWS_X ? a.dK[row * a.lddk + k] : a.dK[k * a.lddk + row]), voc, acc);
+    }
+    if (dist) acc += r * (4.f * dist_f2(nself) * sdot * zc + 2.f * dist_f1(nself) * vc);
+    out[c] = acc;
+  }
+}
+
+cudaError_t launch_kernel_xy_bwd2(const KernelFn& kf, const float* Z, const float* norms, int64_t dpitch, int64_t m,
+                                  int64_t n, int64_t d, const float* dK, int64_t lddk, const float* VX, const float* VY,
+                                  float* ddK, float* A, float* B, float* gX, float* gY, cudaStream_t s) {
+  Kxy2Args a;
+  a.kf = kf;
+  a.Z = Z;
+  a.norms = norms;
+  a.dpitch = dpitch;
+  a.m = m;
+  a.n = n;
+  a.d = d;
+  a.dK = dK;
+  a.lddk = lddk;
+  a.VX = VX;
+  a.VY = VY;
+  a.ddK = ddK;
+  a.A = A;
+  a.B = B;
+  a.gX = gX;
+  a.gY = gY;
+  a.kg = kf.family == FAM_DOT ? 1.f : (kf.family == FAM_RQ ? kf.add_dot : 0.f);
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 7) / 8));
+  kxy_bwd2_pair_kernel<<<grid, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  kxy_bwd2_rows_kernel<true><<<(unsigned)m, 128, 0, s>>>(a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  kxy_bwd2_rows_kernel<false><<<(unsigned)n, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace smmd

@@ -25,7 +25,7 @@ EXPORTS = [
     "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
     "smmd_mmd2_and_ratio",
-    "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
+    "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_poly_sums_workspace_bytes", "smmd_poly_sums",
     "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms",
 ]
@@ -98,6 +98,8 @@ def load():
     lib.smmd_kernel_xy.argtypes = [C.POINTER(Problem), vp, vp, vp, i64, vp]
     lib.smmd_kernel_xy_bwd.restype = C.c_int
     lib.smmd_kernel_xy_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, i64, vp, vp, vp]
+    lib.smmd_kernel_xy_bwd2.restype = C.c_int
+    lib.smmd_kernel_xy_bwd2.argtypes = [C.POINTER(Problem), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.smmd_kid_workspace_bytes.restype = C.c_size_t
     lib.smmd_kid_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
     lib.smmd_kid_subsets.restype = C.c_int

@@ -181,30 +181,73 @@ class _KernelXY(torch.autograd.Function):
         with torch.cuda.device(Xc.device):
             st = lib.smmd_kernel_xy(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(K), n, _stream_ptr(Xc.device))
         _lib.check(st, "smmd_kernel_xy")
-        ctx.save_for_backward(Xc, Yc)
+        ctx.save_for_backward(X, Y)   # the inputs themselves: the backward is differentiable w.r.t. them
         ctx.spec = spec
-        ctx.in_dtypes = (X.dtype, Y.dtype)
         return K
 
     @staticmethod
     def backward(ctx, dK):
-        Xc, Yc = ctx.saved_tensors
+        X, Y = ctx.saved_tensors
+        dX, dY = _KernelXYBackward.apply(X, Y, dK, ctx.spec)
+        return dX, dY, None
+
+
+class _KernelXYBackward(torch.autograd.Function):
+    """(X, Y, dK) -> (dX, dY) of the witness block, itself differentiable once more: the gradient penalty
+    (model.py:336-341) takes the gradient of the witness w.r.t. the critic input and then differentiates its norm
+    w.r.t. the critic weights, which runs through this op's backward (smmd_kernel_xy_bwd2)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, dK, spec):
         lib = _lib.load()
-        spec = ctx.spec
+        Xc, _ = _rows(X.detach().float())
+        Yc, _ = _rows(Y.detach().float())
         m, d = Xc.shape
         n = Yc.shape[0]
-        dK = dK.contiguous().float()
+        dKc = dK.detach().contiguous().float()
         prob = spec.problem(m, n, d, Xc.stride(0), Yc.stride(0), torch.float32, precision="fp32")
         dX = torch.empty((m, d), dtype=torch.float32, device=Xc.device)
         dY = torch.empty((n, d), dtype=torch.float32, device=Xc.device)
         with torch.cuda.device(Xc.device):
-            st = lib.smmd_kernel_xy_bwd(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(dK), n, _as_ptr(dX),
+            st = lib.smmd_kernel_xy_bwd(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(dKc), n, _as_ptr(dX),
                                         _as_ptr(dY), _stream_ptr(Xc.device))
         _lib.check(st, "smmd_kernel_xy_bwd")
-        return dX.to(ctx.in_dtypes[0]), dY.to(ctx.in_dtypes[1]), None
+        ctx.save_for_backward(Xc, Yc, dKc)
+        ctx.spec = spec
+        ctx.dtypes = (X.dtype, Y.dtype, dK.dtype)
+        return dX.to(X.dtype), dY.to(Y.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, VX, VY):
+        Xc, Yc, dKc = ctx.saved_tensors
+        lib = _lib.load()
+        spec = ctx.spec
+        m, d = Xc.shape
+        n = Yc.shape[0]
+        VXc = VX.contiguous().float() if VX is not None else None
+        VYc = VY.contiguous().float() if VY is not None else None
+        prob = spec.problem(m, n, d, Xc.stride(0), Yc.stride(0), torch.float32, precision="fp32")
+        ddK = torch.empty((m, n), dtype=torch.float32, device=Xc.device)
+        gX = torch.empty((m, d), dtype=torch.float32, device=Xc.device)
+        gY = torch.empty((n, d), dtype=torch.float32, device=Xc.device)
+        with torch.cuda.device(Xc.device):
+            st = lib.smmd_kernel_xy_bwd2(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(dKc), n, _as_ptr(VXc),
+                                         _as_ptr(VYc), _as_ptr(ddK), _as_ptr(gX), _as_ptr(gY), _stream_ptr(Xc.device))
+        _lib.check(st, "smmd_kernel_xy_bwd2")
+        return gX.to(ctx.dtypes[0]), gY.to(ctx.dtypes[1]), ddK.to(ctx.dtypes[2]), None
+
+
+_TANH_BASE = {_lib.K_TANH_DISTANCE: _lib.K_DISTANCE, _lib.K_TANH_MIX_RQ: _lib.K_MIX_RQ}
 
 
 def kernel_xy(spec, X, Y):
+    """Dense, twice-differentiable K_XY (K_XY_only=True).  tanh_* kernels (mmd.py:40,139) apply tanh to the
+    features first, exactly as the reference does, and then use the base kernel."""
+    if spec.kernel_id in _TANH_BASE:
+        base = KernelSpec(_TANH_BASE[spec.kernel_id], spec.params, spec.wts, spec.add_dot, spec.const_diagonal,
+                          spec.degree, spec.name)
+        return _KernelXY.apply(torch.tanh(X), torch.tanh(Y), base)
     return _KernelXY.apply(X, Y, spec)
 
 
