@@ -52,7 +52,7 @@ const Tuning& tuning() {
     v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
     v.wz_min_d = 256;
     if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
-    v.wz_panel_bytes = (int64_t)4 << 30;
+    v.wz_panel_bytes = (int64_t)6 << 30;
     if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
     return v;
   }();
@@ -1273,8 +1273,8 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // The two-pass path below reaches 42% / 51% and has no upper limit on d:
 //   pass 1 (tc_wgen_kernel):  128 x 256 tiles of S = Z_i Z_j^T with K streamed through a 4-stage TMA ring (both
 //          operands, 48 KB per 64-deep step: 25% less L2 traffic per flop than 128 x 128), two 256-column TMEM
-//          accumulators alternate between the two epilogue groups; epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
-//          buffer W[panel rows][Mp] (K-major for pass 2).  The panel is sized by a byte budget (default 4 GB), so
+//          accumulators alternate between tiles, all 16 epilogue warps drain each tile; epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
+//          buffer W[panel rows][Mp] (K-major for pass 2).  The panel is sized by a byte budget (default 6 GB), so
 //          the N x N matrix never exists as a whole; panels run back to back on the stream.
 //   pass 2 (tc_wz_kernel):    O[256 rows x 256 features] = W[256 x Mp] Z[Mp x 256]: 2 x 128-row A panels and one
 //          64-row MN-major Z tile per 64-deep K step (64 KB / 1024 tensor cycles, the macro-tile ratio), all 512
@@ -1294,7 +1294,7 @@ struct WgenArgs {
   int slots;
   __nv_bfloat16* W;                 // [panel row blocks * 128][ldw]
   int64_t ldw;
-  float* rpart;                     // [grid][slots][4][128]   (part = epilogue group * 2 + column half)
+  float* rpart;                     // [grid][slots][4][128]   (part = column quarter of the tile)
   double* spart;                    // [grid][slots][4][128][2]
 };
 
@@ -1303,7 +1303,7 @@ constexpr int kWgStages = 4;
 constexpr int kWgStageBytes = BM * 128 + BNW * 128;       // one 128-row A panel + one 256-row B panel = 48 KB
 constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 1024;
 
-constexpr int kWgEpiWarps = 16;                           // 2 groups x (4 TMEM lane quarters x 2 column halves)
+constexpr int kWgEpiWarps = 16;                           // 4 TMEM lane quarters x 4 column quarters
 constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
 
 template <class Math>
@@ -1328,7 +1328,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 256);
+      mbar_init(&acc_empty[i], 512);
     }
     fence_mbar_init();
   }
@@ -1404,10 +1404,11 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       ab ^= 1;
     }
   } else {
-    // ===================== epilogue groups: tile parity = group; 8 warps per group =====================
-    const int grp = warp >> 3;
-    const int half = (warp >> 2) & 1;   // columns [half * 128, +128) of the tile
-    const int part = grp * 2 + half;
+    // ===================== epilogue: all 16 warps on every tile (TMEM lane quarter x column quarter) ==========
+    // With only two accumulators the issuer can start tile t+2 as soon as tile t is drained, so the drain latency
+    // of ONE tile is what matters: 16 warps on one tile halve it compared with two groups on alternate tiles
+    // (measured: tensor pipe 52% -> see profiles/).
+    const int part = warp >> 2;         // columns [part * 64, +64) of the tile
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -1428,7 +1429,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       double dsame = 0.0, dcross = 0.0;
       __nv_bfloat16* wrow = a.W + ((int64_t)rbl * BM + r) * a.ldw;
       for (int lt = 0; lt < TU; ++lt, ++tc) {
-        if ((int)(tc & 1) != grp) continue;
+        const int grp = (int)(tc & 1);   // accumulator buffer of this tile
         const int ct = ct0 + lt;
         const int c0 = col0_of(ct);
         const bool colX = ct < a.TX;
@@ -1442,8 +1443,8 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         tc_fence_after();
         const float* nj = a.norms + c0;
         float2 tsum = make_float2(0.f, 0.f);
-        const int h0 = half * (BNW / 32);
-        const int h1 = nch < h0 + BNW / 32 ? nch : h0 + BNW / 32;
+        const int h0 = part * (BNW / 64);
+        const int h1 = nch < h0 + BNW / 64 ? nch : h0 + BNW / 64;
         if (h1 <= h0) {   // nothing of this tile in my column half: only release the accumulator
           tc_fence_before();
           mbar_arrive(&acc_empty[grp]);
@@ -1900,7 +1901,14 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
   p.KT = (int)(p.Mp / 64);
   p.FB = (int)((p.dp + 255) / 256);
   int64_t P = tuning().wz_panel_bytes / (BM * p.Mp * 2);
-  P = std::max<int64_t>(2, P & ~int64_t(1));
+  const int sm = sm_count();
+  if (p.nrb > sm && P >= sm && sm % 2 == 0) {
+    // whole row blocks per CTA: all CTAs then sweep the column tiles in lockstep, so a Z_j tile is fetched from
+    // HBM once per wave instead of once per CTA (Z no longer fits L2 at N = 65536, d >= 512)
+    P = P / sm * sm;
+  } else {
+    P = std::max<int64_t>(2, P & ~int64_t(1));
+  }
   P = std::min<int64_t>(P, (p.nrb + 1) & ~1);
   p.P = (int)std::max<int64_t>(2, P);
   p.npanels = std::max(1, (p.nrb + p.P - 1) / p.P);
