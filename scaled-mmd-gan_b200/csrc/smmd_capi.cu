@@ -3,6 +3,7 @@
 // No CPU fallback exists: unsupported devices get SMMD_EARCH.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "smmd_internal.h"
 #include "smmd_tc.h"
@@ -225,9 +226,18 @@ static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double
   const int prec = resolve_precision(p, want_grad);
 
   if (prec == SMMD_PREC_FP32) {
-    g_path = "simt_fp32";
     const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
     char* ws = static_cast<char*>(workspace);
+    static const bool no_small = getenv("SMMD_DISABLE_SMALL") != nullptr;   // tests: force the general exact path
+    if (!no_small && small_mmd2_eligible(kf, g, src)) {   // latency-bound shapes: one launch (+ a 4-byte memset node)
+      g_path = "simt_fp32_small";
+      prof_begin(s);
+      SMMD_CUDA(launch_small_mmd2(kf, g, c, src, dX, dY, reinterpret_cast<double*>(ws + pl.off_stats),
+                                  reinterpret_cast<unsigned int*>(ws + pl.off_norm), scalars, s));
+      prof_end(s);
+      return SMMD_OK;
+    }
+    g_path = "simt_fp32";
     float* Z = reinterpret_cast<float*>(ws + pl.off_Z);
     float* norms = reinterpret_cast<float*>(ws + pl.off_norm);
     double* stats = reinterpret_cast<double*>(ws + pl.off_stats);

@@ -116,6 +116,9 @@ cudaError_t launch_combine_mmd2(const KernelFn& kf, const Geometry& g, const dou
                                 cudaStream_t s);
 cudaError_t launch_finalize_ratio(const KernelFn& kf, const Geometry& g, const double* stats, double min_var_est,
                                   double* scalars, cudaStream_t s);
+bool small_mmd2_eligible(const KernelFn& kf, const Geometry& g, const SrcLayout& src);
+cudaError_t launch_small_mmd2(const KernelFn& kf, const Geometry& g, const Coefs& c, const SrcLayout& src, float* dX,
+                              float* dY, double* partials, unsigned int* counter, double* scalars, cudaStream_t s);
 cudaError_t launch_poly_sums(const double* stats, int64_t m, double* out, cudaStream_t s);
 cudaError_t launch_finalize_kid(const double* stats, int64_t nsub, int64_t msub, int64_t first, int est,
                                 int ret_var, int64_t var_at_m, double* mmd2_out, double* var_out, cudaStream_t s);

@@ -697,6 +697,199 @@ cudaError_t launch_finalize_kid(const double* stats, int64_t nsub, int64_t msub,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// latency-bound shapes: ONE launch (every shipped YAML runs batch 64 with dof_dim 1..16)
+// ------------------------------------------------------------------------------------------------
+// Warp = row i, lanes = columns j (no shared column tiles, no block barriers in the pair loop): z_i and z_j live in
+// registers (DMAX features, template), S / D / |z_j|^2 straight from the fp32 inputs (8 KB in total, L1 resident),
+// eval_exact, fp64 row sums, and the gradient contribution of the pair is accumulated right there from the same
+// registers; the 32 per-lane partial rows are folded through shared memory in fixed order.  (A first version with
+// lanes = features in a second pass over the weights was a 5800-instruction dependent chain per warp: 28 us.)
+// The last CTA to finish
+// (ticket counter, zeroed by a memset node in front of the launch) folds the per-CTA partial sums in fixed order
+// and writes the scalars -- prep, row kernel and finalize of the general exact path in a single kernel.
+constexpr int kSmallMaxD = 64;
+constexpr int kSmallMaxM = 1024;
+
+struct SmallArgs {
+  KernelFn kf;
+  const float* X;
+  const float* Y;
+  int64_t ldx, ldy;
+  int m, n, d;
+  float a_xx, a_yy, a_xy;
+  int diag_in_sum, biased;
+  float* dX;
+  float* dY;
+  double* partials;        // [gridDim.x][6]
+  unsigned int* counter;
+  double* scalars;
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(256) small_mmd2_kernel(SmallArgs a) {
+  extern __shared__ float sm[];
+  const int M = a.m + a.n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* accS = sm + (warp * 32 + lane) * (DMAX + 1);   // [8][32][DMAX + 1]: per-lane partial gradient rows
+  __shared__ double red[kRowsPerCta][6];
+  __shared__ int is_last;
+  const int ig = blockIdx.x * kRowsPerCta + warp;
+  const bool row_valid = ig < M;
+  const bool rowX = ig < a.m;
+  double q[6] = {0, 0, 0, 0, 0, 0};   // sxx, syy, sxy, syx, dgx, dgy of this row
+  if (row_valid) {
+    const float* zi_p = rowX ? a.X + (int64_t)ig * a.ldx : a.Y + (int64_t)(ig - a.m) * a.ldy;
+    float zi[DMAX], acc[DMAX];
+    float ni = 0.f;
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) {
+      zi[c] = c < a.d ? zi_p[c] : 0.f;     // same address in all lanes: one broadcast load per feature
+      ni = fmaf(zi[c], zi[c], ni);
+      acc[c] = 0.f;
+    }
+    double s_same = 0.0, s_cross = 0.0;
+    for (int j = lane; j < M; j += 32) {
+      const bool colX = j < a.m;
+      const float* zj_p = colX ? a.X + (int64_t)j * a.ldx : a.Y + (int64_t)(j - a.m) * a.ldy;
+      float zj[DMAX];
+      float S = 0.f, Dd = 0.f, nj = 0.f;
+#pragma unroll
+      for (int c = 0; c < DMAX; ++c) {
+        zj[c] = c < a.d ? zj_p[c] : 0.f;
+        const float e = zi[c] - zj[c];
+        S = fmaf(zi[c], zj[c], S);
+        Dd = fmaf(e, e, Dd);
+        nj = fmaf(zj[c], zj[c], nj);
+      }
+      const PairVal pv = eval_exact(a.kf, S, Dd, ni, nj);
+      const bool same = (colX == rowX);
+      const float aco = same ? (rowX ? a.a_xx : a.a_yy) : a.a_xy;
+      float wd = 0.f, wg = 0.f;
+      if (j == ig) {
+        wg = a.diag_in_sum ? 2.f * aco * pv.kg : 0.f;
+      } else {
+        wd = 4.f * aco * pv.kd;
+        wg = 2.f * aco * pv.kg;
+        if (same) s_same += (double)pv.k;
+        else s_cross += (double)pv.k;
+      }
+      if (a.dX) {
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) acc[c] = fmaf(wd, zi[c] - zj[c], fmaf(wg, zj[c], acc[c]));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_same += __shfl_xor_sync(0xffffffffu, s_same, o);
+      s_cross += __shfl_xor_sync(0xffffffffu, s_cross, o);
+    }
+    const double dg = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                            : (double)diag_value(a.kf, ni);
+    q[rowX ? 0 : 1] = s_same;
+    q[rowX ? 2 : 3] = s_cross;
+    q[rowX ? 4 : 5] = dg;
+    if (a.dX) {
+      // fold the 32 per-lane partial rows: lane c sums feature c over the lanes in fixed order
+#pragma unroll
+      for (int c = 0; c < DMAX; ++c) accS[c] = acc[c];
+      __syncwarp();
+      const float* wbase = sm + warp * 32 * (DMAX + 1);
+      float* out = rowX ? a.dX + (int64_t)ig * a.d : a.dY + (int64_t)(ig - a.m) * a.d;
+      for (int c = lane; c < a.d; c += 32) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) t += wbase[l * (DMAX + 1) + c];
+        out[c] = t;
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) red[warp][i] = q[i];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) {
+      double t = 0.0;
+      for (int w = 0; w < kRowsPerCta; ++w) t += red[w][i];   // fixed order
+      a.partials[(int64_t)blockIdx.x * 6 + i] = t;
+    }
+    __threadfence();
+    is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < 6) {
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(a.partials + (int64_t)b * 6 + tid);   // fixed order
+    red[0][tid] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double* o = a.scalars;
+    const double* t = red[0];
+    for (int i = 0; i < SMMD_NUM_SCALARS; ++i) o[i] = 0.0;
+    o[SMMD_S_SUM_XX] = t[0];
+    o[SMMD_S_SUM_YY] = t[1];
+    o[SMMD_S_SUM_XY] = t[2];
+    o[SMMD_S_SUM_YX] = t[3];
+    o[SMMD_S_DIAG_X] = t[4];
+    o[SMMD_S_DIAG_Y] = t[5];
+    o[SMMD_S_MMD2] = mmd2_from_sums(a.kf, (double)a.m, (double)a.n, a.biased, t[0], t[1], t[2], t[3], t[4], t[5]);
+    bool bad = false;
+    for (int i = 0; i < 6; ++i) bad = bad || !isfinite(t[i]);
+    o[SMMD_S_NONFINITE] = bad ? 1.0 : 0.0;
+  }
+}
+
+bool small_mmd2_eligible(const KernelFn& kf, const Geometry& g, const SrcLayout& src) {
+  return src.dtype == SMMD_F32 && src.blk_x == 0 && src.blk_y == 0 && src.Xo == nullptr && !kf.tanh_features &&
+         g.d <= kSmallMaxD && g.m + g.n <= kSmallMaxM && g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n &&
+         kf.family != FAM_POLY;
+}
+
+cudaError_t launch_small_mmd2(const KernelFn& kf, const Geometry& g, const Coefs& c, const SrcLayout& src, float* dX,
+                              float* dY, double* partials, unsigned int* counter, double* scalars, cudaStream_t s) {
+  SmallArgs a;
+  a.kf = kf;
+  a.X = static_cast<const float*>(src.X);
+  a.Y = static_cast<const float*>(src.Y);
+  a.ldx = src.ldx;
+  a.ldy = src.ldy;
+  a.m = (int)g.m;
+  a.n = (int)g.n;
+  a.d = (int)g.d;
+  a.a_xx = (float)c.a_xx;
+  a.a_yy = (float)c.a_yy;
+  a.a_xy = (float)c.a_xy;
+  a.diag_in_sum = c.diag_in_sum;
+  a.biased = g.biased;
+  a.dX = dX;
+  a.dY = dY;
+  a.partials = partials;
+  a.counter = counter;
+  a.scalars = scalars;
+  const int M = a.m + a.n;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((M + kRowsPerCta - 1) / kRowsPerCta);
+  auto go = [&](auto kern, int dmax) -> cudaError_t {
+    const size_t smem = (size_t)kRowsPerCta * 32 * (dmax + 1) * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 != cudaSuccess) return e2;
+    }
+    kern<<<grid, 256, smem, s>>>(a);
+    return cudaGetLastError();
+  };
+  if (a.d <= 4) return go(small_mmd2_kernel<4>, 4);
+  if (a.d <= 16) return go(small_mmd2_kernel<16>, 16);
+  if (a.d <= 32) return go(small_mmd2_kernel<32>, 32);
+  return go(small_mmd2_kernel<64>, 64);
+}
+
 // gan/core/mmd.py:515-539 (_np_get_sums): per-row statistics -> the five "Y related sums" of the 3-sample test.
 // stats: [2m][RS_COUNT] (X rows then Y rows); out: [0,m) Kt_YY_sums, [m,2m) K_XY_sums_0 (per y_j), [2m,3m)
 // K_XY_sums_1 (per x_i), [3m] Kt_YY_2_sum, [3m+1] K_XY_2_sum.  One CTA, fixed reduction order.

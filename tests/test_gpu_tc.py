@@ -188,8 +188,8 @@ def test_auto_precision_dispatch_and_refusals():
 
     X, Y = _data(64, 64, 16, 1)
     Xt, Yt = torch.tensor(X, device=DEV, requires_grad=True), torch.tensor(Y, device=DEV, requires_grad=True)
-    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # small -> exact path
-    assert _lib.last_path() == "simt_fp32"
+    mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # small -> exact path, single launch
+    assert _lib.last_path() == "simt_fp32_small"
     Xb, Yb = _data(1024, 1024, 128, 2)
     Xt, Yt = torch.tensor(Xb, device=DEV, requires_grad=True), torch.tensor(Yb, device=DEV, requires_grad=True)
     mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt)).backward()                 # large -> tensor cores
