@@ -68,6 +68,7 @@ class KernelSpec:
         self.const_diagonal = const_diagonal
         self.degree = int(degree)
         self.name = name
+        self._key = (self.kernel_id, tuple(self.params), tuple(self.wts), self.add_dot, self.degree)
         if len(self.params) > _lib.MAX_PARAMS:
             raise ValueError("at most %d sigmas/alphas are supported" % _lib.MAX_PARAMS)
 
@@ -96,6 +97,9 @@ def _rows(t):
     return t, t.stride(0)
 
 
+_problem_cache = {}   # (kernel, shapes, strides, dtype, flags) -> (smmd_problem, byref, workspace bytes)
+
+
 def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, rank=0, world=1):
     """One call of smmd_mmd2_fwd_bwd.  Returns (scalars[16] f64 device tensor, dX, dY) for the owned rows."""
     _check_features(X, Y)
@@ -104,12 +108,25 @@ def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, ran
     Yc, ldy = _rows(Y.detach())
     m, d = Xc.shape
     n = Yc.shape[0]
-    prob = spec.problem(m, n, d, ldx, ldy, Xc.dtype, biased, precision, rank, world)
-    dev = Xc.device
-    with torch.cuda.device(dev):
+    # latency-bound shapes are host-bound: the problem struct and its workspace size are cached per call signature
+    key = (spec._key, m, n, d, ldx, ldy, Xc.dtype, bool(biased), precision or _default_precision, rank, world,
+           bool(want_grad))
+    cached = _problem_cache.get(key)
+    if cached is None:
+        prob = spec.problem(m, n, d, ldx, ldy, Xc.dtype, biased, precision, rank, world)
         nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1 if want_grad else 0)
         if nbytes == 0:
             raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
+        if len(_problem_cache) > 256:
+            _problem_cache.clear()
+        cached = _problem_cache[key] = (prob, C.byref(prob), nbytes)
+    prob, prob_ref, nbytes = cached
+    dev = Xc.device
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
         dX = dY = None
@@ -118,9 +135,13 @@ def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, ran
             on = n * (rank + 1) // world - n * rank // world
             dX = torch.empty((om, d), dtype=torch.float32, device=dev)
             dY = torch.empty((on, d), dtype=torch.float32, device=dev)
-        st = lib.smmd_mmd2_fwd_bwd(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(scalars), _as_ptr(dX),
+        st = lib.smmd_mmd2_fwd_bwd(prob_ref, _as_ptr(Xc), _as_ptr(Yc), _as_ptr(scalars), _as_ptr(dX),
                                    _as_ptr(dY), _as_ptr(ws), nbytes, _stream_ptr(dev))
-        _lib.check(st, "smmd_mmd2_fwd_bwd")
+        if st != 0:
+            _lib.check(st, "smmd_mmd2_fwd_bwd")
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
     return scalars, dX, dY
 
 
