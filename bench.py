@@ -67,15 +67,18 @@ def measured_peak():
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML (nvidia-smi's library) during the timed region."""
 
-    def __init__(self, gpu_index):
-        """NVML is initialised HERE, before the timed region: nvmlInit / handle lookup take 100s of ms and hold
+    def __init__(self, gpu_index, enabled=True):
+        """Only rank 0 samples (its line is the one printed).  NVML is initialised HERE, before the timed region: nvmlInit / handle lookup take 100s of ms and hold
         driver locks (measured: doing it inside the region cost 6 ms/step at N = 65536); the thread only polls."""
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop = threading.Event()
         self.gpu = gpu_index
         self.nv = self.h = None
+        self.enabled = enabled
         try:
+            if not enabled:
+                raise RuntimeError("disabled")
             import pynvml as nv
 
             nv.nvmlInit()
@@ -87,10 +90,13 @@ class ClockSampler:
                                 or nv.nvmlDeviceGetCurrentClocksThrottleReasons)
             self.nv = nv
         except Exception as e:  # NVML missing: one nvidia-smi sample in the thread instead
-            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+            if enabled:
+                self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if not self.enabled:
+            return
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         if self.nv is not None:
             nv, h = self.nv, self.h
@@ -104,7 +110,7 @@ class ClockSampler:
                 except Exception as e:
                     self.reasons.add("nvml_error:%s" % type(e).__name__)
                     break
-                self._stop.wait(0.04)   # polling faster than ~25 Hz slows kernel submission measurably
+                self._stop.wait(0.1)    # NVML queries take driver locks: 25 Hz polling cost 14 % at 3 ms/step (8 GPUs)
             return
         try:
             out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
@@ -217,7 +223,7 @@ def run_ours(args):
         launches[0] += _lib.last_launch_count() + 1
         return val, dX, dY
 
-    sampler = ClockSampler(local_rank)   # NVML init happens here, outside the timed region
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))   # NVML init happens here, outside the timed region
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         flush.zero_()

@@ -50,7 +50,7 @@ def mix_rq_fwd_bwd(Xnp, Ynp, **kw):
     Y = torch.from_numpy(Ynp).requires_grad_(True)
     v = mix_rq_mmd2(X, Y, **kw)
     gX, gY = torch.autograd.grad(v, [X, Y])
-    return float(v), gX.numpy(), gY.numpy()
+    return float(v.detach()), gX.numpy(), gY.numpy()
 
 
 def kid_subsets(codes_g, codes_r, idx_g, idx_r, ret_var=False):
