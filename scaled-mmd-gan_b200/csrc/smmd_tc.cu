@@ -1289,6 +1289,10 @@ struct WgenArgs {
   int nrb_x, rb_x0, nrb_y, rb_y0;   // owned row blocks (as FusedArgs)
   int rbi0;                         // first owned row block (flat index) of this panel
   int TX, CT;                       // 256-column tiles of the X columns / per row block (X tiles, then Y tiles)
+  int Wc, nwin, nrb_p;              // column window (tiles), windows, row blocks of the panel.  Every CTA walks the
+                                    // windows in order and takes `chunk` of the nrb_p * Wc positions (row block,
+                                    // tile) of each: at any time all CTAs work inside ONE window of Z_j tiles (L2)
+  int spw;                          // result slots per (CTA, window)
   int nkp;                          // 64-feature panels
   int64_t total_tiles, chunk;
   int slots;
@@ -1341,20 +1345,25 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
-  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
   auto rb_of = [&](int rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + rbi : a.rb_y0 + (rbi - a.nrb_x); };
   // tile ct of a row block: first column / end of its column set (X tiles never run into the Y columns)
   auto col0_of = [&](int ct) -> int { return ct < a.TX ? ct * BNW : (int)a.mp + (ct - a.TX) * BNW; };
 
+  // this CTA's positions inside every window: [wp0, wp1) of the nrb_p * Wc (row block, tile) pairs
+  const int wtot = a.nrb_p * a.Wc;
+  const int wp0 = (int)std::min<int64_t>((int64_t)blockIdx.x * a.chunk, wtot);
+  const int wp1 = (int)std::min<int64_t>((int64_t)wp0 + a.chunk, wtot);
+  const int rbl_first = wp0 / a.Wc, t_first = wp0 - rbl_first * a.Wc;
+
   if (warp == kWgEpiWarps) {
     // ===================== TMA producer =====================
     uint32_t st = 0, ph = 0;
-    int rbl = (int)(pos0 / a.CT);
-    int ct = (int)(pos0 - (int64_t)rbl * a.CT);
-    for (int64_t pos = pos0; pos < pos1; ++pos) {
-      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = col0_of(ct);
-      for (int p = 0; p < a.nkp; ++p) {
+    for (int w = 0; w < a.nwin; ++w) {
+    int rbl = rbl_first, t = t_first;
+    for (int pos = wp0; pos < wp1; ++pos) {
+      const int ct = w * a.Wc + t;
+      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = ct < a.CT ? col0_of(ct) : 0;
+      for (int p = 0; p < (ct < a.CT ? a.nkp : 0); ++p) {
         mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[st], kWgStageBytes);
@@ -1368,10 +1377,11 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           ph ^= 1;
         }
       }
-      if (++ct == a.CT) {
-        ct = 0;
+      if (++t == a.Wc) {
+        t = 0;
         ++rbl;
       }
+    }
     }
   } else if (warp == kWgEpiWarps + 1) {
     // ===================== UMMA issuer =====================
@@ -1379,7 +1389,12 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
-    for (int64_t pos = pos0; pos < pos1; ++pos) {
+    for (int w = 0; w < a.nwin; ++w) {
+    int t = t_first;
+    for (int pos = wp0; pos < wp1; ++pos) {
+      const bool real = w * a.Wc + t < a.CT;
+      if (++t == a.Wc) t = 0;
+      if (!real) continue;   // padding position of the last window
       mbar_wait(&acc_empty[ab], aph ^ 1);
       tc_fence_after();
       const uint32_t dad = tmem + ab * BNW;
@@ -1403,6 +1418,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       aph ^= ab;
       ab ^= 1;
     }
+    }
   } else {
     // ===================== epilogue: all 16 warps on every tile (TMEM lane quarter x column quarter) ==========
     // With only two accumulators the issuer can start tile t+2 as soon as tile t is drained, so the drain latency
@@ -1415,12 +1431,12 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const Math math(a.kf, sParams);
     const float kscale = math.k_scale(), kdscale = math.kd_scale();
     const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
-    int rbl = (int)(pos0 / a.CT);
-    int ct0 = (int)(pos0 - (int64_t)rbl * a.CT);
-    uint32_t tc = 0;   // tiles of this CTA so far (parity = accumulator buffer = group)
-    int slot = 0;
-    for (int64_t left = pos1 - pos0; left > 0; ++rbl, ct0 = 0, ++slot) {
-      const int TU = (int)std::min<int64_t>(a.CT - ct0, left);
+    uint32_t tc = 0;   // real tiles of this CTA so far (parity = accumulator buffer)
+    for (int w = 0; w < a.nwin; ++w) {
+    int rbl = rbl_first, ct0 = t_first;
+    int slot = w * a.spw;
+    for (int left = wp1 - wp0; left > 0; ct0 = 0, ++slot, ++rbl) {
+      const int TU = std::min(a.Wc - ct0, left);   // positions of this (window, row block) unit
       const int rb = rb_of(a.rbi0 + rbl);
       const int gi = rb * BM + r;
       const bool rowX = gi < mp;
@@ -1428,9 +1444,10 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       float2 rsum = make_float2(0.f, 0.f);
       double dsame = 0.0, dcross = 0.0;
       __nv_bfloat16* wrow = a.W + ((int64_t)rbl * BM + r) * a.ldw;
-      for (int lt = 0; lt < TU; ++lt, ++tc) {
+      for (int lt = 0; lt < TU; ++lt) {
+        const int ct = w * a.Wc + ct0 + lt;
+        if (ct >= a.CT) break;           // padding positions at the end of the last window
         const int grp = (int)(tc & 1);   // accumulator buffer of this tile
-        const int ct = ct0 + lt;
         const int c0 = col0_of(ct);
         const bool colX = ct < a.TX;
         const bool same = (colX == rowX);
@@ -1466,6 +1483,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
         else dcross += (double)((tsum.x + tsum.y) * kscale);
+        ++tc;
       }
       const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
       a.rpart[(sl * 4 + part) * BM + r] = rsum.x + rsum.y;
@@ -1473,6 +1491,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       sp[0] = dsame;
       sp[1] = dcross;
       left -= TU;
+    }
     }
   }
   tc_fence_before();
@@ -1613,8 +1632,9 @@ struct WzFinArgs {
   int dp;
   int nrb_x, rb_x0, nrb_y, rb_y0;
   int rbi0, nrb_p;           // panel: first owned row block (flat) / count
-  int CT;                    // pass-1 tiles per row block
-  int64_t chunk;             // pass-1 tiles per CTA
+  int Wc, nwin;              // pass-1 column window (tiles) / number of windows
+  int spw;                   // pass-1 slots per (CTA, window)
+  int64_t chunk;             // pass-1 positions per CTA inside one window
   int slots;
   int FB, S;                 // pass-2 feature blocks / K splits
   double a_xx, a_yy, a_xy;
@@ -1644,18 +1664,20 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
     const bool rowX = gi < a.mp;
     const int64_t li = rowX ? gi : gi - a.mp;
     if (rowX ? (li < a.x0 || li >= a.x0 + a.ox) : (li < a.y0 || li >= a.y0 + a.oy)) continue;   // not owned / padding
-    // pass-1 slabs of this row block
-    const int64_t f0 = (int64_t)rbl * a.CT, f1 = f0 + a.CT - 1;
-    const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
+    // pass-1 slabs of this row block: one (window, row block) unit per window, each cut over <= 2 CTAs
     float rs = 0.f;
     double ssame = 0.0, scross = 0.0;
-    for (int64_t g = g0; g <= g1; ++g) {
-      const int64_t sl = g * a.slots + (rbl - (g * a.chunk) / a.CT);
-      for (int pt = 0; pt < 4; ++pt) {
-        rs += a.rpart[(sl * 4 + pt) * BM + r];
-        const double* sp = a.spart + ((sl * 4 + pt) * BM + r) * 2;
-        ssame += sp[0];
-        scross += sp[1];
+    for (int w = 0; w < a.nwin; ++w) {
+      const int64_t f0 = (int64_t)rbl * a.Wc, f1 = f0 + a.Wc - 1;   // positions of this unit inside the window
+      const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
+      for (int64_t g = g0; g <= g1; ++g) {
+        const int64_t sl = g * a.slots + (int64_t)w * a.spw + (rbl - (g * a.chunk) / a.Wc);
+        for (int pt = 0; pt < 4; ++pt) {
+          rs += a.rpart[(sl * 4 + pt) * BM + r];
+          const double* sp = a.spart + ((sl * 4 + pt) * BM + r) * 2;
+          ssame += sp[0];
+          scross += sp[1];
+        }
       }
     }
     const double a_same = rowX ? a.a_xx : a.a_yy;
@@ -1834,6 +1856,7 @@ cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap&
 struct WzPlan {
   int64_t mp, np, Mp, dp;
   int nrb_x, rb_x0, nrb_y, rb_y0, nrb;
+  int Wc, nwin;         // pass-1 column window (tiles) / windows per row block
   int TX, CT, KT, FB;   // pass-1 tiles (256 columns) over the X columns / per row block
   int P, npanels;   // row blocks per panel (even) / panels
   size_t off_Z, off_norm, off_csum, off_W, off_r, off_s, off_O, off_stats, off_end;
@@ -1841,7 +1864,7 @@ struct WzPlan {
 };
 struct WzPanel {
   int rbi0, nrb_p;
-  int grid1, slots1;
+  int grid1, slots1, spw1;
   int64_t tiles1, chunk1;
   int nmb, units, S, ksteps, grid2;
   int fin_blocks, fin_block0;
@@ -1869,12 +1892,13 @@ WzPanel wz_panel(const WzPlan& p, int idx) {
   WzPanel q;
   q.rbi0 = idx * p.P;
   q.nrb_p = std::min(p.P, p.nrb - q.rbi0);
-  q.tiles1 = (int64_t)q.nrb_p * p.CT;
+  q.tiles1 = (int64_t)q.nrb_p * p.Wc;   // positions of ONE window (every CTA takes chunk1 of them, per window)
   q.grid1 = (int)std::min<int64_t>(sm_count(), q.tiles1);
   if (q.grid1 < 1) q.grid1 = 1;
   q.chunk1 = (q.tiles1 + q.grid1 - 1) / q.grid1;
   q.grid1 = (int)((q.tiles1 + q.chunk1 - 1) / q.chunk1);
-  q.slots1 = (int)((q.chunk1 + p.CT - 1) / p.CT) + 1;
+  q.spw1 = (int)((q.chunk1 + p.Wc - 1) / p.Wc) + 1;
+  q.slots1 = p.nwin * q.spw1;
   q.nmb = (q.nrb_p + 1) / 2;
   q.units = q.nmb * p.FB;
   q.S = wz_choose_split(q.units, p.KT);
@@ -1900,15 +1924,13 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
   p.CT = p.TX + (int)((p.np + BNW - 1) / BNW);
   p.KT = (int)(p.Mp / 64);
   p.FB = (int)((p.dp + 255) / 256);
+  // column window: ~24 MB of Z_j tiles, so that window + the panel's row blocks stay L2 resident whatever the
+  // chunk alignment (whole-Z sweeps per row block thrashed L2 once Z > 126 MB: 86.9 ms instead of 66 at d = 1024)
+  p.Wc = (int)std::max<int64_t>(4, std::min<int64_t>(p.CT, ((int64_t)24 << 20) / (BNW * p.dp * 2)));
+  if (p.Mp * p.dp * 2 <= ((int64_t)96 << 20)) p.Wc = p.CT;   // Z fits L2: one window (measured 5% faster)
+  p.nwin = (p.CT + p.Wc - 1) / p.Wc;
   int64_t P = tuning().wz_panel_bytes / (BM * p.Mp * 2);
-  const int sm = sm_count();
-  if (p.nrb > sm && P >= sm && sm % 2 == 0) {
-    // whole row blocks per CTA: all CTAs then sweep the column tiles in lockstep, so a Z_j tile is fetched from
-    // HBM once per wave instead of once per CTA (Z no longer fits L2 at N = 65536, d >= 512)
-    P = P / sm * sm;
-  } else {
-    P = std::max<int64_t>(2, P & ~int64_t(1));
-  }
+  P = std::max<int64_t>(2, P & ~int64_t(1));
   P = std::min<int64_t>(P, (p.nrb + 1) & ~1);
   p.P = (int)std::max<int64_t>(2, P);
   p.npanels = std::max(1, (p.nrb + p.P - 1) / p.P);
@@ -2177,6 +2199,10 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       ga.rbi0 = q.rbi0;
       ga.TX = p.TX;
       ga.CT = p.CT;
+      ga.Wc = p.Wc;
+      ga.nwin = p.nwin;
+      ga.nrb_p = q.nrb_p;
+      ga.spw = q.spw1;
       ga.nkp = (int)(p.dp / 64);
       ga.total_tiles = q.tiles1;
       ga.chunk = q.chunk1;
@@ -2215,7 +2241,9 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       fr.rb_y0 = p.rb_y0;
       fr.rbi0 = q.rbi0;
       fr.nrb_p = q.nrb_p;
-      fr.CT = p.CT;
+      fr.Wc = p.Wc;
+      fr.nwin = p.nwin;
+      fr.spw = q.spw1;
       fr.chunk = q.chunk1;
       fr.slots = q.slots1;
       fr.FB = p.FB;
