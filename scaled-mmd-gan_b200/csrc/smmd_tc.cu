@@ -1270,12 +1270,14 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // variant (feature-sliced O, partial Gram tiles reduce-scattered and W all-gathered over distributed shared
 // memory) was built and measured first: correct, but shared memory left only a 2-3 stage TMA ring next to the
 // exchange buffers and it reached 23% (d = 512) / 6% (d = 1024) of peak (profiles/r01_cluster_*.log).
-// The two-pass path below reaches 42% / 51% and has no upper limit on d:
+// The two-pass path below reaches 45% / 57% and has no upper limit on d:
 //   pass 1 (tc_wgen_kernel):  128 x 256 tiles of S = Z_i Z_j^T with K streamed through a 4-stage TMA ring (both
 //          operands, 48 KB per 64-deep step: 25% less L2 traffic per flop than 128 x 128), two 256-column TMEM
-//          accumulators alternate between tiles, all 16 epilogue warps drain each tile; epilogue = kernel transform -> tile sums, row sums of W, W tile (bf16) stored to a row-panel
-//          buffer W[panel rows][Mp] (K-major for pass 2).  The panel is sized by a byte budget (default 6 GB), so
-//          the N x N matrix never exists as a whole; panels run back to back on the stream.
+//          accumulators alternate between tiles, all 16 epilogue warps drain each tile; epilogue = kernel transform
+//          -> tile sums, row sums of W, W tile (bf16) stored to a row-panel buffer W[panel rows][Mp] (K-major for
+//          pass 2).  The panel is sized by a byte budget (default 6 GB), so the N x N matrix never exists as a
+//          whole; panels run back to back on the stream.  Inside a panel the column tiles are walked in windows of
+//          ~24 MB of Z_j that all CTAs share at any time (L2 residency for any panel size / row shard).
 //   pass 2 (tc_wz_kernel):    O[256 rows x 256 features] = W[256 x Mp] Z[Mp x 256]: 2 x 128-row A panels and one
 //          64-row MN-major Z tile per 64-deep K step (64 KB / 1024 tensor cycles, the macro-tile ratio), all 512
 //          TMEM columns as accumulators, K split S ways per unit so that units * S fills the SMs; partial tiles go
