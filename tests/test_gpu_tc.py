@@ -133,6 +133,39 @@ def test_tc_wide_long_stream_and_shards():
         assert abs(acc[i].item() - full[i].item()) <= 1e-9 * abs(full[i].item())
 
 
+def test_tc_wide_bf16_inputs_and_strided_rows():
+    """Two-pass path with bf16 critic features and with row-strided fp32 views (ld > d), against the fp64 oracle on
+    exactly the values the kernel sees."""
+    from smmd import _lib, mmd
+
+    m, n, d = 520, 600, 448
+    X, Y = _data(m, n, d, 11)
+    # (a) bf16 inputs: oracle on the bf16-rounded values
+    Xb = torch.tensor(X, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    Yb = torch.tensor(Y, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    loss = mmd.mmd2(mmd._mix_rq_kernel(Xb, Yb), precision="bf16")
+    loss.backward()
+    assert _lib.last_path() == "tc_bf16_wz"
+    Xr, Yr = Xb.detach().float().cpu().numpy(), Yb.detach().float().cpu().numpy()
+    v, gx, gy = mmd_oracle.mmd2_and_grads("mix_rq", Xr, Yr, False, np.float64)
+    assert abs(loss.item() - v) <= 1e-3 * abs(v) + 2e-6 * _kscale("mix_rq", {}, Xr, Yr)
+    for got, ref in ((Xb.grad, gx), (Yb.grad, gy)):
+        assert got.dtype == torch.bfloat16
+        err = np.abs(got.float().cpu().numpy().astype(np.float64) - ref).max()
+        assert err <= 8e-3 * np.abs(ref).max(), (err, np.abs(ref).max())   # + bf16 rounding of the returned gradient
+    # (b) strided rows: a [m, d] view into a wider buffer
+    big = torch.zeros((m, d + 72), device=DEV)
+    big[:, :d] = torch.tensor(X, device=DEV)
+    Xs = big[:, :d].requires_grad_(True)
+    Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+    loss = mmd.mmd2(mmd._mix_rq_kernel(Xs, Yt), precision="bf16")
+    gxs, gys = torch.autograd.grad(loss, [Xs, Yt])
+    v, gx, gy = mmd_oracle.mmd2_and_grads("mix_rq", X, Y, False, np.float64)
+    assert abs(loss.item() - v) <= 1e-3 * abs(v) + 2e-6 * _kscale("mix_rq", {}, X, Y)
+    assert np.abs(gxs.cpu().numpy() - gx).max() <= 4e-3 * np.abs(gx).max()
+    assert np.abs(gys.cpu().numpy() - gy).max() <= 4e-3 * np.abs(gy).max()
+
+
 _PANEL_SNIPPET = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, {pkg!r})
