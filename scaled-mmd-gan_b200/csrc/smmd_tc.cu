@@ -43,6 +43,7 @@ struct Tuning {
   int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
   int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
   int64_t wz_panel_bytes;   // byte budget of one W row panel
+  int wz_pair;      // pass 1 as CTA pairs with cta_group::2 UMMAs (SMMD_WZ_PAIR=0 disables)
 };
 const Tuning& tuning() {
   static Tuning t = [] {
@@ -52,6 +53,8 @@ const Tuning& tuning() {
     v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
     v.wz_min_d = 256;
     if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
+    v.wz_pair = 1;
+    if (const char* e = getenv("SMMD_WZ_PAIR")) v.wz_pair = atoi(e) != 0;
     v.wz_panel_bytes = (int64_t)6 << 30;
     if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
     return v;
@@ -1305,19 +1308,33 @@ struct WgenArgs {
 };
 
 constexpr int BNW = 256;                                  // tile width of pass 1
-constexpr int kWgStages = 4;
-constexpr int kWgStageBytes = BM * 128 + BNW * 128;       // one 128-row A panel + one 256-row B panel = 48 KB
-constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 1024;
+template <bool PAIR>
+struct WgCfg {
+  static constexpr int kStages = PAIR ? 6 : 4;
+  // one 128-row Z_i panel + the Z_j tile (256 rows; PAIR: this CTA's 128-row half) per 64-deep step
+  static constexpr int kStageBytes = BM * 128 + (PAIR ? BM : BNW) * 128;
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + 1024;
+};
 
 constexpr int kWgEpiWarps = 16;                           // 4 TMEM lane quarters x 4 column quarters
 constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
 
-template <class Math>
+// PAIR: the kernel runs as clusters of two CTAs that take the two row blocks of a row-block pair through the same
+// column tiles with ONE UMMA stream: `tcgen05.mma.cta_group::2` (M = 256: 128 rows per CTA, each CTA supplies half
+// of the Z_j tile from its own shared memory).  Per 64-deep step a CTA then receives 16 KB (its Z_i panel) + 16 KB
+// (half a Z_j tile) instead of 48 KB -- the SM's operand ingest (~44 B/clk, measured identical for pass 1 and
+// pass 2) is what bounds this kernel, and a TMA-multicast variant that still delivered the whole tile to both SMs
+// gained only 3%.  Stages shrink to 32 KB, so the ring is 6 deep.  Protocol: both producers load into their own
+// shared memory and signal the LEADER's `full` barrier (cta_group::2 TMA); the leader's issuer runs the UMMAs and
+// multicasts its commits to both CTAs' `empty` / `acc_full` barriers; both CTAs' epilogue warps release the
+// accumulator on the leader's `acc_empty` (remote arrive).
+template <class Math, bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 1)
 tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ WgenArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kWgStages = WgCfg<PAIR>::kStages, kWgStageBytes = WgCfg<PAIR>::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgStages;
@@ -1334,28 +1351,40 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 512);
+      mbar_init(&acc_empty[i], PAIR ? 2 * kWgEpiWarps : kWgEpiWarps);   // one elected arrive per epilogue warp
     }
     fence_mbar_init();
   }
-  if (warp == kWgEpiWarps + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kWgEpiWarps + 1) {
+    if (PAIR) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   if (warp == kWgEpiWarps && lane == 0) {
     prefetch_tmap(&tmap);
     prefetch_tmap(&tmap_b);
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   auto rb_of = [&](int rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + rbi : a.rb_y0 + (rbi - a.nrb_x); };
   // tile ct of a row block: first column / end of its column set (X tiles never run into the Y columns)
   auto col0_of = [&](int ct) -> int { return ct < a.TX ? ct * BNW : (int)a.mp + (ct - a.TX) * BNW; };
 
-  // this CTA's positions inside every window: [wp0, wp1) of the nrb_p * Wc (row block, tile) pairs
-  const int wtot = a.nrb_p * a.Wc;
-  const int wp0 = (int)std::min<int64_t>((int64_t)blockIdx.x * a.chunk, wtot);
+  // this work unit's positions inside every window: [wp0, wp1) of the (row block [pair], tile) pairs.
+  // PAIR: a position's row-block index counts row-block PAIRS; this CTA takes block 2 * index + rank of it.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int unit_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nrbu = PAIR ? (a.nrb_p + 1) / 2 : a.nrb_p;       // row-block units of the panel
+  const int wtot = nrbu * a.Wc;
+  const int wp0 = (int)std::min<int64_t>((int64_t)unit_id * a.chunk, wtot);
   const int wp1 = (int)std::min<int64_t>((int64_t)wp0 + a.chunk, wtot);
   const int rbl_first = wp0 / a.Wc, t_first = wp0 - rbl_first * a.Wc;
+  // row block of unit index u for this CTA (an odd panel's last pair has a dummy second block: it follows the
+  // pipeline with the last real block's data and stores nothing)
+  auto rbl_of = [&](int u) -> int { return PAIR ? 2 * u + rank : u; };
+  auto rbl_ld = [&](int u) -> int { const int b = rbl_of(u); return b < a.nrb_p ? b : a.nrb_p - 1; };
 
   if (warp == kWgEpiWarps) {
     // ===================== TMA producer =====================
@@ -1364,14 +1393,21 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     int rbl = rbl_first, t = t_first;
     for (int pos = wp0; pos < wp1; ++pos) {
       const int ct = w * a.Wc + t;
-      const int32_t arow = rb_of(a.rbi0 + rbl) * BM, brow = ct < a.CT ? col0_of(ct) : 0;
+      const int32_t arow = rb_of(a.rbi0 + rbl_ld(rbl)) * BM, brow = ct < a.CT ? col0_of(ct) : 0;
       for (int p = 0; p < (ct < a.CT ? a.nkp : 0); ++p) {
         mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[st], kWgStageBytes);
           uint8_t* sa = smem + st * kWgStageBytes;
-          tma_load_2d(sa, &tmap, &full[st], p * 64, arow);
-          tma_load_2d(sa + BM * 128, &tmap_b, &full[st], p * 64, brow);
+          if (PAIR) {   // own Z_i panel + own half of the Z_j tile; the bytes of both CTAs count on the leader's barrier
+            const uint32_t lbar = map_to_cta(smem_u32(&full[st]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * kWgStageBytes);
+            tma_load_2d_pair(sa, &tmap, lbar, p * 64, arow);
+            tma_load_2d_pair(sa + BM * 128, &tmap, lbar, p * 64, brow + rank * BM);
+          } else {
+            mbar_arrive_expect_tx(&full[st], kWgStageBytes);
+            tma_load_2d(sa, &tmap, &full[st], p * 64, arow);
+            tma_load_2d(sa + BM * 128, &tmap_b, &full[st], p * 64, brow);
+          }
         }
         __syncwarp();
         if (++st == kWgStages) {
@@ -1387,17 +1423,18 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
   } else if (warp == kWgEpiWarps + 1) {
     // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BM, BNW, kFmtBF16, false, false);
+    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BNW, kFmtBF16, false, false);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
-    for (int w = 0; w < a.nwin; ++w) {
+    for (int w = 0; w < (PAIR && rank != 0 ? 0 : a.nwin); ++w) {   // PAIR: only the leader issues
     int t = t_first;
     for (int pos = wp0; pos < wp1; ++pos) {
       const bool real = w * a.Wc + t < a.CT;
       if (++t == a.Wc) t = 0;
       if (!real) continue;   // padding position of the last window
-      mbar_wait(&acc_empty[ab], aph ^ 1);
+      if (PAIR) mbar_wait_cluster(&acc_empty[ab], aph ^ 1);   // the peer's epilogue arrives remotely
+      else mbar_wait(&acc_empty[ab], aph ^ 1);
       tc_fence_after();
       const uint32_t dad = tmem + ab * BNW;
       for (int kk = 0; kk < a.nkp; ++kk) {
@@ -1406,8 +1443,12 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const uint32_t alo = a_lo0 + st * (kWgStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
-          umma_commit(&empty[st]);
+          for (int k = 0; k < 4; ++k) {
+            if (PAIR) umma_ss2_pair(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
+            else umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_pair(&empty[st], 3);
+          else umma_commit(&empty[st]);
         }
         __syncwarp();
         if (++st == kWgStages) {
@@ -1415,7 +1456,10 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           ph ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&acc_full[ab]);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(&acc_full[ab], 3);
+        else umma_commit(&acc_full[ab]);
+      }
       __syncwarp();
       aph ^= ab;
       ab ^= 1;
@@ -1439,13 +1483,14 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     int slot = w * a.spw;
     for (int left = wp1 - wp0; left > 0; ct0 = 0, ++slot, ++rbl) {
       const int TU = std::min(a.Wc - ct0, left);   // positions of this (window, row block) unit
-      const int rb = rb_of(a.rbi0 + rbl);
+      const bool real_rb = rbl_of(rbl) < a.nrb_p;
+      const int rb = rb_of(a.rbi0 + rbl_ld(rbl));
       const int gi = rb * BM + r;
       const bool rowX = gi < mp;
       const float ni = a.norms[gi];
       float2 rsum = make_float2(0.f, 0.f);
       double dsame = 0.0, dcross = 0.0;
-      __nv_bfloat16* wrow = a.W + ((int64_t)rbl * BM + r) * a.ldw;
+      __nv_bfloat16* wrow = a.W + ((int64_t)rbl_ld(rbl) * BM + r) * a.ldw;
       for (int lt = 0; lt < TU; ++lt) {
         const int ct = w * a.Wc + ct0 + lt;
         if (ct >= a.CT) break;           // padding positions at the end of the last window
@@ -1464,30 +1509,35 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         float2 tsum = make_float2(0.f, 0.f);
         const int h0 = part * (BNW / 64);
         const int h1 = nch < h0 + BNW / 64 ? nch : h0 + BNW / 64;
-        if (h1 <= h0) {   // nothing of this tile in my column half: only release the accumulator
+        auto release_acc = [&]() {   // whole warp has finished its tcgen05.ld of this tile: one elected arrive
           tc_fence_before();
-          mbar_arrive(&acc_empty[grp]);
-        }
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty[grp]), 0));
+            else mbar_arrive(&acc_empty[grp]);
+          }
+        };
+        if (h1 <= h0) release_acc();   // nothing of this tile in my column quarter
 #pragma unroll 1
         for (int h = h0; h < h1; ++h) {
           uint32_t v[16], wpk[8];
           tmem_ld_x16(tmem + grp * BNW + h * 16 + lane_base, v);
           tmem_ld_wait();
-          if (h == h1 - 1) {
-            tc_fence_before();
-            mbar_arrive(&acc_empty[grp]);
-          }
+          if (h == h1 - 1) release_acc();
           if (!special) fused_chunk16<Math, false>(math, v, nj + h * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
           else fused_chunk16<Math, true>(math, v, nj + h * 16, ni, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
-          uint4* dst = reinterpret_cast<uint4*>(wrow + c0 + h * 16);
-          dst[0] = make_uint4(wpk[0], wpk[1], wpk[2], wpk[3]);
-          dst[1] = make_uint4(wpk[4], wpk[5], wpk[6], wpk[7]);
+          if (real_rb) {
+            uint4* dst = reinterpret_cast<uint4*>(wrow + c0 + h * 16);
+            dst[0] = make_uint4(wpk[0], wpk[1], wpk[2], wpk[3]);
+            dst[1] = make_uint4(wpk[4], wpk[5], wpk[6], wpk[7]);
+          }
         }
         if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
         else dcross += (double)((tsum.x + tsum.y) * kscale);
         ++tc;
       }
-      const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
+      // slab of (work unit, slot[, rank]): PAIR keeps the two row blocks of a pair side by side
+      const int64_t sl = PAIR ? ((int64_t)unit_id * a.slots + slot) * 2 + rank : (int64_t)unit_id * a.slots + slot;
       a.rpart[(sl * 4 + part) * BM + r] = rsum.x + rsum.y;
       double* sp = a.spart + ((sl * 4 + part) * BM + r) * 2;
       sp[0] = dsame;
@@ -1498,7 +1548,11 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWgEpiWarps + 1) tmem_dealloc<512>(tmem);
+  if (PAIR) cluster_sync();   // nobody leaves while the peer may still multicast into its shared memory
+  if (warp == kWgEpiWarps + 1) {
+    if (PAIR) tmem_dealloc_pair<512>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
 }
 
 // ---- pass 2: O = W Z ----
@@ -1635,8 +1689,9 @@ struct WzFinArgs {
   int nrb_x, rb_x0, nrb_y, rb_y0;
   int rbi0, nrb_p;           // panel: first owned row block (flat) / count
   int Wc, nwin;              // pass-1 column window (tiles) / number of windows
-  int spw;                   // pass-1 slots per (CTA, window)
-  int64_t chunk;             // pass-1 positions per CTA inside one window
+  int spw;                   // pass-1 slots per (work unit, window)
+  int pair;                  // pass 1 ran as CTA pairs (row-block pairs, two slabs per slot)
+  int64_t chunk;             // pass-1 positions per work unit inside one window
   int slots;
   int FB, S;                 // pass-2 feature blocks / K splits
   double a_xx, a_yy, a_xy;
@@ -1670,10 +1725,12 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
     float rs = 0.f;
     double ssame = 0.0, scross = 0.0;
     for (int w = 0; w < a.nwin; ++w) {
-      const int64_t f0 = (int64_t)rbl * a.Wc, f1 = f0 + a.Wc - 1;   // positions of this unit inside the window
+      const int ru = a.pair ? rbl >> 1 : rbl;                      // row-block unit of this row block
+      const int64_t f0 = (int64_t)ru * a.Wc, f1 = f0 + a.Wc - 1;   // positions of this unit inside the window
       const int64_t g0 = f0 / a.chunk, g1 = f1 / a.chunk;
       for (int64_t g = g0; g <= g1; ++g) {
-        const int64_t sl = g * a.slots + (int64_t)w * a.spw + (rbl - (g * a.chunk) / a.Wc);
+        int64_t sl = g * a.slots + (int64_t)w * a.spw + (ru - (g * a.chunk) / a.Wc);
+        if (a.pair) sl = sl * 2 + (rbl & 1);
         for (int pt = 0; pt < 4; ++pt) {
           rs += a.rpart[(sl * 4 + pt) * BM + r];
           const double* sp = a.spart + ((sl * 4 + pt) * BM + r) * 2;
@@ -1866,7 +1923,7 @@ struct WzPlan {
 };
 struct WzPanel {
   int rbi0, nrb_p;
-  int grid1, slots1, spw1;
+  int grid1, slots1, spw1, pair;   // grid1 counts work units (CTAs, or CTA pairs when pair = 1)
   int64_t tiles1, chunk1;
   int nmb, units, S, ksteps, grid2;
   int fin_blocks, fin_block0;
@@ -1894,8 +1951,10 @@ WzPanel wz_panel(const WzPlan& p, int idx) {
   WzPanel q;
   q.rbi0 = idx * p.P;
   q.nrb_p = std::min(p.P, p.nrb - q.rbi0);
-  q.tiles1 = (int64_t)q.nrb_p * p.Wc;   // positions of ONE window (every CTA takes chunk1 of them, per window)
-  q.grid1 = (int)std::min<int64_t>(sm_count(), q.tiles1);
+  q.pair = tuning().wz_pair && q.nrb_p >= sm_count() ? 1 : 0;   // pairs need >= 1 row-block pair per CTA pair
+  const int nrbu = q.pair ? (q.nrb_p + 1) / 2 : q.nrb_p;
+  q.tiles1 = (int64_t)nrbu * p.Wc;   // positions of ONE window (every work unit takes chunk1 of them, per window)
+  q.grid1 = (int)std::min<int64_t>(q.pair ? sm_count() / 2 : sm_count(), q.tiles1);
   if (q.grid1 < 1) q.grid1 = 1;
   q.chunk1 = (q.tiles1 + q.grid1 - 1) / q.grid1;
   q.grid1 = (int)((q.tiles1 + q.chunk1 - 1) / q.chunk1);
@@ -1940,7 +1999,7 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
   int fin_total = 0;
   for (int i = 0; i < p.npanels; i += std::max(1, p.npanels - 1)) {   // first (full) and last panel bound all others
     const WzPanel q = wz_panel(p, i);
-    need_r = std::max(need_r, (size_t)q.grid1 * q.slots1 * 4 * BM);
+    need_r = std::max(need_r, (size_t)q.grid1 * q.slots1 * (q.pair ? 2 : 1) * 4 * BM);
     need_O = std::max(need_O, (size_t)q.units * q.S * 256 * 256 * 4);
     if (p.npanels == 1) break;
   }
@@ -1971,23 +2030,44 @@ WzPlan wz_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, int64_t 
 }
 
 template <class Math>
-cudaError_t launch_wgen_t(const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid, cudaStream_t s) {
-  auto kern = tc_wgen_kernel<Math>;
+cudaError_t launch_wgen_t(const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid, int pair,
+                          cudaStream_t s) {
+  if (!pair) {
+    auto kern = tc_wgen_kernel<Math, false>;
+    constexpr int kWgSmem = WgCfg<false>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kWgThreads, kWgSmem, s>>>(tm, tb, a);
+    return cudaGetLastError();
+  }
+  auto kern = tc_wgen_kernel<Math, true>;
+  constexpr int kWgSmem = WgCfg<true>::kSmem;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kWgThreads, kWgSmem, s>>>(tm, tb, a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * grid));
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = (size_t)kWgSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tm, tb, a);
 }
 cudaError_t launch_wgen(TcVariant v, const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid,
-                        cudaStream_t s) {
+                        int pair, cudaStream_t s) {
   switch (v) {
-    case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, tb, a, grid, s);
-    case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, tb, a, grid, s);
-    case TV_RBF_GENERIC: return launch_wgen_t<MathGeneric<FAM_RBF>>(tm, tb, a, grid, s);
-    case TV_RQ3_DEFAULT: return launch_wgen_t<MathRq3Default>(tm, tb, a, grid, s);
-    case TV_RQ_GENERIC: return launch_wgen_t<MathGeneric<FAM_RQ>>(tm, tb, a, grid, s);
-    case TV_DISTANCE: return launch_wgen_t<MathDistance>(tm, tb, a, grid, s);
-    case TV_NULL: return launch_wgen_t<MathNull>(tm, tb, a, grid, s);
+    case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, tb, a, grid, pair, s);
+    case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, tb, a, grid, pair, s);
+    case TV_RBF_GENERIC: return launch_wgen_t<MathGeneric<FAM_RBF>>(tm, tb, a, grid, pair, s);
+    case TV_RQ3_DEFAULT: return launch_wgen_t<MathRq3Default>(tm, tb, a, grid, pair, s);
+    case TV_RQ_GENERIC: return launch_wgen_t<MathGeneric<FAM_RQ>>(tm, tb, a, grid, pair, s);
+    case TV_DISTANCE: return launch_wgen_t<MathDistance>(tm, tb, a, grid, pair, s);
+    case TV_NULL: return launch_wgen_t<MathNull>(tm, tb, a, grid, pair, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -2213,7 +2293,8 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       ga.ldw = p.Mp;
       ga.rpart = reinterpret_cast<float*>(w + p.off_r);
       ga.spart = reinterpret_cast<double*>(w + p.off_s);
-      if ((e = launch_wgen(variant, t1, t1b, ga, q.grid1, s)) != cudaSuccess) return e;
+      if (q.pair) *path = "tc_bf16_wz_pair";   // at least one panel ran pass 1 as CTA pairs (cta_group::2)
+      if ((e = launch_wgen(variant, t1, t1b, ga, q.grid1, q.pair, s)) != cudaSuccess) return e;
       ++*launches;
       WzArgs za;
       za.nmb = q.nmb;
@@ -2246,6 +2327,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       fr.Wc = p.Wc;
       fr.nwin = p.nwin;
       fr.spw = q.spw1;
+      fr.pair = q.pair;
       fr.chunk = q.chunk1;
       fr.slots = q.slots1;
       fr.FB = p.FB;

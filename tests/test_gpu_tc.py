@@ -133,6 +133,28 @@ def test_tc_wide_long_stream_and_shards():
         assert abs(acc[i].item() - full[i].item()) <= 1e-9 * abs(full[i].item())
 
 
+def test_tc_wide_cta_pair_path():
+    """>= 148 row blocks per panel: pass 1 runs as CTA pairs (cta_group::2 UMMAs, each CTA supplies half of every
+    Z_j tile).  Odd number of row blocks (dummy second block in the last pair), m != n, checked against the exact
+    fp32 path on the GPU (itself pinned to the oracle) with the bf16 tolerance."""
+    from smmd import _lib, mmd
+
+    m, n, d = 9700, 9500, 320          # 76 + 75 = 151 row blocks
+    X, Y = _data(m, n, d, 5)
+    Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+    spec = mmd._mix_rq_kernel(Xt, Yt).spec
+    sc, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert _lib.last_path() == "tc_bf16_wz_pair"
+    rs, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
+    assert abs(sc[_lib.S_MMD2].item() - rs[_lib.S_MMD2].item()) <= 1e-3 * abs(rs[_lib.S_MMD2].item())
+    for i in (_lib.S_SUM_XX, _lib.S_SUM_YY, _lib.S_SUM_XY, _lib.S_SUM_YX):
+        assert abs(sc[i].item() - rs[i].item()) <= 1e-4 * abs(rs[i].item())
+    assert (gX - rX).abs().max() <= 4e-3 * rX.abs().max()
+    assert (gY - rY).abs().max() <= 4e-3 * rY.abs().max()
+    sc2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert torch.equal(gX, gX2) and torch.equal(gY, gY2) and torch.equal(sc, sc2)   # deterministic
+
+
 def test_tc_wide_bf16_inputs_and_strided_rows():
     """Two-pass path with bf16 critic features and with row-strided fp32 views (ld > d), against the fp64 oracle on
     exactly the values the kernel sees."""
