@@ -309,26 +309,6 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// One TMA box delivered to the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's
-// mbarrier (same offset) receives the complete_tx for the bytes that land in ITS shared memory.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0,
-                                                      int32_t c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-      "h"(cta_mask)
-      : "memory");
-}
-// tcgen05.commit whose mbarrier arrive is delivered to the barrier at the same offset in every CTA of `cta_mask`
-// (a shared-memory stage written by multicast may only be refilled once ALL its readers are done).
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-
 // ---- cta_group::2: one UMMA spans the CTA pair (M = 256: 128 rows per CTA, each CTA supplies half of B) ----
 // shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {

@@ -1299,7 +1299,7 @@ struct WgenArgs {
                                     // tile) of each: at any time all CTAs work inside ONE window of Z_j tiles (L2)
   int spw;                          // result slots per (CTA, window)
   int nkp;                          // 64-feature panels
-  int64_t total_tiles, chunk;
+  int64_t chunk;                    // positions per work unit inside one window
   int slots;
   __nv_bfloat16* W;                 // [panel row blocks * 128][ldw]
   int64_t ldw;
@@ -2286,7 +2286,6 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
       ga.nrb_p = q.nrb_p;
       ga.spw = q.spw1;
       ga.nkp = (int)(p.dp / 64);
-      ga.total_tiles = q.tiles1;
       ga.chunk = q.chunk1;
       ga.slots = q.slots1;
       ga.W = Wb;
