@@ -1427,18 +1427,35 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
+#ifdef SMMD_PIPE_TIMING
+    long long wg_acc = 0, wg_full = 0, wg_tiles = 0;
+    const long long wg_start = clock64();
+#endif
     for (int w = 0; w < (PAIR && rank != 0 ? 0 : a.nwin); ++w) {   // PAIR: only the leader issues
     int t = t_first;
     for (int pos = wp0; pos < wp1; ++pos) {
       const bool real = w * a.Wc + t < a.CT;
       if (++t == a.Wc) t = 0;
       if (!real) continue;   // padding position of the last window
+#ifdef SMMD_PIPE_TIMING
+      const long long wg_t0 = clock64();
+#endif
       if (PAIR) mbar_wait_cluster(&acc_empty[ab], aph ^ 1);   // the peer's epilogue arrives remotely
       else mbar_wait(&acc_empty[ab], aph ^ 1);
+#ifdef SMMD_PIPE_TIMING
+      wg_acc += clock64() - wg_t0;
+      ++wg_tiles;
+#endif
       tc_fence_after();
       const uint32_t dad = tmem + ab * BNW;
       for (int kk = 0; kk < a.nkp; ++kk) {
+#ifdef SMMD_PIPE_TIMING
+        const long long wg_t1 = clock64();
+#endif
         mbar_wait(&full[st], ph);
+#ifdef SMMD_PIPE_TIMING
+        wg_full += clock64() - wg_t1;
+#endif
         tc_fence_after();
         const uint32_t alo = a_lo0 + st * (kWgStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
         if (elect_one()) {
@@ -1465,6 +1482,11 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       ab ^= 1;
     }
     }
+#ifdef SMMD_PIPE_TIMING
+    if (blockIdx.x == 0 && lane == 0 && wg_tiles > 0)
+      printf("[wgen issuer] tiles %lld  cycles/tile: total %lld  wait acc_empty %lld  wait full %lld\n", wg_tiles,
+             (clock64() - wg_start) / wg_tiles, wg_acc / wg_tiles, wg_full / wg_tiles);
+#endif
   } else {
     // ===================== epilogue: all 16 warps on every tile (TMEM lane quarter x column quarter) ==========
     // With only two accumulators the issuer can start tile t+2 as soon as tile t is drained, so the drain latency
