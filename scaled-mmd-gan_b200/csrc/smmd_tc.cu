@@ -1540,18 +1540,27 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
         };
         if (h1 <= h0) release_acc();   // nothing of this tile in my column quarter
-#pragma unroll 1
-        for (int h = h0; h < h1; ++h) {
-          uint32_t v[16], wpk[8];
-          tmem_ld_x16(tmem + grp * BNW + h * 16 + lane_base, v);
-          tmem_ld_wait();
-          if (h == h1 - 1) release_acc();
+        // software pipeline over the 16-column chunks: the tcgen05.ld of chunk h+1 is in flight during the math of
+        // chunk h (two register buffers, as in the fused kernel); one 32-byte store per chunk and row
+        auto do_chunk = [&](const uint32_t (&v)[16], int h) {
+          uint32_t wpk[8];
           if (!special) fused_chunk16<Math, false>(math, v, nj + h * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
           else fused_chunk16<Math, true>(math, v, nj + h * 16, ni, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
-          if (real_rb) {
-            uint4* dst = reinterpret_cast<uint4*>(wrow + c0 + h * 16);
-            dst[0] = make_uint4(wpk[0], wpk[1], wpk[2], wpk[3]);
-            dst[1] = make_uint4(wpk[4], wpk[5], wpk[6], wpk[7]);
+          if (real_rb) st_global_v8(wrow + c0 + h * 16, wpk);
+        };
+        uint32_t va[16], vb[16];
+        if (h0 < h1) tmem_ld_x16(tmem + grp * BNW + h0 * 16 + lane_base, va);
+#pragma unroll 1
+        for (int h = h0; h < h1; h += 2) {
+          tmem_ld_wait();                                   // va = chunk h
+          if (h + 1 < h1) tmem_ld_x16(tmem + grp * BNW + (h + 1) * 16 + lane_base, vb);
+          else release_acc();
+          do_chunk(va, h);
+          if (h + 1 < h1) {
+            tmem_ld_wait();                                 // vb = chunk h + 1
+            if (h + 2 < h1) tmem_ld_x16(tmem + grp * BNW + (h + 2) * 16 + lane_base, va);
+            else release_acc();
+            do_chunk(vb, h + 1);
           }
         }
         if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
