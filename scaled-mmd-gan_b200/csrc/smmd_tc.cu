@@ -8,9 +8,13 @@
 //                      so neither the N x N kernel matrix nor its derivative ever reaches HBM.
 //                      Replaces gan/core/mmd.py:55-188 (kernels) + :194-220 (mmd2) + the TF autodiff graph
 //                      (gan/core/model.py:446,452) for d <= 256.
-//  tc_stream_kernel  : K-streaming Gram tiles + fused reduction epilogue (row stats), batched over problems;
-//                      used for KID (gan/compute_scores.py:232-335, all subsets in one launch) and for
-//                      value-only MMD^2.  bf16 or split-bf16 (hi*hi + lo*hi + hi*lo) operands.
+//  tc_wgen_kernel    : pass 1 of the wide-feature (d > 256) backward: 128 x 256 Gram tiles with K streamed, the same
+//  tc_wz_kernel        epilogue math, bf16 W tiles stored per row panel; pass 2 is O = W Z as a 256 x 256 macro-tile GEMM
+//  wz_finalize_rows_kernel  (details at the kernels; pass 1 runs as cta_group::2 CTA pairs on large panels).
+//  tc_stream_kernel  : K-streaming 128 x 128 Gram tiles + fused reduction epilogue (row stats): value-only MMD^2.
+//  tc_macro_kernel   : 256 x 256 macro-tile Gram + reduction epilogue, batched over problems: KID
+//                      (gan/compute_scores.py:232-335, all subsets in one launch) and the 3-sample sums
+//                      (gan/core/mmd.py:515-539).  bf16 or split-bf16 (hi*hi + lo*hi + hi*lo) operands.
 //
 // Work distribution is "stream-K" style: the flattened (row block, column tile) space is cut into equal
 // contiguous chunks, one per persistent CTA (grid = #SMs), partial results land in per-(CTA, slot)
