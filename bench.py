@@ -70,7 +70,7 @@ class ClockSampler:
     def __init__(self, gpu_index, enabled=True):
         """Only rank 0 samples (its line is the one printed).  NVML is initialised HERE, before the timed region: nvmlInit / handle lookup take 100s of ms and hold
         driver locks (measured: doing it inside the region cost 6 ms/step at N = 65536); the thread only polls."""
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.query_ms = [], set(), []
         self.max_mhz = None
         self._stop = threading.Event()
         self.gpu = gpu_index
@@ -102,15 +102,17 @@ class ClockSampler:
             nv, h = self.nv, self.h
             while not self._stop.is_set():
                 try:
+                    tq = time.perf_counter()
                     self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                     r = int(self.get_reasons(h))
+                    self.query_ms.append((time.perf_counter() - tq) * 1e3)
                     for nm, b in bits.items():
                         if r & b:
                             self.reasons.add(nm)
                 except Exception as e:
                     self.reasons.add("nvml_error:%s" % type(e).__name__)
                     break
-                self._stop.wait(0.1)    # NVML queries take driver locks: 25 Hz polling cost 14 % at 3 ms/step (8 GPUs)
+                self._stop.wait(0.2)    # NVML queries take driver locks: 25 Hz polling cost 14 % at 3 ms/step (8 GPUs)
             return
         try:
             out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
@@ -256,6 +258,9 @@ def run_ours(args):
     launches[0] = saved_launches
     lib.smmd_profile_enable(0)
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    if os.environ.get("SMMD_BENCH_DEBUG") and rank == 0:
+        print("step_ms:", " ".join("%.2f" % v for v in step_ms), "| sampler query ms:",
+              " ".join("%.1f" % v for v in getattr(sampler, "query_ms", [])), file=sys.stderr)
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -350,6 +355,8 @@ def run_ours(args):
             "clocks": clocks.summary(), "gpu_launches": n_launch, "roofline": roofline, "e2e": e2e, "kid": kid,
             "tflops_algorithmic": 14.0 * n * n * d / (ms_per_step * 1e-3) / 1e12,
             "wall_s_timed_region": t_wall,
+            # rank 0's per-step device times (the headline `ms_per_step` is the mean of all K, max over ranks)
+            "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
