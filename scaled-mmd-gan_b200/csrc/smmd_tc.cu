@@ -842,20 +842,19 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int64_t Mp = a.mp + a.np;
-  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
-  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  // tiles are dealt round-robin (tile t -> CTA t mod grid): the CTAs work on ~grid consecutive tiles at any time
+  // (one row block, neighbouring column tiles), so the streamed operands stay L2 resident for any problem size
   const int nk = a.nkp * a.ncombo;
 
   if (warp == 0) {
     {  // whole warp, elected lane issues (see tc_fused_kernel)
       uint32_t st = 0, ph = 0;
-      // decompose the first flattened tile index once, then step (ct, rb, b) incrementally
-      int ct = (int)(pos0 % a.CT);
-      int64_t brb = pos0 / a.CT;
-      int rb = (int)(brb % a.RB);
-      int64_t b = brb / a.RB;
       const int dpi = (int)a.dp;
-      for (int64_t pos = pos0; pos < pos1; ++pos) {
+      for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x) {
+        const int ct = (int)(pos % a.CT);
+        const int64_t brb = pos / a.CT;
+        const int rb = (int)(brb % a.RB);
+        const int64_t b = brb / a.RB;
         const int32_t arow = (int32_t)(b * Mp) + rb * BM, brow = (int32_t)(b * Mp) + ct * BNS;
         for (int combo = 0; combo < a.ncombo; ++combo) {
           const int32_t aoff = combo == 1 ? dpi : 0, boff = combo == 2 ? dpi : 0;
@@ -874,13 +873,6 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
           }
         }
-        if (++ct == a.CT) {
-          ct = 0;
-          if (++rb == a.RB) {
-            rb = 0;
-            ++b;
-          }
-        }
       }
     }
   } else if (warp == 1) {
@@ -889,7 +881,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const uint32_t hi = desc_hi_sw128(1024);
       const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
       uint32_t st = 0, ph = 0, ab = 0, aph = 0;
-      for (int64_t pos = pos0; pos < pos1; ++pos) {
+      for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x) {
         mbar_wait(&acc_empty[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t dad = tmem + ab * BNS;
@@ -945,7 +937,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       s_same = s_cross = q_same = q_cross = pairv = 0.0;
     };
     uint64_t tc = 0;
-    for (int64_t pos = pos0; pos < pos1; ++pos, ++tc) {
+    for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x, ++tc) {
       if ((int)(tc & 1) != grp) continue;
       const int ct = (int)(pos % a.CT);
       const int64_t brb = pos / a.CT;
@@ -1091,15 +1083,16 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int64_t Mp = a.mp + a.np;
-  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;
-  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  // Tiles are dealt round-robin (tile t -> CTA t mod grid): at any time the CTAs work on ~grid consecutive tiles,
+  // i.e. on a handful of problems whose operands (16.8 MB per KID subset) stay L2 resident.  Contiguous chunks per
+  // CTA had every CTA inside a different subset: all operand traffic came from HBM (22 GB per KID call).
   const int nk = a.nkp * a.ncombo;
 
   if (warp == 8) {
     // ---- TMA producer (whole warp, elected lane issues) ----
     uint32_t st = 0, ph = 0;
     const int dpi = (int)a.dp;
-    for (int64_t pos = pos0; pos < pos1; ++pos) {
+    for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x) {
       const int64_t b = pos / a.tiles_per_batch;
       int I, J;
       macro_decode(a, (int)(pos - b * a.tiles_per_batch), I, J);
@@ -1130,7 +1123,7 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t base_lo = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, aph = 0;
-    for (int64_t pos = pos0; pos < pos1; ++pos) {
+    for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x) {
       mbar_wait(acc_empty, aph ^ 1);
       tc_fence_after();
       for (int kk = 0; kk < nk; ++kk) {
@@ -1186,7 +1179,7 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       s_same = s_cross = q_same = q_cross = pairv = 0.0;
     };
     uint32_t fph = 0;
-    for (int64_t pos = pos0; pos < pos1; ++pos) {
+    for (int64_t pos = blockIdx.x; pos < a.total_tiles; pos += gridDim.x) {
       const int64_t b = pos / a.tiles_per_batch;
       int I, J;
       macro_decode(a, (int)(pos - b * a.tiles_per_batch), I, J);
