@@ -278,7 +278,7 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("tc_fused_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get("tc_fused_kernel_dram_bytes_per_launch") if world == 1 else None   # 1-GPU capture
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

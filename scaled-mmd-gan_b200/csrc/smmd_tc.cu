@@ -45,6 +45,7 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 struct Tuning {
   int fused_ksplit;
   int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
+  int fused_lockstep;   // whole row blocks per CTA for large Z (SMMD_FUSED_LOCKSTEP=0 disables)
   int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
   int64_t wz_panel_bytes;   // byte budget of one W row panel
   int wz_pair;      // pass 1 as CTA pairs with cta_group::2 UMMAs (SMMD_WZ_PAIR=0 disables)
@@ -55,6 +56,8 @@ const Tuning& tuning() {
     v.fused_ksplit = 2;
     if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
     v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
+    v.fused_lockstep = 1;
+    if (const char* e = getenv("SMMD_FUSED_LOCKSTEP")) v.fused_lockstep = atoi(e) != 0;
     v.wz_min_d = 256;
     if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
     v.wz_pair = 1;
@@ -1889,6 +1892,15 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
   p.grid = (int)std::min<int64_t>(sm_count(), p.total);
   if (p.grid < 1) p.grid = 1;
   p.chunk = (p.total + p.grid - 1) / p.grid;
+  // Large Z: give every CTA WHOLE row blocks when that costs < 2% balance.  All CTAs then start their sweeps at
+  // column tile 0 together and stay in step, so the Z_j tiles in flight are a narrow window instead of all of Z
+  // (ncu at N = 65536, d = 256: 2.0 GB of DRAM reads per launch with free-running chunks, 29x the 67 MB of Z;
+  // no change in run time -- L2 misses were only 1.4% of it -- but the re-reads are gone).
+  if (tuning().fused_lockstep && (int64_t)p.Mp * p.dp * 2 > ((int64_t)32 << 20)) {
+    const int64_t nrb = p.nrb_x + p.nrb_y;
+    const int64_t aligned = (nrb + p.grid - 1) / p.grid * p.T;
+    if (aligned * p.grid * 100 <= p.total * 102) p.chunk = aligned;
+  }
   p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
   p.slots = (int)((p.chunk + p.T - 1) / p.T) + 1;
   size_t o = 0;
