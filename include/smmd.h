@@ -70,7 +70,10 @@ typedef enum smmd_kernel_id {
  * BF16: tcgen05 tensor cores, bf16 operands / fp32 accumulate (tier rel 1e-3).
  * BF16X3: tcgen05 with a 3-term split-bf16 Gram (hi*hi + lo*hi + hi*lo), forward-only paths
  * (KID, value-only MMD^2); ~fp32-accurate Gram at 3x the tensor work.
- * AUTO: FP32 for small problems, BF16 otherwise. */
+ * AUTO: FP32 for small problems (m + n < 1024 or d < 32) and for combinations the tensor-core kernels do not
+ * cover (dot kernel), BF16 otherwise.  The exact gradient kernel keeps a feature row in registers and supports
+ * d <= 2048: with gradients and a wider d, AUTO takes BF16 whatever the size, and an explicit FP32 request returns
+ * SMMD_EUNSUPPORTED.  An explicit BF16 / BF16X3 request is honoured or refused, never silently downgraded. */
 typedef enum smmd_precision {
   SMMD_PREC_FP32 = 0,
   SMMD_PREC_BF16 = 1,

@@ -129,11 +129,14 @@ Geometry make_geometry(const smmd_problem* p) {
 // AUTO: tensor cores only pay off once the Gram is big and the contraction deep enough; combinations the
 // tensor-core kernels do not cover stay on the exact path.  An explicit BF16/BF16X3 request is honoured or
 // refused (SMMD_EUNSUPPORTED), never silently downgraded.
+constexpr int64_t kExactGradMaxD = 2048;
+
 int resolve_precision(const smmd_problem* p, int want_grad) {
   int prec = p->precision;
   if (prec == SMMD_PREC_AUTO) {
     KernelFn kf;
-    const bool big = (p->m + p->n) >= 1024 && p->d >= 32;
+    // the exact gradient kernel keeps a row's features in registers: d <= 2048; wider rows take the tensor-core path
+    const bool big = ((p->m + p->n) >= 1024 && p->d >= 32) || (want_grad && p->d > kExactGradMaxD);
     const bool ok = big &&
                     build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf) ==
                         SMMD_OK &&
@@ -226,6 +229,7 @@ static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double
   const int prec = resolve_precision(p, want_grad);
 
   if (prec == SMMD_PREC_FP32) {
+    if (want_grad && p->d > kExactGradMaxD) return SMMD_EUNSUPPORTED;   // (dot kernel / explicit fp32 with d > 2048)
     const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
     char* ws = static_cast<char*>(workspace);
     static const bool no_small = getenv("SMMD_DISABLE_SMALL") != nullptr;   // tests: force the general exact path
@@ -367,7 +371,7 @@ int smmd_kernel_xy_bwd(const smmd_problem* p, const void* X, const void* Y, cons
   g_launches = 0;
   g_path = "simt_fp32_kxy_bwd";
   if (!dK || !dX || !dY || (p && lddk < p->n)) return SMMD_EINVAL;
-  if (p && p->d > 2048) return SMMD_EUNSUPPORTED;
+  if (p && p->d > kExactGradMaxD) return SMMD_EUNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   KernelFn kf;
   float *Z, *norms;
