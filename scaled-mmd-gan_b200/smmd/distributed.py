@@ -35,7 +35,7 @@ def _tc_eligible(spec, m, n, d, precision):
     if precision in (None, "auto"):
         covered = spec.kernel_id in (_lib.K_DISTANCE, _lib.K_TANH_DISTANCE, _lib.K_RBF, _lib.K_MIX_RBF, _lib.K_MIX_RQ,
                                      _lib.K_TANH_MIX_RQ)
-        return covered and (m + n) >= 1024 and d >= 32
+        return covered and (((m + n) >= 1024 and d >= 32) or d > 2048)   # include/smmd.h, SMMD_PREC_AUTO
     return False
 
 
