@@ -1,0 +1,151 @@
+// smmd_tc_common.cuh -- pieces shared by the tensor-core translation units (smmd_tc.cu: operand preparation and
+// dispatch; smmd_tc_fused.cu: fused fwd+bwd kernel; smmd_tc_wz.cu: two-pass path for wide features;
+// smmd_tc_gram.cu: Gram + reduction kernels for KID / 3-sample sums / value-only MMD^2).
+#pragma once
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "sm100_ptx.cuh"
+#include "smmd_kfun.cuh"
+#include "smmd_tc.h"
+#include "smmd_tc_math.cuh"
+#include "tmap_host.h"
+
+namespace smmd {
+namespace tc {
+using namespace sm100;
+
+constexpr int BM = 128;            // rows per row block (UMMA M)
+constexpr int BNF = 64;            // fused kernel: columns per tile
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue groups
+constexpr int kMaxSmem = 232448;   // 227 KB
+
+inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+// Developer tuning knobs (environment overrides are read once; defaults are the measured best).
+struct Tuning {
+  int fused_ksplit;
+  int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
+  int fused_lockstep;   // whole row blocks per CTA for large Z (SMMD_FUSED_LOCKSTEP=0 disables)
+  int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
+  int64_t wz_panel_bytes;   // byte budget of one W row panel
+  int wz_pair;      // pass 1 as CTA pairs with cta_group::2 UMMAs (SMMD_WZ_PAIR=0 disables)
+};
+inline const Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning v;
+    v.fused_ksplit = 2;
+    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
+    v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
+    v.fused_lockstep = 1;
+    if (const char* e = getenv("SMMD_FUSED_LOCKSTEP")) v.fused_lockstep = atoi(e) != 0;
+    v.wz_min_d = 256;
+    if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
+    v.wz_pair = 1;
+    if (const char* e = getenv("SMMD_WZ_PAIR")) v.wz_pair = atoi(e) != 0;
+    v.wz_panel_bytes = (int64_t)6 << 30;
+    if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
+    return v;
+  }();
+  return t;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+// ------------------------------------------------------------------------------------------------
+// prep: fp32/bf16 rows -> padded bf16 operand matrix (+ optional lo part), squared norms of exactly the
+// values the tensor core will see, optional gather (KID subsets), optional tanh, stats initialisation.
+// Layout per problem b: rows [0,mp) = X (valid < m), rows [mp, mp+np) = Y (valid < n); pad rows are zero.
+// ------------------------------------------------------------------------------------------------
+struct PrepTcArgs {
+  const void* A;
+  const void* B;
+  int dtype;
+  int64_t lda, ldb, m, n, mp, np, d, dp, dpz;
+  const int32_t* idxA;
+  const int32_t* idxB;
+  int64_t first_batch;
+  int tanh_features, split;
+  __nv_bfloat16* Z;
+  float* norms;
+  double* stats;  // optional [batch][m+n][RS_COUNT]: zeroed, RS_DIAG set analytically
+  KernelFn kf;
+  int64_t blk_a, blk_b;  // gathered block layout (0 = plain), see SrcLayout
+};
+
+// launch wrappers (kernels live in smmd_tc.cu): grid = (ceil(rows / 8), batch)
+cudaError_t launch_prep_tc(const PrepTcArgs& a, int64_t rows, unsigned batch, cudaStream_t s);
+cudaError_t launch_colsum_tc(const __nv_bfloat16* Z, int64_t dpz, int64_t dp, int64_t m, int64_t mp, int64_t n,
+                             double* csum, cudaStream_t s);
+
+// copy the mixture parameters to shared memory for the generic math variants: sp[0..7]=p0, [8..15]=p1, [16..23]=w
+__device__ __forceinline__ void stage_params(const KernelFn& kf, float* sp) {
+  if (threadIdx.x < 8) {
+    sp[threadIdx.x] = kf.p0[threadIdx.x];
+    sp[8 + threadIdx.x] = kf.p1[threadIdx.x];
+    sp[16 + threadIdx.x] = kf.w[threadIdx.x];
+  }
+}
+
+// 16 columns of one row of a fused-epilogue tile: kernel transform, tile sum, row sum of W, and W packed to
+// bf16x2.  SPECIAL tiles (diagonal inside / padded columns) mask per element; interior tiles run the
+// unmasked instruction stream.  Kept small and called from a ROLLED loop: the whole hot loop must fit the
+// instruction caches (a fully unrolled 64-column epilogue stalled ~50% on instruction fetch).
+template <class Math, bool SPECIAL>
+__device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (&v)[16], const float* __restrict__ nj,
+                                              float ni, float2 cw, int col0, int lim, int gi, float2& tsum,
+                                              float2& rsum, uint32_t (&wpk)[8]) {
+  const float2 ni2 = bc2(ni);
+#pragma unroll
+  for (int c = 0; c < 16; c += 8) {   // 4 pairs (8 columns) evaluated in lock-step
+    const float4 na = *reinterpret_cast<const float4*>(nj + c);
+    const float4 nb = *reinterpret_cast<const float4*>(nj + c + 4);
+    float2 S[4], nij[4], k[4], kd[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S[e] = make_float2(__uint_as_float(v[c + 2 * e]), __uint_as_float(v[c + 2 * e + 1]));
+    nij[0] = add2(ni2, make_float2(na.x, na.y));
+    nij[1] = add2(ni2, make_float2(na.z, na.w));
+    nij[2] = add2(ni2, make_float2(nb.x, nb.y));
+    nij[3] = add2(ni2, make_float2(nb.z, nb.w));
+    eval_pairs<Math, 4>(math, S, nij, k, kd);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (SPECIAL) {
+        const int col = col0 + c + 2 * e;
+        const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
+        k[e] = make_float2(ok0 ? k[e].x : 0.f, ok1 ? k[e].y : 0.f);
+        kd[e] = make_float2(ok0 ? kd[e].x : 0.f, ok1 ? kd[e].y : 0.f);
+      }
+      tsum = add2(tsum, k[e]);
+      const float2 ww = mul2(kd[e], cw);
+      rsum = add2(rsum, ww);
+      wpk[(c >> 1) + e] = pack_bf16x2(ww.x, ww.y);
+    }
+  }
+}
+
+// ---- per-path entry points (one translation unit each); `variant` = select_tc_variant(kf) ----
+cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
+                         float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
+size_t tc_fused_workspace_bytes(int64_t m, int64_t n, int64_t d);
+cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
+                      float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
+size_t tc_wz_workspace_bytes(int64_t m, int64_t n, int64_t d);
+cudaError_t tc_run_value_only(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision, double* scalars,
+                              float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
+size_t tc_value_only_workspace_bytes(int64_t m, int64_t n, int64_t d, int precision);
+
+}  // namespace tc
+}  // namespace smmd
