@@ -1,4 +1,4 @@
-// smmd_tc.h -- interface of the tcgen05 tensor-core path (implemented in smmd_tc.cu).
+// smmd_tc.h -- interface of the tcgen05 tensor-core path (smmd_tc.cu dispatches to smmd_tc_fused / _wz / _gram.cu).
 #pragma once
 #include "smmd_internal.h"
 
