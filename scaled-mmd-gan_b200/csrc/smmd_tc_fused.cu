@@ -59,7 +59,8 @@ inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes 
 //
 // mbarriers (all phases tracked with running counters, no div/mod):
 //   zj_full[nst]   TMA -> UMMA issuer                      (Zj tile landed)
-//   zj_empty[nst]  UMMA #2 commit -> TMA producer AND the epilogue group (its W buffer is drained)
+//   zj_empty[nst]  UMMA #2 commit -> TMA producer
+//   w_free[2][4]   UMMA #2 commit per 16-column slice -> the epilogue group that owns the W buffer
 //   s_full[3]      UMMA #1 commit -> epilogue group
 //   w_full[2]      epilogue group -> UMMA issuer            (W published; also implies the S buffer is free,
 //                                                            because a thread loads S before it writes W)
@@ -82,7 +83,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   uint64_t* zj_empty = bars + NST;      // [NST]
   uint64_t* s_full = bars + 2 * NST;    // [3]
   uint64_t* w_full = s_full + 3;        // [2]
-  uint64_t* zi_full = w_full + 2;
+  uint64_t* w_free = w_full + 2;        // [2][4]  UMMA #2 has read 16-column slice kk of group g's W buffer
+  uint64_t* zi_full = w_free + 8;
   uint64_t* zi_empty = zi_full + 1;
   uint64_t* o_full = zi_empty + 1;
   uint64_t* o_empty = o_full + 1;
@@ -98,6 +100,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     }
     for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&w_full[i], 128 * KSPLIT);
+    for (int i = 0; i < 8; ++i) mbar_init(&w_free[i], 1);
     mbar_init(zi_full, 1);
     mbar_init(zi_empty, 1);
     mbar_init(o_full, 1);
@@ -171,7 +174,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
         const int TU = (int)std::min<int64_t>(a.T - t0, left);
         mbar_wait(zi_full, unit & 1);
-        // static order, UMMA #1 three tiles ahead of UMMA #2; 2 waits + 2 commits per tile
+        // static order, UMMA #1 three tiles ahead of UMMA #2; 2 waits per tile
         for (int jj = 0; jj < TU + 3; ++jj) {
           const int b2 = jj - 3;
           if (b2 >= 0) {  // ---- UMMA #2 for local tile b2: O += W * Zj
@@ -184,9 +187,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
             const uint32_t wad = tmem + TM_W + wb2 * 32;
             if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < BNF / 16; ++kk)
+              for (int kk = 0; kk < BNF / 16; ++kk) {
                 umma_ts2(tmem + TM_O, wad + kk * 8, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
-              umma_commit(&zj_empty[st2]);     // frees the Zj stage (producer) and this W buffer (epilogue group)
+                umma_commit(&w_free[wb2 * 4 + kk]);   // slice kk of this W buffer may be overwritten
+              }
+              umma_commit(&zj_empty[st2]);     // frees the Zj stage (producer)
               if (b2 == TU - 1) umma_commit(o_full);
             }
             __syncwarp();
@@ -240,8 +245,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     uint32_t par = 0;                       // parity of the global tile counter
     uint32_t sb = 0, sph = 0;               // S buffer / phase of the current tile
     uint32_t st = 0, ph = 0;                // Zj stage / phase of the current tile
-    uint32_t st_m2 = 0, ph_m2 = 0;          // ... and of the tile two back (whose UMMA #2 drains this group's W buffer)
-    uint32_t gcount = 0;                    // global tile counter (only its first two values matter)
+    uint32_t gk = 0;                        // tiles this group has processed (W buffer phase)
     int rbi = (int)(pos0 / a.T);
     int t0 = (int)(pos0 - (int64_t)rbi * a.T);
     const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
@@ -266,6 +270,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           const float* nj = a.norms + c0 + half * (CH_PER * 16);        // column norms: tiny, L1/L2 resident
           const uint32_t s_addr = tmem + TM_S + sb * 64 + half * (CH_PER * 16) + lane_base;
           const uint32_t w_addr = tmem + TM_W + grp * 32 + half * (CH_PER * 8) + lane_base;
+          uint64_t* wfree_g = w_free + grp * 4;
           float2 tsum = make_float2(0.f, 0.f);
           mbar_wait(&s_full[sb], sph);
           tc_fence_after();
@@ -279,11 +284,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
               tmem_ld_wait();
               tmem_ld_x16(s_addr + (2 * it + 1) * 16, vb);
               fused_chunk16<Math, false>(math, va, nj + (2 * it) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
-              if (it == 0 && gcount >= 2) mbar_wait(&zj_empty[st_m2], ph_m2);   // W buffer drained by UMMA #2 of tile-2
+              // the group's previous tile shares this W buffer: wait, slice by slice, until its UMMA #2 has read it
+              // (one commit per 16-column slice: waiting for the whole UMMA #2 stalled every tile by ~800 cycles)
+              if (gk) mbar_wait(&wfree_g[half * CH_PER + 2 * it], (gk - 1) & 1);
               tmem_st_x8(w_addr + (2 * it) * 8, wpk);
               tmem_ld_wait();
               if (2 * it + 2 < CH_PER) tmem_ld_x16(s_addr + (2 * it + 2) * 16, va);
               fused_chunk16<Math, false>(math, vb, nj + (2 * it + 1) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+              if (gk) mbar_wait(&wfree_g[half * CH_PER + 2 * it + 1], (gk - 1) & 1);
               tmem_st_x8(w_addr + (2 * it + 1) * 8, wpk);
             }
           } else {
@@ -294,7 +302,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
               tmem_ld_wait();
               fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + half * (CH_PER * 16) + ch * 16, lim, gi, tsum,
                                         rsum, wpk);
-              if (ch == 0 && gcount >= 2) mbar_wait(&zj_empty[st_m2], ph_m2);
+              if (gk) mbar_wait(&wfree_g[half * CH_PER + ch], (gk - 1) & 1);
               tmem_st_x8(w_addr + ch * 8, wpk);
             }
           }
@@ -306,16 +314,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           PT_COUNT(14);
           if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
           else dcross += (double)((tsum.x + tsum.y) * kscale);
+          ++gk;
         }
         // advance the ring state by one tile of the CTA's stream
         par ^= 1;
-        if (gcount >= 2) {
-          if (++st_m2 == (uint32_t)NST) {
-            st_m2 = 0;
-            ph_m2 ^= 1;
-          }
-        }
-        ++gcount;
         if (++st == (uint32_t)NST) {
           st = 0;
           ph ^= 1;
