@@ -60,7 +60,7 @@ inline int fused_smem(int npanel, int nst) { return 1024 + npanel * kZiRowBytes 
 // mbarriers (all phases tracked with running counters, no div/mod):
 //   zj_full[nst]   TMA -> UMMA issuer                      (Zj tile landed)
 //   zj_empty[nst]  UMMA #2 commit -> TMA producer
-//   w_free[2][4]   UMMA #2 commit per 16-column slice -> the epilogue group that owns the W buffer
+//   w_free[2][2]   UMMA #2 commit per 32-column half -> the epilogue group that owns the W buffer
 //   s_full[3]      UMMA #1 commit -> epilogue group
 //   w_full[2]      epilogue group -> UMMA issuer            (W published; also implies the S buffer is free,
 //                                                            because a thread loads S before it writes W)
@@ -83,8 +83,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   uint64_t* zj_empty = bars + NST;      // [NST]
   uint64_t* s_full = bars + 2 * NST;    // [3]
   uint64_t* w_full = s_full + 3;        // [2]
-  uint64_t* w_free = w_full + 2;        // [2][4]  UMMA #2 has read 16-column slice kk of group g's W buffer
-  uint64_t* zi_full = w_free + 8;
+  uint64_t* w_free = w_full + 2;        // [2][2]  UMMA #2 has read 32-column half h of group g's W buffer
+  uint64_t* zi_full = w_free + 4;
   uint64_t* zi_empty = zi_full + 1;
   uint64_t* o_full = zi_empty + 1;
   uint64_t* o_empty = o_full + 1;
@@ -100,7 +100,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
     }
     for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&w_full[i], 128 * KSPLIT);
-    for (int i = 0; i < 8; ++i) mbar_init(&w_free[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&w_free[i], 1);
     mbar_init(zi_full, 1);
     mbar_init(zi_empty, 1);
     mbar_init(o_full, 1);
@@ -189,7 +189,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
 #pragma unroll
               for (int kk = 0; kk < BNF / 16; ++kk) {
                 umma_ts2(tmem + TM_O, wad + kk * 8, blo + kk * (2048 >> 4), hi, idesc2, (b2 > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(&w_free[wb2 * 4 + kk]);   // slice kk of this W buffer may be overwritten
+                if (kk & 1) umma_commit(&w_free[wb2 * 2 + (kk >> 1)]);   // this half of the W buffer may be overwritten
               }
               umma_commit(&zj_empty[st2]);     // frees the Zj stage (producer)
               if (b2 == TU - 1) umma_commit(o_full);
@@ -270,7 +270,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
           const float* nj = a.norms + c0 + half * (CH_PER * 16);        // column norms: tiny, L1/L2 resident
           const uint32_t s_addr = tmem + TM_S + sb * 64 + half * (CH_PER * 16) + lane_base;
           const uint32_t w_addr = tmem + TM_W + grp * 32 + half * (CH_PER * 8) + lane_base;
-          uint64_t* wfree_g = w_free + grp * 4;
+          uint64_t* wfree_g = w_free + grp * 2;
           float2 tsum = make_float2(0.f, 0.f);
           mbar_wait(&s_full[sb], sph);
           tc_fence_after();
@@ -284,14 +284,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
               tmem_ld_wait();
               tmem_ld_x16(s_addr + (2 * it + 1) * 16, vb);
               fused_chunk16<Math, false>(math, va, nj + (2 * it) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
-              // the group's previous tile shares this W buffer: wait, slice by slice, until its UMMA #2 has read it
-              // (one commit per 16-column slice: waiting for the whole UMMA #2 stalled every tile by ~800 cycles)
-              if (gk) mbar_wait(&wfree_g[half * CH_PER + 2 * it], (gk - 1) & 1);
+              // the group's previous tile shares this W buffer: wait, half by half, until its UMMA #2 has read it
+              // (one commit per 32-column half: waiting for the whole UMMA #2 stalled every tile by ~800 cycles)
+              if (gk && ((half * CH_PER + 2 * it) & 1) == 0) mbar_wait(&wfree_g[(half * CH_PER + 2 * it) >> 1], (gk - 1) & 1);
               tmem_st_x8(w_addr + (2 * it) * 8, wpk);
               tmem_ld_wait();
               if (2 * it + 2 < CH_PER) tmem_ld_x16(s_addr + (2 * it + 2) * 16, va);
               fused_chunk16<Math, false>(math, vb, nj + (2 * it + 1) * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
-              if (gk) mbar_wait(&wfree_g[half * CH_PER + 2 * it + 1], (gk - 1) & 1);
               tmem_st_x8(w_addr + (2 * it + 1) * 8, wpk);
             }
           } else {
@@ -302,7 +301,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
               tmem_ld_wait();
               fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + half * (CH_PER * 16) + ch * 16, lim, gi, tsum,
                                         rsum, wpk);
-              if (gk) mbar_wait(&wfree_g[half * CH_PER + ch], (gk - 1) & 1);
+              if (gk && ((half * CH_PER + ch) & 1) == 0) mbar_wait(&wfree_g[(half * CH_PER + ch) >> 1], (gk - 1) & 1);
               tmem_st_x8(w_addr + ch * 8, wpk);
             }
           }
