@@ -127,7 +127,9 @@ SMMD_API int smmd_device_supported(void);
  *   gan/core/mmd.py:18-220 (kernels + _mmd2), called from gan/core/model.py:313-319 and
  *   gan/core/smmd.py:10-19; autodiff at gan/core/model.py:446,452.
  * scalars: device double[SMMD_NUM_SCALARS].  dX [owned_m, d] / dY [owned_n, d] fp32 row-major
- * (ld = d) receive dMMD2/dX, dMMD2/dY for the owned rows; both NULL = forward only. */
+ * (ld = d) receive dMMD2/dX, dMMD2/dY for the owned rows; both NULL = forward only.
+ * smmd_mmd2_workspace_bytes is exact for the problem AS GIVEN, including its rank / world row shard (the
+ * work split of a shard is not bounded by the unsharded one): query it with the struct you will pass. */
 SMMD_API size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad);
 SMMD_API int smmd_mmd2_fwd_bwd(const smmd_problem* p, const void* X, const void* Y, double* scalars,
                       float* dX, float* dY, void* workspace, size_t workspace_bytes, void* stream);

@@ -204,7 +204,7 @@ size_t smmd_mmd2_workspace_bytes(const smmd_problem* p, int want_grad) {
   if (validate_problem(p) != SMMD_OK) return 0;
   const int prec = resolve_precision(p, want_grad);
   if (prec == SMMD_PREC_FP32) return simt_plan(p->m, p->n, p->d, 1).off_end;
-  return tc_mmd2_workspace_bytes(p->m, p->n, p->d, want_grad, prec);
+  return tc_mmd2_workspace_bytes(make_geometry(p), want_grad, prec);   // exact for this rank's row range
 }
 
 static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double* scalars, float* dX, float* dY,

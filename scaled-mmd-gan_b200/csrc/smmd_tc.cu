@@ -173,10 +173,11 @@ bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad) {
   return true;
 }
 
-size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision) {
-  // worst case over shards: a full-range plan bounds every rank's plan
-  const size_t grad = !want_grad ? 0 : (use_two_pass(d) ? tc_wz_workspace_bytes(m, n, d) : tc_fused_workspace_bytes(m, n, d));
-  return std::max(grad, tc_value_only_workspace_bytes(m, n, d, precision));
+size_t tc_mmd2_workspace_bytes(const Geometry& g, int want_grad, int precision) {
+  // the plan of exactly this row range (rank / world): slab counts are not monotone in the range, so a full-range
+  // plan does not bound a shard's plan
+  const size_t grad = !want_grad ? 0 : (use_two_pass(g.d) ? tc_wz_workspace_bytes(g) : tc_fused_workspace_bytes(g));
+  return std::max(grad, tc_value_only_workspace_bytes(g.m, g.n, g.d, precision));
 }
 
 cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision,

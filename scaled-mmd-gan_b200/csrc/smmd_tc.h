@@ -7,7 +7,7 @@ namespace smmd {
 // fused fwd(+bwd) MMD^2 on tensor cores
 bool tc_mmd2_supported(int64_t d, int want_grad);
 bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad);
-size_t tc_mmd2_workspace_bytes(int64_t m, int64_t n, int64_t d, int want_grad, int precision);
+size_t tc_mmd2_workspace_bytes(const Geometry& g, int want_grad, int precision);
 cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision,
                         double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
                         const char** path);

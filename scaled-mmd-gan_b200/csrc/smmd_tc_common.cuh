@@ -27,6 +27,7 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 struct Tuning {
   int fused_ksplit;
   int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
+  int fused_pair;  // tile-pair variant of the fused kernel (default; SMMD_FUSED_PAIR=0 selects the single-tile kernel)
   int fused_lockstep;   // whole row blocks per CTA for large Z (SMMD_FUSED_LOCKSTEP=0 disables)
   int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
   int64_t wz_panel_bytes;   // byte budget of one W row panel
@@ -38,6 +39,8 @@ inline const Tuning& tuning() {
     v.fused_ksplit = 2;
     if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
     v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
+    v.fused_pair = 1;
+    if (const char* e = getenv("SMMD_FUSED_PAIR")) v.fused_pair = atoi(e) != 0;
     v.fused_lockstep = 1;
     if (const char* e = getenv("SMMD_FUSED_LOCKSTEP")) v.fused_lockstep = atoi(e) != 0;
     v.wz_min_d = 256;
@@ -139,10 +142,10 @@ __device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (
 // ---- per-path entry points (one translation unit each); `variant` = select_tc_variant(kf) ----
 cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
                          float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
-size_t tc_fused_workspace_bytes(int64_t m, int64_t n, int64_t d);
+size_t tc_fused_workspace_bytes(const Geometry& g);
 cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
                       float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
-size_t tc_wz_workspace_bytes(int64_t m, int64_t n, int64_t d);
+size_t tc_wz_workspace_bytes(const Geometry& g);
 cudaError_t tc_run_value_only(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision, double* scalars,
                               float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
 size_t tc_value_only_workspace_bytes(int64_t m, int64_t n, int64_t d, int precision);

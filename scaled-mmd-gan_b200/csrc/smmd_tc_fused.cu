@@ -357,6 +357,282 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
   if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
 }
 
+// ================================================================================================
+// tile-pair variant of the fused kernel
+// ================================================================================================
+// UMMA #1 at N = 64 is bound by the shared-memory read of its A operand (Z_i: 4 KB per instruction for 32 tensor
+// cycles, ~65 cycles each, 1040 per tile) and made the issuer the longest role.  Here one UMMA #1 covers TWO
+// column tiles (N = 128, same A read, tensor-bound at 64 cycles): 1040 cycles per PAIR.  What makes room for the
+// 128-column S buffers in tensor memory is writing W in place: a warp overwrites the first half of the 32 S
+// columns it has just read with its 16 packed bf16x2 W columns (chunk 0 -> columns [0,8), chunk 1 -> [8,16) of its
+// own slice, both already consumed), so there are no separate W buffers:
+//   TMEM  O[dp <= 256] | pair buffer 0 [tile A: 64 | tile B: 64] | pair buffer 1 [128]
+// and an S/W buffer lives from UMMA #1 of its pair until UMMA #2 of both tiles has completed (pb_free).
+// The Z_j ring is panel-major ([panel][stage][64 rows x 128 B], 4 stages) so that the two tiles of a pair are 128
+// contiguous rows per k-panel for UMMA #1, while UMMA #2 reads one tile MN-major with LBO = the panel stride.
+// Group g of the epilogue takes tile g of every pair; work chunks are cut at even tile positions.
+constexpr uint32_t TMP_S = 256;
+constexpr int kPairStages = 4;
+inline int fused_pair_smem(int npanel) { return 1024 + npanel * kZiRowBytes + kPairStages * npanel * kZjRowBytes + 512; }
+
+template <class Math>
+__global__ void __launch_bounds__(576, 1)
+tc_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
+                     const __grid_constant__ FusedArgs a) {
+  constexpr int KSPLIT = 2, NPART = 4, CH_PER = 2, EPI_WARPS = 16, NST = kPairStages;
+  const int NPANEL = a.npanel, DP = a.dp;
+  const int ZI_BYTES = NPANEL * kZiRowBytes;
+  constexpr int PANEL_STRIDE = NST * kZjRowBytes;     // bytes between k-panels of the ring
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sZi = smem;
+  uint8_t* sZj = smem + ZI_BYTES;                     // [NPANEL][NST][64 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sZj + NPANEL * PANEL_STRIDE);
+  uint64_t* zj_full = bars;             // [NST]
+  uint64_t* zj_empty = bars + NST;      // [NST]
+  uint64_t* s_full = bars + 2 * NST;    // [2]  UMMA #1 of a pair -> both epilogue groups
+  // w_full is indexed [pair buffer][group]: a fast group may finish pair P+1 before the issuer has consumed the slow
+  // group's arrival for pair P (nothing orders them: W is written in place), and a barrier that completes two phases
+  // between waits deadlocks a parity wait.  The same (buffer, group) barrier is next used by pair P+2, which cannot
+  // start before UMMA #2 of pair P -- i.e. after the issuer has consumed it.
+  uint64_t* w_full = s_full + 2;        // [2][2]  epilogue group g -> issuer (W of its tile is in place)
+  uint64_t* pb_free = w_full + 4;       // [2]  UMMA #2 of both tiles of a pair done -> issuer may refill the buffer
+  uint64_t* zi_full = pb_free + 2;
+  uint64_t* zi_empty = zi_full + 1;
+  uint64_t* o_full = zi_empty + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&zj_full[i], 1);
+      mbar_init(&zj_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&w_full[2 * i], 128 * KSPLIT);
+      mbar_init(&w_full[2 * i + 1], 128 * KSPLIT);
+      mbar_init(&pb_free[i], 1);
+    }
+    mbar_init(zi_full, 1);
+    mbar_init(zi_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 256 * KSPLIT);
+    fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tmap_zi);
+    prefetch_tmap(&tmap_zj);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t pos0 = (int64_t)blockIdx.x * a.chunk;   // even (fused_plan)
+  const int64_t pos1 = pos0 + a.chunk < a.total_tiles ? pos0 + a.chunk : a.total_tiles;
+  auto rb_of = [&](int64_t rbi) -> int { return rbi < a.nrb_x ? a.rb_x0 + (int)rbi : a.rb_y0 + (int)(rbi - a.nrb_x); };
+
+  if (warp == EPI_WARPS) {
+    // ===================== TMA producer =====================
+    uint32_t unit = 0, st = 0, ph = 0;
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      const int rb = rb_of(rbi);
+      mbar_wait(zi_empty, (unit & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
+        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
+      }
+      __syncwarp();
+      for (int t = t0; t < t0 + TU; ++t) {
+        mbar_wait(&zj_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&zj_full[st], NPANEL * kZjRowBytes);
+          uint8_t* dst = sZj + st * kZjRowBytes;
+          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * PANEL_STRIDE, &tmap_zj, &zj_full[st], p * 64, t * BNF);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)NST) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      left -= TU;
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ===================== UMMA issuer =====================
+    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, kFmtBF16, false, false);
+    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
+    const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);                 // K-major B of UMMA #1 (two stages = 128 rows)
+    const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), PANEL_STRIDE);       // MN-major B of UMMA #2: LBO = panel stride
+    constexpr uint32_t stage_step = (uint32_t)kZjRowBytes >> 4, panel_step = (uint32_t)PANEL_STRIDE >> 4;
+    uint32_t unit = 0;
+    uint32_t st1 = 0, ph1 = 0, gp1 = 0;        // UMMA #1 stream: first stage of the pair / phase, global pair counter
+    uint32_t st2 = 0, gp2 = 0;                 // UMMA #2 stream: stage, global pair counter
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      const int NP = TU >> 1;
+      mbar_wait(zi_full, unit & 1);
+      // static order: UMMA #1 runs two pairs ahead of the UMMA #2 of a pair
+      for (int j = 0; j < NP + 2; ++j) {
+        const int pm2 = j - 2;
+        if (pm2 >= 0) {
+          const uint32_t pb = gp2 & 1;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {   // ---- UMMA #2 for tile g of pair pm2: O += W * Zj
+            mbar_wait(&w_full[pb * 2 + g], (gp2 >> 1) & 1);
+            if (pm2 == 0 && g == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t blo = zj_lo2 + st2 * stage_step;
+            const uint32_t wad = tmem + TMP_S + pb * 128 + g * 64;
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < BNF / 16; ++kk)   // W slice kk sits at columns (kk/2)*32 + (kk%2)*8 of the tile
+                umma_ts2(tmem + TM_O, wad + (kk >> 1) * 32 + (kk & 1) * 8, blo + kk * (2048 >> 4), hi, idesc2,
+                         (pm2 > 0 || g > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&zj_empty[st2]);
+              if (g == 1) umma_commit(&pb_free[pb]);
+              if (pm2 == NP - 1 && g == 1) umma_commit(o_full);
+            }
+            __syncwarp();
+            if (++st2 == (uint32_t)NST) st2 = 0;
+          }
+          ++gp2;
+        }
+        if (j < NP) {   // ---- UMMA #1 for pair j: S[128 x 128] = Zi * [Zj(2j); Zj(2j+1)]^T
+          const uint32_t pb = gp1 & 1;
+          mbar_wait(&zj_full[st1], ph1);
+          mbar_wait(&zj_full[st1 + 1], ph1);
+          if (gp1 >= 2) mbar_wait(&pb_free[pb], ((gp1 >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t blo = zj_lo1 + st1 * stage_step;
+          const uint32_t sad = tmem + TMP_S + pb * 128;
+          if (elect_one()) {
+            for (int p = 0; p < NPANEL; ++p) {
+              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * panel_step;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+            }
+            umma_commit(&s_full[pb]);
+            if (j == NP - 1) umma_commit(zi_empty);
+          }
+          __syncwarp();
+          st1 += 2;
+          if (st1 == (uint32_t)NST) {
+            st1 = 0;
+            ph1 ^= 1;
+          }
+          ++gp1;
+        }
+      }
+      left -= TU;
+    }
+  } else {
+    // ===================== epilogue groups: group g takes tile g of every pair =====================
+    const int grp = warp >> 3;
+    const int half = (warp >> 2) & 1;
+    const int part = grp * KSPLIT + half;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
+    uint32_t unit = 0, gp = 0;   // global pair counter
+    int slot = 0;
+    int rbi = (int)(pos0 / a.T);
+    int t0 = (int)(pos0 - (int64_t)rbi * a.T);
+    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit, ++slot) {
+      const int TU = (int)std::min<int64_t>(a.T - t0, left);
+      const int rb = rb_of(rbi);
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
+      const float ni = a.norms[gi];
+      float2 rsum = make_float2(0.f, 0.f);
+      double dsame = 0.0, dcross = 0.0;
+      for (int lp = 0; lp < (TU >> 1); ++lp, ++gp) {
+        const uint32_t pb = gp & 1;
+        const int c0 = (t0 + 2 * lp + grp) * BNF;
+        const bool colX = c0 < mp;
+        const bool same = (colX == rowX);
+        const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
+        const int lim = colX ? mvalid : yvalid;
+        const bool special = (c0 + BNF > lim) || ((c0 >> 7) == rb);
+        const float* nj = a.norms + c0 + half * (CH_PER * 16);
+        // this warp's 32 S columns; its 16 packed W columns go over the first half of them
+        const uint32_t s_addr = tmem + TMP_S + pb * 128 + grp * 64 + half * 32 + lane_base;
+        float2 tsum = make_float2(0.f, 0.f);
+        mbar_wait(&s_full[pb], (gp >> 1) & 1);
+        tc_fence_after();
+        if (!special) {
+          uint32_t va[16], vb[16], wpk[8];
+          tmem_ld_x16(s_addr, va);
+          tmem_ld_wait();
+          tmem_ld_x16(s_addr + 16, vb);
+          fused_chunk16<Math, false>(math, va, nj, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+          tmem_st_x8(s_addr, wpk);            // columns [0, 8): read with chunk 0
+          tmem_ld_wait();
+          fused_chunk16<Math, false>(math, vb, nj + 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+          tmem_st_x8(s_addr + 8, wpk);        // columns [8, 16): read with chunk 0
+        } else {
+#pragma unroll 1
+          for (int ch = 0; ch < CH_PER; ++ch) {
+            uint32_t v[16], wpk[8];
+            tmem_ld_x16(s_addr + ch * 16, v);
+            tmem_ld_wait();
+            fused_chunk16<Math, true>(math, v, nj + ch * 16, ni, cw, c0 + half * (CH_PER * 16) + ch * 16, lim, gi, tsum,
+                                      rsum, wpk);
+            tmem_st_x8(s_addr + ch * 8, wpk);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&w_full[pb * 2 + grp]);
+        if (same) dsame += (double)((tsum.x + tsum.y) * kscale);
+        else dcross += (double)((tsum.x + tsum.y) * kscale);
+      }
+      // ---- unit end: drain O (this thread's slice of the feature columns) ----
+      mbar_wait(o_full, unit & 1);
+      tc_fence_after();
+      {
+        const int64_t sl = (int64_t)blockIdx.x * a.slots + slot;
+        const int seg = DP / NPART;
+        float* orow = a.Opart + (sl * BM + r) * DP + part * seg;
+        for (int c = 0; c < seg; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem + TM_O + part * seg + c + lane_base, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+        a.rpart[(sl * NPART + part) * BM + r] = rsum.x + rsum.y;
+        double* sp = a.spart + ((sl * NPART + part) * BM + r) * 2;
+        sp[0] = dsame;
+        sp[1] = dcross;
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+      left -= TU;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
+}
+
 // ---- finalisation of the fused kernel: reduce slabs, form gradients and per-row stats ---------------
 struct FinRowsArgs {
   KernelFn kf;
@@ -575,6 +851,7 @@ FusedPlan fused_plan(int64_t m, int64_t n, int64_t d, int64_t x0, int64_t x1, in
     const int64_t aligned = (nrb + p.grid - 1) / p.grid * p.T;
     if (aligned * p.grid * 100 <= p.total * 102) p.chunk = aligned;
   }
+  p.chunk += p.chunk & 1;   // chunks start at even tile positions (the tile-pair kernel works on pairs; T is even)
   p.grid = (int)((p.total + p.chunk - 1) / p.chunk);
   p.slots = (int)((p.chunk + p.T - 1) / p.T) + 1;
   size_t o = 0;
@@ -611,6 +888,31 @@ cudaError_t launch_fused_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const
   return a.ksplit == 2 ? launch_fused_k<Math, 2>(tzi, tzj, a, grid, s) : launch_fused_k<Math, 1>(tzi, tzj, a, grid, s);
 }
 
+template <class Math>
+cudaError_t launch_fused_pair_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid, cudaStream_t s) {
+  const int smem = fused_pair_smem(a.npanel);
+  if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
+  auto kern = tc_fused_pair_kernel<Math>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 576, smem, s>>>(tzi, tzj, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused_pair(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
+                              cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_fused_pair_t<MathRbf1>(tzi, tzj, a, grid, s);
+    case TV_RBF_LADDER5: return launch_fused_pair_t<MathRbfLadder<5>>(tzi, tzj, a, grid, s);
+    case TV_RBF_GENERIC: return launch_fused_pair_t<MathGeneric<FAM_RBF>>(tzi, tzj, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_fused_pair_t<MathRq3Default>(tzi, tzj, a, grid, s);
+    case TV_RQ_GENERIC: return launch_fused_pair_t<MathGeneric<FAM_RQ>>(tzi, tzj, a, grid, s);
+    case TV_DISTANCE: return launch_fused_pair_t<MathDistance>(tzi, tzj, a, grid, s);
+    case TV_NULL: return launch_fused_pair_t<MathNull>(tzi, tzj, a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launch_fused(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
                          cudaStream_t s) {
   switch (v) {
@@ -644,7 +946,7 @@ void pipe_timing_dump_impl(bool reset) {
 }
 #endif
 
-size_t tc_fused_workspace_bytes(int64_t m, int64_t n, int64_t d) { return fused_plan(m, n, d, 0, m, 0, n).off_end; }
+size_t tc_fused_workspace_bytes(const Geometry& g) { return fused_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1).off_end; }
 
 cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
                          float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
@@ -698,7 +1000,7 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   fa.rpart = reinterpret_cast<float*>(w + p.off_r);
   fa.spart = reinterpret_cast<double*>(w + p.off_s);
   prof_begin(s);
-  e = launch_fused(variant, tzi, tzj, fa, p.grid, s);
+  e = tuning().fused_pair ? launch_fused_pair(variant, tzi, tzj, fa, p.grid, s) : launch_fused(variant, tzi, tzj, fa, p.grid, s);
   prof_end(s);
   if (e != cudaSuccess) return e;
   ++*launches;

@@ -780,7 +780,7 @@ cudaError_t launch_wz(const CUtensorMap& tw, const CUtensorMap& tz, const WzArgs
 
 }  // namespace
 
-size_t tc_wz_workspace_bytes(int64_t m, int64_t n, int64_t d) { return wz_plan(m, n, d, 0, m, 0, n).off_end; }
+size_t tc_wz_workspace_bytes(const Geometry& g) { return wz_plan(g.m, g.n, g.d, g.x0, g.x1, g.y0, g.y1).off_end; }
 
 cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
                       float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path) {
