@@ -282,7 +282,7 @@ def run_ours(args):
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "tc_fused_kernel<MathRq3Default>", "kernel_ms": k_ms, "peak_source": peak_src,
+                "traffic": traffic, "kernel": "tc_fused_pair_kernel<MathRq3Default>", "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_rank}
 
     # ---- e2e: public Python API, HOST buffers in, loss + gradients back on the host, every step ----
