@@ -515,3 +515,10 @@ def _np_get_sums(K_XY, K_YY, const_diagonal=False):
 
 
 _get_sums = _np_get_sums   # mmd.py:405-426
+
+
+def _diff_mmd2_and_ratio(K_XY, K_XZ, K_YY, K_ZZ, const_diagonal=False):
+    """mmd.py:322-336 on dense blocks the caller already holds (numpy or torch): MMD^2(X,Y) - MMD^2(X,Z) and ratio."""
+    m = float(K_YY.shape[0])
+    return _diff_mmd2_and_ratio_from_sums(_np_get_sums(K_XY, K_YY, const_diagonal),
+                                          _np_get_sums(K_XZ, K_ZZ, const_diagonal), m, const_diagonal=const_diagonal)

@@ -49,3 +49,17 @@ def test_variance_floor():
     ys = tso.related_sums(tso.cubic_kernel(X, Y), tso.cubic_kernel(Y, Y))
     diff, ratio = tso.diff_from_sums(ys, ys, float(len(Y)))
     assert diff == 0.0 and ratio == 0.0
+
+
+def test_dense_block_entry_point_matches_oracle():
+    """_diff_mmd2_and_ratio(K_XY, K_XZ, K_YY, K_ZZ) (mmd.py:322-336) on numpy blocks."""
+    from smmd import mmd
+
+    X, Y, Z = three_sample_codes(Z3, "small", np.float64)
+    kxy, kxz = tso.cubic_kernel(X, Y), tso.cubic_kernel(X, Z)
+    kyy, kzz = tso.cubic_kernel(Y, Y), tso.cubic_kernel(Z, Z)
+    got = mmd._diff_mmd2_and_ratio(kxy, kxz, kyy, kzz)
+    want = tso.diff_from_sums(tso.related_sums(kxy, kyy), tso.related_sums(kxz, kzz), float(len(Y)))
+    assert abs(got[0] - want[0]) <= 1e-12 * abs(want[0]) and abs(got[1] - want[1]) <= 1e-10 * abs(want[1])
+    ref = Z3["res_f64_small"]
+    assert abs(got[0] - ref[0]) <= 1e-10 * abs(ref[0]) and abs(got[1] - ref[1]) <= 1e-8 * abs(ref[1])
