@@ -384,6 +384,43 @@ def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
     return (scalars[_lib.S_MMD2].float(), scalars[_lib.S_RATIO].float(), scalars[_lib.S_VAR].float())
 
 
+def _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=False, biased=False):
+    """mmd.py:236-293 on caller-materialised dense blocks (torch): (mmd2, var_est).  Compatibility path made of plain
+    reductions, including the reference's quirk that the unbiased estimate keeps the diagonal (:273-276)."""
+    m = float(K_XX.shape[0])
+    if const_diagonal is not False:
+        cd = float(const_diagonal)
+        dg_x = dg_y = cd
+        sdg_x = sdg_y = m * cd
+        sdg2_x = sdg2_y = m * cd * cd
+    else:
+        dg_x, dg_y = torch.diagonal(K_XX), torch.diagonal(K_YY)
+        sdg_x, sdg_y = dg_x.sum(), dg_y.sum()
+        sdg2_x, sdg2_y = (dg_x * dg_x).sum(), (dg_y * dg_y).sum()
+    r_x, r_y = K_XX.sum(1) - dg_x, K_YY.sum(1) - dg_y
+    c0, c1 = K_XY.sum(0), K_XY.sum(1)
+    s_x, s_y, s_xy = r_x.sum(), r_y.sum(), c0.sum()
+    q_x, q_y, q_xy = (K_XX * K_XX).sum() - sdg2_x, (K_YY * K_YY).sum() - sdg2_y, (K_XY * K_XY).sum()
+    if biased:
+        mmd2_val = (s_x + sdg_x) / (m * m) + (s_y + sdg_y) / (m * m) - 2 * s_xy / (m * m)
+    else:
+        mmd2_val = (s_x + sdg_x) / (m * (m - 1)) + (s_y + sdg_y) / (m * (m - 1)) - 2 * s_xy / (m * m)
+    var_est = (2 / (m ** 2 * (m - 1) ** 2) * (2 * (r_x * r_x).sum() - q_x + 2 * (r_y * r_y).sum() - q_y)
+               - (4 * m - 6) / (m ** 3 * (m - 1) ** 3) * (s_x ** 2 + s_y ** 2)
+               + 4 * (m - 2) / (m ** 3 * (m - 1) ** 2) * ((c1 * c1).sum() + (c0 * c0).sum())
+               - 4 * (m - 3) / (m ** 3 * (m - 1) ** 2) * q_xy
+               - (8 * m - 12) / (m ** 5 * (m - 1)) * s_xy ** 2
+               + 8 / (m ** 3 * (m - 1)) * (1 / m * (s_x + s_y) * s_xy - (r_x * c1).sum() - (r_y * c0).sum()))
+    return mmd2_val, var_est
+
+
+def _mmd2_and_ratio(K_XX, K_XY, K_YY, const_diagonal=False, biased=False, min_var_est=_eps):
+    """mmd.py:228-233 on dense blocks: (mmd2, ratio = mmd2 / sqrt(max(var_est, min_var_est)))."""
+    mmd2_val, var_est = _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=const_diagonal, biased=biased)
+    ratio = mmd2_val / torch.sqrt(torch.clamp(var_est, min=min_var_est))
+    return mmd2_val, ratio
+
+
 # ---------------------------------------------------------------------------------------------------
 # 3-sample test of the scorer (reference gan/core/mmd.py:296-539, caller gan/utils/scorer.py:119-163)
 # ---------------------------------------------------------------------------------------------------
