@@ -238,6 +238,25 @@ def test_tc_value_only_stream_path(name, kw, precision):
     assert abs(got - v) <= tol * abs(v) + 2e-6 * _kscale(name, kw, X, Y), (got, v)
 
 
+def test_fused_kernel_is_repeatable_under_stress():
+    """A few hundred back-to-back launches of the fused kernel (tile-pair variant) on shapes with many tiles per CTA,
+    several row-block units per CTA and special (diagonal / padded) tiles: every launch must return bit-identical
+    sums and gradients (fixed reduction order), and none may trip the bounded barrier waits (a lost or doubled
+    mbarrier phase shows up as a CUDA error here, not as a hang)."""
+    from smmd import _lib, mmd
+
+    for (m, n, d, reps) in ((3000, 5000, 192, 150), (4100, 4000, 256, 150), (1000, 1100, 128, 200)):
+        X, Y = _data(m, n, d, 3)
+        Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+        spec = mmd._mix_rq_kernel(Xt, Yt).spec
+        ref, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+        assert _lib.last_path() == "tc_bf16_fused"
+        for _ in range(reps):
+            sc, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+        torch.cuda.synchronize()
+        assert torch.equal(sc, ref) and torch.equal(gX, rX) and torch.equal(gY, rY)
+
+
 def test_auto_precision_dispatch_and_refusals():
     from smmd import _lib, mmd
 
