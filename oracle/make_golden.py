@@ -164,6 +164,12 @@ def make_three_sample_golden(path):
                 out["%s_%s_%s_vec" % (name, dn, tag)] = np.stack([sums[0], sums[2], sums[3]]).astype(np.float64)
                 out["%s_%s_%s_sc" % (name, dn, tag)] = np.array([sums[1], sums[4]], dtype=np.float64)
             out["res_%s_%s" % (dn, tag)] = np.array([diff, ratio], dtype=np.float64)
+            if dt is np.float64:
+                # the graph variant (mmd.py:296-304 over the torch-backed tf shim): same sums, but the ratio divides
+                # by mysqrt(max(var, eps)) = sqrt(max(var, eps) + eps) (mmd.py:398 with :12)
+                import torch
+                tdiff, tratio = ref.diff_polynomial_mmd2_and_ratio(torch.tensor(x), torch.tensor(y), torch.tensor(z))
+                out["res_graph_%s_%s" % (dn, tag)] = np.array([float(tdiff), float(tratio)], dtype=np.float64)
     np.savez_compressed(path, **out)
 
 

@@ -26,7 +26,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SMMD_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.py (travels to the GPU box)
+
+
+def _pick_root():
+    env = os.environ.get("SMMD_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "gan", "core", "mmd.py")):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
@@ -43,13 +55,27 @@ def _make_tf_shim(torch, dtype):
     class _Dim(int):
         pass
 
+    class _Shape(tuple):   # TensorShape stand-in: iterable of dims + the one method ops.py:221-222 calls
+        def assert_has_rank(self, rank):
+            assert len(self) == rank, "shape %s must have rank %d" % (tuple(self), rank)
+
+    class _NameScope:      # tf.name_scope(name, default_name, values) is a no-op context manager here
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
     def _t(x):
         if isinstance(x, torch.Tensor):
             return x
         return torch.as_tensor(x, dtype=dtype)
 
     if not hasattr(torch.Tensor, "get_shape"):
-        torch.Tensor.get_shape = lambda self: tuple(_Dim(s) for s in self.shape)
+        torch.Tensor.get_shape = lambda self: _Shape(_Dim(s) for s in self.shape)
 
     def matmul(a, b, transpose_a=False, transpose_b=False):
         a, b = _t(a), _t(b)
@@ -87,6 +113,7 @@ def _make_tf_shim(torch, dtype):
     tf.trace = lambda x: torch.diagonal(_t(x)).sum()
     tf.cast = cast
     tf.squeeze = lambda x: _t(x).squeeze()
+    tf.name_scope = _NameScope
     tf.convert_to_tensor = lambda x, name=None: _t(x)
     nn = types.ModuleType("tensorflow.nn")
     nn.l2_loss = lambda t: (_t(t) ** 2).sum() / 2
@@ -110,10 +137,21 @@ def load_reference_mmd(dtype_name: str = "float32"):
         core = types.ModuleType("core")
         core.__path__ = []  # mark as package
         ops = types.ModuleType("core.ops")
-        # semantics of gan/core/ops.py:209-225 (sq_sum = 2*l2_loss = sum of squares; dot of 1-D)
-        ops.sq_sum = lambda t, name=None: 2 * tf.nn.l2_loss(t)
-        ops.dot = lambda x, y, name=None: (x.reshape(1, -1) @ y.reshape(-1, 1)).squeeze()
         ops.tf = tf
+        src_ops = os.path.join(REFERENCE_ROOT, "gan", "core", "ops.py")
+        staged_ops = os.path.join(REFERENCE_ROOT, "gan", "core", "ops_sq_sum_dot.py")
+        if os.path.isfile(staged_ops) or os.path.isfile(src_ops):
+            # the reference's own `sq_sum` / `dot` (gan/core/ops.py:209-225), executed verbatim over the shim
+            if os.path.isfile(staged_ops):
+                with open(staged_ops) as f:
+                    code = f.read()
+            else:
+                with open(src_ops) as f:
+                    code = "".join(f.readlines()[208:225])
+            exec(compile(code, "gan/core/ops.py:209-225", "exec"), ops.__dict__)
+        else:   # restated: sq_sum = 2*l2_loss = sum of squares; dot of two 1-D vectors
+            ops.sq_sum = lambda t, name=None: 2 * tf.nn.l2_loss(t)
+            ops.dot = lambda x, y, name=None: (x.reshape(1, -1) @ y.reshape(-1, 1)).squeeze()
         core.ops = ops
         sys.modules["core"] = core
         sys.modules["core.ops"] = ops

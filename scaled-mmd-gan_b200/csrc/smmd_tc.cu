@@ -176,7 +176,9 @@ bool tc_mmd2_covers(const KernelFn& kf, const Geometry& g, int want_grad) {
 size_t tc_mmd2_workspace_bytes(const Geometry& g, int want_grad, int precision) {
   // the plan of exactly this row range (rank / world): slab counts are not monotone in the range, so a full-range
   // plan does not bound a shard's plan
-  const size_t grad = !want_grad ? 0 : (use_two_pass(g.d) ? tc_wz_workspace_bytes(g) : tc_fused_workspace_bytes(g));
+  const size_t grad = !want_grad ? 0
+                      : tc_sym_eligible(g) ? tc_sym_workspace_bytes(g)
+                                           : (use_two_pass(g.d) ? tc_wz_workspace_bytes(g) : tc_fused_workspace_bytes(g));
   return std::max(grad, tc_value_only_workspace_bytes(g.m, g.n, g.d, precision));
 }
 
@@ -188,6 +190,7 @@ cudaError_t tc_mmd2_run(const KernelFn& kf_in, const Geometry& g, const Coefs& c
   TcVariant variant = select_tc_variant(kf);
   if (tuning().null_math) variant = TV_NULL;
   if (dX != nullptr) {
+    if (tc_sym_eligible(g)) return tc_run_sym(kf, variant, g, c, src, scalars, dX, dY, ws, ws_bytes, s, launches, path);
     if (use_two_pass(g.d)) return tc_run_wz(kf, variant, g, c, src, scalars, dX, dY, ws, ws_bytes, s, launches, path);
     return tc_run_fused(kf, variant, g, c, src, scalars, dX, dY, ws, ws_bytes, s, launches, path);
   }

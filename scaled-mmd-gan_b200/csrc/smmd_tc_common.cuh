@@ -32,6 +32,10 @@ struct Tuning {
   int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
   int64_t wz_panel_bytes;   // byte budget of one W row panel
   int wz_pair;      // pass 1 as CTA pairs with cta_group::2 UMMAs (SMMD_WZ_PAIR=0 disables)
+  int sym;          // symmetric two-pass path for whole problems (SMMD_SYM=0 disables)
+  int sym_only;     // developer timing knob (SMMD_SYM_ONLY=1|2: run only pass 1 / pass 2; results meaningless)
+  int64_t sym_min_rows;      // stacked rows from which the symmetric path is used
+  int64_t sym_max_w_bytes;   // largest W (Mp x Mp bf16) the symmetric path may place in the workspace
 };
 inline const Tuning& tuning() {
   static Tuning t = [] {
@@ -49,6 +53,14 @@ inline const Tuning& tuning() {
     if (const char* e = getenv("SMMD_WZ_PAIR")) v.wz_pair = atoi(e) != 0;
     v.wz_panel_bytes = (int64_t)6 << 30;
     if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
+    v.sym = 1;
+    if (const char* e = getenv("SMMD_SYM")) v.sym = atoi(e) != 0;
+    v.sym_only = 0;
+    if (const char* e = getenv("SMMD_SYM_ONLY")) v.sym_only = atoi(e);
+    v.sym_min_rows = 2048;
+    if (const char* e = getenv("SMMD_SYM_MIN_ROWS")) v.sym_min_rows = atoll(e);
+    v.sym_max_w_bytes = (int64_t)48 << 30;
+    if (const char* e = getenv("SMMD_SYM_MAX_W_MB")) v.sym_max_w_bytes = (int64_t)atoll(e) << 20;
     return v;
   }();
   return t;
@@ -146,6 +158,11 @@ size_t tc_fused_workspace_bytes(const Geometry& g);
 cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
                       float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
 size_t tc_wz_workspace_bytes(const Geometry& g);
+// symmetric two-pass path (smmd_tc_sym.cu): whole problem on this GPU, every unordered pair evaluated once
+bool tc_sym_eligible(const Geometry& g);
+cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, double* scalars,
+                       float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
+size_t tc_sym_workspace_bytes(const Geometry& g);
 cudaError_t tc_run_value_only(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src, int precision, double* scalars,
                               float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches, const char** path);
 size_t tc_value_only_workspace_bytes(int64_t m, int64_t n, int64_t d, int precision);

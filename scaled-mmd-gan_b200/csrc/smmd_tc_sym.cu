@@ -1,0 +1,880 @@
+// smmd_tc_sym.cu -- symmetric two-pass MMD^2 forward + backward on tcgen05 (any d, whole problem on one GPU).
+//
+// The stacked Gram of Z = [X ; Y] is symmetric, and so is the weight matrix W = 4 A o k'(D) of the backward pass.
+// The epilogue (3 MUFU + ~23 packed fp32 ops per element for the default RQ mixture), not the tensor pipe, bounds
+// the loss at d <= 512, so this path evaluates every UNORDERED pair once:
+//   pass 1 (tc_sym_wgen_kernel)  upper-triangle 128 x 256 tiles of S = Z_i Z_j^T (K streamed through a TMA ring,
+//          two 256-column TMEM accumulators) -> kernel transform -> weighted block sums (off-diagonal blocks count
+//          twice), row sums of W, and the bf16 W tile staged in shared memory (SW128 panels) and written with one
+//          TMA store per 128 x 64 panel.  The column sums of an off-diagonal block (= its contribution to the row
+//          sums r_j of the mirrored block) are taken from the staged bf16 tile.  Row / column sums go to a
+//          fixed-point int64 accumulator (atomics whose result does not depend on their order).
+//   pass 2 (tc_sym_wz_kernel)    O = W_sym Z: 256 rows x 256 features per CTA; for a column block J >= R the stored
+//          tile W[R, J] is the K-major A operand, for J < R the stored tile W[J, R] is read "transposed" as an
+//          MN-major A operand (descriptor LBO = 8 KB between the two 64-wide M panels) -- W is stored once and read
+//          twice.  B = Z_j tile MN-major, all 512 TMEM columns as accumulators, K split over CTAs.
+//   finalize (sym_finalize_rows_kernel)  g_i = r_i z_i - O_i (+ closed-form add_dot term), diagonal values.
+// Executed tensor work 12 N^2 d (4 + 8) against 14 N^2 d algorithmic and 16 N^2 d for the row-stacked fused kernel;
+// epilogue elements 2 N^2 instead of 4 N^2.  Replaces gan/core/mmd.py:55-188 + :194-220 + the TF autodiff graph
+// (gan/core/model.py:446,452).
+#include "smmd_tc_common.cuh"
+
+namespace smmd {
+namespace tc {
+namespace {
+
+constexpr int BNW = 256;                                   // pass-1 tile width
+constexpr int kSyEpiWarps = 16;                            // 4 TMEM lane quarters x 4 column quarters
+constexpr int kSyThreads = (kSyEpiWarps + 2) * 32;
+constexpr int kSyStages = 3;
+constexpr int kSyStageBytes = BM * 128 + BNW * 128;        // Z_i panel + Z_j tile per 64-deep step = 48 KB
+constexpr int kSyStagingBytes = kSyEpiWarps * 4096;        // 64 KB: one 32-row x 64-column bf16 block per epilogue warp
+constexpr int kSySmem = 1024 + kSyStages * kSyStageBytes + kSyStagingBytes + 1024;
+static_assert(kSySmem <= kMaxSmem, "pass-1 shared memory");
+
+constexpr int kFinRowsPerWarp = 4;
+constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
+
+// ---- work units of pass 1 -----------------------------------------------------------------------------------
+// The upper triangle is walked band by band (RB row blocks) and, inside a band, window by window (CW column
+// tiles): the Z rows of one band + one window stay L2 resident while all CTAs work inside them.  A unit is a run
+// of <= PL consecutive column tiles of ONE row block (row sums stay in registers over the run); units are numbered
+// as fixed slots (band, window, row block, piece) -- slots below the diagonal are empty -- and dealt round-robin.
+struct SymGeo {
+  int NB, CT;          // row blocks of 128, column tiles of 256 (the last tile may be half)
+  int RB, CW, PL, PPW; // band (row blocks), window (tiles), piece length (tiles), pieces per window
+  int nbands, nwin;
+};
+
+struct UnitWalk {
+  int b, w, rows;
+  int64_t base;
+  __device__ __forceinline__ int first_win(const SymGeo& g, int band) const { return ((band * g.RB) >> 1) / g.CW; }
+  __device__ __forceinline__ void init(const SymGeo& g) {
+    b = 0;
+    w = 0;
+    base = 0;
+    rows = g.RB < g.NB ? g.RB : g.NB;
+  }
+  // slot `idx` (non-decreasing over calls) -> (row block, [ct0, ct1)); false when idx is past the last slot
+  __device__ __forceinline__ bool locate(const SymGeo& g, int64_t idx, int& rb, int& ct0, int& ct1) {
+    for (;;) {
+      if (b >= g.nbands) return false;
+      const int64_t slots = (int64_t)rows * g.PPW;
+      if (idx < base + slots) {
+        const int s = (int)(idx - base);
+        const int rbl = s / g.PPW, k = s - rbl * g.PPW;
+        rb = b * g.RB + rbl;
+        const int wend = (w + 1) * g.CW < g.CT ? (w + 1) * g.CW : g.CT;
+        ct0 = w * g.CW + k * g.PL;
+        ct1 = ct0 + g.PL < wend ? ct0 + g.PL : wend;
+        if (ct0 < (rb >> 1)) ct0 = rb >> 1;
+        return true;
+      }
+      base += slots;
+      if (++w >= g.nwin) {
+        ++b;
+        if (b < g.nbands) {
+          const int lo = b * g.RB;
+          rows = lo + g.RB < g.NB ? g.RB : g.NB - lo;
+          w = first_win(g, b);
+        }
+      }
+    }
+  }
+};
+
+struct SymWgenArgs {
+  KernelFn kf;
+  SymGeo geo;
+  int64_t m, n, mp, np, Mp;
+  float c_xx, c_yy, c_xy;        // 4 a_xx etc.
+  const float* norms;            // [Mp]
+  int nkp;                       // 64-feature panels
+  float rscale, rclamp;          // fixed-point scale (power of two) / clamp of one contribution to the row sums of W
+  unsigned long long* racc;      // [Mp] fixed-point row sums of W
+  double* partials;              // [gridDim.x][6]: (sxx, syy, sxy, syx, 0, 0) of this CTA
+};
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fixed_add(unsigned long long* p, float v, float scale, float clamp) {
+  v = fminf(fmaxf(v, -clamp), clamp);
+  atomicAdd(p, (unsigned long long)__float2ll_rn(v * scale));
+}
+
+template <class Math>
+__global__ void __launch_bounds__(kSyThreads, 1)
+tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
+                   const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SymWgenArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kSyStages * kSyStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSyStagingBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kSyStages;
+  uint64_t* acc_full = empty + kSyStages;    // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);   // [24]
+  double* sRed = reinterpret_cast<double*>(sParams + 24);     // [16][3] end-of-kernel reduction of the block sums
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
+  if (tid == 0) {
+    for (int i = 0; i < kSyStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kSyEpiWarps);   // one elected arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == kSyEpiWarps + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kSyEpiWarps && lane == 0) {
+    prefetch_tmap(&tmap_zi);
+    prefetch_tmap(&tmap_zj);
+    prefetch_tmap(&tmap_w);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const SymGeo& geo = a.geo;
+
+  if (warp == kSyEpiWarps) {
+    // ===================== TMA producer =====================
+    uint32_t st = 0, ph = 0;
+    UnitWalk uw;
+    uw.init(geo);
+    int rb, ct0, ct1;
+    for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
+      for (int ct = ct0; ct < ct1; ++ct) {
+        for (int p = 0; p < a.nkp; ++p) {
+          mbar_wait(&empty[st], ph ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + st * kSyStageBytes;
+            mbar_arrive_expect_tx(&full[st], kSyStageBytes);
+            tma_load_2d(sa, &tmap_zi, &full[st], p * 64, rb * BM);
+            tma_load_2d(sa + BM * 128, &tmap_zj, &full[st], p * 64, ct * BNW);   // rows past Mp are zero-filled
+          }
+          __syncwarp();
+          if (++st == kSyStages) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kSyEpiWarps + 1) {
+    // ===================== UMMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BM, BNW, kFmtBF16, false, false);
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+    uint32_t st = 0, ph = 0, ab = 0, aph = 0;
+    UnitWalk uw;
+    uw.init(geo);
+    int rb, ct0, ct1;
+    for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
+      for (int ct = ct0; ct < ct1; ++ct) {
+        mbar_wait(&acc_empty[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t dad = tmem + ab * BNW;
+        for (int kk = 0; kk < a.nkp; ++kk) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t alo = a_lo0 + st * (kSyStageBytes >> 4), blo = alo + ((BM * 128) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss2(dad, alo + k * 2, blo + k * 2, hi, idesc, (kk | k) ? 1u : 0u);
+            umma_commit(&empty[st]);
+          }
+          __syncwarp();
+          if (++st == kSyStages) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&acc_full[ab]);
+        __syncwarp();
+        aph ^= ab;
+        ab ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: 16 warps = 4 TMEM lane quarters x 4 column quarters (64 columns each) =====
+    // Every warp is self-contained: it owns 32 rows x 64 columns of each tile, stages its bf16 W block in its own
+    // 4 KB of shared memory (SW128 atoms of 8 rows), stores it with its own TMA store and takes the column sums of
+    // its block from the staged copy -- no barrier between warps, so the four warps of a scheduler drift apart and
+    // their MUFU / FMA phases overlap (a first version synchronised the four row quarters of a column quarter three
+    // times per tile through named barriers: 6850 cycles per 16K elements instead of the fused kernel's 4700).
+    const int part = warp >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                     // row inside the row block
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* stg_ptr = staging + warp * 4096;        // this warp's 32 rows x 128 B
+    const uint32_t stg = smem_u32(stg_ptr);
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
+    const int mp = (int)a.mp, Mp = (int)a.Mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    double sxx = 0.0, syy = 0.0, sxy = 0.0;
+    uint32_t tc = 0;        // tiles of this CTA so far (parity = accumulator buffer)
+    bool stored = false;    // this warp has a TMA store in flight that may still read its staging block
+    UnitWalk uw;
+    uw.init(geo);
+    int rb, ct0, ct1;
+    for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
+      if (ct0 >= ct1) continue;
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
+      const bool row_ok = rowX ? gi < mvalid : gi < yvalid;
+      const bool pad_rows = rowX ? (rb + 1) * BM > mvalid : (rb + 1) * BM > yvalid;   // block holds padding rows
+      const float ni = a.norms[gi];
+      float2 rsum = make_float2(0.f, 0.f);
+      bool any = false;
+      for (int ct = ct0; ct < ct1; ++ct, ++tc) {
+        const int grp = (int)(tc & 1);
+        const int c0 = ct * BNW + part * 64;          // first column of this warp's quarter
+        const int J = c0 >> 7;                        // its 128-column block
+        const bool active = (J >= rb) && (c0 < Mp);
+        mbar_wait(&acc_full[grp], (tc >> 1) & 1);
+        tc_fence_after();
+        auto release_acc = [&]() {   // the whole warp has finished its tcgen05.ld of this tile: one elected arrive
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[grp]);
+        };
+        if (!active) {
+          release_acc();
+          continue;
+        }
+        any = true;
+        const bool colX = c0 < mp;
+        const bool same = (colX == rowX);
+        const bool diag = (J == rb);
+        const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
+        const int lim = row_ok ? (colX ? mvalid : yvalid) : 0;   // padding rows: every column masked
+        const bool special = diag || pad_rows || (c0 + 64 > (colX ? mvalid : yvalid));
+        const float* nj = a.norms + c0;
+        float2 tsum = make_float2(0.f, 0.f);
+        const uint32_t srow = stg + lane * 128;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        auto do_chunk = [&](const uint32_t (&v)[16], int h) {
+          uint32_t wpk[8];
+          if (!special) fused_chunk16<Math, false>(math, v, nj + h * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
+          else fused_chunk16<Math, true>(math, v, nj + h * 16, ni, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
+          if (h == 0 && stored) {   // the previous tile's TMA store must have read the block before it is overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+          }
+          st_shared_v4(srow + (((2 * h) ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
+          st_shared_v4(srow + (((2 * h + 1) ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
+        };
+        {
+          uint32_t va[16], vb[16];
+          const uint32_t tbase = tmem + grp * BNW + part * 64 + lane_base;
+          tmem_ld_x16(tbase, va);
+          tmem_ld_wait();
+          tmem_ld_x16(tbase + 16, vb);
+          do_chunk(va, 0);
+          tmem_ld_wait();
+          tmem_ld_x16(tbase + 32, va);
+          do_chunk(vb, 1);
+          tmem_ld_wait();
+          tmem_ld_x16(tbase + 48, vb);
+          do_chunk(va, 2);
+          tmem_ld_wait();
+          release_acc();
+          do_chunk(vb, 3);
+        }
+        // a cross block is seen once (X rows, Y columns) and stands for K_XY and K_YX; a same-set block above the
+        // diagonal stands for itself and its mirror
+        const double ts = (double)((tsum.x + tsum.y) * kscale);
+        if (!same) sxy += ts;
+        else if (rowX) sxx += diag ? ts : 2.0 * ts;
+        else syy += diag ? ts : 2.0 * ts;
+        // ---- staged block complete: TMA store, and (off-diagonal blocks) its column sums -> r_j of the mirror ----
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_w, stg_ptr, c0, rb * BM + q * 32);
+          bulk_commit();
+        }
+        stored = true;
+        if (!diag) {
+          // lane = column pair (2 lane, 2 lane + 1) of the block: sum its 32 rows from the staged bf16 values
+          const uint32_t wofs = (uint32_t)(lane & 3) * 4;
+          const uint32_t wch = (uint32_t)(lane >> 2);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t p0 = ld_shared_u32(stg + i * 128 + ((wch ^ (uint32_t)(i & 7)) << 4) + wofs);
+            const uint32_t p1 = ld_shared_u32(stg + (i + 1) * 128 + ((wch ^ (uint32_t)((i + 1) & 7)) << 4) + wofs);
+            acc0 = add2(acc0, make_float2(bf16_lo_to_f32(p0), bf16_hi_to_f32(p0)));
+            acc1 = add2(acc1, make_float2(bf16_lo_to_f32(p1), bf16_hi_to_f32(p1)));
+          }
+          const float2 t = add2(acc0, acc1);
+          fixed_add(a.racc + c0 + 2 * lane, t.x, a.rscale, a.rclamp);
+          fixed_add(a.racc + c0 + 2 * lane + 1, t.y, a.rscale, a.rclamp);
+        }
+      }
+      if (any && row_ok) fixed_add(a.racc + gi, rsum.x + rsum.y, a.rscale, a.rclamp);
+    }
+    if (stored && lane == 0) bulk_wait0();   // all W stores of this warp have completed before the CTA exits
+    // ---- block sums of this CTA: fixed-order reduction over the 16 epilogue warps ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+    }
+    if (lane == 0) {
+      sRed[warp * 3 + 0] = sxx;
+      sRed[warp * 3 + 1] = syy;
+      sRed[warp * 3 + 2] = sxy;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 6) {   // (sxx, syy, sxy, syx = sxy, 0, 0)
+    double t = 0.0;
+    const int src = tid == 3 ? 2 : tid;
+    if (tid < 4)
+      for (int w = 0; w < kSyEpiWarps; ++w) t += sRed[w * 3 + src];
+    a.partials[(int64_t)blockIdx.x * 6 + tid] = t;
+  }
+  if (warp == kSyEpiWarps + 1) tmem_dealloc<512>(tmem);
+}
+
+// ---- pass 2: O = W_sym Z -----------------------------------------------------------------------------------
+constexpr int kSzStages = 3;
+constexpr int kSzStageBytes = 2 * BM * 128 + 4 * BNF * 128;   // two 128-row W operands + four 64-feature Z panels = 64 KB
+constexpr int kSzSmem = 1024 + kSzStages * kSzStageBytes + 1024;
+
+struct SymWzArgs {
+  int nmb;        // 256-row macro blocks
+  int FB;         // 256-feature blocks
+  int dp;         // padded feature count (multiple of 64)
+  int KT;         // K steps of 64 (= Mp / 64)
+  int S;          // K splits per unit
+  int ksteps;     // K steps per piece
+  float* Opart;   // [unit = mb * FB + fb][S][256][256]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_constant__ CUtensorMap tmap_wt,
+                 const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ SymWzArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSzStages * kSzStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kSzStages;
+  uint64_t* acc_full = empty + kSzStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kSzStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap_wd);
+    prefetch_tmap(&tmap_wt);
+    prefetch_tmap(&tmap_z);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // piece = (split s, unit u), s-major so that one wave of CTAs walks the same rows of Z (L2 reuse)
+  const int units = a.nmb * a.FB;
+  const int s = (int)blockIdx.x / units;
+  const int u = (int)blockIdx.x - s * units;
+  const int mb = u / a.FB, fb = u - mb * a.FB;
+  const int k0 = s * a.ksteps;
+  const int k1 = k0 + a.ksteps < a.KT ? k0 + a.ksteps : a.KT;
+  const int nf = a.dp - fb * 256 < 256 ? a.dp - fb * 256 : 256;   // features of this block (multiple of 64)
+  const int npan = nf / 64;
+
+  if (warp == 8) {
+    uint32_t st = 0, ph = 0;
+    for (int ks = k0; ks < k1; ++ks) {
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[st], 2 * BM * 128 + npan * BNF * 128);
+        uint8_t* sa = smem + st * kSzStageBytes;
+        const int J = ks >> 1;   // 128-column block of this K step
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int R = 2 * mb + h;
+          uint8_t* dst = sa + h * (BM * 128);
+          if (J >= R) {   // stored tile W[R, J]: 128 rows x 64 columns, K-major A
+            tma_load_2d(dst, &tmap_wd, &full[st], ks * 64, R * BM);
+          } else {        // stored tile W[J, R] read transposed: 64 K-rows x 128 columns = two 64 x 64 boxes, MN-major A
+            tma_load_2d(dst, &tmap_wt, &full[st], R * BM, ks * 64);
+            tma_load_2d(dst + 64 * 128, &tmap_wt, &full[st], R * BM + 64, ks * 64);
+          }
+        }
+        uint8_t* sb = sa + 2 * BM * 128;
+        for (int p = 0; p < npan; ++p) tma_load_2d(sb + p * (BNF * 128), &tmap_z, &full[st], fb * 256 + p * 64, ks * 64);
+      }
+      __syncwarp();
+      if (++st == kSzStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 9) {
+    const uint32_t idesc_d = make_idesc(BM, (uint32_t)nf, kFmtBF16, false, true);   // A K-major, B = Z tile MN-major
+    const uint32_t idesc_t = make_idesc(BM, (uint32_t)nf, kFmtBF16, true, true);    // A MN-major (transposed tile)
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t ad_lo0 = desc_lo(smem_u32(smem), 16);
+    const uint32_t at_lo0 = desc_lo(smem_u32(smem), 64 * 128);   // LBO = distance between the two 64-wide M panels
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem + 2 * BM * 128), BNF * 128);
+    uint32_t st = 0, ph = 0;
+    for (int ks = k0; ks < k1; ++ks) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t sofs = st * (kSzStageBytes >> 4);
+      const uint32_t blo = b_lo0 + sofs;
+      const int J = ks >> 1;
+      if (elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool direct = J >= 2 * mb + h;
+          const uint32_t hofs = sofs + h * ((BM * 128) >> 4);
+          if (direct) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss2(tmem + h * 256, ad_lo0 + hofs + k * 2, blo + k * (2048 >> 4), hi, idesc_d, (ks > k0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss2(tmem + h * 256, at_lo0 + hofs + k * (2048 >> 4), blo + k * (2048 >> 4), hi, idesc_t,
+                       (ks > k0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[st]);
+        if (ks == k1 - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++st == kSzStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // drain: warp -> (row half, TMEM lane quarter); each thread stores its row of the partial tile
+    const int half = warp >> 2, q = warp & 3;
+    const int row = half * BM + q * 32 + lane;
+    float* orow = a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
+    if (k1 > k0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t base = tmem + half * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < nf; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(base + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+    } else {
+      for (int c = 0; c < nf; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// ---- finalize: warp per row, lanes over features -------------------------------------------------------------
+struct SymFinArgs {
+  KernelFn kf;
+  int64_t m, n, mp, np, d;
+  int dp;
+  int FB, S;                 // pass-2 feature blocks / K splits
+  double a_xx, a_yy, a_xy;
+  double rinv;               // 1 / fixed-point scale of racc
+  SrcLayout src;
+  const float* norms;
+  const double* csum;
+  const float* Opart;
+  const unsigned long long* racc;
+  float* dX;
+  float* dY;
+  double* partials;          // [gridDim.x][6]: (dot same X, dot same Y, dot cross X, dot cross Y, dgx, dgy)
+};
+
+__global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double sh[8][6];
+  double q[6] = {0, 0, 0, 0, 0, 0};
+  const bool dot = a.kf.family == FAM_RQ && a.kf.add_dot > 0.f && a.csum != nullptr;
+  for (int rr = 0; rr < kFinRowsPerWarp; ++rr) {
+    const int64_t gi = ((int64_t)blockIdx.x * 8 + warp) * kFinRowsPerWarp + rr;   // padded stacked row
+    if (gi >= a.mp + a.np) break;
+    const bool rowX = gi < a.mp;
+    const int64_t li = rowX ? gi : gi - a.mp;
+    if (li >= (rowX ? a.m : a.n)) continue;   // padding row
+    const float rs = (float)((double)(long long)a.racc[gi] * a.rinv);
+    const double a_same = rowX ? a.a_xx : a.a_yy;
+    double dsame = 0.0, dcross = 0.0;
+    float* out = nullptr;
+    if (a.dX) out = rowX ? a.dX + li * a.d : a.dY + li * a.d;
+    const void* src = rowX ? a.src.X : a.src.Y;
+    const int64_t ld = rowX ? a.src.ldx : a.src.ldy;
+    const int sdtype = a.src.dtype;
+    const int64_t srow = src_row(li, rowX, a.src.blk_x, a.src.blk_y);
+    const int rbl = (int)(gi / BM), r = (int)(gi % BM);
+    const int mbl = rbl >> 1;
+    const int row256 = (rbl & 1) * BM + r;
+    const float* obase = a.Opart + (((int64_t)mbl * a.FB) * a.S * 256 + row256) * 256;   // + (fb * S + s) * 65536 + cc
+    const bool vec = out != nullptr && !dot && sdtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+      const float* zsrc = reinterpret_cast<const float*>(src) + srow * ld;
+      for (int c = 4 * lane; c < a.d; c += 128) {   // 4 consecutive features per lane (never straddle a 256 block)
+        const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.S; ++s) {   // fixed order
+          const float4 t = *reinterpret_cast<const float4*>(op + (int64_t)s * 65536);
+          o.x += t.x;
+          o.y += t.y;
+          o.z += t.z;
+          o.w += t.w;
+        }
+        const float4 z4 = *reinterpret_cast<const float4*>(zsrc + c);
+        float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+        const float oo[4] = {o.x, o.y, o.z, o.w};
+        float gv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
+          gv[e] = rs * zz[e] - oo[e];
+          if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
+        }
+        *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      }
+    } else {
+      for (int c = lane; c < a.d; c += 32) {
+        float o = 0.f;
+        if (out) {
+          const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
+          for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 65536];   // fixed order
+        }
+        const int64_t sidx = srow * ld + c;
+        float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
+                                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
+        if (a.kf.tanh_features) z = tanhf(z);
+        if (out) {
+          float gv = rs * z - o;
+          if (dot) {
+            const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
+            gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
+          }
+          if (a.kf.tanh_features) gv *= (1.f - z * z);
+          out[c] = gv;
+        }
+        if (dot) {
+          dsame += (double)z * a.csum[(rowX ? 0 : 1) * a.dp + c];
+          dcross += (double)z * a.csum[(rowX ? 1 : 0) * a.dp + c];
+        }
+      }
+    }
+    if (dot) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsame += __shfl_xor_sync(0xffffffffu, dsame, o);
+        dcross += __shfl_xor_sync(0xffffffffu, dcross, o);
+      }
+    }
+    // the dot part of the kernel is closed form: sum_{j != i} <z_i, z_j> = <z_i, colsum> - |z_i|^2
+    const float ni = a.norms[gi];
+    const double v_same = dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0;
+    const double v_cross = dot ? (double)a.kf.add_dot * dcross : 0.0;
+    const double v_diag = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                                : (double)diag_value(a.kf, ni);
+    if (rowX) {
+      q[0] += v_same;
+      q[2] += v_cross;
+      q[4] += v_diag;
+    } else {
+      q[1] += v_same;
+      q[3] += v_cross;
+      q[5] += v_diag;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sh[warp][i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    a.partials[(int64_t)blockIdx.x * 6 + threadIdx.x] = t;
+  }
+}
+
+// ---- plan --------------------------------------------------------------------------------------------------
+struct SymPlan {
+  int64_t mp, np, Mp, dp;
+  SymGeo geo;
+  int grid1;
+  int KT, FB, nmb, units, S, ksteps, grid2;
+  int fin_blocks;
+  size_t off_Z, off_norm, off_csum, off_W, off_racc, off_O, off_stats, off_end;
+};
+
+// K splits per unit so that units * S fills whole waves of SMs (>= 8 K steps per piece, <= 16 splits)
+int sym_choose_split(int units, int KT) {
+  const int sm = sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= 16 && KT / S >= 8; ++S) {
+    const int64_t pieces = (int64_t)units * S;
+    const int64_t waves = (pieces + sm - 1) / sm;
+    const double eff = (double)pieces / (double)(waves * sm);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = S;
+    }
+    if (eff >= 0.92) return S;
+  }
+  return best;
+}
+
+SymPlan sym_plan(int64_t m, int64_t n, int64_t d) {
+  SymPlan p;
+  p.mp = round_up(m, BM);
+  p.np = round_up(n, BM);
+  p.Mp = p.mp + p.np;
+  p.dp = round_up(d, 64);
+  SymGeo& g = p.geo;
+  g.NB = (int)(p.Mp / BM);
+  g.CT = (g.NB + 1) / 2;
+  // band / window: ~16 MB of Z rows each (both stay L2 resident while every CTA works inside them)
+  const int64_t rows16 = std::max<int64_t>(1024, ((int64_t)16 << 20) / (p.dp * 2));
+  g.RB = (int)std::min<int64_t>(g.NB, rows16 / BM);
+  g.CW = (int)std::min<int64_t>(g.CT, rows16 / BNW);
+  if (p.Mp * p.dp * 2 <= ((int64_t)64 << 20)) {   // Z fits L2: one band, one window
+    g.RB = g.NB;
+    g.CW = g.CT;
+  }
+  g.PL = std::min(8, g.CW);
+  // small problems: shorter pieces so that every SM gets work
+  while (g.PL > 1 && (int64_t)g.NB * g.CT / 2 / g.PL < 2 * sm_count()) g.PL >>= 1;
+  g.PPW = (g.CW + g.PL - 1) / g.PL;
+  g.nbands = (g.NB + g.RB - 1) / g.RB;
+  g.nwin = (g.CT + g.CW - 1) / g.CW;
+  p.grid1 = sm_count();
+  p.KT = (int)(p.Mp / 64);
+  p.FB = (int)((p.dp + 255) / 256);
+  p.nmb = (g.NB + 1) / 2;
+  p.units = p.nmb * p.FB;
+  p.S = sym_choose_split(p.units, p.KT);
+  p.ksteps = (p.KT + p.S - 1) / p.S;
+  p.grid2 = p.units * p.S;
+  p.fin_blocks = (int)((p.Mp + kFinRowsPerCta - 1) / kFinRowsPerCta);
+  size_t o = 0;
+  p.off_Z = o;
+  o = up256(o + (size_t)p.Mp * p.dp * 2);
+  p.off_norm = o;
+  o = up256(o + (size_t)p.Mp * 4);
+  p.off_csum = o;
+  o = up256(o + (size_t)2 * p.dp * 8);
+  p.off_W = o;
+  o = up256(o + (size_t)p.Mp * p.Mp * 2);
+  p.off_racc = o;
+  o = up256(o + (size_t)p.Mp * 8);
+  p.off_O = o;
+  o = up256(o + (size_t)p.units * p.S * 256 * 256 * 4);
+  p.off_stats = o;
+  o = up256(o + (size_t)(p.grid1 + p.fin_blocks) * 6 * 8);
+  p.off_end = o;
+  return p;
+}
+
+// bound of |dk/dD| over D >= 0 (sizes the fixed-point accumulator of the row sums of W)
+double kd_abs_bound(const KernelFn& kf) {
+  double b = 0.0;
+  switch (kf.family) {
+    case FAM_RBF:
+      for (int i = 0; i < kf.np; ++i) b += fabs((double)kf.w[i]) * (double)kf.p0[i];
+      break;
+    case FAM_RQ:
+      for (int i = 0; i < kf.np; ++i) b += 0.5 * fabs((double)kf.w[i]);
+      break;
+    case FAM_DISTANCE: b = 0.5 / sqrt(1.0e-7); break;
+    default: b = 1.0;
+  }
+  return b > 0.0 ? b : 1.0;
+}
+
+template <class Math>
+cudaError_t launch_sym_wgen_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymWgenArgs& a,
+                              int grid, cudaStream_t s) {
+  auto kern = tc_sym_wgen_kernel<Math>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSySmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kSyThreads, kSySmem, s>>>(tzi, tzj, tw, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_sym_wgen(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw,
+                            const SymWgenArgs& a, int grid, cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_sym_wgen_t<MathRbf1>(tzi, tzj, tw, a, grid, s);
+    case TV_RBF_LADDER5: return launch_sym_wgen_t<MathRbfLadder<5>>(tzi, tzj, tw, a, grid, s);
+    case TV_RBF_GENERIC: return launch_sym_wgen_t<MathGeneric<FAM_RBF>>(tzi, tzj, tw, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_sym_wgen_t<MathRq3Default>(tzi, tzj, tw, a, grid, s);
+    case TV_RQ_GENERIC: return launch_sym_wgen_t<MathGeneric<FAM_RQ>>(tzi, tzj, tw, a, grid, s);
+    case TV_DISTANCE: return launch_sym_wgen_t<MathDistance>(tzi, tzj, tw, a, grid, s);
+    case TV_NULL: return launch_sym_wgen_t<MathNull>(tzi, tzj, tw, a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+bool tc_sym_eligible(const Geometry& g) {
+  if (!tuning().sym) return false;
+  if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return false;   // whole problem on this GPU
+  const int64_t Mp = round_up(g.m, BM) + round_up(g.n, BM);
+  if (Mp < tuning().sym_min_rows) return false;
+  return Mp * Mp * 2 <= tuning().sym_max_w_bytes;
+}
+
+size_t tc_sym_workspace_bytes(const Geometry& g) { return sym_plan(g.m, g.n, g.d).off_end; }
+
+cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src,
+                       double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
+                       const char** path) {
+  char* w = static_cast<char*>(ws);
+  cudaError_t e;
+  *path = "tc_bf16_sym";
+  const SymPlan p = sym_plan(g.m, g.n, g.d);
+  if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+  __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+  float* norms = reinterpret_cast<float*>(w + p.off_norm);
+  double* csum = reinterpret_cast<double*>(w + p.off_csum);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(w + p.off_W);
+  unsigned long long* racc = reinterpret_cast<unsigned long long*>(w + p.off_racc);
+  double* partials = reinterpret_cast<double*>(w + p.off_stats);
+  PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
+                kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
+  ++*launches;
+  if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
+  const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
+  if (dot) {
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    ++*launches;
+  }
+  CUtensorMap tzi, tzj, tz, twd, twt, tws;
+  if (!smmd_host::make_tmap_bf16_2d(&tzi, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&tzj, Z, p.Mp, p.dp, p.dp, BNW)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&tz, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&twd, Wb, p.Mp, p.Mp, p.Mp, BM)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, p.Mp, p.Mp, p.Mp, 64)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&tws, Wb, p.Mp, p.Mp, p.Mp, 32)) return cudaErrorUnknown;   // pass-1 stores
+  // fixed-point scale of the row sums of W: |W| <= cmax * kd bound, |r_i| <= that * Mp < 2^61 after scaling
+  const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
+  const double wb = cmax * kd_abs_bound(kf);
+  int ex = 0;
+  frexp(wb * (double)p.Mp, &ex);           // wb * Mp < 2^ex
+  const int shift = std::max(-100, std::min(100, 61 - ex));
+  SymWgenArgs ga;
+  ga.kf = kf;
+  ga.geo = p.geo;
+  ga.m = g.m;
+  ga.n = g.n;
+  ga.mp = p.mp;
+  ga.np = p.np;
+  ga.Mp = p.Mp;
+  ga.c_xx = (float)(4.0 * c.a_xx);
+  ga.c_yy = (float)(4.0 * c.a_yy);
+  ga.c_xy = (float)(4.0 * c.a_xy);
+  ga.norms = norms;
+  ga.nkp = (int)(p.dp / 64);
+  ga.rscale = (float)ldexp(1.0, shift);
+  ga.rclamp = (float)(wb * (double)p.Mp);
+  ga.racc = racc;
+  ga.partials = partials;
+  prof_begin(s);
+  const int only = tuning().sym_only;   // developer timing knob: 1 = pass 1 only, 2 = pass 2 only (results meaningless)
+  if (only != 2) {
+    if ((e = launch_sym_wgen(variant, tzi, tzj, tws, ga, p.grid1, s)) != cudaSuccess) return e;
+    ++*launches;
+  }
+  SymWzArgs za;
+  za.nmb = p.nmb;
+  za.FB = p.FB;
+  za.dp = (int)p.dp;
+  za.KT = p.KT;
+  za.S = p.S;
+  za.ksteps = p.ksteps;
+  za.Opart = reinterpret_cast<float*>(w + p.off_O);
+  if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
+    return e;
+  if (only != 1) {
+    tc_sym_wz_kernel<<<p.grid2, kThreads, kSzSmem, s>>>(twd, twt, tz, za);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+  }
+  prof_end(s);
+  SymFinArgs fr;
+  fr.kf = kf;
+  fr.m = g.m;
+  fr.n = g.n;
+  fr.mp = p.mp;
+  fr.np = p.np;
+  fr.d = g.d;
+  fr.dp = (int)p.dp;
+  fr.FB = p.FB;
+  fr.S = p.S;
+  fr.a_xx = c.a_xx;
+  fr.a_yy = c.a_yy;
+  fr.a_xy = c.a_xy;
+  fr.rinv = ldexp(1.0, -shift);
+  fr.src = src;
+  fr.norms = norms;
+  fr.csum = dot ? csum : nullptr;
+  fr.Opart = za.Opart;
+  fr.racc = racc;
+  fr.dX = dX;
+  fr.dY = dY;
+  fr.partials = partials + (int64_t)p.grid1 * 6;
+  sym_finalize_rows_kernel<<<(unsigned)p.fin_blocks, 256, 0, s>>>(fr);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++*launches;
+  e = launch_finalize_partials(kf, g, partials, (int64_t)p.grid1 + p.fin_blocks, scalars, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  return cudaSuccess;
+}
+
+}  // namespace tc
+}  // namespace smmd

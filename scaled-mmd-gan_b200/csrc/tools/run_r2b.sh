@@ -1,0 +1,26 @@
+#!/bin/bash
+# round 2, call B: symmetric two-pass path: parity vs the exact path + timings
+mkdir -p gpurun_out
+L=gpurun_out/r2b.log
+: > $L
+B=scaled-mmd-gan_b200/build/tc_check
+run() { echo "\$ $*  [SYM=$SMMD_SYM MIN=$SMMD_SYM_MIN_ROWS]" >> $L; timeout 300 "$@" >> $L 2>&1; echo "exit=$?" >> $L; }
+export SMMD_SYM_MIN_ROWS=1
+run $B mmd mix_rq 300 200 100 1
+run $B mmd mix_rq 1000 1100 256 2
+run $B mmd mix_rq_dot 900 1000 320 2
+run $B mmd rbf 1024 1024 512 2
+run $B mmd mix_rbf 2000 1500 64 2
+run $B mmd distance 1500 1500 192 2
+run $B mmd mix_rq 4096 4096 256 20
+unset SMMD_SYM_MIN_ROWS
+run $B mmd mix_rq 8192 8192 256 20 0
+run $B mmd mix_rq 16384 16384 256 10 0
+run $B mmd mix_rq 32768 32768 256 5 0
+run $B mmd mix_rq 65536 65536 256 3 0
+run $B mmd mix_rq 8192 8192 512 10 0
+run $B mmd mix_rq 32768 32768 512 3 0
+run $B mmd mix_rq 8192 8192 1024 10 0
+run $B mmd mix_rq 32768 32768 1024 3 0
+run $B mmd rbf 32768 32768 256 5 0
+grep -vE "^   sum\[" $L

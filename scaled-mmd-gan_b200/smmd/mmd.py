@@ -361,8 +361,9 @@ def _mmd2(K_XX, K_XY, K_YY, const_diagonal=False, biased=False):
 
 def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
     """mmd.py:223-232 -> (mmd2, ratio, var_est); fused statistics pass, not differentiable."""
-    if not isinstance(K, KernelHandle):
-        raise TypeError("mmd2_and_ratio expects the handle returned by a _<name>_kernel(X, Y) call")
+    if not isinstance(K, KernelHandle):   # explicit dense 4-tuple, as mmd2() accepts (mmd.py:224-225)
+        K_XX, K_XY, K_YY, const_diagonal = K
+        return _mmd2_and_ratio(K_XX, K_XY, K_YY, const_diagonal, biased, min_var_est)
     X, Y, spec = K.X, K.Y, K.spec
     lib = _lib.load()
     Xc, ldx = _rows(X.detach())
@@ -415,10 +416,10 @@ def _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=False, biased=False):
 
 
 def _mmd2_and_ratio(K_XX, K_XY, K_YY, const_diagonal=False, biased=False, min_var_est=_eps):
-    """mmd.py:228-233 on dense blocks: (mmd2, ratio = mmd2 / sqrt(max(var_est, min_var_est)))."""
+    """mmd.py:228-233 on dense blocks: (mmd2, ratio = mmd2 / sqrt(max(var_est, min_var_est)), var_est)."""
     mmd2_val, var_est = _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=const_diagonal, biased=biased)
     ratio = mmd2_val / torch.sqrt(torch.clamp(var_est, min=min_var_est))
-    return mmd2_val, ratio
+    return mmd2_val, ratio, var_est
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -464,7 +465,9 @@ def polynomial_related_sums(X, Y, precision=None):
 def _diff_mmd2_and_ratio_from_sums(Y_related_sums, Z_related_sums, m, const_diagonal=False):
     """mmd.py:339-402 / 447-512: MMD^2(X,Y) - MMD^2(X,Z), and its ratio to the estimated standard deviation.
     Works on torch tensors or numpy arrays (vectors of length m and scalars); `const_diagonal` is accepted for
-    signature compatibility (the reference ignores it here as well)."""
+    signature compatibility (the reference ignores it here as well).  The two reference variants clamp differently
+    and both are kept: the graph (tensor) variant divides by mysqrt(max(var, eps)) = sqrt(max(var, eps) + eps)
+    (mmd.py:398 with :12), the numpy variant by sqrt(max(var, eps)) (mmd.py:510)."""
     yy_r, yy_q, xy_c, xy_r, xy_q = Y_related_sums
     zz_r, zz_q, xz_c, xz_r, xz_q = Z_related_sums
     m = float(m)
@@ -485,7 +488,7 @@ def _diff_mmd2_and_ratio_from_sums(Y_related_sums, Z_related_sums, m, const_diag
                               + zz_q / mm1 - mu_zz ** 2 + 2 * xz_q / mm - 2 * mu_xz ** 2 + 2 * cross)
     var_est = first_order + second_order
     if isinstance(var_est, torch.Tensor):
-        ratio = mmd2_diff / torch.sqrt(torch.clamp(var_est, min=_eps))
+        ratio = mmd2_diff / torch.sqrt(torch.clamp(var_est, min=_eps) + _eps)
     else:
         ratio = mmd2_diff / max(float(var_est), _eps) ** 0.5
     return mmd2_diff, ratio

@@ -53,7 +53,7 @@ def test_scorer_size_vs_oracle():
     X64, Y64, Z64 = X.astype(np.float64), Y.astype(np.float64), Z.astype(np.float64)
     ys = tso.related_sums(tso.cubic_kernel(X64, Y64), tso.cubic_kernel(Y64, Y64))
     zs = tso.related_sums(tso.cubic_kernel(X64, Z64), tso.cubic_kernel(Z64, Z64))
-    want = tso.diff_from_sums(ys, zs, 2048.0)
+    want = tso.diff_from_sums(ys, zs, 2048.0, graph=True)   # torch tensors in: the graph variant's clamp (mmd.py:398)
     got_ys = mmd.polynomial_related_sums(Xt, Yt)
     _check_sums([g.cpu().numpy() for g in got_ys], ys, 1e-4)
     assert abs(diff.item() - want[0]) <= 5e-3 * abs(want[0]), (diff.item(), want[0])

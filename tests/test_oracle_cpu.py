@@ -139,6 +139,10 @@ def test_dense_block_ratio_helpers_match_oracle():
             v, ratio, var = mmd_oracle.mmd2_and_ratio(name, X, Y, biased, 1e-5, np.float64, **kw)
             blocks = [torch.tensor(K) for K in (Kxx, Kxy, Kyy)]
             gv, gvar = mmd._mmd2_and_variance(*blocks, const_diagonal=cd, biased=biased)
-            gv2, gr = mmd._mmd2_and_ratio(*blocks, const_diagonal=cd, biased=biased)
+            gv2, gr, gvar2 = mmd._mmd2_and_ratio(*blocks, const_diagonal=cd, biased=biased)   # 3-tuple: mmd.py:233
             assert abs(float(gv) - v) <= 1e-12 * abs(v) and abs(float(gvar) - var) <= 1e-9 * abs(var) + 1e-18
             assert abs(float(gv2) - v) <= 1e-12 * abs(v) and abs(float(gr) - ratio) <= 1e-9 * abs(ratio)
+            assert float(gvar2) == float(gvar)
+            # mmd2_and_ratio takes the explicit 4-tuple as well (mmd.py:224-225)
+            tv, tr, tvar = mmd.mmd2_and_ratio((blocks[0], blocks[1], blocks[2], cd), biased=biased)
+            assert float(tv) == float(gv2) and float(tr) == float(gr) and float(tvar) == float(gvar)

@@ -63,3 +63,23 @@ def test_dense_block_entry_point_matches_oracle():
     assert abs(got[0] - want[0]) <= 1e-12 * abs(want[0]) and abs(got[1] - want[1]) <= 1e-10 * abs(want[1])
     ref = Z3["res_f64_small"]
     assert abs(got[0] - ref[0]) <= 1e-10 * abs(ref[0]) and abs(got[1] - ref[1]) <= 1e-8 * abs(ref[1])
+
+
+@pytest.mark.parametrize("tag", ["small", "mid"])
+def test_graph_variant_ratio_clamp(tag):
+    """The TF variant (mmd.py:339-399) divides by mysqrt(max(var, eps)) = sqrt(max(var, eps) + eps); the fixture holds
+    the reference's own output (executed over the torch-backed tf shim).  Oracle and the product's tensor branch."""
+    import torch
+
+    from smmd import mmd
+
+    X, Y, Z = three_sample_codes(Z3, tag, np.float64)
+    ys = tso.related_sums(tso.cubic_kernel(X, Y), tso.cubic_kernel(Y, Y))
+    zs = tso.related_sums(tso.cubic_kernel(X, Z), tso.cubic_kernel(Z, Z))
+    ref = Z3["res_graph_f64_%s" % tag]
+    want = tso.diff_from_sums(ys, zs, float(len(Y)), graph=True)
+    assert abs(want[0] - ref[0]) <= 1e-12 * abs(ref[0]) and abs(want[1] - ref[1]) <= 1e-10 * abs(ref[1])
+    tys = tuple(torch.as_tensor(v, dtype=torch.float64) for v in ys)
+    tzs = tuple(torch.as_tensor(v, dtype=torch.float64) for v in zs)
+    got = mmd._diff_mmd2_and_ratio_from_sums(tys, tzs, float(len(Y)))
+    assert abs(float(got[0]) - ref[0]) <= 1e-12 * abs(ref[0]) and abs(float(got[1]) - ref[1]) <= 1e-10 * abs(ref[1])
