@@ -42,6 +42,7 @@ __device__ __forceinline__ float2 rcp_2(float2 x) { return make_float2(fast_rcp(
 
 struct MathRbf1 {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   float c1, w, g;
   __device__ explicit MathRbf1(const KernelFn& f, const float*) : c1(f.p1[0]), w(f.w[0]), g(-f.p0[0] * f.w[0]) {}
   __device__ __forceinline__ float k_scale() const { return w; }
@@ -57,6 +58,7 @@ struct MathRbf1 {
 template <int NP>
 struct MathRbfLadder {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   float c1, w[NP], g[NP];
   __device__ explicit MathRbfLadder(const KernelFn& f, const float*) : c1(f.p1[0]) {
 #pragma unroll
@@ -81,6 +83,21 @@ struct MathRbfLadder {
   }
 };
 
+// "Pair term" hooks (symmetric path): a variant may fold |z_i|^2 + |z_j|^2 into its first affine step,
+//     rt = row_term(|z_i|^2)  once per row,   pt = pair_term(rt, |z_j|^2 pair)  one packed op per column pair,
+//     evalPt(S, pt, k, kd)    which then needs no separate D = nij - 2 S.
+// Variants without the hooks get rt = |z_i|^2, pt = nij and their ordinary eval.
+template <class Math>
+__device__ __forceinline__ float math_row_term(const Math& m, float ni) {
+  if constexpr (Math::kHasPt) return m.row_term(ni);
+  else return ni;
+}
+template <class Math>
+__device__ __forceinline__ float2 math_pair_term(const Math& m, float2 rt, float2 nj) {
+  if constexpr (Math::kHasPt) return m.pair_term(rt, nj);
+  else return add2(rt, nj);
+}
+
 // Default interleave helper: variants without a hand-interleaved evalN fall back to eval2 per pair.
 template <class Math, int NP>
 __device__ __forceinline__ void eval_pairs(const Math& m, const float2 (&S)[NP], const float2 (&nij)[NP],
@@ -92,9 +109,56 @@ __device__ __forceinline__ void eval_pairs(const Math& m, const float2 (&S)[NP],
     for (int i = 0; i < NP; ++i) m.eval2(S[i], nij[i], k[i], kd[i]);
   }
 }
+template <class Math, int NP>
+__device__ __forceinline__ void eval_pairs_pt(const Math& m, const float2 (&S)[NP], const float2 (&pt)[NP],
+                                              float2 (&k)[NP], float2 (&kd)[NP]) {
+  if constexpr (Math::kHasPt) m.template evalPt<NP>(S, pt, k, kd);
+  else eval_pairs<Math, NP>(m, S, pt, k, kd);
+}
 
 struct MathRq3Default {
   static constexpr bool kHasEvalN = true;
+  static constexpr bool kHasPt = true;
+  // b1 = 1 + 5 D = (1 + 5 |z_i|^2) + 5 |z_j|^2 - 10 S;  b2 = 1 + D/2 = .1 b1 + .9;  b3 = 1 + D/20 = .01 b1 + .99
+  __device__ __forceinline__ float row_term(float ni) const { return fmaf(5.f, ni, 1.f); }
+  __device__ __forceinline__ float2 pair_term(float2 rt, float2 nj) const { return fma2(nj, bc2(5.f), rt); }
+  // No upper clamp here: the product of the bases stays finite up to D ~ 1e12 and beyond that rcp(inf) = 0 zeroes
+  // every term; only |z|^2 > 1e18 could produce 0 * inf, and such rows are reported as non-finite by the caller.
+  template <int NP>
+  __device__ __forceinline__ void evalPt(const float2 (&S)[NP], const float2 (&pt)[NP], float2 (&k)[NP],
+                                         float2 (&kd)[NP]) const {
+    float2 b1[NP], b2[NP], b3[NP], p23[NP], R[NP], L[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      b1[i] = fma2(S[i], bc2(-10.f), pt[i]);
+      b2[i] = fma2(b1[i], bc2(.1f), bc2(.9f));
+      b3[i] = fma2(b1[i], bc2(.01f), bc2(.99f));
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = lg2_2(b1[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      p23[i] = mul2(b2[i], b3[i]);
+      R[i] = mul2(b1[i], p23[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) R[i] = rcp_2(R[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = mul2(L[i], bc2(-0.1f));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) L[i] = ex2_2(L[i]);           // e1 = b1^-0.1
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float2 r1 = mul2(R[i], p23[i]);
+      const float2 t = mul2(R[i], b1[i]);
+      const float2 r2 = mul2(t, b3[i]);
+      const float2 r3 = mul2(t, b2[i]);
+      const float2 q2 = mul2(r3, r3), q4 = mul2(q2, q2), q8 = mul2(q4, q4);
+      const float2 e3 = mul2(q8, q2);
+      k[i] = add2(add2(L[i], r2), e3);
+      kd[i] = fma2(e3, r3, fma2(r2, r2, mul2(L[i], r1)));
+    }
+  }
   __device__ explicit MathRq3Default(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
@@ -162,6 +226,7 @@ struct MathRq3Default {
 template <int FAM>
 struct MathGeneric {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   const float* sp;
   int np;
   __device__ explicit MathGeneric(const KernelFn& f, const float* smem_params) : sp(smem_params), np(f.np) {}
@@ -191,6 +256,7 @@ struct MathGeneric {
 
 struct MathDistance {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   __device__ explicit MathDistance(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return -1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
@@ -203,6 +269,7 @@ struct MathDistance {
 
 struct MathNull {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   __device__ explicit MathNull(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 1.f; }
@@ -214,6 +281,7 @@ struct MathNull {
 
 struct MathPoly3 {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   float gamma, c0;
   __device__ explicit MathPoly3(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
@@ -227,6 +295,7 @@ struct MathPoly3 {
 
 struct MathPolyN {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kHasPt = false;
   float gamma, c0;
   int degree;
   __device__ explicit MathPolyN(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0), degree(f.degree) {}

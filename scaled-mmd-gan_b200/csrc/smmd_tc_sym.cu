@@ -29,7 +29,9 @@ constexpr int kSyThreads = (kSyEpiWarps + 2) * 32;
 constexpr int kSyStages = 3;
 constexpr int kSyStageBytes = BM * 128 + BNW * 128;        // Z_i panel + Z_j tile per 64-deep step = 48 KB
 constexpr int kSyStagingBytes = kSyEpiWarps * 4096;        // 64 KB: one 32-row x 64-column bf16 block per epilogue warp
-constexpr int kSySmem = 1024 + kSyStages * kSyStageBytes + kSyStagingBytes + 1024;
+constexpr int kSyNormBufs = 8;                             // column norms of the tiles in flight (1 KB each)
+constexpr int kSyNormBytes = kSyNormBufs * BNW * 4;
+constexpr int kSySmem = 1024 + kSyStages * kSyStageBytes + kSyStagingBytes + kSyNormBytes + 1024;
 static_assert(kSySmem <= kMaxSmem, "pass-1 shared memory");
 
 constexpr int kFinRowsPerWarp = 4;
@@ -39,7 +41,7 @@ constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
 // The upper triangle is walked band by band (RB row blocks) and, inside a band, window by window (CW column
 // tiles): the Z rows of one band + one window stay L2 resident while all CTAs work inside them.  A unit is a run
 // of <= PL consecutive column tiles of ONE row block (row sums stay in registers over the run); units are numbered
-// as fixed slots (band, window, row block, piece) -- slots below the diagonal are empty -- and dealt round-robin.
+// compactly in that order and dealt round-robin to the persistent CTAs.
 struct SymGeo {
   int NB, CT;          // row blocks of 128, column tiles of 256 (the last tile may be half)
   int RB, CW, PL, PPW; // band (row blocks), window (tiles), piece length (tiles), pieces per window
@@ -47,38 +49,43 @@ struct SymGeo {
 };
 
 struct UnitWalk {
-  int b, w, rows;
+  int b, w, rb, rb_end, wst, wend;
   int64_t base;
-  __device__ __forceinline__ int first_win(const SymGeo& g, int band) const { return ((band * g.RB) >> 1) / g.CW; }
+  __device__ __forceinline__ void set_block(const SymGeo& g) {
+    rb = b * g.RB;
+    rb_end = rb + g.RB < g.NB ? rb + g.RB : g.NB;
+    wst = w * g.CW;
+    wend = wst + g.CW < g.CT ? wst + g.CW : g.CT;
+  }
   __device__ __forceinline__ void init(const SymGeo& g) {
     b = 0;
     w = 0;
     base = 0;
-    rows = g.RB < g.NB ? g.RB : g.NB;
+    set_block(g);
   }
-  // slot `idx` (non-decreasing over calls) -> (row block, [ct0, ct1)); false when idx is past the last slot
-  __device__ __forceinline__ bool locate(const SymGeo& g, int64_t idx, int& rb, int& ct0, int& ct1) {
+  // unit `idx` (non-decreasing over calls) -> (row block, [ct0, ct1)); false when idx is past the last unit.
+  // Units are numbered compactly (rows / windows below the diagonal contribute none), so dealing them round-robin
+  // balances the CTAs to within one unit.
+  __device__ __forceinline__ bool locate(const SymGeo& g, int64_t idx, int& rb_out, int& ct0, int& ct1) {
     for (;;) {
       if (b >= g.nbands) return false;
-      const int64_t slots = (int64_t)rows * g.PPW;
-      if (idx < base + slots) {
-        const int s = (int)(idx - base);
-        const int rbl = s / g.PPW, k = s - rbl * g.PPW;
-        rb = b * g.RB + rbl;
-        const int wend = (w + 1) * g.CW < g.CT ? (w + 1) * g.CW : g.CT;
-        ct0 = w * g.CW + k * g.PL;
+      const int lo = wst > (rb >> 1) ? wst : (rb >> 1);   // first tile of row block rb inside this window
+      const int nt = wend - lo;
+      const int np = nt > 0 ? (nt + g.PL - 1) / g.PL : 0;
+      if (idx < base + np) {
+        const int k = (int)(idx - base);
+        ct0 = lo + k * g.PL;
         ct1 = ct0 + g.PL < wend ? ct0 + g.PL : wend;
-        if (ct0 < (rb >> 1)) ct0 = rb >> 1;
+        rb_out = rb;
         return true;
       }
-      base += slots;
-      if (++w >= g.nwin) {
-        ++b;
-        if (b < g.nbands) {
-          const int lo = b * g.RB;
-          rows = lo + g.RB < g.NB ? g.RB : g.NB - lo;
-          w = first_win(g, b);
+      base += np;
+      if (++rb >= rb_end) {
+        if (++w >= g.nwin) {
+          ++b;
+          w = ((b * g.RB) >> 1) / g.CW;   // windows left of it lie below the band's diagonal
         }
+        if (b < g.nbands) set_block(g);
       }
     }
   }
@@ -118,6 +125,47 @@ __device__ __forceinline__ void fixed_add(unsigned long long* p, float v, float 
   atomicAdd(p, (unsigned long long)__float2ll_rn(v * scale));
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// 16 columns of one row (as fused_chunk16), with the column norms read from shared memory and folded into the
+// variant's first affine step (pair terms): no global load and no separate D = nij - 2 S in the element stream.
+template <class Math, bool SPECIAL>
+__device__ __forceinline__ void sym_chunk16(const Math& math, const uint32_t (&v)[16], uint32_t nj_smem, float rt,
+                                            float2 cw, int col0, int lim, int gi, float2& tsum, float2& rsum,
+                                            uint32_t (&wpk)[8]) {
+  const float2 rt2 = bc2(rt);
+#pragma unroll
+  for (int c = 0; c < 16; c += 8) {   // 4 pairs (8 columns) evaluated in lock-step
+    const float4 na = ld_shared_f4(nj_smem + c * 4);
+    const float4 nb = ld_shared_f4(nj_smem + c * 4 + 16);
+    float2 S[4], pt[4], k[4], kd[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S[e] = make_float2(__uint_as_float(v[c + 2 * e]), __uint_as_float(v[c + 2 * e + 1]));
+    pt[0] = math_pair_term(math, rt2, make_float2(na.x, na.y));
+    pt[1] = math_pair_term(math, rt2, make_float2(na.z, na.w));
+    pt[2] = math_pair_term(math, rt2, make_float2(nb.x, nb.y));
+    pt[3] = math_pair_term(math, rt2, make_float2(nb.z, nb.w));
+    eval_pairs_pt<Math, 4>(math, S, pt, k, kd);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (SPECIAL) {
+        const int col = col0 + c + 2 * e;
+        const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
+        k[e] = make_float2(ok0 ? k[e].x : 0.f, ok1 ? k[e].y : 0.f);
+        kd[e] = make_float2(ok0 ? kd[e].x : 0.f, ok1 ? kd[e].y : 0.f);
+      }
+      tsum = add2(tsum, k[e]);
+      const float2 ww = mul2(kd[e], cw);
+      rsum = add2(rsum, ww);
+      wpk[(c >> 1) + e] = pack_bf16x2(ww.x, ww.y);
+    }
+  }
+}
+
 template <class Math>
 __global__ void __launch_bounds__(kSyThreads, 1)
 tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
@@ -125,12 +173,14 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kSyStages * kSyStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSyStagingBytes);
+  float* nbuf = reinterpret_cast<float*>(staging + kSyStagingBytes);   // [kSyNormBufs][256] column norms per tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSyStagingBytes + kSyNormBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kSyStages;
   uint64_t* acc_full = empty + kSyStages;    // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* nfull = acc_empty + 2;           // [kSyNormBufs] column norms of tile t landed in nbuf[t % 8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nfull + kSyNormBufs);
   float* sParams = reinterpret_cast<float*>(tmem_slot + 4);   // [24]
   double* sRed = reinterpret_cast<double*>(sParams + 24);     // [16][3] end-of-kernel reduction of the block sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,6 +194,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kSyEpiWarps);   // one elected arrive per epilogue warp
     }
+    for (int i = 0; i < kSyNormBufs; ++i) mbar_init(&nfull[i], 1);
     fence_mbar_init();
   }
   if (warp == kSyEpiWarps + 1) tmem_alloc<512>(tmem_slot);
@@ -160,14 +211,23 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
 
   if (warp == kSyEpiWarps) {
     // ===================== TMA producer =====================
-    uint32_t st = 0, ph = 0;
+    // The column norms of tile t go to nbuf[t % 8] with one 1 KB bulk copy.  Buffer reuse needs no barrier: the
+    // producer is at most kSyStages = 3 tiles ahead of the issuer (one stage per tile when d <= 64), the issuer at most
+    // 2 tiles (accumulators) ahead of the epilogue's release, and a warp that has released tile s may still be doing
+    // the math of s: the oldest tile whose norms can still be read while tile t is loaded is t - 6 > t - 8.
+    uint32_t st = 0, ph = 0, tcnt = 0;
     UnitWalk uw;
     uw.init(geo);
     int rb, ct0, ct1;
     for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
-      for (int ct = ct0; ct < ct1; ++ct) {
+      for (int ct = ct0; ct < ct1; ++ct, ++tcnt) {
         for (int p = 0; p < a.nkp; ++p) {
           mbar_wait(&empty[st], ph ^ 1);
+          if (p == 0 && elect_one()) {
+            const uint32_t nb = tcnt & (kSyNormBufs - 1);
+            mbar_arrive_expect_tx(&nfull[nb], BNW * 4);
+            bulk_load_1d(nbuf + nb * BNW, a.norms + (int64_t)ct * BNW, BNW * 4, &nfull[nb]);
+          }
           if (elect_one()) {
             uint8_t* sa = smem + st * kSyStageBytes;
             mbar_arrive_expect_tx(&full[st], kSyStageBytes);
@@ -245,8 +305,9 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
       const bool rowX = gi < mp;
       const bool row_ok = rowX ? gi < mvalid : gi < yvalid;
       const bool pad_rows = rowX ? (rb + 1) * BM > mvalid : (rb + 1) * BM > yvalid;   // block holds padding rows
-      const float ni = a.norms[gi];
+      const float rt = math_row_term(math, a.norms[gi]);
       float2 rsum = make_float2(0.f, 0.f);
+      float fsame = 0.f, fcross = 0.f;   // block sums of this unit (fp32 over <= 8 tiles; fp64 across units)
       bool any = false;
       for (int ct = ct0; ct < ct1; ++ct, ++tc) {
         const int grp = (int)(tc & 1);
@@ -271,14 +332,16 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
         const int lim = row_ok ? (colX ? mvalid : yvalid) : 0;   // padding rows: every column masked
         const bool special = diag || pad_rows || (c0 + 64 > (colX ? mvalid : yvalid));
-        const float* nj = a.norms + c0;
+        const uint32_t nb = tc & (kSyNormBufs - 1);
+        mbar_wait(&nfull[nb], (tc / kSyNormBufs) & 1);
+        const uint32_t nj = smem_u32(nbuf + nb * BNW + part * 64);
         float2 tsum = make_float2(0.f, 0.f);
         const uint32_t srow = stg + lane * 128;
         const uint32_t sw = (uint32_t)(lane & 7);
         auto do_chunk = [&](const uint32_t (&v)[16], int h) {
           uint32_t wpk[8];
-          if (!special) fused_chunk16<Math, false>(math, v, nj + h * 16, ni, cw, 0, 0, 0, tsum, rsum, wpk);
-          else fused_chunk16<Math, true>(math, v, nj + h * 16, ni, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
+          if (!special) sym_chunk16<Math, false>(math, v, nj + h * 64, rt, cw, 0, 0, 0, tsum, rsum, wpk);
+          else sym_chunk16<Math, true>(math, v, nj + h * 64, rt, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
           if (h == 0 && stored) {   // the previous tile's TMA store must have read the block before it is overwritten
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
@@ -305,10 +368,9 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         }
         // a cross block is seen once (X rows, Y columns) and stands for K_XY and K_YX; a same-set block above the
         // diagonal stands for itself and its mirror
-        const double ts = (double)((tsum.x + tsum.y) * kscale);
-        if (!same) sxy += ts;
-        else if (rowX) sxx += diag ? ts : 2.0 * ts;
-        else syy += diag ? ts : 2.0 * ts;
+        const float ts = (tsum.x + tsum.y) * kscale;
+        if (!same) fcross += ts;
+        else fsame += diag ? ts : 2.f * ts;
         // ---- staged block complete: TMA store, and (off-diagonal blocks) its column sums -> r_j of the mirror ----
         fence_proxy_async_smem();
         __syncwarp();
@@ -335,6 +397,9 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         }
       }
       if (any && row_ok) fixed_add(a.racc + gi, rsum.x + rsum.y, a.rscale, a.rclamp);
+      sxy += (double)fcross;
+      if (rowX) sxx += (double)fsame;
+      else syy += (double)fsame;
     }
     if (stored && lane == 0) bulk_wait0();   // all W stores of this warp have completed before the CTA exits
     // ---- block sums of this CTA: fixed-order reduction over the 16 epilogue warps ----
@@ -615,8 +680,10 @@ __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
     const float ni = a.norms[gi];
     const double v_same = dot ? (double)a.kf.add_dot * (dsame - (double)ni) : 0.0;
     const double v_cross = dot ? (double)a.kf.add_dot * dcross : 0.0;
-    const double v_diag = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
-                                                : (double)diag_value(a.kf, ni);
+    double v_diag = a.kf.family == FAM_RQ ? (double)a.kf.const_diag + (double)a.kf.add_dot * (double)ni
+                                          : (double)diag_value(a.kf, ni);
+    // the unclamped epilogue math is finite for |z|^2 <= 1e18; beyond that the result is reported as non-finite
+    if (!(ni <= 1.0e18f)) v_diag = __longlong_as_double(0x7ff8000000000000LL);
     if (rowX) {
       q[0] += v_same;
       q[2] += v_cross;
@@ -685,8 +752,8 @@ SymPlan sym_plan(int64_t m, int64_t n, int64_t d) {
     g.CW = g.CT;
   }
   g.PL = std::min(8, g.CW);
-  // small problems: shorter pieces so that every SM gets work
-  while (g.PL > 1 && (int64_t)g.NB * g.CT / 2 / g.PL < 2 * sm_count()) g.PL >>= 1;
+  // small problems: shorter pieces, so that every CTA gets >= 16 units and the round-robin deal leaves < 6% tail
+  while (g.PL > 1 && (int64_t)g.NB * g.CT / 2 / g.PL < 16 * sm_count()) g.PL >>= 1;
   g.PPW = (g.CW + g.PL - 1) / g.PL;
   g.nbands = (g.NB + g.RB - 1) / g.RB;
   g.nwin = (g.CT + g.CW - 1) / g.CW;
@@ -703,7 +770,7 @@ SymPlan sym_plan(int64_t m, int64_t n, int64_t d) {
   p.off_Z = o;
   o = up256(o + (size_t)p.Mp * p.dp * 2);
   p.off_norm = o;
-  o = up256(o + (size_t)p.Mp * 4);
+  o = up256(o + (size_t)(p.Mp + BNW) * 4);   // + one tile: the bulk copy of the last (half) tile's column norms
   p.off_csum = o;
   o = up256(o + (size_t)2 * p.dp * 8);
   p.off_W = o;
