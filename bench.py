@@ -39,7 +39,7 @@ import torch  # noqa: E402
 
 N_TOTAL = 65536        # fake rows = real rows (global): the largest N of the configs[3] sweep
 D_FEAT = 256
-CPU_SAMPLE_N = 4096    # the CPU port materialises ~12 N x N fp32 temporaries: 32768 would need > 50 GB
+CPU_SAMPLE_N = 4096    # cpu_baseline leg of the product arm (the reference materialises ~12 N x N fp32 temporaries per block)
 KID = dict(n_codes=50000, d=2048, n_subsets=100, subset_size=1000)
 KID_CPU_SUBSETS = 4
 METRIC = "mmd2_fwd_bwd_kernel_pair_evals_per_s"
@@ -138,16 +138,71 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference arm: CPU port on a bounded sample
+# reference arm: the reference's own sources (oracle/_ref, staged by oracle/make_ref.py) on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_step(n, d):
-    from oracle import cpu_port
+def _reference_kind():
+    """("reference", loader) when the staged reference sources (or /root/reference) are present, else ("port", None)."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            return "reference", ref_loader
+    except Exception:
+        pass
+    return "port", None
 
+
+def cpu_step(n, d, kind=None, loader=None):
+    """One mix_rq MMD^2 loss + both feature gradients on the host cores; returns seconds.  kind "reference": the
+    unmodified gan/core/mmd.py executed over the torch-CPU `tf` shim (oracle/ref_loader.py), gradients by autograd
+    through the executed reference code; kind "port": oracle/cpu_port.py (only when the sources are not staged)."""
+    if kind is None:
+        kind, loader = _reference_kind()
     X = synth_features(n, d, 1234, False).numpy()
     Y = synth_features(n, d, 1235, True).numpy()
     t0 = time.perf_counter()
-    cpu_port.mix_rq_fwd_bwd(X, Y)
+    if kind == "reference":
+        loader.reference_loss_and_grads("mix_rq", X, Y, biased=False, dtype_name="float32")
+    else:
+        from oracle import cpu_port
+        cpu_port.mix_rq_fwd_bwd(X, Y)
     return time.perf_counter() - t0
+
+
+def pick_cpu_sample(d, kind, loader, budget_s, n_calls):
+    """Largest N in {2048 .. 16384} whose n_calls evaluations fit `budget_s` seconds (N^2 extrapolation of a 2048 probe)
+    and whose ~40 live N x N fp32 arrays (3 Gram blocks x the reference's temporaries + autograd's saved copies) fit
+    half of the free host memory."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    cpu_step(1024, d, kind, loader)            # import / thread-pool warm-up
+    t2k = cpu_step(2048, d, kind, loader)
+    best = 2048
+    for n in (4096, 8192, 16384):
+        t_est = t2k * (n / 2048.0) ** 2
+        if t_est * n_calls <= budget_s and 40.0 * n * n * 4 <= 0.5 * avail:
+            best = n
+    return best, t2k, avail
+
+
+def reference_kid(loader, n_subsets):
+    """The reference's own polynomial_mmd_averages (gan/compute_scores.py:211-229, numpy + sklearn/BLAS) on the C3
+    codes with `n_subsets` subsets of 1000 (the reference scorer's default is 10, gan/utils/scorer.py:103-109)."""
+    nc, d, m = KID["n_codes"], KID["d"], KID["subset_size"]
+    rs = np.random.RandomState(1234)
+    g = np.maximum(rs.standard_normal((nc, d)).astype(np.float32), 0)
+    r = np.maximum(rs.standard_normal((nc, d)).astype(np.float32) + 0.02, 0)
+    cs = loader.load_reference_compute_scores()
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    mmds = cs.polynomial_mmd_averages(g, r, n_subsets=n_subsets, subset_size=m, ret_var=False, output=None)
+    t = time.perf_counter() - t0
+    return {"metric": "kid_feature_rows_per_s", "value": 2.0 * n_subsets * m / t, "unit": "feature rows/s",
+            "seconds": t, "kid_mean": float(np.mean(mmds)), "cores": os.cpu_count(), "kind": "reference",
+            "sample": "gan/compute_scores.py polynomial_mmd_averages, %d of the %d subsets of %d on %dk vs %dk x %d fp32 codes"
+                      % (n_subsets, KID["n_subsets"], m, nc // 1000, nc // 1000, d)}
 
 
 def run_reference(args):
@@ -155,24 +210,40 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    n, d = CPU_SAMPLE_N, D_FEAT
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_step(n, d)
-    steps = max(1, min(args.steps, 10))
-    ts = [cpu_step(n, d) for _ in range(steps)]
+    kind, loader = _reference_kind()
+    d = D_FEAT
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.ref_n:
+        n, t2k, avail = args.ref_n, None, None
+    else:
+        n, t2k, avail = pick_cpu_sample(d, kind, loader, budget_s=150.0, n_calls=steps + warmup)
+    for _ in range(warmup):
+        cpu_step(n, d, kind, loader)
+    ts = [cpu_step(n, d, kind, loader) for _ in range(steps)]
     t = float(np.mean(ts))
     value = n * n * d / t
-    sample = "mix_rq fwd+bwd on %d+%d x %d (N^2-scaling sample of the %d+%d workload; the port materialises N x N fp32 " \
-             "temporaries like the reference and cannot hold N=%d)" % (n, n, d, N_TOTAL, N_TOTAL, N_TOTAL)
+    what = ("the reference's own gan/core/mmd.py (_mix_rq_kernel + mmd2, unmodified, executed over a torch-CPU tf shim; "
+            "gradients by autograd through it)") if kind == "reference" else "oracle/cpu_port.py (torch-CPU restatement)"
+    sample = ("%s, fp32, fwd+bwd on %d+%d x %d: the largest N of {2048..16384} whose %d evaluations fit ~150 s and whose N x N "
+              "fp32 temporaries fit host memory (the full workload is %d+%d: 17 GB per temporary); pair-dims/s is "
+              "N^2-normalised, so the sample rate is the rate the reference would sustain if it could hold the workload"
+              % (what, n, n, d, steps + warmup, N_TOTAL, N_TOTAL))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C4 large-batch Gram: mix_rq MMD^2 fwd+bwd, N=%d fake + %d real, d=%d" % (N_TOTAL, N_TOTAL, D_FEAT),
-                   "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+                   "l2": "n/a (CPU)", "sample_n": n, "same_config": False,
+                   "note": "bounded sample of the workload (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+                         "probe_seconds_at_2048": t2k, "host_mem_available_bytes": avail},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if kind == "reference" and not args.no_kid:
+        try:
+            line["kid"] = reference_kid(loader, n_subsets=min(10, KID["n_subsets"]))
+        except Exception as e:   # sklearn / memory: the loss line stands on its own
+            line["kid"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
 
 
@@ -566,6 +637,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
+    ap.add_argument("--no-kid", action="store_true", help="reference arm: skip the KID line")
+    ap.add_argument("--ref-n", type=int, default=0, help="reference arm: fixed sample N (default: chosen from time / memory)")
     ap.add_argument("--sweep", action="store_true", help="C4 grid (N x d) instead of the headline line")
     ap.add_argument("--sweep-n", default="4096,8192,16384,32768,65536")
     ap.add_argument("--sweep-d", default="256,512,1024")

@@ -8,7 +8,9 @@ What the reference does on CPU, restated with torch-CPU fp32 (all host threads, 
          materialised N x N temporaries (gan/core/model.py:446,452 `tf.gradients`)
   KID:   per subset: fancy-index gather, three (XY^T/d + 1)^3 Gram blocks, _mmd2_and_variance sums
          (gan/compute_scores.py:211-335) -- numpy/BLAS exactly as the reference (via oracle/kid_oracle.py)
-Checked against oracle/mmd_oracle.py in tests/test_oracle_cpu.py.  Never imported by the product package.
+Pinned to the reference-minted golden fixtures and to the live reference in tests/test_oracle_cpu.py
+(test_cpu_port_matches_reference_golden / _live).  bench.py uses it only when the reference sources are not staged under
+oracle/_ref (then `kind` is "port").  Never imported by the product package.
 """
 from __future__ import annotations
 

@@ -81,16 +81,36 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_t parity) {
+  printf("smmd: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+  __trap();
+}
+// The poll loop proper is try_wait + branch (+ optional sleep): the timer is read once per 1024 polls in an outer
+// loop.  (With the timeout test inside the poll loop the compiler read %globaltimer and evaluated the 64-bit compare
+// on EVERY poll -- 13 instructions per poll, and a few spinning warps took ~10% of their scheduler's issue slots from
+// the epilogue warps next to them.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > SMMD_WAIT_TIMEOUT_NS) {
-      printf("smmd: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (globaltimer_ns() - t0 > SMMD_WAIT_TIMEOUT_NS) mbar_timeout_trap(smem_u32(bar), parity);
+  }
+}
+// Same, for roles with slack (a TMA producer waiting for a free stage, an issuer waiting for a drained accumulator,
+// an epilogue warp that has run ahead of its tile): sleeps `ns` between polls so that the wait costs no issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i) {
+      __nanosleep(ns);
+      if (mbar_try_wait(bar, parity)) return;
     }
+    if (globaltimer_ns() - t0 > SMMD_WAIT_TIMEOUT_NS) mbar_timeout_trap(smem_u32(bar), parity);
   }
 }
 
@@ -359,24 +379,25 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait with acquire at cluster scope (pairs with mbar_arrive_cluster from the peer CTA)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kTryWaitHintNs)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint64_t t0 = 0;
-  uint32_t spins = 0;
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(kTryWaitHintNs)
-        : "memory");
-    if (ok) return;
-    if (spins == 0) t0 = globaltimer_ns();
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > SMMD_WAIT_TIMEOUT_NS) {
-      printf("smmd: cluster mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait_cluster(bar, parity)) return;
+    if (globaltimer_ns() - t0 > SMMD_WAIT_TIMEOUT_NS) mbar_timeout_trap(smem_u32(bar), parity);
   }
 }
 

@@ -43,6 +43,7 @@ __device__ __forceinline__ float2 rcp_2(float2 x) { return make_float2(fast_rcp(
 struct MathRbf1 {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   float c1, w, g;
   __device__ explicit MathRbf1(const KernelFn& f, const float*) : c1(f.p1[0]), w(f.w[0]), g(-f.p0[0] * f.w[0]) {}
   __device__ __forceinline__ float k_scale() const { return w; }
@@ -59,6 +60,7 @@ template <int NP>
 struct MathRbfLadder {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   float c1, w[NP], g[NP];
   __device__ explicit MathRbfLadder(const KernelFn& f, const float*) : c1(f.p1[0]) {
 #pragma unroll
@@ -119,6 +121,36 @@ __device__ __forceinline__ void eval_pairs_pt(const Math& m, const float2 (&S)[N
 struct MathRq3Default {
   static constexpr bool kHasEvalN = true;
   static constexpr bool kHasPt = true;
+#ifdef SMMD_SYM_NOSPLIT
+  static constexpr bool kHasSplit = false;
+#else
+  static constexpr bool kHasSplit = true;
+#endif
+  // Split form for software pipelining: `front` runs the affine steps and all three MUFU ops of a pair, `back` the
+  // FMA-only tail.  The caller issues front(g + 1) next to back(g), so a warp's instruction stream mixes MUFU and
+  // FMA work at every point instead of alternating between a MUFU burst and a long FMA tail.
+  struct Pair {
+    float2 b1, b2, b3, p23, R, e1;
+  };
+  __device__ __forceinline__ void front(float2 S, float2 pt, Pair& s) const {
+    s.b1 = fma2(S, bc2(-10.f), pt);
+    s.b2 = fma2(s.b1, bc2(.1f), bc2(.9f));
+    s.b3 = fma2(s.b1, bc2(.01f), bc2(.99f));
+    const float2 L = lg2_2(s.b1);
+    s.p23 = mul2(s.b2, s.b3);
+    s.R = rcp_2(mul2(s.b1, s.p23));
+    s.e1 = ex2_2(mul2(L, bc2(-0.1f)));
+  }
+  __device__ __forceinline__ void back(const Pair& s, float2& k, float2& kd) const {
+    const float2 r1 = mul2(s.R, s.p23);
+    const float2 t = mul2(s.R, s.b1);
+    const float2 r2 = mul2(t, s.b3);
+    const float2 r3 = mul2(t, s.b2);
+    const float2 q2 = mul2(r3, r3), q4 = mul2(q2, q2), q8 = mul2(q4, q4);
+    const float2 e3 = mul2(q8, q2);
+    k = add2(add2(s.e1, r2), e3);
+    kd = fma2(e3, r3, fma2(r2, r2, mul2(s.e1, r1)));
+  }
   // b1 = 1 + 5 D = (1 + 5 |z_i|^2) + 5 |z_j|^2 - 10 S;  b2 = 1 + D/2 = .1 b1 + .9;  b3 = 1 + D/20 = .01 b1 + .99
   __device__ __forceinline__ float row_term(float ni) const { return fmaf(5.f, ni, 1.f); }
   __device__ __forceinline__ float2 pair_term(float2 rt, float2 nj) const { return fma2(nj, bc2(5.f), rt); }
@@ -227,6 +259,7 @@ template <int FAM>
 struct MathGeneric {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   const float* sp;
   int np;
   __device__ explicit MathGeneric(const KernelFn& f, const float* smem_params) : sp(smem_params), np(f.np) {}
@@ -257,6 +290,7 @@ struct MathGeneric {
 struct MathDistance {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   __device__ explicit MathDistance(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return -1.f; }
   __device__ __forceinline__ float kd_scale() const { return -0.5f; }
@@ -270,6 +304,7 @@ struct MathDistance {
 struct MathNull {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   __device__ explicit MathNull(const KernelFn&, const float*) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
   __device__ __forceinline__ float kd_scale() const { return 1.f; }
@@ -282,6 +317,7 @@ struct MathNull {
 struct MathPoly3 {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   float gamma, c0;
   __device__ explicit MathPoly3(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0) {}
   __device__ __forceinline__ float k_scale() const { return 1.f; }
@@ -296,6 +332,7 @@ struct MathPoly3 {
 struct MathPolyN {
   static constexpr bool kHasEvalN = false;
   static constexpr bool kHasPt = false;
+  static constexpr bool kHasSplit = false;
   float gamma, c0;
   int degree;
   __device__ explicit MathPolyN(const KernelFn& f, const float*) : gamma(f.poly_gamma), c0(f.poly_coef0), degree(f.degree) {}

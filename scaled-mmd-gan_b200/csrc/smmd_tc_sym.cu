@@ -44,7 +44,7 @@ constexpr int kFinRowsPerCta = 8 * kFinRowsPerWarp;
 // compactly in that order and dealt round-robin to the persistent CTAs.
 struct SymGeo {
   int NB, CT;          // row blocks of 128, column tiles of 256 (the last tile may be half)
-  int RB, CW, PL, PPW; // band (row blocks), window (tiles), piece length (tiles), pieces per window
+  int RB, CW, PL, PLs; // band (row blocks), window (tiles), piece length (tiles, a power of two) and its log2
   int nbands, nwin;
 };
 
@@ -71,10 +71,10 @@ struct UnitWalk {
       if (b >= g.nbands) return false;
       const int lo = wst > (rb >> 1) ? wst : (rb >> 1);   // first tile of row block rb inside this window
       const int nt = wend - lo;
-      const int np = nt > 0 ? (nt + g.PL - 1) / g.PL : 0;
+      const int np = nt > 0 ? (nt + g.PL - 1) >> g.PLs : 0;
       if (idx < base + np) {
         const int k = (int)(idx - base);
-        ct0 = lo + k * g.PL;
+        ct0 = lo + (k << g.PLs);
         ct1 = ct0 + g.PL < wend ? ct0 + g.PL : wend;
         rb_out = rb;
         return true;
@@ -166,6 +166,75 @@ __device__ __forceinline__ void sym_chunk16(const Math& math, const uint32_t (&v
   }
 }
 
+// 64 columns of one row for a variant with a front/back split, software-pipelined over groups of 2 column pairs:
+// front(g + 1) (affine steps + MUFU) is issued next to back(g) (FMA tail), see MathRq3Default::Pair.  TMEM loads are
+// double-buffered per 16-column chunk; W goes to the warp's staging block.  `wait_prev` = the previous tile's TMA
+// store may still be reading the staging block.
+template <class Math, bool SPECIAL>
+__device__ __forceinline__ void sym_quarter_split(const Math& math, uint32_t tbase, uint32_t nj_smem, float rt, float2 cw,
+                                                  int col0, int lim, int gi, uint32_t srow, uint32_t sw, bool wait_prev,
+                                                  int lane, uint64_t* acc_empty_bar, float2& tsum, float2& rsum) {
+  using Pair = typename Math::Pair;
+  const float2 rt2 = bc2(rt);
+  uint32_t v[2][16];
+  Pair st[2][2];
+  auto run_front = [&](const uint32_t (&vv)[16], int g, int ch, Pair (&dst)[2]) {   // group g (0..3) of chunk ch
+    const float4 nn = ld_shared_f4(nj_smem + (ch * 16 + g * 4) * 4);
+    math.front(make_float2(__uint_as_float(vv[4 * g]), __uint_as_float(vv[4 * g + 1])),
+               math.pair_term(rt2, make_float2(nn.x, nn.y)), dst[0]);
+    math.front(make_float2(__uint_as_float(vv[4 * g + 2]), __uint_as_float(vv[4 * g + 3])),
+               math.pair_term(rt2, make_float2(nn.z, nn.w)), dst[1]);
+  };
+  tmem_ld_x16(tbase, v[0]);
+  tmem_ld_wait();
+  tmem_ld_x16(tbase + 16, v[1]);
+  run_front(v[0], 0, 0, st[0]);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t wpk[8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int cur = (ch * 4 + g) & 1;
+      // front of the next group (next chunk's first group needs that chunk's TMEM load to have landed)
+      if (g < 3) {
+        run_front(v[ch & 1], g + 1, ch, st[cur ^ 1]);
+      } else if (ch < 3) {
+        tmem_ld_wait();
+        run_front(v[(ch + 1) & 1], 0, ch + 1, st[cur ^ 1]);
+      }
+      float2 k[2], kd[2];
+      math.back(st[cur][0], k[0], kd[0]);
+      math.back(st[cur][1], k[1], kd[1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (SPECIAL) {
+          const int col = col0 + ch * 16 + g * 4 + 2 * e;
+          const bool ok0 = (col < lim) && (col != gi), ok1 = (col + 1 < lim) && (col + 1 != gi);
+          k[e] = make_float2(ok0 ? k[e].x : 0.f, ok1 ? k[e].y : 0.f);
+          kd[e] = make_float2(ok0 ? kd[e].x : 0.f, ok1 ? kd[e].y : 0.f);
+        }
+        tsum = add2(tsum, k[e]);
+        const float2 ww = mul2(kd[e], cw);
+        rsum = add2(rsum, ww);
+        wpk[2 * g + e] = pack_bf16x2(ww.x, ww.y);
+      }
+    }
+    // chunk ch is consumed: its TMEM buffer takes chunk ch + 2 (the load of chunk ch + 1 was waited for above)
+    if (ch + 2 < 4) tmem_ld_x16(tbase + (ch + 2) * 16, v[ch & 1]);
+    if (ch == 0 && wait_prev) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+    st_shared_v4(srow + (((2 * ch) ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
+    st_shared_v4(srow + (((2 * ch + 1) ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
+    if (ch == 2) {   // the last TMEM load (chunk 3) was waited for at g == 3 of this chunk: release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_bar);
+    }
+  }
+}
+
 template <class Math>
 __global__ void __launch_bounds__(kSyThreads, 1)
 tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
@@ -222,7 +291,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
     for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
       for (int ct = ct0; ct < ct1; ++ct, ++tcnt) {
         for (int p = 0; p < a.nkp; ++p) {
-          mbar_wait(&empty[st], ph ^ 1);
+          mbar_wait_sleep(&empty[st], ph ^ 1, 128);
           if (p == 0 && elect_one()) {
             const uint32_t nb = tcnt & (kSyNormBufs - 1);
             mbar_arrive_expect_tx(&nfull[nb], BNW * 4);
@@ -253,7 +322,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
     int rb, ct0, ct1;
     for (int64_t u = blockIdx.x; uw.locate(geo, u, rb, ct0, ct1); u += gridDim.x) {
       for (int ct = ct0; ct < ct1; ++ct) {
-        mbar_wait(&acc_empty[ab], aph ^ 1);
+        mbar_wait_sleep(&acc_empty[ab], aph ^ 1, 64);
         tc_fence_after();
         const uint32_t dad = tmem + ab * BNW;
         for (int kk = 0; kk < a.nkp; ++kk) {
@@ -314,7 +383,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         const int c0 = ct * BNW + part * 64;          // first column of this warp's quarter
         const int J = c0 >> 7;                        // its 128-column block
         const bool active = (J >= rb) && (c0 < Mp);
-        mbar_wait(&acc_full[grp], (tc >> 1) & 1);
+        mbar_wait_sleep(&acc_full[grp], (tc >> 1) & 1, 64);
         tc_fence_after();
         auto release_acc = [&]() {   // the whole warp has finished its tcgen05.ld of this tile: one elected arrive
           tc_fence_before();
@@ -338,33 +407,42 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         float2 tsum = make_float2(0.f, 0.f);
         const uint32_t srow = stg + lane * 128;
         const uint32_t sw = (uint32_t)(lane & 7);
-        auto do_chunk = [&](const uint32_t (&v)[16], int h) {
-          uint32_t wpk[8];
-          if (!special) sym_chunk16<Math, false>(math, v, nj + h * 64, rt, cw, 0, 0, 0, tsum, rsum, wpk);
-          else sym_chunk16<Math, true>(math, v, nj + h * 64, rt, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
-          if (h == 0 && stored) {   // the previous tile's TMA store must have read the block before it is overwritten
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-          }
-          st_shared_v4(srow + (((2 * h) ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
-          st_shared_v4(srow + (((2 * h + 1) ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
-        };
-        {
-          uint32_t va[16], vb[16];
+        if constexpr (Math::kHasSplit) {
           const uint32_t tbase = tmem + grp * BNW + part * 64 + lane_base;
-          tmem_ld_x16(tbase, va);
-          tmem_ld_wait();
-          tmem_ld_x16(tbase + 16, vb);
-          do_chunk(va, 0);
-          tmem_ld_wait();
-          tmem_ld_x16(tbase + 32, va);
-          do_chunk(vb, 1);
-          tmem_ld_wait();
-          tmem_ld_x16(tbase + 48, vb);
-          do_chunk(va, 2);
-          tmem_ld_wait();
-          release_acc();
-          do_chunk(vb, 3);
+          if (!special)
+            sym_quarter_split<Math, false>(math, tbase, nj, rt, cw, 0, 0, 0, srow, sw, stored, lane, &acc_empty[grp], tsum, rsum);
+          else
+            sym_quarter_split<Math, true>(math, tbase, nj, rt, cw, c0, lim, gi, srow, sw, stored, lane, &acc_empty[grp], tsum,
+                                          rsum);
+        } else {
+        auto do_chunk = [&](const uint32_t (&v)[16], int h) {
+            uint32_t wpk[8];
+            if (!special) sym_chunk16<Math, false>(math, v, nj + h * 64, rt, cw, 0, 0, 0, tsum, rsum, wpk);
+            else sym_chunk16<Math, true>(math, v, nj + h * 64, rt, cw, c0 + h * 16, lim, gi, tsum, rsum, wpk);
+            if (h == 0 && stored) {   // the previous tile's TMA store must have read the block before it is overwritten
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
+            st_shared_v4(srow + (((2 * h) ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
+            st_shared_v4(srow + (((2 * h + 1) ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
+          };
+          {
+            uint32_t va[16], vb[16];
+            const uint32_t tbase = tmem + grp * BNW + part * 64 + lane_base;
+            tmem_ld_x16(tbase, va);
+            tmem_ld_wait();
+            tmem_ld_x16(tbase + 16, vb);
+            do_chunk(va, 0);
+            tmem_ld_wait();
+            tmem_ld_x16(tbase + 32, va);
+            do_chunk(vb, 1);
+            tmem_ld_wait();
+            tmem_ld_x16(tbase + 48, vb);
+            do_chunk(va, 2);
+            tmem_ld_wait();
+            release_acc();
+            do_chunk(vb, 3);
+          }
         }
         // a cross block is seen once (X rows, Y columns) and stands for K_XY and K_YX; a same-set block above the
         // diagonal stands for itself and its mirror
@@ -554,7 +632,7 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
     const int row = half * BM + q * 32 + lane;
     float* orow = a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
     if (k1 > k0) {
-      mbar_wait(acc_full, 0);
+      mbar_wait_sleep(acc_full, 0, 1000);   // the drain warps idle for the whole K loop: no polling next to the issuer
       tc_fence_after();
       const uint32_t base = tmem + half * 256 + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < nf; c += 16) {
@@ -751,10 +829,12 @@ SymPlan sym_plan(int64_t m, int64_t n, int64_t d) {
     g.RB = g.NB;
     g.CW = g.CT;
   }
-  g.PL = std::min(8, g.CW);
+  g.PL = 8;
   // small problems: shorter pieces, so that every CTA gets >= 16 units and the round-robin deal leaves < 6% tail
   while (g.PL > 1 && (int64_t)g.NB * g.CT / 2 / g.PL < 16 * sm_count()) g.PL >>= 1;
-  g.PPW = (g.CW + g.PL - 1) / g.PL;
+  g.PLs = 0;
+  while ((1 << g.PLs) < g.PL) ++g.PLs;
+  g.PL = 1 << g.PLs;
   g.nbands = (g.NB + g.RB - 1) / g.RB;
   g.nwin = (g.CT + g.CW - 1) / g.CW;
   p.grid1 = sm_count();

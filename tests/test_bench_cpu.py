@@ -15,14 +15,15 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-n", "1024", "--no-kid"])
     assert r.returncode == 0, r.stderr[-800:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["vs_baseline"] is None and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["config"]["same_config"] is False
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
 

@@ -146,3 +146,41 @@ def test_dense_block_ratio_helpers_match_oracle():
             # mmd2_and_ratio takes the explicit 4-tuple as well (mmd.py:224-225)
             tv, tr, tvar = mmd.mmd2_and_ratio((blocks[0], blocks[1], blocks[2], cd), biased=biased)
             assert float(tv) == float(gv2) and float(tr) == float(gr) and float(tvar) == float(gvar)
+
+
+def test_cpu_port_matches_reference_golden():
+    """oracle/cpu_port.py (the bench's fallback CPU arm when the reference sources are not staged) against the
+    reference-minted golden values and gradients of the mix_rq cases."""
+    from oracle import cpu_port
+
+    n = 0
+    for case in INDEX:
+        if case["kernel"] != "mix_rq":
+            continue
+        kw = dict(case["kwargs"])
+        X, Y = Z["X_" + case["shape"]].astype(np.float32), Z["Y_" + case["shape"]].astype(np.float32)
+        v, gx, gy = cpu_port.mix_rq_fwd_bwd(X, Y, biased=case["biased"], **kw)
+        key = case["key"]
+        assert abs(v - float(Z[key + "|v32"])) <= 1e-5 * max(1.0, abs(float(Z[key + "|v32"]))), key
+        gx64, gy64 = Z[key + "|gx64"], Z[key + "|gy64"]
+        # fp32 Gram-form distances (as in the reference): up to ~3e-5 of max|g| away from the fp64 gradients at d = 1
+        assert np.abs(gx - gx64).max() <= 1e-4 * np.abs(gx64).max() + 1e-12, key
+        assert np.abs(gy - gy64).max() <= 1e-4 * np.abs(gy64).max() + 1e-12, key
+        n += 1
+    assert n >= 5
+
+
+def test_cpu_port_matches_reference_live():
+    """Same, against the reference executed live (build container / staged oracle/_ref only)."""
+    from oracle import cpu_port, ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference sources not present")
+    rs = np.random.RandomState(7)
+    X = (rs.randn(300, 48) / 7).astype(np.float32)
+    Y = ((1.05 * rs.randn(280, 48) + 0.1) / 7).astype(np.float32)
+    v, gx, gy = cpu_port.mix_rq_fwd_bwd(X, Y)
+    rv, rgx, rgy = ref_loader.reference_loss_and_grads("mix_rq", X, Y, biased=False, dtype_name="float32")
+    assert abs(v - float(rv)) <= 1e-6 * max(1.0, abs(float(rv)))
+    assert np.abs(gx - rgx).max() <= 1e-5 * np.abs(rgx).max()
+    assert np.abs(gy - rgy).max() <= 1e-5 * np.abs(rgy).max()
