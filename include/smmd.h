@@ -224,6 +224,13 @@ SMMD_API int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void
 SMMD_API void smmd_profile_enable(int on);
 SMMD_API float smmd_profile_last_ms(void);
 
+/* Path-selection options (process-wide; set them before concurrent use).  Values are validated and clamped to what
+ * the kernels support.  Names: "sym" (0/1: symmetric two-pass path), "sym_min_rows" (stacked rows from which it is
+ * used; 0 = measured default), "sym_max_w_mb", "fused_pair", "fused_lockstep", "fused_ksplit", "wz_pair",
+ * "wz_min_d" (clamped to [0, 256]), "wz_panel_mb", "disable_small".  Tests use them to run a given code path on a
+ * small shape; there is no reference counterpart.  Returns SMMD_EINVAL for an unknown name. */
+SMMD_API int smmd_set_option(const char* name, long long value);
+
 /* Introspection for tests/bench: number of kernels the last call on this thread launched, and the
  * name of the code path it took ("simt_fp32", "tc_bf16_fused", "tc_bf16_fwd", ...). */
 SMMD_API int smmd_last_launch_count(void);

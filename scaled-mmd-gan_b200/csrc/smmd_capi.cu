@@ -197,6 +197,7 @@ const char* smmd_strerror(int status) {
 
 const char* smmd_last_cuda_error(void) { return g_cuda_err; }
 int smmd_device_supported(void) { return device_ok(); }
+int smmd_set_option(const char* name, long long value) { return tc_set_option(name, value) ? SMMD_OK : SMMD_EINVAL; }
 int smmd_last_launch_count(void) { return g_launches; }
 const char* smmd_last_path(void) { return g_path; }
 
@@ -232,8 +233,7 @@ static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double
     if (want_grad && p->d > kExactGradMaxD) return SMMD_EUNSUPPORTED;   // (dot kernel / explicit fp32 with d > 2048)
     const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
     char* ws = static_cast<char*>(workspace);
-    static const bool no_small = getenv("SMMD_DISABLE_SMALL") != nullptr;   // tests: force the general exact path
-    if (!no_small && small_mmd2_eligible(kf, g, src)) {   // latency-bound shapes: one launch (+ a 4-byte memset node)
+    if (!tc_small_kernel_disabled() && small_mmd2_eligible(kf, g, src)) {   // latency-bound shapes: one launch (+ a 4-byte memset node)
       g_path = "simt_fp32_small";
       prof_begin(s);
       SMMD_CUDA(launch_small_mmd2(kf, g, c, src, dX, dY, reinterpret_cast<double*>(ws + pl.off_stats),
@@ -430,12 +430,13 @@ static int validate_kid(const smmd_kid_problem* p) {
 static int kid_local(const smmd_kid_problem* p) { return p->n_local > 0 ? p->n_local : p->n_subsets - p->first_subset; }
 static int kid_precision(const smmd_kid_problem* p) {
   int prec = p->precision;
-  if (prec == SMMD_PREC_AUTO) prec = tc_kid_supported(p->d) ? SMMD_PREC_BF16X3 : SMMD_PREC_FP32;
+  if (prec == SMMD_PREC_AUTO) prec = tc_kid_supported(p->d, p->subset_size, kid_local(p)) ? SMMD_PREC_BF16X3 : SMMD_PREC_FP32;
   return prec;
 }
 
 size_t smmd_kid_workspace_bytes(const smmd_kid_problem* p) {
   if (validate_kid(p) != SMMD_OK) return 0;
+  if (kid_precision(p) != SMMD_PREC_FP32 && !tc_kid_supported(p->d, p->subset_size, kid_local(p))) return 0;   // refused
   if (kid_precision(p) == SMMD_PREC_FP32) return simt_plan(p->subset_size, p->subset_size, p->d, kid_local(p)).off_end;
   return tc_kid_workspace_bytes(p->subset_size, p->d, kid_local(p), kid_precision(p));
 }
@@ -465,7 +466,7 @@ static int kid_row_stats(const smmd_kid_problem* p, const void* codes_g, const v
     SMMD_CUDA(launch_simt_rows(kf, g, c, Z, norms, pl.dpitch, nloc, *stats_out, nullptr, nullptr, 1, s));
     prof_end(s);
   } else {
-    if (!tc_kid_supported(p->d)) return SMMD_EUNSUPPORTED;
+    if (!tc_kid_supported(p->d, m, nloc)) return SMMD_EUNSUPPORTED;
     int launches = 0;
     cudaError_t e = tc_kid_run(kf, codes_g, codes_r, p->dtype, p->ldg, p->ldr, p->d, idx_g, idx_r, p->first_subset, nloc,
                                m, prec, want_second_order, workspace, workspace_bytes, stats_out, s, &launches, &g_path);
@@ -485,6 +486,7 @@ int smmd_kid_subsets(const smmd_kid_problem* p, const void* codes_g, const void*
   if (!codes_g || !codes_r || !idx_g || !idx_r || !mmd2_out) return SMMD_EINVAL;
   if (p->ret_var && !var_out) return SMMD_EINVAL;
   if (!device_ok()) return SMMD_EARCH;
+  if (kid_precision(p) != SMMD_PREC_FP32 && !tc_kid_supported(p->d, p->subset_size, kid_local(p))) return SMMD_EUNSUPPORTED;
   const size_t need = smmd_kid_workspace_bytes(p);
   if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -521,6 +523,7 @@ int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void* Y, doub
   if (st != SMMD_OK) return st;
   if (!X || !Y || !sums_out) return SMMD_EINVAL;
   if (!device_ok()) return SMMD_EARCH;
+  if (kid_precision(p) != SMMD_PREC_FP32 && !tc_kid_supported(p->d, p->subset_size, kid_local(p))) return SMMD_EUNSUPPORTED;
   const size_t need = smmd_poly_sums_workspace_bytes(p);
   if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

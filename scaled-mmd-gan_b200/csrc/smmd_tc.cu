@@ -73,6 +73,22 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
       }
       *reinterpret_cast<uint4*>(zrow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
+  } else if (a.dtype == SMMD_BF16 && !a.split && !a.tanh_features && (ld % 8 == 0) && (a.d % 8 == 0) &&
+             ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+    // bf16 rows (the all-gathered block of the multi-GPU path): straight 16-byte copies + norms of the same values
+    const __nv_bfloat16* srow = reinterpret_cast<const __nv_bfloat16*>(base) + src * ld;
+    for (int64_t c = 8 * lane; c < a.dp; c += 256) {
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      if (valid && c < a.d) pk = *reinterpret_cast<const uint4*>(srow + c);
+      const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float f0 = __uint_as_float(w[e] << 16), f1 = __uint_as_float(w[e] & 0xffff0000u);
+        acc = fmaf(f0, f0, acc);
+        acc = fmaf(f1, f1, acc);
+      }
+      *reinterpret_cast<uint4*>(zrow + c) = pk;
+    }
   } else
   for (int64_t c = 2 * lane; c < a.dp; c += 64) {
     float v[2] = {0.f, 0.f};
@@ -154,6 +170,9 @@ using namespace tc;
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) interface
 // ------------------------------------------------------------------------------------------------
+bool tc_set_option(const char* name, long long value) { return name && tuning_set(tuning_mut(), name, (int64_t)value); }
+bool tc_small_kernel_disabled() { return tuning().disable_small != 0; }
+
 bool tc_mmd2_supported(int64_t d, int want_grad) { return d >= 1 && d <= 65536; }
 
 static bool use_two_pass(int64_t d) { return d > tuning().wz_min_d; }

@@ -12,8 +12,12 @@ cudaError_t tc_mmd2_run(const KernelFn& kf, const Geometry& g, const Coefs& c, c
                         double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
                         const char** path);
 
+// path-selection options (smmd_tc_common.cuh: Tuning); false = unknown name
+bool tc_set_option(const char* name, long long value);
+bool tc_small_kernel_disabled();
+
 // KID: batched Gram sums over subsets; returns per-row statistics [nsub][2m][RS_COUNT] inside the workspace
-bool tc_kid_supported(int64_t d);
+bool tc_kid_supported(int64_t d, int64_t msub, int64_t nsub);
 size_t tc_kid_workspace_bytes(int64_t msub, int64_t d, int64_t nsub, int precision);
 cudaError_t tc_kid_run(const KernelFn& kf, const void* G, const void* R, int dtype, int64_t ldg, int64_t ldr, int64_t d,
                        const int32_t* idx_g, const int32_t* idx_r, int64_t first, int64_t nsub, int64_t msub,

@@ -23,48 +23,75 @@ constexpr int kMaxSmem = 232448;   // 227 KB
 
 inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
-// Developer tuning knobs (environment overrides are read once; defaults are the measured best).
+// Path-selection options.  Defaults are the measured best; every value is validated (an out-of-range request is
+// clamped to what the kernels support -- never a silently corrupt configuration).  They can be changed per process
+// through smmd_set_option() (tests use it to force a path on small shapes) and, for convenience in the developer
+// harness, through SMMD_<NAME> environment variables read once at first use.  Knobs that produce meaningless results
+// (null epilogue math, single-pass timing) exist only in developer builds (-DSMMD_DEV_KNOBS, `make DEV=1`).
 struct Tuning {
-  int fused_ksplit;
-  int null_math;   // developer ablation (SMMD_DEBUG_NULLMATH=1): results are meaningless
-  int fused_pair;  // tile-pair variant of the fused kernel (default; SMMD_FUSED_PAIR=0 selects the single-tile kernel)
-  int fused_lockstep;   // whole row blocks per CTA for large Z (SMMD_FUSED_LOCKSTEP=0 disables)
-  int wz_min_d;    // features above which the fused backward switches to the two-pass (W panel + GEMM) path
-  int64_t wz_panel_bytes;   // byte budget of one W row panel
-  int wz_pair;      // pass 1 as CTA pairs with cta_group::2 UMMAs (SMMD_WZ_PAIR=0 disables)
-  int sym;          // symmetric two-pass path for whole problems (SMMD_SYM=0 disables)
-  int sym_only;     // developer timing knob (SMMD_SYM_ONLY=1|2: run only pass 1 / pass 2; results meaningless)
-  int64_t sym_min_rows;      // stacked rows from which the symmetric path is used
+  int fused_ksplit;     // epilogue column slices per tile of the single-tile fused kernel (1 or 2)
+  int null_math;        // DEV: results are meaningless
+  int fused_pair;       // tile-pair variant of the fused kernel (default 1)
+  int fused_lockstep;   // whole row blocks per CTA for large Z (default 1)
+  int wz_min_d;         // features above which the fused backward switches to the two-pass path; clamped to [0, 256]
+                        // (the fused kernel keeps O[128 x d] in tensor memory: d <= 256)
+  int64_t wz_panel_bytes;   // byte budget of one W row panel (>= 1 MB)
+  int wz_pair;          // pass 1 as CTA pairs with cta_group::2 UMMAs (default 1)
+  int sym;              // symmetric two-pass path for whole problems (default 1)
+  int sym_only;         // DEV timing knob: 1 = pass 1 only, 2 = pass 2 only; results are meaningless
+  int64_t sym_min_rows;      // stacked rows from which the symmetric path is used (0 = the measured per-d default)
   int64_t sym_max_w_bytes;   // largest W (Mp x Mp bf16) the symmetric path may place in the workspace
+  int disable_small;    // exact path: skip the one-launch small-problem kernel (tests: force the general kernels)
 };
-inline const Tuning& tuning() {
+inline int64_t clamp_i64(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// returns false for an unknown name
+inline bool tuning_set(Tuning& v, const char* name, int64_t x) {
+  if (!strcmp(name, "fused_ksplit")) v.fused_ksplit = x == 1 ? 1 : 2;
+  else if (!strcmp(name, "fused_pair")) v.fused_pair = x != 0;
+  else if (!strcmp(name, "fused_lockstep")) v.fused_lockstep = x != 0;
+  else if (!strcmp(name, "wz_min_d")) v.wz_min_d = (int)clamp_i64(x, 0, 256);
+  else if (!strcmp(name, "wz_panel_mb")) v.wz_panel_bytes = clamp_i64(x, 1, (int64_t)1 << 20) << 20;
+  else if (!strcmp(name, "wz_pair")) v.wz_pair = x != 0;
+  else if (!strcmp(name, "sym")) v.sym = x != 0;
+  else if (!strcmp(name, "sym_min_rows")) v.sym_min_rows = clamp_i64(x, 0, (int64_t)1 << 40);
+  else if (!strcmp(name, "sym_max_w_mb")) v.sym_max_w_bytes = clamp_i64(x, 0, (int64_t)1 << 24) << 20;
+  else if (!strcmp(name, "disable_small")) v.disable_small = x != 0;
+#ifdef SMMD_DEV_KNOBS
+  else if (!strcmp(name, "debug_nullmath")) v.null_math = x != 0;
+  else if (!strcmp(name, "sym_only")) v.sym_only = (int)clamp_i64(x, 0, 2);
+#endif
+  else return false;
+  return true;
+}
+inline Tuning& tuning_mut() {
   static Tuning t = [] {
     Tuning v;
     v.fused_ksplit = 2;
-    if (const char* e = getenv("SMMD_FUSED_KSPLIT")) v.fused_ksplit = atoi(e) == 1 ? 1 : 2;
-    v.null_math = getenv("SMMD_DEBUG_NULLMATH") ? 1 : 0;
+    v.null_math = 0;
     v.fused_pair = 1;
-    if (const char* e = getenv("SMMD_FUSED_PAIR")) v.fused_pair = atoi(e) != 0;
     v.fused_lockstep = 1;
-    if (const char* e = getenv("SMMD_FUSED_LOCKSTEP")) v.fused_lockstep = atoi(e) != 0;
     v.wz_min_d = 256;
-    if (const char* e = getenv("SMMD_WZ_MIN_D")) v.wz_min_d = atoi(e);
     v.wz_pair = 1;
-    if (const char* e = getenv("SMMD_WZ_PAIR")) v.wz_pair = atoi(e) != 0;
     v.wz_panel_bytes = (int64_t)6 << 30;
-    if (const char* e = getenv("SMMD_WZ_PANEL_MB")) v.wz_panel_bytes = (int64_t)atoll(e) << 20;
     v.sym = 1;
-    if (const char* e = getenv("SMMD_SYM")) v.sym = atoi(e) != 0;
     v.sym_only = 0;
-    if (const char* e = getenv("SMMD_SYM_ONLY")) v.sym_only = atoi(e);
-    v.sym_min_rows = 2048;
-    if (const char* e = getenv("SMMD_SYM_MIN_ROWS")) v.sym_min_rows = atoll(e);
+    v.sym_min_rows = 0;
     v.sym_max_w_bytes = (int64_t)48 << 30;
-    if (const char* e = getenv("SMMD_SYM_MAX_W_MB")) v.sym_max_w_bytes = (int64_t)atoll(e) << 20;
+    v.disable_small = 0;
+    static const char* const names[] = {"fused_ksplit", "fused_pair", "fused_lockstep", "wz_min_d", "wz_panel_mb", "wz_pair",
+                                        "sym", "sym_min_rows", "sym_max_w_mb", "disable_small", "debug_nullmath", "sym_only"};
+    for (const char* nm : names) {
+      char env[64] = "SMMD_";
+      size_t k = 5;
+      for (const char* c = nm; *c && k + 1 < sizeof(env); ++c) env[k++] = (char)(*c >= 'a' && *c <= 'z' ? *c - 32 : *c);
+      env[k] = 0;
+      if (const char* e = getenv(env)) tuning_set(v, nm, atoll(e));
+    }
     return v;
   }();
   return t;
 }
+inline const Tuning& tuning() { return tuning_mut(); }
 
 inline int sm_count() {
   static int n = 0;

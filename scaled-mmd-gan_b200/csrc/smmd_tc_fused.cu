@@ -133,14 +133,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_consta
       for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
         const int TU = (int)std::min<int64_t>(a.T - t0, left);
         const int rb = rb_of(rbi);
-        mbar_wait(zi_empty, (unit & 1) ^ 1);
+        mbar_wait_sleep(zi_empty, (unit & 1) ^ 1, 128);
         if (elect_one()) {
           mbar_arrive_expect_tx(zi_full, ZI_BYTES);
           for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
         }
         __syncwarp();
         for (int t = t0; t < t0 + TU; ++t) {
-          mbar_wait(&zj_empty[st], ph ^ 1);
+          mbar_wait_sleep(&zj_empty[st], ph ^ 1, 128);
           if (elect_one()) {
             mbar_arrive_expect_tx(&zj_full[st], ZJ_BYTES);
             uint8_t* dst = sZj + st * ZJ_BYTES;
@@ -445,14 +445,14 @@ tc_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_c
     for (int64_t left = pos1 - pos0; left > 0; ++rbi, t0 = 0, ++unit) {
       const int TU = (int)std::min<int64_t>(a.T - t0, left);
       const int rb = rb_of(rbi);
-      mbar_wait(zi_empty, (unit & 1) ^ 1);
+      mbar_wait_sleep(zi_empty, (unit & 1) ^ 1, 128);
       if (elect_one()) {
         mbar_arrive_expect_tx(zi_full, ZI_BYTES);
         for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, rb * BM);
       }
       __syncwarp();
       for (int t = t0; t < t0 + TU; ++t) {
-        mbar_wait(&zj_empty[st], ph ^ 1);
+        mbar_wait_sleep(&zj_empty[st], ph ^ 1, 128);
         if (elect_one()) {
           mbar_arrive_expect_tx(&zj_full[st], NPANEL * kZjRowBytes);
           uint8_t* dst = sZj + st * kZjRowBytes;

@@ -173,7 +173,7 @@ tc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const int64_t lim = colX ? a.m : a.mp + a.n;
       const int64_t pair_col = rowX ? a.mp + gi : -1;  // the (x_i, y_i) element
       const bool special = (c0 + BNS > lim) || (ct == rb) || (rowX && ct == rb + (int)(a.mp / BNS));
-      mbar_wait(&acc_full[grp], (uint32_t)((tc >> 1) & 1));
+      mbar_wait_sleep(&acc_full[grp], (uint32_t)((tc >> 1) & 1), 64);
       tc_fence_after();
       const float* nj = a.norms + b * Mp + c0;
       float2 tsum = make_float2(0.f, 0.f), tsq = make_float2(0.f, 0.f);
@@ -417,7 +417,7 @@ tc_macro_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const int64_t pair_col = rowX ? a.mp + gi : -1;
       const bool special = (c0 + BMAC > lim) || (I == J) || (rowX && J == I + a.Rx);
       const float wgt = (a.sym && same && J > I) ? 2.f : 1.f;
-      mbar_wait(acc_full, fph);
+      mbar_wait_sleep(acc_full, fph, 200);
       fph ^= 1;
       tc_fence_after();
       const float* nj = a.norms + b * Mp + c0;
@@ -636,7 +636,14 @@ cudaError_t tc_run_value_only(const KernelFn& kf, TcVariant variant, const Geome
 
 using namespace tc;
 
-bool tc_kid_supported(int64_t d) { return d >= 1 && d <= 65536; }
+// Shapes the macro-tile kernel covers: the tile index of a subset is decoded with R <= 64 row blocks of 256 (stacked
+// rows 2 * round_up(msub, 256) <= 16384, i.e. msub <= 8192) and the stacked operand matrix is addressed with 32-bit TMA
+// row coordinates.  Anything else runs on the exact path (AUTO) or is refused before a launch (explicit bf16 / bf16x3).
+bool tc_kid_supported(int64_t d, int64_t msub, int64_t nsub) {
+  if (!(d >= 1 && d <= 65536) || msub < 1 || nsub < 1) return false;
+  const int64_t Mp = 2 * round_up(msub, 256);
+  return Mp / 256 <= 64 && nsub * Mp < ((int64_t)1 << 31);
+}
 
 // KID runs on the 256 x 256 macro-tile kernel (polynomial kernels only reach this entry point)
 size_t tc_kid_workspace_bytes(int64_t msub, int64_t d, int64_t nsub, int precision) {

@@ -910,7 +910,10 @@ bool tc_sym_eligible(const Geometry& g) {
   if (!tuning().sym) return false;
   if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return false;   // whole problem on this GPU
   const int64_t Mp = round_up(g.m, BM) + round_up(g.n, BM);
-  if (Mp < tuning().sym_min_rows) return false;
+  // measured cross-over against the one-sweep fused kernel (d <= 256: its four launches win below N ~ 24K per side) and
+  // against the row-stacked two-pass path (d > 256: the symmetric path wins from N = 4096 per side on)
+  const int64_t min_rows = tuning().sym_min_rows > 0 ? tuning().sym_min_rows : (g.d <= 256 ? 49152 : 8192);
+  if (Mp < min_rows) return false;
   return Mp * Mp * 2 <= tuning().sym_max_w_bytes;
 }
 

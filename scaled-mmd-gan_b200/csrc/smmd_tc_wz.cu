@@ -138,7 +138,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const int ct = w * a.Wc + t;
       const int32_t arow = rb_of(a.rbi0 + rbl_ld(rbl)) * BM, brow = ct < a.CT ? col0_of(ct) : 0;
       for (int p = 0; p < (ct < a.CT ? a.nkp : 0); ++p) {
-        mbar_wait(&empty[st], ph ^ 1);
+        mbar_wait_sleep(&empty[st], ph ^ 1, 128);
         if (elect_one()) {
           uint8_t* sa = smem + st * kWgStageBytes;
           if (PAIR) {   // own Z_i panel + own half of the Z_j tile; the bytes of both CTAs count on the leader's barrier
@@ -184,7 +184,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const long long wg_t0 = clock64();
 #endif
       if (PAIR) mbar_wait_cluster(&acc_empty[ab], aph ^ 1);   // the peer's epilogue arrives remotely
-      else mbar_wait(&acc_empty[ab], aph ^ 1);
+      else mbar_wait_sleep(&acc_empty[ab], aph ^ 1, 64);
 #ifdef SMMD_PIPE_TIMING
       wg_acc += clock64() - wg_t0;
       ++wg_tiles;
@@ -268,7 +268,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int cend = colX ? mp : (int)(a.mp + a.np);               // end of this column set
         const int nch = (cend - c0 < BNW ? cend - c0 : BNW) / 16;      // chunks that belong to this tile
         const bool special = (c0 + BNW > lim) || (rb * BM >= c0 && rb * BM < c0 + BNW);
-        mbar_wait(&acc_full[grp], (tc >> 1) & 1);
+        mbar_wait_sleep(&acc_full[grp], (tc >> 1) & 1, 64);
         tc_fence_after();
         const float* nj = a.norms + c0;
         float2 tsum = make_float2(0.f, 0.f);
@@ -433,7 +433,7 @@ tc_wz_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     const int row = half * BM + q * 32 + lane;
     float* orow = a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
     if (k1 > k0) {
-      mbar_wait(acc_full, 0);
+      mbar_wait_sleep(acc_full, 0, 1000);
       tc_fence_after();
       const uint32_t base = tmem + half * 256 + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < nf; c += 16) {

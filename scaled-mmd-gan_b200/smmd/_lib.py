@@ -27,7 +27,7 @@ EXPORTS = [
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_poly_sums_workspace_bytes", "smmd_poly_sums",
-    "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms",
+    "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms", "smmd_set_option",
 ]
 
 
@@ -108,6 +108,8 @@ def load():
     lib.smmd_poly_sums_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
     lib.smmd_poly_sums.restype = C.c_int
     lib.smmd_poly_sums.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_set_option.restype = C.c_int
+    lib.smmd_set_option.argtypes = [C.c_char_p, C.c_longlong]
     _lib = lib
     return lib
 
@@ -128,3 +130,8 @@ def last_path():
 
 def last_launch_count():
     return int(load().smmd_last_launch_count())
+
+
+def set_option(name, value):
+    """Path-selection option of the library (include/smmd.h: smmd_set_option), e.g. set_option("sym_min_rows", 1)."""
+    check(load().smmd_set_option(name.encode(), int(value)), "smmd_set_option(%s)" % name)

@@ -88,11 +88,13 @@ def sharded_mmd2_raw(spec, Xl, Yl, biased=False, precision=None, group=None, loc
     ml, nl, d = Xl.shape[0], Yl.shape[0], Xl.shape[1]
     m, n = ml * world, nl * world
     gdtype = torch.bfloat16 if (Xl.is_cuda and _tc_eligible(spec, m, n, d, precision)) else torch.float32
-    local = torch.cat([Xl.detach(), Yl.detach()]).to(gdtype).contiguous()
-    gathered = torch.empty((world * (ml + nl), d), dtype=gdtype, device=local.device)
+    # this rank's block goes straight into its slot of the gather buffer (one converting copy per set, no cat + cast)
+    gathered = torch.empty((world * (ml + nl), d), dtype=gdtype, device=Xl.device)
+    local = gathered[rank * (ml + nl):(rank + 1) * (ml + nl)]
+    local[:ml].copy_(Xl.detach())
+    local[ml:].copy_(Yl.detach())
     dist.all_gather_into_tensor(gathered, local, group=group)
-    scalars, dX, dY = (local_compute or _default_local_compute)(spec, gathered, Xl, Yl, m, n, biased, precision, rank, world)
-    sums = scalars.clone()
+    sums, dX, dY = (local_compute or _default_local_compute)(spec, gathered, Xl, Yl, m, n, biased, precision, rank, world)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)   # 16 doubles; entries 1..7 are additive
     value = (combine or _default_combine)(spec, sums, m, n, d, biased, gdtype)
     return value, dX, dY, sums
@@ -101,9 +103,6 @@ def sharded_mmd2_raw(spec, Xl, Yl, biased=False, precision=None, group=None, loc
 class _ShardedMMD2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X_local, Y_local, spec, biased, precision, group, local_compute, combine):
-        world = dist.get_world_size(group)
-        sizes = torch.tensor([X_local.shape[0], Y_local.shape[0]], device=X_local.device)
-        del sizes, world  # every rank must contribute the same number of rows (checked by the collective's shapes)
         value, dX, dY, sums = sharded_mmd2_raw(spec, X_local, Y_local, biased, precision, group, local_compute, combine)
         ctx.save_for_backward(dX, dY)
         ctx.in_dtypes = (X_local.dtype, Y_local.dtype)
@@ -117,15 +116,36 @@ class _ShardedMMD2(torch.autograd.Function):
         return (g * dX).to(ctx.in_dtypes[0]), (g * dY).to(ctx.in_dtypes[1]), None, None, None, None, None, None
 
 
-def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=None, _combine=None):
+def check_equal_shards(ml, nl, device, group=None):
+    """All ranks must contribute equally sized blocks; raises ValueError on every rank otherwise."""
+    t = torch.tensor([ml, nl, -ml, -nl], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    mx_m, mx_n, mn_m, mn_n = int(t[0]), int(t[1]), -int(t[2]), -int(t[3])
+    if mx_m != mn_m or mx_n != mn_n:
+        raise ValueError("sharded_mmd2: ranks hold different numbers of rows (fake %d..%d, real %d..%d)"
+                         % (mn_m, mx_m, mn_n, mx_n))
+
+
+def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=None, _combine=None, check_sizes=False):
     """Global-batch ``mmd2(kernel(G, images))`` where ``K = mmd._<name>_kernel(G_local, images_local)`` holds
     this rank's rows.  Returns the same scalar on every rank; backward yields gradients for the local rows.
+
+    Requirements / conventions:
+      * every rank passes the same number of fake rows and the same number of real rows (the gather buffer is
+        `world` equal blocks; set ``check_sizes=True`` to all_reduce (min, max) the local counts once and raise on a
+        mismatch instead of letting the collective hang or mis-size the problem);
+      * the backward returns d(GLOBAL loss)/d(local rows) on every rank -- the gradient of the one scalar all ranks
+        share, not of a per-rank average.  When the critic's parameter gradients are then averaged by DDP (all_reduce
+        / world), the result is (1 / world) x the true parameter gradient: scale the loss by `world` or use a SUM
+        reduction of parameter gradients to reproduce single-device training.
 
     ``_local_compute`` / ``_combine`` are injection points for the CPU tests of the host-side logic."""
     from .mmd import KernelHandle
 
     if not isinstance(K, KernelHandle):
         raise TypeError("sharded_mmd2 expects the handle returned by a _<name>_kernel(X_local, Y_local) call")
+    if check_sizes:
+        check_equal_shards(K.X.shape[0], K.Y.shape[0], K.X.device, group)
     return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group, _local_compute, _combine)
 
 

@@ -85,3 +85,31 @@ def test_kid_validation():
     assert lib.smmd_kid_workspace_bytes(C.byref(p)) > 0
     p.subset_size = 101  # replace=False cannot draw more rows than exist
     assert lib.smmd_kid_workspace_bytes(C.byref(p)) == 0
+
+
+def test_kid_shapes_outside_the_tensor_core_kernel_are_settled_before_any_launch():
+    """subset_size > 8192 (more than 64 row blocks of 256 per stacked subset) is not covered by the macro-tile kernel:
+    AUTO resolves to the exact path, an explicit bf16 / bf16x3 request is refused (workspace query 0, call returns
+    SMMD_EUNSUPPORTED on a B200) -- nothing is queued first."""
+    lib = _lib.load()
+    p = _lib.KidProblem()
+    p.n_g, p.n_r, p.d, p.ldg, p.ldr = 20000, 20000, 64, 64, 64
+    p.n_subsets, p.subset_size, p.degree, p.coef0 = 2, 9000, 3, 1.0
+    p.precision = _lib.PREC_AUTO
+    auto_bytes = lib.smmd_kid_workspace_bytes(C.byref(p))
+    p.precision = _lib.PREC_FP32
+    assert auto_bytes > 0 and auto_bytes == lib.smmd_kid_workspace_bytes(C.byref(p))
+    for prec in (_lib.PREC_BF16, _lib.PREC_BF16X3):
+        p.precision = prec
+        assert lib.smmd_kid_workspace_bytes(C.byref(p)) == 0
+    p.subset_size, p.precision = 8192, _lib.PREC_BF16X3
+    assert lib.smmd_kid_workspace_bytes(C.byref(p)) > 0
+
+
+def test_set_option_validates_names_and_clamps():
+    lib = _lib.load()
+    assert lib.smmd_set_option(b"no_such_option", 1) == -1
+    assert lib.smmd_set_option(b"wz_min_d", 100000) == 0     # clamped to 256: the fused kernel cannot hold a wider O
+    assert lib.smmd_set_option(b"wz_min_d", 256) == 0
+    assert lib.smmd_set_option(b"sym_min_rows", 0) == 0
+    assert lib.smmd_set_option(b"debug_nullmath", 1) == -1   # ablation knobs exist only in developer builds

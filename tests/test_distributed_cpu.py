@@ -140,3 +140,37 @@ def test_shard_arithmetic_matches_c_abi_contract():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert sum(kid_shard(total, r, world)[1] for r in range(world)) == total
+
+
+def _mismatch_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "scaled-mmd-gan_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smmd.distributed import check_equal_shards
+
+        try:
+            check_equal_shards(12 + rank, 12, torch.device("cpu"))    # rank 1 holds one more fake row
+            q.put((rank, "no error"))
+        except ValueError as e:
+            q.put((rank, str(e)))
+        check_equal_shards(12, 9, torch.device("cpu"))                # equal on every rank: passes
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unequal_shards_raise_on_every_rank():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_mismatch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all("different numbers of rows" in msg for _, msg in res), res

@@ -1,0 +1,169 @@
+"""GPU parity tests: (1) the symmetric two-pass path (csrc/smmd_tc_sym.cu) forced on small and ragged shapes,
+(2) the bf16 tensor-core loss at BASELINE configs[3] sizes (N = 4096 / 8192, d = 256 / 512 / 1024) and (3) KID at the
+configs[2] subset size (1000 x 2048) -- all against the fp64 numpy oracle on the same seeded fp32 inputs, through the
+Python drop-in -> C ABI.
+
+Tolerances (north_star: rel 1e-3 for the tensor-core path, gradients element-wise):
+  * value: |v - v64| <= 1e-3 |v64| + 2e-6 * kscale
+  * gradients: EVERY element |g - g64| <= 4e-3 * max|g64|, and the whole gradient ||g - g64||_F <= 2e-3 ||g64||_F.
+    g_i = sum_j W_ij (z_i - z_j) is a sum of M products whose two factors are both rounded to bf16 (unit roundoff
+    2^-9 = 2e-3) and which largely cancel, so an element's error is a random walk of size ~2^-9 |W z| / sqrt(3)
+    per term: it does not shrink relative to a small |g_i|, hence the bound relative to max|g| (element-wise) and
+    the Frobenius bound for the vector as a whole.
+  * KID (split-bf16): per subset |k - k64| <= 1e-3 |k64| + 2e-7 (the floor is 2 fp32 ulps of the O(1) block
+    means that cancel in a ~5e-4 difference).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kid_oracle, mmd_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _data(m, n, d, seed):
+    rng = np.random.RandomState(seed)
+    X = (rng.randn(m, d) / np.sqrt(d)).astype(np.float32)
+    Y = ((1.05 * rng.randn(n, d) + 0.1) / np.sqrt(d)).astype(np.float32)
+    return X, Y
+
+
+def _kscale(name, kw, X, Y):
+    n = min(len(X), 256)
+    Kxx, Kxy, Kyy, _ = mmd_oracle.kernel_matrices(name, X[:n], Y[:n], np.float64, **kw)
+    return max(abs(Kxx).mean(), abs(Kxy).mean(), abs(Kyy).mean())
+
+
+def _check(name, kw, X, Y, biased, loss, gX, gY):
+    v, gx, gy = mmd_oracle.mmd2_and_grads(name, X, Y, biased, np.float64, **kw)
+    # a set with a handful of rows averages nothing: the bound is then bf16's unit roundoff on single kernel values
+    tiny = min(len(X), len(Y)) < 16
+    floor = (4e-3 if tiny else 2e-6) * _kscale(name, kw, X, Y)
+    assert abs(loss - v) <= 1e-3 * abs(v) + floor, (name, biased, loss, v)
+    for got, ref in ((gX, gx), (gY, gy)):
+        diff = got.astype(np.float64) - ref
+        assert np.abs(diff).max() <= (1.2e-2 if tiny else 4e-3) * np.abs(ref).max(), (name, biased, np.abs(diff).max(), np.abs(ref).max())
+        assert np.linalg.norm(diff) <= (6e-3 if tiny else 2e-3) * np.linalg.norm(ref), (name, biased, np.linalg.norm(diff), np.linalg.norm(ref))
+
+
+@pytest.fixture
+def force_sym():
+    from smmd import _lib
+
+    _lib.set_option("sym_min_rows", 1)
+    yield
+    _lib.set_option("sym_min_rows", 0)
+
+
+SYM_SHAPES = [(300, 200, 100), (1000, 1100, 256), (513, 700, 256), (129, 127, 64), (700, 900, 512), (257, 255, 600),
+              (640, 520, 1024), (2048, 2048, 192), (5, 300, 32), (130, 7, 320)]
+SYM_CASES = [("mix_rq", {}), ("rbf", {}), ("mix_rbf", {"sigmas": [1.0, 2.0, 4.0, 8.0, 16.0]}), ("mix_rbf", {}),
+             ("mix_rq", {"alphas": [0.2, 0.5, 1.0, 2.0, 5.0], "wts": [1.0, 0.5, 2.0, 1.0, 0.25]}), ("mix_rq_dot", {}),
+             ("tanh_mix_rq", {}), ("distance", {})]
+
+
+@pytest.mark.parametrize("shape", SYM_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("case", SYM_CASES, ids=lambda c: c[0] + ("+" if c[1] else ""))
+def test_sym_fwd_bwd_vs_oracle(case, shape, force_sym):
+    from smmd import _lib, mmd
+
+    name, kw = case
+    m, n, d = shape
+    X, Y = _data(m, n, d, m + n + d)
+    for biased in (False, True):
+        if not biased and min(m, n) < 2:
+            continue
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), biased=biased, precision="bf16")
+        loss.backward()
+        assert _lib.last_path() == "tc_bf16_sym"
+        _check(name, kw, X, Y, biased, loss.item(), Xt.grad.cpu().numpy(), Yt.grad.cpu().numpy())
+
+
+def test_sym_deterministic_and_matches_row_stacked_path(force_sym):
+    """Two runs are bit-identical (fixed-order slab reduction + integer row-sum accumulator), and the symmetric path
+    agrees with the row-stacked fused kernel far inside the bf16 tolerance (both round the same W to bf16; only the
+    fp32 accumulation order and the r_i bookkeeping differ)."""
+    from smmd import _lib, mmd
+
+    X, Y = _data(3000, 2600, 256, 5)
+    Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
+    spec = mmd._mix_rq_kernel(Xt, Yt).spec
+    a, gXa, gYa = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert _lib.last_path() == "tc_bf16_sym"
+    b, gXb, gYb = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert torch.equal(a, b) and torch.equal(gXa, gXb) and torch.equal(gYa, gYb)
+    _lib.set_option("sym", 0)
+    try:
+        c, gXc, gYc = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+        assert _lib.last_path() == "tc_bf16_fused"
+    finally:
+        _lib.set_option("sym", 1)
+    assert abs(a[_lib.S_MMD2].item() - c[_lib.S_MMD2].item()) <= 2e-5 * abs(c[_lib.S_MMD2].item())
+    # (row sums of W: fp32 everywhere in the fused kernel; fp32 for the row part and the stored bf16 tile for the mirrored
+    # part here -- a 2^-9 / sqrt(M) difference in r_i z_i, measured 8e-4 of max|g|; both sit inside 4e-3 of the oracle)
+    assert (gXa - gXc).abs().max() <= 2e-3 * gXc.abs().max()
+    assert (gYa - gYc).abs().max() <= 2e-3 * gYc.abs().max()
+
+
+# ---- BASELINE configs[3] sizes against the fp64 oracle (SURVEY 8d inputs: X = N(0,1)/sqrt(d), Y = (1.05 N + 0.1)/sqrt(d)) ----
+C4_CELLS = [(4096, 256), (4096, 512), (4096, 1024), (8192, 256), (8192, 512), (8192, 1024)]
+
+
+@pytest.mark.parametrize("cell", C4_CELLS, ids=lambda c: "N%dxd%d" % c)
+def test_c4_sizes_vs_fp64_oracle(cell):
+    from smmd import _lib, mmd
+
+    n, d = cell
+    X, Y = _data(n, n, d, 1234 + d)
+    Xt = torch.tensor(X, device=DEV, requires_grad=True)
+    Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+    loss = mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt), precision="bf16")
+    loss.backward()
+    path = _lib.last_path()
+    assert path == ("tc_bf16_sym" if d > 256 else "tc_bf16_fused"), path   # the paths bench.py --sweep runs at these cells
+    _check("mix_rq", {}, X, Y, False, loss.item(), Xt.grad.cpu().numpy(), Yt.grad.cpu().numpy())
+
+
+def test_c4_symmetric_path_at_bench_row_count():
+    """The bench.py headline workload (N = 65536, d = 256) takes the symmetric path; the fp64 oracle cannot hold it.
+    Here: the same path at the smallest size it is selected for by default (Mp = 49152) against the exact fp32
+    SIMT path (itself oracle-pinned at 1e-5), value and every gradient element."""
+    from smmd import _lib, mmd
+
+    n, d = 24576, 256
+    g = torch.Generator(device=DEV).manual_seed(7)
+    Xt = torch.randn(n, d, device=DEV, generator=g) / d ** 0.5
+    Yt = (1.05 * torch.randn(n, d, device=DEV, generator=g) + 0.1) / d ** 0.5
+    spec = mmd._mix_rq_kernel(Xt, Yt).spec
+    a, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    assert _lib.last_path() == "tc_bf16_sym"
+    b, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
+    assert abs(a[_lib.S_MMD2].item() - b[_lib.S_MMD2].item()) <= 1e-3 * abs(b[_lib.S_MMD2].item()) + 4e-6
+    for got, ref in ((gX, rX), (gY, rY)):
+        assert (got - ref).abs().max() <= 4e-3 * ref.abs().max()
+        assert torch.linalg.norm((got - ref).double()) <= 2e-3 * torch.linalg.norm(ref.double())
+
+
+# ---- KID at the configs[2] subset size: 1000 x 2048, per-subset relative ----
+def test_kid_c3_subset_size_per_subset_vs_oracle():
+    from smmd import _lib, compute_scores
+
+    g = np.maximum(np.random.RandomState(1234).randn(6000, 2048), 0).astype(np.float32)
+    r = np.maximum(np.random.RandomState(1235).randn(6000, 2048) + 0.02, 0).astype(np.float32)
+    np.random.seed(0)
+    mm, vv = compute_scores.polynomial_mmd_averages(g, r, n_subsets=5, subset_size=1000, ret_var=True)
+    assert _lib.last_path() == "tc_bf16x3_kid"
+    np.random.seed(0)
+    m2 = compute_scores.polynomial_mmd_averages(g, r, n_subsets=5, subset_size=1000, ret_var=False)
+    assert _lib.last_path() == "tc_bf16x3_kid_sym"
+    np.random.seed(0)
+    rm, rv = kid_oracle.polynomial_mmd_averages(g.astype(np.float64), r.astype(np.float64), n_subsets=5,
+                                                subset_size=1000, ret_var=True)
+    for got in (mm, m2):
+        err = np.abs(np.asarray(got, dtype=np.float64) - rm)
+        assert np.all(err <= 1e-3 * np.abs(rm) + 2e-7), (got, rm)
+    assert np.all(np.abs(np.asarray(vv, dtype=np.float64) - rv) <= 2e-2 * np.abs(rv) + 1e-12), (vv, rv)

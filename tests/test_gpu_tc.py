@@ -109,13 +109,17 @@ def test_tc_wide_long_stream_and_shards():
     X, Y = _data(5000, 4600, 512, 77)
     Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
     spec = mmd._mix_rq_kernel(Xt, Yt).spec
-    full, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
-    assert _lib.last_path() == "tc_bf16_wz"
+    _lib.set_option("sym", 0)   # whole problems of this size take the symmetric path by default (tests/test_gpu_sym.py)
+    try:
+        full, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+        assert _lib.last_path() == "tc_bf16_wz"
+        full2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    finally:
+        _lib.set_option("sym", 1)
     ref, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
     assert abs(full[_lib.S_MMD2].item() - ref[_lib.S_MMD2].item()) <= 1e-3 * abs(ref[_lib.S_MMD2].item())
     assert (gX - rX).abs().max() <= 4e-3 * rX.abs().max()
     assert (gY - rY).abs().max() <= 4e-3 * rY.abs().max()
-    full2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
     assert torch.equal(gX, gX2) and torch.equal(gY, gY2) and torch.equal(full, full2)   # deterministic
     world = 3
     acc = torch.zeros_like(full)
@@ -143,15 +147,19 @@ def test_tc_wide_cta_pair_path():
     X, Y = _data(m, n, d, 5)
     Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
     spec = mmd._mix_rq_kernel(Xt, Yt).spec
-    sc, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
-    assert _lib.last_path() == "tc_bf16_wz_pair"
+    _lib.set_option("sym", 0)   # (whole problems of this size take the symmetric path by default; row shards take this one)
+    try:
+        sc, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+        assert _lib.last_path() == "tc_bf16_wz_pair"
+        sc2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
+    finally:
+        _lib.set_option("sym", 1)
     rs, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
     assert abs(sc[_lib.S_MMD2].item() - rs[_lib.S_MMD2].item()) <= 1e-3 * abs(rs[_lib.S_MMD2].item())
     for i in (_lib.S_SUM_XX, _lib.S_SUM_YY, _lib.S_SUM_XY, _lib.S_SUM_YX):
         assert abs(sc[i].item() - rs[i].item()) <= 1e-4 * abs(rs[i].item())
     assert (gX - rX).abs().max() <= 4e-3 * rX.abs().max()
     assert (gY - rY).abs().max() <= 4e-3 * rY.abs().max()
-    sc2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
     assert torch.equal(gX, gX2) and torch.equal(gY, gY2) and torch.equal(sc, sc2)   # deterministic
 
 
