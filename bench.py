@@ -42,6 +42,12 @@ D_FEAT = 256
 CPU_SAMPLE_N = 4096    # cpu_baseline leg of the product arm (the reference materialises ~12 N x N fp32 temporaries per block)
 KID = dict(n_codes=50000, d=2048, n_subsets=100, subset_size=1000)
 KID_CPU_SUBSETS = 4
+KERNEL_OF_PATH = {
+    "tc_bf16_sym": "tc_sym_wgen_kernel<MathRq3Default> + tc_sym_wz_kernel (the two launches of the symmetric path, timed together)",
+    "tc_bf16_symf": "tc_symf_kernel<MathRq3Default> + tc_sym_wz_kernel (fused symmetric path: Gram + W + direct products, then the mirrored products; timed together)",
+    "tc_bf16_fused": "tc_fused_pair_kernel<MathRq3Default>",
+    "tc_bf16_wz": "tc_wgen_kernel<MathRq3Default> + tc_wz_kernel", "tc_bf16_wz_pair": "tc_wgen_kernel<MathRq3Default, pair> + tc_wz_kernel",
+}
 METRIC = "mmd2_fwd_bwd_kernel_pair_evals_per_s"
 UNIT = "N^2*d pair-dims/s"
 
@@ -300,7 +306,7 @@ def run_ours(args):
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
-        device_step()
+        val, dX, dY = device_step()    # (same retention pattern as the timed loop: the allocator sees identical requests)
     barrier()
 
     # ---- timed: K steps back to back, device time per step (L2 flushed between iterations; the flush sits
@@ -320,12 +326,13 @@ def run_ours(args):
     # ---- roofline: the dominant kernel alone, event pair recorded inside the library on the launching stream
     #      (separate short loop: reading the pair back synchronises, which must not sit in the timed region) ----
     lib.smmd_profile_enable(1)
-    kern_ms = []
+    kern_ms, split_ms = [], []
     saved_launches = launches[0]
     for _ in range(5):
         flush.zero_()
         device_step()
         kern_ms.append(lib.smmd_profile_last_ms())
+        split_ms.append(_lib.profile_last_split_ms())
     launches[0] = saved_launches
     lib.smmd_profile_enable(0)
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -346,24 +353,40 @@ def run_ours(args):
     k_ms = float(np.mean([k for k in kern_ms if k is not None and k > 0]))
     flops_rank = 14.0 * n * n * d / world
     achieved = flops_rank / (k_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, kernel_name, kernels = None, KERNEL_OF_PATH.get(path, path), None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("tc_fused_kernel_dram_bytes_per_launch") if world == 1 else None   # 1-GPU capture
+            traffic = json.load(f).get("dram_bytes_per_call", {}).get(path) if world == 1 else None   # 1-GPU captures
     except Exception:
         pass
+    if all(sp is not None for sp in split_ms):
+        # two-kernel path: the event pair brackets both launches of one call; per-kernel times from the mid event.
+        # Attribution of the algorithmic flops: 6 N^2 d Gram (W generation) + 8 N^2 d gradient GEMMs (O = W Z).
+        t1 = float(np.mean([sp[0] for sp in split_ms])); t2 = float(np.mean([sp[1] for sp in split_ms]))
+        if path == "tc_bf16_symf":   # direct products (4 N^2 d of the 8 N^2 d gradient flops) run inside the first kernel
+            f1, f2, n1 = 10.0, 4.0, "tc_symf_kernel<MathRq3Default>"
+        else:
+            f1, f2, n1 = 6.0, 8.0, "tc_sym_wgen_kernel<MathRq3Default>"
+        kernels = [{"name": n1, "ms": t1, "algorithmic_flops": f1 * n * n * d / world,
+                    "frac": f1 * n * n * d / world / (t1 * 1e-3) / 1e12 / peak, "bound": "MUFU/FMA epilogue (3 MUFU + 24 packed fp32 ops per element pair); tensor pipe 20-40% busy"},
+                   {"name": "tc_sym_wz_kernel", "ms": t2, "algorithmic_flops": f2 * n * n * d / world,
+                    "frac": f2 * n * n * d / world / (t2 * 1e-3) / 1e12 / peak, "bound": "tensor / HBM reads of W"}]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "tc_fused_pair_kernel<MathRq3Default>", "kernel_ms": k_ms, "peak_source": peak_src,
-                "algorithmic_flops_per_launch": flops_rank}
+                "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
+                "algorithmic_flops_per_launch": flops_rank,
+                "frac_from_step_loop": 14.0 * n * n * d / world / (ms_per_step * 1e-3) / 1e12 / peak}
+    if kernels:
+        roofline["kernels"] = kernels
 
     # ---- e2e: public Python API, HOST buffers in, loss + gradients back on the host, every step ----
     # Two steps are kept in flight on two streams (double-buffered pinned result buffers), so one step's PCIe copies
     # overlap the other's kernels; every step still copies its inputs in and its loss + gradients out.
-    nbuf = 2 if world == 1 else 1
+    nbuf = 2
     gXh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
     gYh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
     lossh = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    streams = [torch.cuda.Stream(dev) for _ in range(nbuf)] if world == 1 else [torch.cuda.current_stream(dev)]
+    # (N > 1: NCCL collectives are enqueued in program order on every rank, whichever stream they wait on)
+    streams = [torch.cuda.Stream(dev) for _ in range(nbuf)]
 
     def e2e_step(i):
         b = i % nbuf
@@ -402,16 +425,46 @@ def run_ours(args):
     # ---- latency-bound shapes (configs[0] and the shipped YAML shape): microseconds per loss fwd+bwd ----
     small = run_small(dev, mmd, args) if (rank == 0 and world == 1) else None
 
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----
+    # ---- parity of the sharded path, visible to the driver (its GPU-test box has one GPU): every rank's owned-row
+    #      gradients and the combined scalar against the SAME problem evaluated unsharded on rank 0 (outside all timed
+    #      regions; the full feature sets are regenerated from the seeds) ----
+    parity = None
+    if world > 1:
+        from smmd.distributed import sharded_mmd2_raw
+        val_s, dXs, dYs, _ = sharded_mmd2_raw(spec, Xd, Yd, biased=False, precision="bf16")
+        gx_all = [torch.empty_like(dXs) for _ in range(world)] if rank == 0 else None
+        gy_all = [torch.empty_like(dYs) for _ in range(world)] if rank == 0 else None
+        dist.gather(dXs, gx_all, dst=0)
+        dist.gather(dYs, gy_all, dst=0)
+        if rank == 0:
+            Xf = synth_features(n, d, 1234, False).to(dev)
+            Yf = synth_features(n, d, 1235, True).to(dev)
+            sc1, dX1, dY1 = mmd.fused_mmd2_raw(spec, Xf, Yf, biased=False, want_grad=True, precision="bf16")
+            path1 = _lib.last_path()
+            ex = max(float((torch.cat(gx_all) - dX1).abs().max()), float((torch.cat(gy_all) - dY1).abs().max()))
+            gmax = max(float(dX1.abs().max()), float(dY1.abs().max()))
+            v1 = float(sc1[_lib.S_MMD2])
+            parity = {"against": "the same N=%d+%d problem unsharded on rank 0 (path %s)" % (n, n, path1),
+                      "mmd2_sharded": float(val_s), "mmd2_single": v1, "mmd2_rel_diff": abs(float(val_s) - v1) / abs(v1),
+                      "grad_max_abs_diff": ex, "grad_max_abs": gmax, "grad_rel_to_max": ex / gmax,
+                      "tolerance": "both are bf16 tensor-core evaluations (each within 4e-3 max|g| of the fp64 oracle); "
+                                   "they differ by fp32 accumulation order and the r_i bookkeeping: expected <= 2e-3",
+                      "ok": bool(ex <= 2e-3 * gmax and abs(float(val_s) - v1) <= 1e-4 * abs(v1))}
+            del Xf, Yf, dX1, dY1
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): the reference's own code when staged ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        cpu_step(CPU_SAMPLE_N, d)
-        tc = min(cpu_step(CPU_SAMPLE_N, d) for _ in range(2))
-        cpu = {"value": CPU_SAMPLE_N * CPU_SAMPLE_N * d / tc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "oracle/cpu_port.py (torch-CPU fp32 restatement of mmd.py + autograd) on %d+%d x %d, best of 2; "
-                         "N^2-scaling sample -- the reference materialises N x N temporaries and cannot hold N=%d"
-                         % (CPU_SAMPLE_N, CPU_SAMPLE_N, d, n), "seconds_per_step_at_sample": tc}
+        kind, loader = _reference_kind()
+        cpu_step(CPU_SAMPLE_N, d, kind, loader)
+        tc = min(cpu_step(CPU_SAMPLE_N, d, kind, loader) for _ in range(2))
+        cpu = {"value": CPU_SAMPLE_N * CPU_SAMPLE_N * d / tc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "%s on %d+%d x %d fp32, fwd + autograd bwd, best of 2; N^2-normalised sample -- the reference "
+                         "materialises N x N temporaries and cannot hold N=%d"
+                         % ("the reference's gan/core/mmd.py over the torch-CPU tf shim (oracle/_ref)" if kind == "reference"
+                            else "oracle/cpu_port.py", CPU_SAMPLE_N, CPU_SAMPLE_N, d, n), "seconds_per_step_at_sample": tc}
 
     if rank == 0:
         line = {
@@ -428,7 +481,10 @@ def run_ours(args):
             "wall_s_timed_region": t_wall,
             # rank 0's per-step device times (the headline `ms_per_step` is the mean of all K, max over ranks)
             "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+            "ms_each_step": [round(v, 3) for v in step_ms],
         }
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if small is not None:
@@ -497,6 +553,10 @@ def run_small(dev, mmd, args):
 
 
 def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
+    """configs[2]: polynomial_mmd_averages, 50k vs 50k x 2048 codes, 100 subsets of 1000, ret_var=False (the scorer's
+    call, gan/utils/scorer.py:103-109).  `value`: codes and subset indices resident in HBM; `e2e`: the reference call
+    signature with HOST codes (pinned), i.e. subset draw on the host (numpy global RNG, reference order) + H2D of both
+    code matrices + the batched kernel + D2H of the 100 estimates, every call."""
     from smmd import _lib
 
     nc, d, S, m = KID["n_codes"], KID["d"], KID["n_subsets"], KID["subset_size"]
@@ -510,22 +570,25 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
     from smmd.distributed import kid_shard
 
     first, count = kid_shard(S, rank, world)
+    nl = [0]
 
     def step():
         mm, _ = compute_scores.kid_subsets(g, r, igd, ird, var_at_m=nc, ret_var=False, first_subset=first, n_local=count)
+        nl[0] += _lib.last_launch_count() + 1
         if world > 1:
             dist.all_reduce(mm)
         return mm
 
-    for _ in range(2):
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
     lib.smmd_profile_enable(1)
-    reps = 5
+    reps = max(5, min(args.steps, 20))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    nl[0] = 0
     e0.record()
     for _ in range(reps):
         mm = step()
@@ -539,7 +602,9 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
     ms = t.item()
     rows = 2.0 * S * m
     out = {"metric": "kid_feature_rows_per_s", "value": rows / (ms * 1e-3), "unit": "feature rows/s", "ms_per_call": ms,
-           "config": "polynomial_mmd_averages: %dk vs %dk x %d codes, %d subsets of %d, ret_var=False, codes resident in HBM"
+           "calls_timed": reps, "gpu_launches": nl[0],
+           "config": "polynomial_mmd_averages: %dk vs %dk x %d codes, %d subsets of %d, ret_var=False, codes resident in HBM "
+                     "(codes 2 x 410 MB + a 1.7 GB gathered [hi|lo] workspace: larger than L2, no flush needed)"
                      % (nc // 1000, nc // 1000, d, S, m),
            "path": _lib.last_path(), "kid_mean": float(mm.mean().item()),
            "tflops_algorithmic_6m2d": 6.0 * m * m * d * S / (ms * 1e-3) / 1e12,
@@ -548,17 +613,87 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
                         "kernel": "tc_macro_kernel<MathPoly3> 256x256 macro tiles (split-bf16: executes 3x the algorithmic flops; symmetric enumeration skips 25% of them)", "kernel_ms": kms}}
     if out["roofline"]["achieved"]:
         out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
-    if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import cpu_port
-        gh, rh = g[:].cpu().numpy(), r[:].cpu().numpy()
+    # ---- e2e through the reference signature with host codes (rank 0, 1 GPU) ----
+    if rank == 0 and world == 1:
+        gh, rh = g.cpu().pin_memory(), r.cpu().pin_memory()
+        def host_call():
+            np.random.seed(0)
+            return compute_scores.polynomial_mmd_averages(gh, rh, n_subsets=S, subset_size=m, ret_var=False, output=None)
+        host_call()
+        torch.cuda.synchronize()
+        nrep = 3
         t0 = time.perf_counter()
-        cpu_port.kid_subsets(gh, rh, ig[:KID_CPU_SUBSETS], ir[:KID_CPU_SUBSETS])
+        for _ in range(nrep):
+            mmh = host_call()
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / nrep
+        t0 = time.perf_counter()
+        np.random.seed(0)
+        compute_scores.draw_subsets(nc, nc, S, m)
+        t_draw = time.perf_counter() - t0
+        out["e2e"] = {"value": rows / te, "unit": "feature rows/s", "ms_per_call": te * 1e3,
+                      "h2d_bytes_per_step": 2 * nc * d * 4 + 2 * S * m * 4, "d2h_bytes_per_step": S * 8,
+                      "host_subset_draw_ms": t_draw * 1e3,
+                      "kid_mean": float(np.mean(np.asarray(mmh))),
+                      "api": "smmd.compute_scores.polynomial_mmd_averages(codes_g, codes_r, n_subsets=100, subset_size=1000, "
+                             "ret_var=False) with pinned HOST codes: 200 np.random.choice(50000, 1000, replace=False) draws in "
+                             "the reference's order (host, numpy's global RNG: %.0f ms of the call), H2D of both code "
+                             "matrices, one batched kernel pass, D2H of the estimates" % (t_draw * 1e3)}
+        del gh, rh
+    if rank == 0 and world == 1 and not args.no_cpu:
+        kind, loader = _reference_kind()
+        gh, rh = g.cpu().numpy(), r.cpu().numpy()
+        t0 = time.perf_counter()
+        if kind == "reference":
+            cs = loader.load_reference_compute_scores()
+            np.random.seed(0)
+            cs.polynomial_mmd_averages(gh, rh, n_subsets=KID_CPU_SUBSETS, subset_size=m, ret_var=False, output=None)
+        else:
+            from oracle import cpu_port
+            cpu_port.kid_subsets(gh, rh, ig[:KID_CPU_SUBSETS], ir[:KID_CPU_SUBSETS])
         tc = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": 2.0 * KID_CPU_SUBSETS * m / tc, "unit": "feature rows/s", "cores": os.cpu_count(),
-                               "kind": "port", "sample": "%d of the %d subsets (numpy/BLAS restatement of compute_scores.py:211-335)"
-                                                         % (KID_CPU_SUBSETS, S)}
+                               "kind": kind, "sample": "%d of the %d subsets (%s)" % (
+                                   KID_CPU_SUBSETS, S, "the reference's gan/compute_scores.py polynomial_mmd_averages, numpy + sklearn/BLAS"
+                                   if kind == "reference" else "numpy/BLAS restatement of compute_scores.py:211-335")}
     del g, r
     return out
+
+
+def run_kid_workload(args):
+    """`--workload kid`: the KID half of the headline metric as its own contract line."""
+    import torch.distributed as dist
+
+    from smmd import _lib, compute_scores
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    lib = _lib.load()
+    peak, _ = measured_peak()
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
+    with sampler as clocks:
+        kid = run_kid(dev, rank, world, args, compute_scores, lib, dist, peak)
+    if rank == 0:
+        line = {"metric": kid["metric"], "value": kid["value"], "unit": kid["unit"], "n_gpus": world, "steps": kid["calls_timed"],
+                "warmup": 3, "ms_per_step": kid["ms_per_call"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "C3 " + kid["config"], "parallelism": "subsets split across %d rank(s)" % world,
+                           "l2": "working set (2.5 GB) exceeds L2", "path": kid["path"], "kid_mean": kid["kid_mean"]},
+                "clocks": clocks.summary(), "gpu_launches": kid["gpu_launches"], "roofline": kid["roofline"]}
+        for k in ("e2e", "cpu_baseline"):
+            if k in kid:
+                line[k] = kid[k]
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_sweep(args):
@@ -639,6 +774,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
     ap.add_argument("--no-kid", action="store_true", help="reference arm: skip the KID line")
     ap.add_argument("--ref-n", type=int, default=0, help="reference arm: fixed sample N (default: chosen from time / memory)")
+    ap.add_argument("--workload", default="mmd", choices=["mmd", "kid"], help="kid: the KID half of the metric as its own line")
     ap.add_argument("--sweep", action="store_true", help="C4 grid (N x d) instead of the headline line")
     ap.add_argument("--sweep-n", default="4096,8192,16384,32768,65536")
     ap.add_argument("--sweep-d", default="256,512,1024")
@@ -647,6 +783,8 @@ def main():
         run_sweep(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "kid":
+        run_kid_workload(args)
     else:
         run_ours(args)
 

@@ -223,6 +223,10 @@ SMMD_API int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void
  * event and returns that launch's device time in milliseconds (< 0 if nothing was recorded). */
 SMMD_API void smmd_profile_enable(int on);
 SMMD_API float smmd_profile_last_ms(void);
+/* Two-kernel paths (symmetric MMD^2: W generation, then O = W Z) also record the boundary between the two launches:
+ * device time of the first and of the second kernel of the last recorded call.  SMMD_EINVAL if that call was a
+ * single-kernel path. */
+SMMD_API int smmd_profile_last_split_ms(float* first_ms, float* second_ms);
 
 /* Path-selection options (process-wide; set them before concurrent use).  Values are validated and clamped to what
  * the kernels support.  Names: "sym" (0/1: symmetric two-pass path), "sym_min_rows" (stacked rows from which it is

@@ -17,7 +17,8 @@ thread_local const char* g_path = "none";
 
 thread_local int g_prof_on = 0;
 thread_local int g_prof_recorded = 0;
-thread_local cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+thread_local cudaEvent_t g_prof_ev[3] = {nullptr, nullptr, nullptr};   // begin, end, mid (two-kernel paths)
+thread_local int g_prof_mid = 0;
 
 int cuda_fail(cudaError_t e) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -155,8 +156,15 @@ void prof_begin(cudaStream_t s) {
   if (!g_prof_ev[0]) {
     cudaEventCreate(&g_prof_ev[0]);
     cudaEventCreate(&g_prof_ev[1]);
+    cudaEventCreate(&g_prof_ev[2]);
   }
+  g_prof_mid = 0;
   cudaEventRecord(g_prof_ev[0], s);
+}
+void prof_mark(cudaStream_t s) {
+  if (!g_prof_on || !g_prof_ev[0]) return;
+  cudaEventRecord(g_prof_ev[2], s);
+  g_prof_mid = 1;
 }
 void prof_end(cudaStream_t s) {
   if (!g_prof_on || !g_prof_ev[0]) return;
@@ -177,6 +185,14 @@ float smmd_profile_last_ms(void) {
   if (cudaEventSynchronize(g_prof_ev[1]) != cudaSuccess) return -1.f;
   if (cudaEventElapsedTime(&ms, g_prof_ev[0], g_prof_ev[1]) != cudaSuccess) return -1.f;
   return ms;
+}
+
+int smmd_profile_last_split_ms(float* first_ms, float* second_ms) {
+  if (!g_prof_recorded || !g_prof_mid || !first_ms || !second_ms) return SMMD_EINVAL;
+  if (cudaEventSynchronize(g_prof_ev[1]) != cudaSuccess) return SMMD_ECUDA;
+  if (cudaEventElapsedTime(first_ms, g_prof_ev[0], g_prof_ev[2]) != cudaSuccess) return SMMD_ECUDA;
+  if (cudaEventElapsedTime(second_ms, g_prof_ev[2], g_prof_ev[1]) != cudaSuccess) return SMMD_ECUDA;
+  return SMMD_OK;
 }
 
 int smmd_version(void) { return SMMD_VERSION; }

@@ -90,6 +90,7 @@ enum RowStat : int {
 // ---- roofline instrumentation (smmd_capi.cu): event pair around the dominant kernel of a call ----------
 void prof_begin(cudaStream_t s);
 void prof_end(cudaStream_t s);
+void prof_mark(cudaStream_t s);   // boundary between the two kernels of a two-pass path
 
 // ---- launches implemented in smmd_simt.cu -------------------------------------------------------
 struct SimtPlan {

@@ -38,6 +38,7 @@ struct Tuning {
   int64_t wz_panel_bytes;   // byte budget of one W row panel (>= 1 MB)
   int wz_pair;          // pass 1 as CTA pairs with cta_group::2 UMMAs (default 1)
   int sym;              // symmetric two-pass path for whole problems (default 1)
+  int symf;             // d <= 256: fused variant of the symmetric path (direct products inside pass 1; default 1)
   int sym_only;         // DEV timing knob: 1 = pass 1 only, 2 = pass 2 only; results are meaningless
   int64_t sym_min_rows;      // stacked rows from which the symmetric path is used (0 = the measured per-d default)
   int64_t sym_max_w_bytes;   // largest W (Mp x Mp bf16) the symmetric path may place in the workspace
@@ -53,6 +54,7 @@ inline bool tuning_set(Tuning& v, const char* name, int64_t x) {
   else if (!strcmp(name, "wz_panel_mb")) v.wz_panel_bytes = clamp_i64(x, 1, (int64_t)1 << 20) << 20;
   else if (!strcmp(name, "wz_pair")) v.wz_pair = x != 0;
   else if (!strcmp(name, "sym")) v.sym = x != 0;
+  else if (!strcmp(name, "symf")) v.symf = x != 0;
   else if (!strcmp(name, "sym_min_rows")) v.sym_min_rows = clamp_i64(x, 0, (int64_t)1 << 40);
   else if (!strcmp(name, "sym_max_w_mb")) v.sym_max_w_bytes = clamp_i64(x, 0, (int64_t)1 << 24) << 20;
   else if (!strcmp(name, "disable_small")) v.disable_small = x != 0;
@@ -74,12 +76,13 @@ inline Tuning& tuning_mut() {
     v.wz_pair = 1;
     v.wz_panel_bytes = (int64_t)6 << 30;
     v.sym = 1;
+    v.symf = 1;
     v.sym_only = 0;
     v.sym_min_rows = 0;
     v.sym_max_w_bytes = (int64_t)48 << 30;
     v.disable_small = 0;
     static const char* const names[] = {"fused_ksplit", "fused_pair", "fused_lockstep", "wz_min_d", "wz_panel_mb", "wz_pair",
-                                        "sym", "sym_min_rows", "sym_max_w_mb", "disable_small", "debug_nullmath", "sym_only"};
+                                        "sym", "symf", "sym_min_rows", "sym_max_w_mb", "disable_small", "debug_nullmath", "sym_only"};
     for (const char* nm : names) {
       char env[64] = "SMMD_";
       size_t k = 5;

@@ -236,7 +236,7 @@ __device__ __forceinline__ void sym_quarter_split(const Math& math, uint32_t tba
 }
 
 template <class Math>
-__global__ void __launch_bounds__(kSyThreads, 1)
+__global__ void __launch_bounds__(kSyThreads, 1)   // 18 warps: 5 on two sub-partitions -> 16384 / (5 * 32) = 102 -> 96 registers is the cap
 tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SymWgenArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -505,6 +505,387 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
   if (warp == kSyEpiWarps + 1) tmem_dealloc<512>(tmem);
 }
 
+// ---- fused pass 1 for d <= 256 (tc_symf_kernel): upper-triangle tiles, O_I += W Z_J in the same sweep -------------
+// For d <= 256 the accumulator O_I [128 x d] fits tensor memory next to two 128-column S buffers, exactly as in the
+// row-stacked fused kernel (smmd_tc_fused.cu: tile pairs, W written in place over S, UMMA #2 in TS form).  This kernel
+// runs that pipeline over the UPPER TRIANGLE only: a unit is one row block I against a run of 128-column blocks
+// J in [J0, J1), J >= I.  Per tile it does everything the row-stacked kernel does for the direct product
+// (O_I += W[I,J] Z_J on the otherwise ~20%-busy tensor pipe), and additionally stages the bf16 W block in shared
+// memory and stores it with TMA, so that a second, tensor-bound pass only has to add the MIRRORED products
+// O_J += W[I,J]^T Z_I (tc_sym_wz_kernel with tonly = 1).  Against the plain symmetric path this halves pass 2 (and its
+// reads of W); against the row-stacked kernel it halves the epilogue elements.
+// Units: "full" units (row block above the window, all WB column blocks of a window) first, window-major -- the CTAs
+// that work at the same time stream the same WB * 128 rows of Z_j out of L2 -- then the NB units that start on the
+// diagonal, longest first; all dealt round-robin, so CTAs finish within one short unit of each other.
+struct SymfGeo {
+  int NB;        // row blocks of 128 (= column blocks of 128)
+  int WB;        // column blocks per window
+  int nwin;      // windows
+  int last_len;  // column blocks in the last window (<= WB)
+  int64_t nfull, nunits;
+};
+struct SymfUnit {
+  int rb, J0, J1;
+};
+__host__ __device__ inline int64_t symf_full_base(const SymfGeo& g, int w) { return (int64_t)g.WB * w * (w - 1) / 2; }
+__host__ __device__ inline int64_t symf_full_index(const SymfGeo& g, int w, int rb) { return symf_full_base(g, w) + rb; }
+__host__ __device__ inline int64_t symf_diag_index(const SymfGeo& g, int w, int k) {   // unit of row block w * WB + k
+  const int64_t A = (int64_t)g.last_len * g.nwin;
+  return g.nfull + (k < g.last_len ? (int64_t)k * g.nwin + w : A + (int64_t)(k - g.last_len) * (g.nwin - 1) + w);
+}
+__device__ __forceinline__ SymfUnit symf_locate(const SymfGeo& g, int64_t u) {
+  SymfUnit r;
+  if (u < g.nfull) {
+    int w = 1;
+    while (symf_full_base(g, w + 1) <= u) ++w;
+    r.rb = (int)(u - symf_full_base(g, w));
+    r.J0 = w * g.WB;
+    r.J1 = r.J0 + g.WB < g.NB ? r.J0 + g.WB : g.NB;
+  } else {
+    const int64_t t = u - g.nfull, A = (int64_t)g.last_len * g.nwin;
+    int k, w;
+    if (t < A) {
+      k = (int)(t / g.nwin);
+      w = (int)(t - (int64_t)k * g.nwin);
+    } else {
+      const int64_t v = t - A;
+      k = g.last_len + (int)(v / (g.nwin - 1));
+      w = (int)(v % (g.nwin - 1));
+    }
+    r.rb = w * g.WB + k;
+    r.J0 = r.rb;
+    r.J1 = (w + 1) * g.WB < g.NB ? (w + 1) * g.WB : g.NB;
+  }
+  return r;
+}
+
+struct SymfArgs {
+  KernelFn kf;
+  SymfGeo geo;
+  int64_t m, n, mp, np, Mp;
+  float c_xx, c_yy, c_xy;
+  const float* norms;
+  int dp, npanel;
+  float rscale, rclamp;
+  unsigned long long* racc;      // [Mp] fixed-point row sums of W (direct rows + mirrored columns)
+  float* Opart;                  // [nunits][128][dp] partial O of the direct products
+  double* partials;              // [gridDim.x][6]
+};
+
+constexpr uint32_t TMF_S = 256;                 // TMEM: O[dp <= 256] | pair buffer 0 [128] | pair buffer 1 [128]
+constexpr int kSfStages = 4;
+constexpr int kSfZjBytes = BNF * 128;           // one 64-wide k-panel of a 64-row column tile
+constexpr int kSfZiBytes = BM * 128;
+constexpr int kSfStagingBytes = 16 * 2048;      // one 32-row x 32-column bf16 block per epilogue warp
+inline int symf_smem(int npanel) { return 1024 + npanel * kSfZiBytes + kSfStages * npanel * kSfZjBytes + kSfStagingBytes + 1536; }
+
+template <class Math>
+__global__ void __launch_bounds__(576, 1)   // 18 warps: 5 on two sub-partitions -> 16384 / (5 * 32) = 102 -> 96 registers is the cap
+tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
+               const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SymfArgs a) {
+  constexpr int KSPLIT = 2, NPART = 4, EPI_WARPS = 16, NST = kSfStages;
+  const int NPANEL = a.npanel, DP = a.dp;
+  const int ZI_BYTES = NPANEL * kSfZiBytes;
+  constexpr int PANEL_STRIDE = NST * kSfZjBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sZi = smem;
+  uint8_t* sZj = smem + ZI_BYTES;                     // [NPANEL][NST][64 rows x 128 B]
+  uint8_t* staging = sZj + NPANEL * PANEL_STRIDE;     // 2 KB aligned: [16 warps][32 rows][64 B], 64-byte swizzle
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSfStagingBytes);
+  uint64_t* zj_full = bars;             // [NST]
+  uint64_t* zj_empty = bars + NST;      // [NST]
+  uint64_t* s_full = bars + 2 * NST;    // [2]
+  uint64_t* w_full = s_full + 2;        // [2][2]  (pair buffer, group), see tc_fused_pair_kernel
+  uint64_t* pb_free = w_full + 4;       // [2]
+  uint64_t* zi_full = pb_free + 2;
+  uint64_t* zi_empty = zi_full + 1;
+  uint64_t* o_full = zi_empty + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* sParams = reinterpret_cast<float*>(tmem_slot + 4);      // [24]
+  // column norms of the tile in ring stage st: copied by the producer together with the tile (same mbarrier), read by the
+  // epilogue from shared memory -- a global load at the head of every 16-column chunk cost 25% of the epilogue's time
+  float* nbuf = sParams + 24 + 8;                                  // [NST][64] (16-byte aligned)
+  double* sRed = reinterpret_cast<double*>(staging);              // [16][3], after the last W store has drained
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_params(a.kf, sParams);
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&zj_full[i], 1);
+      mbar_init(&zj_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&w_full[2 * i], 128 * KSPLIT);
+      mbar_init(&w_full[2 * i + 1], 128 * KSPLIT);
+      mbar_init(&pb_free[i], 1);
+    }
+    mbar_init(zi_full, 1);
+    mbar_init(zi_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 256 * KSPLIT);
+    fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tmap_zi);
+    prefetch_tmap(&tmap_zj);
+    prefetch_tmap(&tmap_w);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const SymfGeo& geo = a.geo;
+
+  if (warp == EPI_WARPS) {
+    // ===================== TMA producer =====================
+    uint32_t unit = 0, st = 0, ph = 0;
+    for (int64_t u = blockIdx.x; u < geo.nunits; u += gridDim.x, ++unit) {
+      const SymfUnit un = symf_locate(geo, u);
+      mbar_wait_sleep(zi_empty, (unit & 1) ^ 1, 128);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(zi_full, ZI_BYTES);
+        for (int p = 0; p < NPANEL; ++p) tma_load_2d(sZi + p * (BM * 128), &tmap_zi, zi_full, p * 64, un.rb * BM);
+      }
+      __syncwarp();
+      for (int t = 2 * un.J0; t < 2 * un.J1; ++t) {
+        mbar_wait_sleep(&zj_empty[st], ph ^ 1, 128);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&zj_full[st], NPANEL * kSfZjBytes + BNF * 4);
+          uint8_t* dst = sZj + st * kSfZjBytes;
+          for (int p = 0; p < NPANEL; ++p) tma_load_2d(dst + p * PANEL_STRIDE, &tmap_zj, &zj_full[st], p * 64, t * BNF);
+          bulk_load_1d(nbuf + st * BNF, a.norms + (int64_t)t * BNF, BNF * 4, &zj_full[st]);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)NST) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ===================== UMMA issuer (as tc_fused_pair_kernel) =====================
+    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, kFmtBF16, false, false);
+    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
+    const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);
+    const uint32_t zj_lo2 = desc_lo(smem_u32(sZj), PANEL_STRIDE);
+    constexpr uint32_t stage_step = (uint32_t)kSfZjBytes >> 4, panel_step = (uint32_t)PANEL_STRIDE >> 4;
+    uint32_t unit = 0;
+    uint32_t st1 = 0, ph1 = 0, gp1 = 0;
+    uint32_t st2 = 0, gp2 = 0;
+    for (int64_t u = blockIdx.x; u < geo.nunits; u += gridDim.x, ++unit) {
+      const SymfUnit un = symf_locate(geo, u);
+      const int NP = un.J1 - un.J0;
+      mbar_wait(zi_full, unit & 1);
+      for (int j = 0; j < NP + 2; ++j) {
+        const int pm2 = j - 2;
+        if (pm2 >= 0) {
+          const uint32_t pb = gp2 & 1;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {   // ---- UMMA #2 for tile g of pair pm2: O += W * Zj
+            mbar_wait(&w_full[pb * 2 + g], (gp2 >> 1) & 1);
+            if (pm2 == 0 && g == 0) mbar_wait(o_empty, (unit & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t blo = zj_lo2 + st2 * stage_step;
+            const uint32_t wad = tmem + TMF_S + pb * 128 + g * 64;
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < BNF / 16; ++kk)
+                umma_ts2(tmem, wad + (kk >> 1) * 32 + (kk & 1) * 8, blo + kk * (2048 >> 4), hi, idesc2,
+                         (pm2 > 0 || g > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&zj_empty[st2]);
+              if (g == 1) umma_commit(&pb_free[pb]);
+              if (pm2 == NP - 1 && g == 1) umma_commit(o_full);
+            }
+            __syncwarp();
+            if (++st2 == (uint32_t)NST) st2 = 0;
+          }
+          ++gp2;
+        }
+        if (j < NP) {   // ---- UMMA #1 for pair j: S[128 x 128] = Zi * [Zj(2J); Zj(2J+1)]^T
+          const uint32_t pb = gp1 & 1;
+          mbar_wait(&zj_full[st1], ph1);
+          mbar_wait(&zj_full[st1 + 1], ph1);
+          if (gp1 >= 2) mbar_wait(&pb_free[pb], ((gp1 >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t blo = zj_lo1 + st1 * stage_step;
+          const uint32_t sad = tmem + TMF_S + pb * 128;
+          if (elect_one()) {
+            for (int p = 0; p < NPANEL; ++p) {
+              const uint32_t ap = zi_lo + p * ((BM * 128) >> 4), bp = blo + p * panel_step;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_ss2(sad, ap + k * 2, bp + k * 2, hi, idesc1, (p | k) ? 1u : 0u);
+            }
+            umma_commit(&s_full[pb]);
+            if (j == NP - 1) umma_commit(zi_empty);
+          }
+          __syncwarp();
+          st1 += 2;
+          if (st1 == (uint32_t)NST) {
+            st1 = 0;
+            ph1 ^= 1;
+          }
+          ++gp1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: group g takes tile g of every pair; warp = 32 rows x 32 columns =====================
+    const int grp = warp >> 3;
+    const int half = (warp >> 2) & 1;
+    const int part = grp * KSPLIT + half;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* stg_ptr = staging + warp * 2048;
+    const uint32_t stg = smem_u32(stg_ptr);
+    const uint32_t srow = stg + lane * 64;
+    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+    const Math math(a.kf, sParams);
+    const float kscale = math.k_scale(), kdscale = math.kd_scale();
+    const int mp = (int)a.mp, mvalid = (int)a.m, yvalid = (int)(a.mp + a.n);
+    double sxx = 0.0, syy = 0.0, sxy = 0.0;
+    uint32_t unit = 0, gp = 0;
+    bool stored = false;
+    for (int64_t u = blockIdx.x; u < geo.nunits; u += gridDim.x, ++unit) {
+      const SymfUnit un = symf_locate(geo, u);
+      const int rb = un.rb;
+      const int gi = rb * BM + r;
+      const bool rowX = gi < mp;
+      const bool row_ok = rowX ? gi < mvalid : gi < yvalid;
+      const bool pad_rows = rowX ? (rb + 1) * BM > mvalid : (rb + 1) * BM > yvalid;
+      const float rt = math_row_term(math, a.norms[gi]);
+      float2 rsum = make_float2(0.f, 0.f);
+      float fsame = 0.f, fcross = 0.f;
+      for (int J = un.J0; J < un.J1; ++J, ++gp) {
+        const uint32_t pb = gp & 1;
+        // ring stage of this group's tile: the stages advance by two per pair (NST = 4: pair parity picks the half)
+        const uint32_t nj = smem_u32(nbuf + (((gp & 1) << 1) + grp) * BNF + half * 32);
+        const int c0 = (2 * J + grp) * BNF;            // first column of this group's 64-column tile
+        const int cb = c0 + half * 32;                 // first column of this warp's 32-column block
+        const bool colX = c0 < mp;
+        const bool same = (colX == rowX);
+        const bool diag = (J == rb);
+        const float2 cw = bc2((same ? (rowX ? a.c_xx : a.c_yy) : a.c_xy) * kdscale);
+        const int cvalid = colX ? mvalid : yvalid;
+        const int lim = row_ok ? cvalid : 0;           // padding rows: every column masked (W = 0 there)
+        const bool special = diag || pad_rows || (c0 + BNF > cvalid);
+        const uint32_t s_addr = tmem + TMF_S + pb * 128 + grp * 64 + half * 32 + lane_base;
+        float2 tsum = make_float2(0.f, 0.f);
+        mbar_wait(&s_full[pb], (gp >> 1) & 1);
+        tc_fence_after();
+        {
+          uint32_t va[16], vb[16], wpk[8];
+          tmem_ld_x16(s_addr, va);
+          tmem_ld_wait();
+          tmem_ld_x16(s_addr + 16, vb);
+          if (!special) sym_chunk16<Math, false>(math, va, nj, rt, cw, 0, 0, 0, tsum, rsum, wpk);
+          else sym_chunk16<Math, true>(math, va, nj, rt, cw, cb, lim, gi, tsum, rsum, wpk);
+          tmem_st_x8(s_addr, wpk);            // W in place: columns [0, 8) of this warp's slice (already read)
+          if (stored) {                       // the previous tile's TMA store must have read the staging block
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+          }
+          st_shared_v4(srow + ((0u ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
+          st_shared_v4(srow + ((1u ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
+          tmem_ld_wait();
+          if (!special) sym_chunk16<Math, false>(math, vb, nj + 64, rt, cw, 0, 0, 0, tsum, rsum, wpk);
+          else sym_chunk16<Math, true>(math, vb, nj + 64, rt, cw, cb + 16, lim, gi, tsum, rsum, wpk);
+          tmem_st_x8(s_addr + 8, wpk);
+          st_shared_v4(srow + ((2u ^ sw) << 4), wpk[0], wpk[1], wpk[2], wpk[3]);
+          st_shared_v4(srow + ((3u ^ sw) << 4), wpk[4], wpk[5], wpk[6], wpk[7]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&w_full[pb * 2 + grp]);
+        const float ts = (tsum.x + tsum.y) * kscale;
+        if (!same) fcross += ts;
+        else fsame += diag ? ts : 2.f * ts;
+        // ---- off the issuer's critical path: W block -> HBM (for the mirrored products of pass 2), column sums ----
+        if (!diag) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_w, stg_ptr, cb, rb * BM + q * 32);
+            bulk_commit();
+          }
+          stored = true;
+          // lanes 0..15 / 16..31 take the even / odd rows; lane & 15 = column pair
+          const uint32_t pcol = (uint32_t)(lane & 15), hrow = (uint32_t)(lane >> 4);
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t rr = 2 * i + hrow;
+            const uint32_t wv = ld_shared_u32(stg + rr * 64 + ((((pcol >> 2) ^ ((uint32_t)i & 3u))) << 4) + (pcol & 3u) * 4);
+            acc = add2(acc, make_float2(bf16_lo_to_f32(wv), bf16_hi_to_f32(wv)));
+          }
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+          if (lane < 16) {
+            fixed_add(a.racc + cb + 2 * lane, acc.x, a.rscale, a.rclamp);
+            fixed_add(a.racc + cb + 2 * lane + 1, acc.y, a.rscale, a.rclamp);
+          }
+        } else {
+          __syncwarp();   // (diagonal blocks are not stored: nothing mirrors them; staging stays owned by this warp)
+        }
+      }
+      // ---- unit end: row sums, block sums, drain O ----
+      if (row_ok) {
+        fixed_add(a.racc + gi, rsum.x + rsum.y, a.rscale, a.rclamp);
+        sxy += (double)fcross;
+        if (rowX) sxx += (double)fsame;
+        else syy += (double)fsame;
+      }
+      mbar_wait(o_full, unit & 1);
+      tc_fence_after();
+      {
+        const int seg = DP / NPART;
+        float* orow = a.Opart + ((int64_t)u * BM + r) * DP + part * seg;
+        for (int c = 0; c < seg; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem + part * seg + c + lane_base, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(orow + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+    }
+    if (stored && lane == 0) bulk_wait0();
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+    }
+    named_bar_sync(1, EPI_WARPS * 32);   // every epilogue warp's stores have drained: the staging area is free
+    if (lane == 0) {
+      sRed[warp * 3 + 0] = sxx;
+      sRed[warp * 3 + 1] = syy;
+      sRed[warp * 3 + 2] = sxy;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 6) {
+    double t = 0.0;
+    const int src = tid == 3 ? 2 : tid;
+    if (tid < 4)
+      for (int w = 0; w < EPI_WARPS; ++w) t += sRed[w * 3 + src];
+    a.partials[(int64_t)blockIdx.x * 6 + tid] = t;
+  }
+  if (warp == EPI_WARPS + 1) tmem_dealloc<512>(tmem);
+}
+
 // ---- pass 2: O = W_sym Z -----------------------------------------------------------------------------------
 constexpr int kSzStages = 3;
 constexpr int kSzStageBytes = 2 * BM * 128 + 4 * BNF * 128;   // two 128-row W operands + four 64-feature Z panels = 64 KB
@@ -518,7 +899,16 @@ struct SymWzArgs {
   int S;          // K splits per unit
   int ksteps;     // K steps per piece
   float* Opart;   // [unit = mb * FB + fb][S][256][256]
+  // mirrored-only mode (after tc_symf_kernel, which has already added the direct products): macro block mb only takes
+  // the stored tiles W[J, R] with J < R, read transposed, i.e. K steps [0, 4 mb + 2) (its second row block reaches two
+  // steps further than its first).  Pieces are runs of 4 * ell K steps; macro block mb has mb / ell + 1 of them and
+  // pieces are numbered mb-major: piece = (P(mb) + s) * FB + fb, P(mb) = sum_{i < mb} (i / ell + 1).
+  int tonly, ell;
 };
+__host__ __device__ inline int64_t symt_prefix(int mb, int ell) {   // P(mb)
+  const int64_t q = mb / ell, r = mb % ell;
+  return mb + (int64_t)ell * q * (q - 1) / 2 + q * r;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_constant__ CUtensorMap tmap_wt,
@@ -549,13 +939,31 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // piece = (split s, unit u), s-major so that one wave of CTAs walks the same rows of Z (L2 reuse)
-  const int units = a.nmb * a.FB;
-  const int s = (int)blockIdx.x / units;
-  const int u = (int)blockIdx.x - s * units;
-  const int mb = u / a.FB, fb = u - mb * a.FB;
-  const int k0 = s * a.ksteps;
-  const int k1 = k0 + a.ksteps < a.KT ? k0 + a.ksteps : a.KT;
+  int s, u, mb, fb, k0, k1;
+  if (!a.tonly) {
+    // piece = (split s, unit u), s-major so that one wave of CTAs walks the same rows of Z (L2 reuse)
+    const int units = a.nmb * a.FB;
+    s = (int)blockIdx.x / units;
+    u = (int)blockIdx.x - s * units;
+    mb = u / a.FB;
+    fb = u - mb * a.FB;
+    k0 = s * a.ksteps;
+    k1 = k0 + a.ksteps < a.KT ? k0 + a.ksteps : a.KT;
+  } else {
+    const int64_t pc = (int64_t)blockIdx.x / a.FB;
+    fb = (int)((int64_t)blockIdx.x - pc * a.FB);
+    int q = 0;                                   // pieces of macro blocks [q ell, (q + 1) ell): (q + 1) each
+    while (symt_prefix((q + 1) * a.ell, a.ell) <= pc) ++q;
+    const int64_t rem = pc - symt_prefix(q * a.ell, a.ell);
+    mb = q * a.ell + (int)(rem / (q + 1));
+    s = (int)(rem % (q + 1));
+    u = mb * a.FB + fb;
+    k0 = s * 4 * a.ell;
+    const int kend = 4 * mb + 2 < a.KT ? 4 * mb + 2 : a.KT;
+    k1 = k0 + 4 * a.ell < kend ? k0 + 4 * a.ell : kend;
+  }
+  // mirrored-only mode: row block h of the macro block is active for K steps ks < 4 mb + 2 h
+  const int hlim0 = a.tonly ? 4 * mb : a.KT, hlim1 = a.tonly ? 4 * mb + 2 : a.KT;
   const int nf = a.dp - fb * 256 < 256 ? a.dp - fb * 256 : 256;   // features of this block (multiple of 64)
   const int npan = nf / 64;
 
@@ -564,14 +972,16 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
     for (int ks = k0; ks < k1; ++ks) {
       mbar_wait(&empty[st], ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], 2 * BM * 128 + npan * BNF * 128);
+        const int nact = (ks < hlim0 ? 1 : 0) + (ks < hlim1 ? 1 : 0);
+        mbar_arrive_expect_tx(&full[st], nact * BM * 128 + npan * BNF * 128);
         uint8_t* sa = smem + st * kSzStageBytes;
         const int J = ks >> 1;   // 128-column block of this K step
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int R = 2 * mb + h;
           uint8_t* dst = sa + h * (BM * 128);
-          if (J >= R) {   // stored tile W[R, J]: 128 rows x 64 columns, K-major A
+          if (ks >= (h ? hlim1 : hlim0)) continue;
+          if (!a.tonly && J >= R) {   // stored tile W[R, J]: 128 rows x 64 columns, K-major A
             tma_load_2d(dst, &tmap_wd, &full[st], ks * 64, R * BM);
           } else {        // stored tile W[J, R] read transposed: 64 K-rows x 128 columns = two 64 x 64 boxes, MN-major A
             tma_load_2d(dst, &tmap_wt, &full[st], R * BM, ks * 64);
@@ -604,7 +1014,8 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
       if (elect_one()) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const bool direct = J >= 2 * mb + h;
+          if (ks >= (h ? hlim1 : hlim0)) continue;
+          const bool direct = !a.tonly && J >= 2 * mb + h;
           const uint32_t hofs = sofs + h * ((BM * 128) >> 4);
           if (direct) {
 #pragma unroll
@@ -630,8 +1041,9 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
     // drain: warp -> (row half, TMEM lane quarter); each thread stores its row of the partial tile
     const int half = warp >> 2, q = warp & 3;
     const int row = half * BM + q * 32 + lane;
-    float* orow = a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
-    if (k1 > k0) {
+    float* orow = a.tonly ? a.Opart + ((int64_t)blockIdx.x * 256 + row) * 256
+                          : a.Opart + (((int64_t)u * a.S + s) * 256 + row) * 256;
+    if (k1 > k0 && k0 < (half ? hlim1 : hlim0)) {
       mbar_wait_sleep(acc_full, 0, 1000);   // the drain warps idle for the whole K loop: no polling next to the issuer
       tc_fence_after();
       const uint32_t base = tmem + half * 256 + ((uint32_t)(q * 32) << 16);
@@ -669,7 +1081,53 @@ struct SymFinArgs {
   float* dX;
   float* dY;
   double* partials;          // [gridDim.x][6]: (dot same X, dot same Y, dot cross X, dot cross Y, dgx, dgy)
+  // fused pass 1 (tc_symf_kernel): O_i = direct slabs of the row block's units + mirrored pieces of pass 2
+  int symf, ell;
+  SymfGeo fgeo;
+  const float* Odir;         // [nunits][128][dp]
 };
+
+// sum of the partial O values of one row at features [c, c + 4) (c % 4 == 0, inside one 256-feature block), fixed order
+__device__ __forceinline__ float4 sym_row_o4(const SymFinArgs& a, int rbl, int r, int c) {
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [&](const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o.x += t.x;
+    o.y += t.y;
+    o.z += t.z;
+    o.w += t.w;
+  };
+  const int mbl = rbl >> 1, row256 = (rbl & 1) * BM + r;
+  if (!a.symf) {
+    const float* op = a.Opart + (((int64_t)mbl * a.FB + (c >> 8)) * a.S * 256 + row256) * 256 + (c & 255);
+    for (int s = 0; s < a.S; ++s) add(op + (int64_t)s * 65536);
+    return o;
+  }
+  const int w0 = rbl / a.fgeo.WB, k = rbl - w0 * a.fgeo.WB;
+  add(a.Odir + ((int64_t)symf_diag_index(a.fgeo, w0, k) * BM + r) * a.dp + c);
+  for (int w = w0 + 1; w < a.fgeo.nwin; ++w) add(a.Odir + ((int64_t)symf_full_index(a.fgeo, w, rbl) * BM + r) * a.dp + c);
+  // mirrored pieces of macro block mbl: row block h = rbl & 1 is active in piece s while 4 ell s < 4 mbl + 2 h
+  const int64_t P = symt_prefix(mbl, a.ell);
+  const int np = mbl / a.ell + 1, klim = 4 * mbl + 2 * (rbl & 1);
+  for (int s = 0; s < np && 4 * a.ell * s < klim; ++s) add(a.Opart + (((P + s) * a.FB + (c >> 8)) * 256 + row256) * 256 + (c & 255));
+  return o;
+}
+__device__ __forceinline__ float sym_row_o1(const SymFinArgs& a, int rbl, int r, int c) {
+  float o = 0.f;
+  const int mbl = rbl >> 1, row256 = (rbl & 1) * BM + r;
+  if (!a.symf) {
+    const float* op = a.Opart + (((int64_t)mbl * a.FB + (c >> 8)) * a.S * 256 + row256) * 256 + (c & 255);
+    for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 65536];
+    return o;
+  }
+  const int w0 = rbl / a.fgeo.WB, k = rbl - w0 * a.fgeo.WB;
+  o += a.Odir[((int64_t)symf_diag_index(a.fgeo, w0, k) * BM + r) * a.dp + c];
+  for (int w = w0 + 1; w < a.fgeo.nwin; ++w) o += a.Odir[((int64_t)symf_full_index(a.fgeo, w, rbl) * BM + r) * a.dp + c];
+  const int64_t P = symt_prefix(mbl, a.ell);
+  const int np = mbl / a.ell + 1, klim = 4 * mbl + 2 * (rbl & 1);
+  for (int s = 0; s < np && 4 * a.ell * s < klim; ++s) o += a.Opart[(((P + s) * a.FB + (c >> 8)) * 256 + row256) * 256 + (c & 255)];
+  return o;
+}
 
 __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -692,23 +1150,12 @@ __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
     const int sdtype = a.src.dtype;
     const int64_t srow = src_row(li, rowX, a.src.blk_x, a.src.blk_y);
     const int rbl = (int)(gi / BM), r = (int)(gi % BM);
-    const int mbl = rbl >> 1;
-    const int row256 = (rbl & 1) * BM + r;
-    const float* obase = a.Opart + (((int64_t)mbl * a.FB) * a.S * 256 + row256) * 256;   // + (fb * S + s) * 65536 + cc
     const bool vec = out != nullptr && !dot && sdtype == SMMD_F32 && (a.d % 4 == 0) && (ld % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec) {
       const float* zsrc = reinterpret_cast<const float*>(src) + srow * ld;
       for (int c = 4 * lane; c < a.d; c += 128) {   // 4 consecutive features per lane (never straddle a 256 block)
-        const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < a.S; ++s) {   // fixed order
-          const float4 t = *reinterpret_cast<const float4*>(op + (int64_t)s * 65536);
-          o.x += t.x;
-          o.y += t.y;
-          o.z += t.z;
-          o.w += t.w;
-        }
+        const float4 o = sym_row_o4(a, rbl, r, c);   // fixed order
         const float4 z4 = *reinterpret_cast<const float4*>(zsrc + c);
         float zz[4] = {z4.x, z4.y, z4.z, z4.w};
         const float oo[4] = {o.x, o.y, o.z, o.w};
@@ -724,10 +1171,7 @@ __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
     } else {
       for (int c = lane; c < a.d; c += 32) {
         float o = 0.f;
-        if (out) {
-          const float* op = obase + (int64_t)(c >> 8) * a.S * 65536 + (c & 255);
-          for (int s = 0; s < a.S; ++s) o += op[(int64_t)s * 65536];   // fixed order
-        }
+        if (out) o = sym_row_o1(a, rbl, r, c);   // fixed order
         const int64_t sidx = srow * ld + c;
         float z = sdtype == SMMD_F32 ? reinterpret_cast<const float*>(src)[sidx]
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
@@ -904,24 +1348,252 @@ cudaError_t launch_sym_wgen(TcVariant v, const CUtensorMap& tzi, const CUtensorM
   }
 }
 
+// ---- plan of the fused variant (d <= 256) ---------------------------------------------------------------------
+struct SymfPlan {
+  int64_t mp, np, Mp, dp;
+  SymfGeo geo;
+  int grid1, nmb, ell, KT;
+  int64_t pieces;
+  int fin_blocks;
+  size_t off_Z, off_norm, off_csum, off_W, off_racc, off_O1, off_O2, off_stats, off_end;
+};
+
+SymfPlan symf_plan(int64_t m, int64_t n, int64_t d) {
+  SymfPlan p;
+  p.mp = round_up(m, BM);
+  p.np = round_up(n, BM);
+  p.Mp = p.mp + p.np;
+  p.dp = round_up(d, 64);
+  SymfGeo& g = p.geo;
+  g.NB = (int)(p.Mp / BM);
+  // window = the largest power of two of column blocks (<= 256: 16 MB of Z_j at d = 256) that still leaves every CTA
+  // >= 20 full units, so that the round-robin deal balances to a few percent
+  g.WB = 256;
+  auto nfull_of = [&](int wb) {
+    const int64_t nw = (g.NB + wb - 1) / wb;
+    return (int64_t)wb * nw * (nw - 1) / 2;
+  };
+  // (every unit ends with a 128 KB drain of O, so units are kept long: >= 4 full units per CTA are enough because the
+  // diagonal units, dealt longest first after them, even the CTAs out to within one short unit)
+  while (g.WB > 4 && nfull_of(g.WB) < (int64_t)4 * sm_count()) g.WB >>= 1;
+  g.nwin = (g.NB + g.WB - 1) / g.WB;
+  g.last_len = g.NB - (g.nwin - 1) * g.WB;
+  g.nfull = nfull_of(g.WB);
+  g.nunits = g.nfull + g.NB;
+  p.grid1 = (int)std::min<int64_t>(sm_count(), g.nunits);
+  p.nmb = (g.NB + 1) / 2;
+  p.KT = (int)(p.Mp / 64);
+  // mirrored pass: pieces of 4 * ell K steps (one CTA each, ~equal length): the longest pieces that still fill whole
+  // waves of SMs to >= 90% (a piece pays a fixed prologue + a 256 KB drain, so short pieces waste the tensor pipe)
+  {
+    const int sm = sm_count();
+    int best = 2;
+    double best_eff = -1.0;
+    for (int ell = 64; ell >= 2; ell >>= 1) {
+      const int64_t pc = symt_prefix(p.nmb, ell);
+      const double eff = (double)pc / (double)((pc + sm - 1) / sm * sm);
+      if (pc >= 2 * sm && eff >= 0.9) {
+        best = ell;
+        break;
+      }
+      if (eff > best_eff) {
+        best_eff = eff;
+        best = ell;
+      }
+    }
+    p.ell = best;
+  }
+  p.pieces = symt_prefix(p.nmb, p.ell);
+  p.fin_blocks = (int)((p.Mp + kFinRowsPerCta - 1) / kFinRowsPerCta);
+  size_t o = 0;
+  p.off_Z = o;
+  o = up256(o + (size_t)p.Mp * p.dp * 2);
+  p.off_norm = o;
+  o = up256(o + (size_t)p.Mp * 4);
+  p.off_csum = o;
+  o = up256(o + (size_t)2 * p.dp * 8);
+  p.off_W = o;
+  o = up256(o + (size_t)p.Mp * p.Mp * 2);
+  p.off_racc = o;
+  o = up256(o + (size_t)p.Mp * 8);
+  p.off_O1 = o;
+  o = up256(o + (size_t)g.nunits * BM * p.dp * 4);
+  p.off_O2 = o;
+  o = up256(o + (size_t)p.pieces * 256 * 256 * 4);
+  p.off_stats = o;
+  o = up256(o + (size_t)(p.grid1 + p.fin_blocks) * 6 * 8);
+  p.off_end = o;
+  return p;
+}
+
+template <class Math>
+cudaError_t launch_symf_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymfArgs& a, int grid,
+                          cudaStream_t s) {
+  const int smem = symf_smem(a.npanel);
+  if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
+  auto kern = tc_symf_kernel<Math>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 576, smem, s>>>(tzi, tzj, tw, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_symf(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymfArgs& a,
+                        int grid, cudaStream_t s) {
+  switch (v) {
+    case TV_RBF1: return launch_symf_t<MathRbf1>(tzi, tzj, tw, a, grid, s);
+    case TV_RBF_LADDER5: return launch_symf_t<MathRbfLadder<5>>(tzi, tzj, tw, a, grid, s);
+    case TV_RBF_GENERIC: return launch_symf_t<MathGeneric<FAM_RBF>>(tzi, tzj, tw, a, grid, s);
+    case TV_RQ3_DEFAULT: return launch_symf_t<MathRq3Default>(tzi, tzj, tw, a, grid, s);
+    case TV_RQ_GENERIC: return launch_symf_t<MathGeneric<FAM_RQ>>(tzi, tzj, tw, a, grid, s);
+    case TV_DISTANCE: return launch_symf_t<MathDistance>(tzi, tzj, tw, a, grid, s);
+    case TV_NULL: return launch_symf_t<MathNull>(tzi, tzj, tw, a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src,
+                     double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
+                     const char** path) {
+  char* w = static_cast<char*>(ws);
+  cudaError_t e;
+  *path = "tc_bf16_symf";
+  const SymfPlan p = symf_plan(g.m, g.n, g.d);
+  if (p.off_end > ws_bytes) return cudaErrorInvalidValue;
+  __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(w + p.off_Z);
+  float* norms = reinterpret_cast<float*>(w + p.off_norm);
+  double* csum = reinterpret_cast<double*>(w + p.off_csum);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(w + p.off_W);
+  unsigned long long* racc = reinterpret_cast<unsigned long long*>(w + p.off_racc);
+  double* partials = reinterpret_cast<double*>(w + p.off_stats);
+  PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
+                kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
+  ++*launches;
+  if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
+  const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
+  if (dot) {
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    ++*launches;
+  }
+  CUtensorMap tzi, tzj, tz, twd, twt, tws;
+  if (!smmd_host::make_tmap_bf16_2d(&tzi, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&tzj, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&tz, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&twd, Wb, p.Mp, p.Mp, p.Mp, BM)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, p.Mp, p.Mp, p.Mp, 64)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d_box32(&tws, Wb, p.Mp, p.Mp, p.Mp, 32)) return cudaErrorUnknown;   // pass-1 stores
+  const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
+  const double wb = cmax * kd_abs_bound(kf);
+  int ex = 0;
+  frexp(wb * (double)p.Mp, &ex);
+  const int shift = std::max(-100, std::min(100, 61 - ex));
+  SymfArgs fa;
+  fa.kf = kf;
+  fa.geo = p.geo;
+  fa.m = g.m;
+  fa.n = g.n;
+  fa.mp = p.mp;
+  fa.np = p.np;
+  fa.Mp = p.Mp;
+  fa.c_xx = (float)(4.0 * c.a_xx);
+  fa.c_yy = (float)(4.0 * c.a_yy);
+  fa.c_xy = (float)(4.0 * c.a_xy);
+  fa.norms = norms;
+  fa.dp = (int)p.dp;
+  fa.npanel = (int)(p.dp / 64);
+  fa.rscale = (float)ldexp(1.0, shift);
+  fa.rclamp = (float)(wb * (double)p.Mp);
+  fa.racc = racc;
+  fa.Opart = reinterpret_cast<float*>(w + p.off_O1);
+  fa.partials = partials;
+  prof_begin(s);
+#ifdef SMMD_DEV_KNOBS
+  const int only = tuning().sym_only;
+#else
+  const int only = 0;
+#endif
+  if (only != 2) {
+    if ((e = launch_symf(variant, tzi, tzj, tws, fa, p.grid1, s)) != cudaSuccess) return e;
+    ++*launches;
+  }
+  prof_mark(s);
+  SymWzArgs za;
+  za.nmb = p.nmb;
+  za.FB = 1;
+  za.dp = (int)p.dp;
+  za.KT = p.KT;
+  za.S = 1;
+  za.ksteps = p.KT;
+  za.Opart = reinterpret_cast<float*>(w + p.off_O2);
+  za.tonly = 1;
+  za.ell = p.ell;
+  if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
+    return e;
+  if (only != 1) {
+    tc_sym_wz_kernel<<<(unsigned)p.pieces, kThreads, kSzSmem, s>>>(twd, twt, tz, za);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+  }
+  prof_end(s);
+  SymFinArgs fr;
+  fr.kf = kf;
+  fr.m = g.m;
+  fr.n = g.n;
+  fr.mp = p.mp;
+  fr.np = p.np;
+  fr.d = g.d;
+  fr.dp = (int)p.dp;
+  fr.FB = 1;
+  fr.S = 1;
+  fr.a_xx = c.a_xx;
+  fr.a_yy = c.a_yy;
+  fr.a_xy = c.a_xy;
+  fr.rinv = ldexp(1.0, -shift);
+  fr.src = src;
+  fr.norms = norms;
+  fr.csum = dot ? csum : nullptr;
+  fr.Opart = za.Opart;
+  fr.racc = racc;
+  fr.dX = dX;
+  fr.dY = dY;
+  fr.partials = partials + (int64_t)p.grid1 * 6;
+  fr.symf = 1;
+  fr.ell = p.ell;
+  fr.fgeo = p.geo;
+  fr.Odir = fa.Opart;
+  sym_finalize_rows_kernel<<<(unsigned)p.fin_blocks, 256, 0, s>>>(fr);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++*launches;
+  e = launch_finalize_partials(kf, g, partials, (int64_t)p.grid1 + p.fin_blocks, scalars, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  return cudaSuccess;
+}
+
 }  // namespace
 
 bool tc_sym_eligible(const Geometry& g) {
   if (!tuning().sym) return false;
   if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return false;   // whole problem on this GPU
   const int64_t Mp = round_up(g.m, BM) + round_up(g.n, BM);
-  // measured cross-over against the one-sweep fused kernel (d <= 256: its four launches win below N ~ 24K per side) and
-  // against the row-stacked two-pass path (d > 256: the symmetric path wins from N = 4096 per side on)
-  const int64_t min_rows = tuning().sym_min_rows > 0 ? tuning().sym_min_rows : (g.d <= 256 ? 49152 : 8192);
+  // measured cross-over against the row-stacked fused kernel (d <= 256: N = 8192 per side 0.48 vs 0.34 ms, 16384: 1.15 vs
+  // 1.17 ms, 32768: 3.93 vs 4.38 ms) and against the row-stacked two-pass path (d > 256: wins from N = 4096 per side on)
+  const int64_t min_rows = tuning().sym_min_rows > 0 ? tuning().sym_min_rows : (g.d <= 256 ? 32768 : 8192);
   if (Mp < min_rows) return false;
   return Mp * Mp * 2 <= tuning().sym_max_w_bytes;
 }
 
-size_t tc_sym_workspace_bytes(const Geometry& g) { return sym_plan(g.m, g.n, g.d).off_end; }
+// d <= 256: the fused variant (direct products inside pass 1, mirrored products in pass 2)
+static bool use_symf(const Geometry& g) { return tuning().symf && round_up(g.d, 64) <= 256; }
+
+size_t tc_sym_workspace_bytes(const Geometry& g) {
+  return use_symf(g) ? symf_plan(g.m, g.n, g.d).off_end : sym_plan(g.m, g.n, g.d).off_end;
+}
 
 cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g, const Coefs& c, const SrcLayout& src,
                        double* scalars, float* dX, float* dY, void* ws, size_t ws_bytes, cudaStream_t s, int* launches,
                        const char** path) {
+  if (use_symf(g)) return run_symf(kf, variant, g, c, src, scalars, dX, dY, ws, ws_bytes, s, launches, path);
   char* w = static_cast<char*>(ws);
   cudaError_t e;
   *path = "tc_bf16_sym";
@@ -979,6 +1651,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
     if ((e = launch_sym_wgen(variant, tzi, tzj, tws, ga, p.grid1, s)) != cudaSuccess) return e;
     ++*launches;
   }
+  prof_mark(s);
   SymWzArgs za;
   za.nmb = p.nmb;
   za.FB = p.FB;
@@ -987,6 +1660,8 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   za.S = p.S;
   za.ksteps = p.ksteps;
   za.Opart = reinterpret_cast<float*>(w + p.off_O);
+  za.tonly = 0;
+  za.ell = 1;
   if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
     return e;
   if (only != 1) {
@@ -1017,6 +1692,10 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   fr.dX = dX;
   fr.dY = dY;
   fr.partials = partials + (int64_t)p.grid1 * 6;
+  fr.symf = 0;
+  fr.ell = 1;
+  fr.fgeo = SymfGeo{};
+  fr.Odir = nullptr;
   sym_finalize_rows_kernel<<<(unsigned)p.fin_blocks, 256, 0, s>>>(fr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;

@@ -40,4 +40,20 @@ inline bool make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows,
   return r == CUDA_SUCCESS;
 }
 
+// Same matrix, box = [box_rows][32 cols] (64 B) with the 64-byte swizzle: the per-warp 32 x 32 W blocks that the
+// fused symmetric pass stores from shared memory (16-byte chunk index XOR ((row >> 1) & 3)).
+inline bool make_tmap_bf16_2d_box32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                                    uint64_t pitch_elems, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace smmd_host

@@ -27,7 +27,7 @@ EXPORTS = [
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_poly_sums_workspace_bytes", "smmd_poly_sums",
-    "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms", "smmd_set_option",
+    "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms", "smmd_profile_last_split_ms", "smmd_set_option",
 ]
 
 
@@ -108,6 +108,8 @@ def load():
     lib.smmd_poly_sums_workspace_bytes.argtypes = [C.POINTER(KidProblem)]
     lib.smmd_poly_sums.restype = C.c_int
     lib.smmd_poly_sums.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_profile_last_split_ms.restype = C.c_int
+    lib.smmd_profile_last_split_ms.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.smmd_set_option.restype = C.c_int
     lib.smmd_set_option.argtypes = [C.c_char_p, C.c_longlong]
     _lib = lib
@@ -132,6 +134,19 @@ def last_launch_count():
     return int(load().smmd_last_launch_count())
 
 
+options_epoch = 0   # bumped by set_option: cached workspace sizes depend on the selected path
+
+
 def set_option(name, value):
     """Path-selection option of the library (include/smmd.h: smmd_set_option), e.g. set_option("sym_min_rows", 1)."""
+    global options_epoch
     check(load().smmd_set_option(name.encode(), int(value)), "smmd_set_option(%s)" % name)
+    options_epoch += 1
+
+
+def profile_last_split_ms():
+    """(first kernel ms, second kernel ms) of the last profiled two-kernel call, or None."""
+    a, b = C.c_float(), C.c_float()
+    if load().smmd_profile_last_split_ms(C.byref(a), C.byref(b)) != 0:
+        return None
+    return float(a.value), float(b.value)

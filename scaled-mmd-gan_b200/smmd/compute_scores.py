@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .mmd import _as_ptr, _stream_ptr
+from .mmd import _as_ptr, _stream_ptr, _workspace
 
 _default_precision = "auto"
 
@@ -86,7 +86,7 @@ def kid_subsets(codes_g, codes_r, idx_g, idx_r, degree=3, gamma=None, coef0=1, v
         nbytes = lib.smmd_kid_workspace_bytes(C.byref(p))
         if nbytes == 0:
             raise _lib.SmmdError(-2, "smmd_kid_workspace_bytes", "problem rejected (shape/params)")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes, dev)
         mm = torch.zeros(S, dtype=torch.float64, device=dev)
         vv = torch.zeros(S, dtype=torch.float64, device=dev) if ret_var else None
         st = lib.smmd_kid_subsets(C.byref(p), _as_ptr(codes_g), _as_ptr(codes_r), _as_ptr(idx_g), _as_ptr(idx_r),

@@ -43,7 +43,7 @@ def _default_local_compute(spec, gathered, Xl, Yl, m, n, biased, precision, rank
     """smmd_mmd2_fwd_bwd_gathered on this rank's row block.  Returns (scalars[16] f64, dX_owned, dY_owned)."""
     import ctypes as C
 
-    from .mmd import _as_ptr, _stream_ptr
+    from .mmd import _as_ptr, _stream_ptr, _workspace
 
     lib = _lib.load()
     d = gathered.shape[1]
@@ -55,7 +55,7 @@ def _default_local_compute(spec, gathered, Xl, Yl, m, n, biased, precision, rank
         nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1)
         if nbytes == 0:
             raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes, dev)
         scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
         dX = torch.empty((m // world, d), dtype=torch.float32, device=dev)
         dY = torch.empty((n // world, d), dtype=torch.float32, device=dev)

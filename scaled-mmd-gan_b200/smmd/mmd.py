@@ -98,6 +98,26 @@ def _rows(t):
 
 
 _problem_cache = {}   # (kernel, shapes, strides, dtype, flags) -> (smmd_problem, byref, workspace bytes)
+_ws_cache = {}        # (device index, stream) -> uint8 workspace tensor, grown on demand
+
+
+def _workspace(nbytes, dev):
+    """Per-(device, stream) workspace reused across calls (the library never keeps state in it between calls).  Calls
+    on one stream are ordered, so reuse is safe; another stream gets its own buffer.  Reusing it (instead of a fresh
+    torch.empty per call) keeps the caching allocator from splitting a multi-GB block for a small request and then
+    paying a cudaMalloc of the full size again (seen as a 50 ms step at the 36 GB workspace of N = 65536)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _ws_cache.pop(key, None)
+        ws = None   # drop the old buffer before asking for the larger one
+        ws = _ws_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return ws
+
+
+def release_workspaces():
+    """Free the cached workspaces (e.g. after a one-off large evaluation)."""
+    _ws_cache.clear()
 
 
 def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, rank=0, world=1):
@@ -110,7 +130,7 @@ def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, ran
     n = Yc.shape[0]
     # latency-bound shapes are host-bound: the problem struct and its workspace size are cached per call signature
     key = (spec._key, m, n, d, ldx, ldy, Xc.dtype, bool(biased), precision or _default_precision, rank, world,
-           bool(want_grad))
+           bool(want_grad), _lib.options_epoch)
     cached = _problem_cache.get(key)
     if cached is None:
         prob = spec.problem(m, n, d, ldx, ldy, Xc.dtype, biased, precision, rank, world)
@@ -127,7 +147,7 @@ def fused_mmd2_raw(spec, X, Y, biased=False, want_grad=True, precision=None, ran
         prev = torch.cuda.current_device()
         torch.cuda.set_device(dev)
     try:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes, dev)
         scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
         dX = dY = None
         if want_grad:
@@ -377,7 +397,7 @@ def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
     with torch.cuda.device(dev):
         # statistics run on the exact path: same workspace formula as a forward-only fp32 problem
         nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 0)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes, dev)
         scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
         st = lib.smmd_mmd2_and_ratio(C.byref(prob), _as_ptr(Xc), _as_ptr(Yc), float(min_var_est), _as_ptr(scalars),
                                      _as_ptr(ws), nbytes, _stream_ptr(dev))
@@ -455,7 +475,7 @@ def polynomial_related_sums(X, Y, precision=None):
         nbytes = lib.smmd_poly_sums_workspace_bytes(C.byref(p))
         if nbytes == 0:
             raise _lib.SmmdError(-2, "smmd_poly_sums_workspace_bytes", "problem rejected (shape/params)")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes, dev)
         out = torch.empty(3 * m + 2, dtype=torch.float64, device=dev)
         st = lib.smmd_poly_sums(C.byref(p), _as_ptr(Xc), _as_ptr(Yc), _as_ptr(out), _as_ptr(ws), nbytes, _stream_ptr(dev))
         _lib.check(st, "smmd_poly_sums")

@@ -79,8 +79,30 @@ def test_sym_fwd_bwd_vs_oracle(case, shape, force_sym):
         Yt = torch.tensor(Y, device=DEV, requires_grad=True)
         loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), biased=biased, precision="bf16")
         loss.backward()
-        assert _lib.last_path() == "tc_bf16_sym"
+        # d <= 256: fused variant (direct products inside pass 1, tc_symf_kernel); wider: W generation + O = W_sym Z
+        assert _lib.last_path() == ("tc_bf16_symf" if d <= 256 else "tc_bf16_sym")
         _check(name, kw, X, Y, biased, loss.item(), Xt.grad.cpu().numpy(), Yt.grad.cpu().numpy())
+
+
+@pytest.mark.parametrize("shape", [(300, 200, 100), (1000, 1100, 256), (2048, 2048, 192)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("case", [("mix_rq", {}), ("rbf", {}), ("mix_rq_dot", {}), ("distance", {})], ids=lambda c: c[0])
+def test_sym_unfused_variant_at_narrow_d(case, shape, force_sym):
+    """The plain two-pass symmetric kernels also cover d <= 256 (option symf = 0)."""
+    from smmd import _lib, mmd
+
+    name, kw = case
+    m, n, d = shape
+    X, Y = _data(m, n, d, m + n + d)
+    _lib.set_option("symf", 0)
+    try:
+        Xt = torch.tensor(X, device=DEV, requires_grad=True)
+        Yt = torch.tensor(Y, device=DEV, requires_grad=True)
+        loss = mmd.mmd2(getattr(mmd, "_%s_kernel" % name)(Xt, Yt, **kw), precision="bf16")
+        loss.backward()
+        assert _lib.last_path() == "tc_bf16_sym"
+    finally:
+        _lib.set_option("symf", 1)
+    _check(name, kw, X, Y, False, loss.item(), Xt.grad.cpu().numpy(), Yt.grad.cpu().numpy())
 
 
 def test_sym_deterministic_and_matches_row_stacked_path(force_sym):
@@ -93,7 +115,7 @@ def test_sym_deterministic_and_matches_row_stacked_path(force_sym):
     Xt, Yt = torch.tensor(X, device=DEV), torch.tensor(Y, device=DEV)
     spec = mmd._mix_rq_kernel(Xt, Yt).spec
     a, gXa, gYa = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
-    assert _lib.last_path() == "tc_bf16_sym"
+    assert _lib.last_path() == "tc_bf16_symf"
     b, gXb, gYb = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
     assert torch.equal(a, b) and torch.equal(gXa, gXb) and torch.equal(gYa, gYb)
     _lib.set_option("sym", 0)
@@ -130,17 +152,17 @@ def test_c4_sizes_vs_fp64_oracle(cell):
 
 def test_c4_symmetric_path_at_bench_row_count():
     """The bench.py headline workload (N = 65536, d = 256) takes the symmetric path; the fp64 oracle cannot hold it.
-    Here: the same path at the smallest size it is selected for by default (Mp = 49152) against the exact fp32
+    Here: the same path at the smallest size it is selected for by default (Mp = 32768) against the exact fp32
     SIMT path (itself oracle-pinned at 1e-5), value and every gradient element."""
     from smmd import _lib, mmd
 
-    n, d = 24576, 256
+    n, d = 16384, 256
     g = torch.Generator(device=DEV).manual_seed(7)
     Xt = torch.randn(n, d, device=DEV, generator=g) / d ** 0.5
     Yt = (1.05 * torch.randn(n, d, device=DEV, generator=g) + 0.1) / d ** 0.5
     spec = mmd._mix_rq_kernel(Xt, Yt).spec
     a, gX, gY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
-    assert _lib.last_path() == "tc_bf16_sym"
+    assert _lib.last_path() == "tc_bf16_symf"
     b, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
     assert abs(a[_lib.S_MMD2].item() - b[_lib.S_MMD2].item()) <= 1e-3 * abs(b[_lib.S_MMD2].item()) + 4e-6
     for got, ref in ((gX, rX), (gY, rY)):
