@@ -217,6 +217,20 @@ SMMD_API size_t smmd_poly_sums_workspace_bytes(const smmd_kid_problem* p);
 SMMD_API int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void* Y, double* sums_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* The estimator arithmetic alone, on row statistics the CALLER has reduced from dense kernel blocks -- the dense-block
+ * compatibility entry points `_mmd2_and_variance(K_XX, K_XY, K_YY, ...)` of gan/compute_scores.py:252-335 and
+ * gan/core/mmd.py:236-293 (callers that already hold K matrices).  stats: device double[2 m][6], X rows then Y rows, per row
+ *   [0] sum_j k(z_i, z_j) over its own set without the diagonal   [1] the same over the other set
+ *   [2] sum of squares of [0]'s terms                              [3] sum of squares of [1]'s terms
+ *   [4] k(z_i, z_i)                                                [5] k(x_i, y_i) (X rows; u-statistic)
+ * smmd_kid_from_row_stats writes mmd2_out[0] (and var_out[0] when ret_var); smmd_ratio_from_row_stats writes
+ * scalars[SMMD_S_MMD2 / _VAR / _RATIO] with the reference's quirks (const-diagonal kernels subtract the constant,
+ * the unbiased branch keeps the diagonal). */
+SMMD_API int smmd_kid_from_row_stats(const double* stats, int64_t m, int mmd_est, int ret_var, int64_t var_at_m,
+                                     double* mmd2_out, double* var_out, void* stream);
+SMMD_API int smmd_ratio_from_row_stats(const double* stats, int64_t m, int biased, int has_const_diagonal,
+                                       double const_diagonal, double min_var_est, double* scalars, void* stream);
+
 /* Roofline instrumentation (bench.py): when enabled on this thread, the library records a CUDA-event
  * pair on the launching stream around the DOMINANT kernel of each call (the fused tcgen05 Gram kernel /
  * the K-streaming KID kernel / the SIMT row kernel).  smmd_profile_last_ms() synchronises on the stop

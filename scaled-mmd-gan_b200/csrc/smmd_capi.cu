@@ -531,6 +531,32 @@ size_t smmd_poly_sums_workspace_bytes(const smmd_kid_problem* p) {
   return smmd_kid_workspace_bytes(p);
 }
 
+// ---- estimators on caller-supplied row statistics (dense-block compatibility entry points of the Python layer) ----
+int smmd_kid_from_row_stats(const double* stats, int64_t m, int mmd_est, int ret_var, int64_t var_at_m, double* mmd2_out,
+                            double* var_out, void* stream) {
+  if (!stats || !mmd2_out || (ret_var && !var_out)) return SMMD_EINVAL;
+  if (m < 3) return SMMD_ESHAPE;
+  if (mmd_est < SMMD_EST_UNBIASED || mmd_est > SMMD_EST_USTAT) return SMMD_EINVAL;
+  if (!device_ok()) return SMMD_EARCH;
+  SMMD_CUDA(launch_finalize_kid(stats, 1, m, 0, mmd_est, ret_var, var_at_m > 0 ? var_at_m : m, mmd2_out, var_out,
+                                static_cast<cudaStream_t>(stream)));
+  return SMMD_OK;
+}
+
+int smmd_ratio_from_row_stats(const double* stats, int64_t m, int biased, int has_const_diagonal, double const_diagonal,
+                              double min_var_est, double* scalars, void* stream) {
+  if (!stats || !scalars) return SMMD_EINVAL;
+  if (m < 2) return SMMD_ESHAPE;
+  if (!device_ok()) return SMMD_EARCH;
+  KernelFn kf;
+  memset(&kf, 0, sizeof(kf));
+  kf.has_const_diag = has_const_diagonal ? 1 : 0;
+  kf.const_diag = (float)const_diagonal;
+  Geometry g{m, m, 1, 0, m, 0, m, biased ? 1 : 0};
+  SMMD_CUDA(launch_finalize_ratio(kf, g, stats, min_var_est, scalars, static_cast<cudaStream_t>(stream)));
+  return SMMD_OK;
+}
+
 int smmd_poly_sums(const smmd_kid_problem* p, const void* X, const void* Y, double* sums_out, void* workspace,
                    size_t workspace_bytes, void* stream) {
   g_launches = 0;

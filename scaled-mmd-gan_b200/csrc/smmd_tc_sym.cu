@@ -811,7 +811,11 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_w, stg_ptr, cb, rb * BM + q * 32);
+            // W is kept column-group-major for this path: [Mp / 64 column groups][Mp rows][64 columns], so the two
+            // 32-column halves of a row quarter interleave into one contiguous 4 KB region and pass 2 reads a transposed
+            // 64 x 64 operand box as 8 KB of consecutive memory (row-major W made every 128-byte row segment a separate
+            // DRAM page visit: the mirrored pass ran at 66% of the HBM rate)
+            tma_store_2d(&tmap_w, stg_ptr, cb & 63, (cb >> 6) * (int32_t)a.Mp + rb * BM + q * 32);
             bulk_commit();
           }
           stored = true;
@@ -904,6 +908,7 @@ struct SymWzArgs {
   // steps further than its first).  Pieces are runs of 4 * ell K steps; macro block mb has mb / ell + 1 of them and
   // pieces are numbered mb-major: piece = (P(mb) + s) * FB + fb, P(mb) = sum_{i < mb} (i / ell + 1).
   int tonly, ell;
+  int Mp;         // stacked padded rows (tonly: row stride of a column group of W)
 };
 __host__ __device__ inline int64_t symt_prefix(int mb, int ell) {   // P(mb)
   const int64_t q = mb / ell, r = mb % ell;
@@ -983,9 +988,12 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
           if (ks >= (h ? hlim1 : hlim0)) continue;
           if (!a.tonly && J >= R) {   // stored tile W[R, J]: 128 rows x 64 columns, K-major A
             tma_load_2d(dst, &tmap_wd, &full[st], ks * 64, R * BM);
-          } else {        // stored tile W[J, R] read transposed: 64 K-rows x 128 columns = two 64 x 64 boxes, MN-major A
+          } else if (!a.tonly) {   // stored tile W[J, R] read transposed: 64 K-rows x 128 columns = two 64 x 64 boxes, MN-major A
             tma_load_2d(dst, &tmap_wt, &full[st], R * BM, ks * 64);
             tma_load_2d(dst + 64 * 128, &tmap_wt, &full[st], R * BM + 64, ks * 64);
+          } else {                 // same operand from the column-group-major W of the fused variant (see tc_symf_kernel)
+            tma_load_2d(dst, &tmap_wt, &full[st], 0, (2 * R) * a.Mp + ks * 64);
+            tma_load_2d(dst + 64 * 128, &tmap_wt, &full[st], 0, (2 * R + 1) * a.Mp + ks * 64);
           }
         }
         uint8_t* sb = sa + 2 * BM * 128;
@@ -1479,9 +1487,11 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   if (!smmd_host::make_tmap_bf16_2d(&tzi, Z, p.Mp, p.dp, p.dp, BM)) return cudaErrorUnknown;
   if (!smmd_host::make_tmap_bf16_2d(&tzj, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
   if (!smmd_host::make_tmap_bf16_2d(&tz, Z, p.Mp, p.dp, p.dp, BNF)) return cudaErrorUnknown;
-  if (!smmd_host::make_tmap_bf16_2d(&twd, Wb, p.Mp, p.Mp, p.Mp, BM)) return cudaErrorUnknown;
-  if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, p.Mp, p.Mp, p.Mp, 64)) return cudaErrorUnknown;
-  if (!smmd_host::make_tmap_bf16_2d_box32(&tws, Wb, p.Mp, p.Mp, p.Mp, 32)) return cudaErrorUnknown;   // pass-1 stores
+  // W column-group-major: a 2-D matrix of (Mp / 64) * Mp rows x 64 columns (row = column group * Mp + row of W)
+  const uint64_t wrows = (uint64_t)(p.Mp / 64) * (uint64_t)p.Mp;
+  if (!smmd_host::make_tmap_bf16_2d(&twd, Wb, wrows, 64, 64, BM)) return cudaErrorUnknown;   // (unused by the mirrored pass)
+  if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, wrows, 64, 64, 64)) return cudaErrorUnknown;
+  if (!smmd_host::make_tmap_bf16_2d_box32(&tws, Wb, wrows, 64, 64, 32)) return cudaErrorUnknown;   // pass-1 stores
   const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
   const double wb = cmax * kd_abs_bound(kf);
   int ex = 0;
@@ -1527,6 +1537,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   za.Opart = reinterpret_cast<float*>(w + p.off_O2);
   za.tonly = 1;
   za.ell = p.ell;
+  za.Mp = (int)p.Mp;
   if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
     return e;
   if (only != 1) {
@@ -1662,6 +1673,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   za.Opart = reinterpret_cast<float*>(w + p.off_O);
   za.tonly = 0;
   za.ell = 1;
+  za.Mp = (int)p.Mp;
   if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
     return e;
   if (only != 1) {

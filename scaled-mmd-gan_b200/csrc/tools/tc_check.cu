@@ -93,8 +93,47 @@ static void warm_and_report(const char* tag) {
   cudaFree(d);
 }
 
+// `tc_check suite`: one short call of every tensor-core gradient path in ONE process (for compute-sanitizer runs): the
+// fused symmetric path (tc_symf_kernel + mirrored pass), the plain symmetric path (d > 256), the row-stacked fused
+// tile-pair kernel and the row-stacked two-pass path, each against the exact fp32 path.
+static int run_suite() {
+  struct Case { const char* label; const char* k; int64_t m, n, d; long long sym, min_rows; };
+  const Case cases[] = {{"symf", "mix_rq", 1500, 1400, 256, 1, 1}, {"sym", "mix_rq", 1200, 1300, 320, 1, 1},
+                        {"fused_pair", "mix_rq", 1500, 1400, 256, 0, 0}, {"wz", "mix_rq", 1200, 1300, 320, 0, 0},
+                        {"symf_rbf_d64", "rbf", 700, 900, 64, 1, 1}};
+  int bad = 0;
+  for (const Case& c : cases) {
+    smmd_set_option("sym", c.sym);
+    smmd_set_option("sym_min_rows", c.min_rows);
+    std::mt19937 rng(99);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> hX(c.m * c.d), hY(c.n * c.d);
+    const float sc = 1.f / sqrtf((float)c.d);
+    for (auto& v : hX) v = nd(rng) * sc;
+    for (auto& v : hY) v = (1.05f * nd(rng) + 0.1f) * sc;
+    float *dXin, *dYin;
+    CK(cudaMalloc(&dXin, hX.size() * 4)); CK(cudaMalloc(&dYin, hY.size() * 4));
+    CK(cudaMemcpy(dXin, hX.data(), hX.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dYin, hY.data(), hY.size() * 4, cudaMemcpyHostToDevice));
+    smmd_problem p; fill_problem(&p, c.k, c.m, c.n, c.d);
+    Result tc = run_mmd(p, SMMD_PREC_BF16, dXin, dYin, 1, true);
+    Result ex = run_mmd(p, SMMD_PREC_FP32, dXin, dYin, 1, true);
+    double gmax = 0, emax = 0;
+    for (size_t i = 0; i < tc.gx.size(); ++i) { gmax = fmax(gmax, fabs((double)ex.gx[i])); emax = fmax(emax, fabs((double)tc.gx[i] - ex.gx[i])); }
+    for (size_t i = 0; i < tc.gy.size(); ++i) { gmax = fmax(gmax, fabs((double)ex.gy[i])); emax = fmax(emax, fabs((double)tc.gy[i] - ex.gy[i])); }
+    const double vrel = fabs(tc.sc[0] - ex.sc[0]) / fabs(ex.sc[0]);
+    const bool ok = vrel <= 1e-3 && emax <= 4e-3 * gmax;
+    printf("[suite %-12s %s %lldx%lldx%lld] path=%s launches=%d  mmd2 rel %.2e  grad err/max %.2e  %s\n", c.label, c.k,
+           (long long)c.m, (long long)c.n, (long long)c.d, tc.path, tc.launches, vrel, emax / gmax, ok ? "ok" : "MISMATCH");
+    bad += !ok;
+    cudaFree(dXin); cudaFree(dYin);
+  }
+  return bad;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 1;
+  if (!strcmp(argv[1], "suite")) return run_suite();
   warm_and_report("start");
   if (!strcmp(argv[1], "mmd")) {
     const char* kname = argv[2];

@@ -26,7 +26,7 @@ EXPORTS = [
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
-    "smmd_poly_sums_workspace_bytes", "smmd_poly_sums",
+    "smmd_poly_sums_workspace_bytes", "smmd_poly_sums", "smmd_kid_from_row_stats", "smmd_ratio_from_row_stats",
     "smmd_last_launch_count", "smmd_last_path", "smmd_profile_enable", "smmd_profile_last_ms", "smmd_profile_last_split_ms", "smmd_set_option",
 ]
 
@@ -110,6 +110,10 @@ def load():
     lib.smmd_poly_sums.argtypes = [C.POINTER(KidProblem), vp, vp, vp, vp, C.c_size_t, vp]
     lib.smmd_profile_last_split_ms.restype = C.c_int
     lib.smmd_profile_last_split_ms.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.smmd_kid_from_row_stats.restype = C.c_int
+    lib.smmd_kid_from_row_stats.argtypes = [vp, i64, C.c_int, C.c_int, i64, vp, vp, vp]
+    lib.smmd_ratio_from_row_stats.restype = C.c_int
+    lib.smmd_ratio_from_row_stats.argtypes = [vp, i64, C.c_int, C.c_int, dbl, dbl, vp, vp]
     lib.smmd_set_option.restype = C.c_int
     lib.smmd_set_option.argtypes = [C.c_char_p, C.c_longlong]
     _lib = lib

@@ -138,10 +138,23 @@ def _sqn(arr):
     return flat.dot(flat)
 
 
+def _row_stats_from_blocks(K_XX, K_XY, K_YY, diag_X=None, diag_Y=None):
+    """Dense m x m blocks -> the [2m][6] fp64 row statistics the library's estimators work on (include/smmd.h:
+    smmd_kid_from_row_stats): own-set sums without the diagonal, cross sums, their squares, the diagonal, k(x_i, y_i)."""
+    dx = torch.diagonal(K_XX) if diag_X is None else diag_X
+    dy = torch.diagonal(K_YY) if diag_Y is None else diag_Y
+    pair = torch.diagonal(K_XY)
+    sx = torch.stack([K_XX.sum(1) - dx, K_XY.sum(1), (K_XX * K_XX).sum(1) - dx * dx, (K_XY * K_XY).sum(1), dx, pair], dim=1)
+    sy = torch.stack([K_YY.sum(1) - dy, K_XY.sum(0), (K_YY * K_YY).sum(1) - dy * dy, (K_XY * K_XY).sum(0), dy, pair], dim=1)
+    return torch.cat([sx, sy]).contiguous()
+
+
 def _mmd2_and_variance(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est='unbiased', block_size=1024,
                        var_at_m=None, ret_var=True):
-    """compute_scores.py:252-335 on caller-materialised dense m x m blocks (compatibility entry point:
-    plain fp64 reductions on the GPU; the fused path is polynomial_mmd / polynomial_mmd_averages)."""
+    """compute_scores.py:252-335 on caller-materialised dense m x m blocks (compatibility entry point; the fused path
+    is polynomial_mmd / polynomial_mmd_averages).  The blocks are reduced to per-row statistics with plain fp64
+    reductions on the GPU and the estimator / variance arithmetic is the library's own (smmd_kid_from_row_stats, the
+    finalizer of the fused KID path)."""
     host_in = isinstance(K_XX, np.ndarray)
     dev = torch.device("cuda")
     as_t = lambda a: (torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a).to(dev).double()
@@ -150,52 +163,15 @@ def _mmd2_and_variance(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est='unbiased'
     assert K_XX.shape == (m, m)
     assert K_XY.shape == (m, m)
     assert K_YY.shape == (m, m)
-    if var_at_m is None:
-        var_at_m = m
-    if unit_diagonal:
-        diag_X = diag_Y = torch.ones(m, dtype=torch.float64, device=dev)
-    else:
-        diag_X, diag_Y = torch.diagonal(K_XX), torch.diagonal(K_YY)
-    sum_diag_X, sum_diag_Y = diag_X.sum(), diag_Y.sum()
-    sum_diag2_X, sum_diag2_Y = _sqn(diag_X), _sqn(diag_Y)
-    Kt_XX_sums = K_XX.sum(dim=1) - diag_X
-    Kt_YY_sums = K_YY.sum(dim=1) - diag_Y
-    K_XY_sums_0 = K_XY.sum(dim=0)
-    K_XY_sums_1 = K_XY.sum(dim=1)
-    Kt_XX_sum, Kt_YY_sum, K_XY_sum = Kt_XX_sums.sum(), Kt_YY_sums.sum(), K_XY_sums_0.sum()
-    if mmd_est == 'biased':
-        mmd2 = ((Kt_XX_sum + sum_diag_X) / (m * m) + (Kt_YY_sum + sum_diag_Y) / (m * m)
-                - 2 * K_XY_sum / (m * m))
-    else:
-        assert mmd_est in {'unbiased', 'u-statistic'}
-        mmd2 = (Kt_XX_sum + Kt_YY_sum) / (m * (m - 1))
-        if mmd_est == 'unbiased':
-            mmd2 = mmd2 - 2 * K_XY_sum / (m * m)
-        else:
-            mmd2 = mmd2 - 2 * (K_XY_sum - torch.trace(K_XY)) / (m * (m - 1))
+    if mmd_est not in _lib.ESTIMATORS:
+        raise AssertionError("mmd_est must be one of %s" % sorted(_lib.ESTIMATORS))
+    ones = torch.ones(m, dtype=torch.float64, device=dev) if unit_diagonal else None   # :266-269: the diagonal is taken as 1
+    stats = _row_stats_from_blocks(K_XX, K_XY, K_YY, ones, ones)
+    out = torch.zeros(2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().smmd_kid_from_row_stats(_as_ptr(stats), m, _lib.ESTIMATORS[mmd_est], 1 if ret_var else 0,
+                                                 int(var_at_m) if var_at_m is not None else m, _as_ptr(out[0:1]),
+                                                 _as_ptr(out[1:2]), _stream_ptr(dev))
+    _lib.check(st, "smmd_kid_from_row_stats")
     fin = (lambda t: float(t.item())) if host_in else (lambda t: t)
-    if not ret_var:
-        return fin(mmd2)
-    Kt_XX_2_sum = _sqn(K_XX) - sum_diag2_X
-    Kt_YY_2_sum = _sqn(K_YY) - sum_diag2_Y
-    K_XY_2_sum = _sqn(K_XY)
-    dot_XX_XY = Kt_XX_sums.dot(K_XY_sums_1)
-    dot_YY_YX = Kt_YY_sums.dot(K_XY_sums_0)
-    m1, m2 = m - 1, m - 2
-    zeta1_est = (
-        1 / (m * m1 * m2) * (_sqn(Kt_XX_sums) - Kt_XX_2_sum + _sqn(Kt_YY_sums) - Kt_YY_2_sum)
-        - 1 / (m * m1) ** 2 * (Kt_XX_sum ** 2 + Kt_YY_sum ** 2)
-        + 1 / (m * m * m1) * (_sqn(K_XY_sums_1) + _sqn(K_XY_sums_0) - 2 * K_XY_2_sum)
-        - 2 / m ** 4 * K_XY_sum ** 2
-        - 2 / (m * m * m1) * (dot_XX_XY + dot_YY_YX)
-        + 2 / (m ** 3 * m1) * (Kt_XX_sum + Kt_YY_sum) * K_XY_sum)
-    zeta2_est = (
-        1 / (m * m1) * (Kt_XX_2_sum + Kt_YY_2_sum)
-        - 1 / (m * m1) ** 2 * (Kt_XX_sum ** 2 + Kt_YY_sum ** 2)
-        + 2 / (m * m) * K_XY_2_sum
-        - 2 / m ** 4 * K_XY_sum ** 2
-        - 4 / (m * m * m1) * (dot_XX_XY + dot_YY_YX)
-        + 4 / (m ** 3 * m1) * (Kt_XX_sum + Kt_YY_sum) * K_XY_sum)
-    var_est = (4 * (var_at_m - 2) / (var_at_m * (var_at_m - 1)) * zeta1_est
-               + 2 / (var_at_m * (var_at_m - 1)) * zeta2_est)
-    return fin(mmd2), fin(var_est)
+    return (fin(out[0]), fin(out[1])) if ret_var else fin(out[0])

@@ -106,6 +106,9 @@ def _workspace(nbytes, dev):
     on one stream are ordered, so reuse is safe; another stream gets its own buffer.  Reusing it (instead of a fresh
     torch.empty per call) keeps the caching allocator from splitting a multi-GB block for a small request and then
     paying a cudaMalloc of the full size again (seen as a 50 ms step at the 36 GB workspace of N = 65536)."""
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture: the buffer must live in the graph's own pool for as long as the graph does
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -405,41 +408,37 @@ def mmd2_and_ratio(K, biased=False, min_var_est=_eps):
     return (scalars[_lib.S_MMD2].float(), scalars[_lib.S_RATIO].float(), scalars[_lib.S_VAR].float())
 
 
+def _ratio_scalars_from_blocks(K_XX, K_XY, K_YY, const_diagonal, biased, min_var_est):
+    """Dense blocks -> row statistics (plain reductions) -> the library's ratio finalizer (smmd_ratio_from_row_stats:
+    the same kernel that finishes the fused mmd2_and_ratio, reference quirks included)."""
+    from .compute_scores import _row_stats_from_blocks
+
+    m = K_XX.shape[0]
+    if K_XX.shape != (m, m) or K_XY.shape != (m, m) or K_YY.shape != (m, m):
+        raise ValueError("mmd2_and_ratio assumes X and Y have the same number of rows (mmd.py:237)")
+    dev = K_XX.device
+    stats = _row_stats_from_blocks(K_XX.double(), K_XY.double(), K_YY.double())
+    scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
+    has_cd = const_diagonal is not False
+    with torch.cuda.device(dev):
+        st = _lib.load().smmd_ratio_from_row_stats(_as_ptr(stats), m, 1 if biased else 0, 1 if has_cd else 0,
+                                                   float(const_diagonal) if has_cd else 0.0, float(min_var_est),
+                                                   _as_ptr(scalars), _stream_ptr(dev))
+    _lib.check(st, "smmd_ratio_from_row_stats")
+    return scalars
+
+
 def _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=False, biased=False):
-    """mmd.py:236-293 on caller-materialised dense blocks (torch): (mmd2, var_est).  Compatibility path made of plain
-    reductions, including the reference's quirk that the unbiased estimate keeps the diagonal (:273-276)."""
-    m = float(K_XX.shape[0])
-    if const_diagonal is not False:
-        cd = float(const_diagonal)
-        dg_x = dg_y = cd
-        sdg_x = sdg_y = m * cd
-        sdg2_x = sdg2_y = m * cd * cd
-    else:
-        dg_x, dg_y = torch.diagonal(K_XX), torch.diagonal(K_YY)
-        sdg_x, sdg_y = dg_x.sum(), dg_y.sum()
-        sdg2_x, sdg2_y = (dg_x * dg_x).sum(), (dg_y * dg_y).sum()
-    r_x, r_y = K_XX.sum(1) - dg_x, K_YY.sum(1) - dg_y
-    c0, c1 = K_XY.sum(0), K_XY.sum(1)
-    s_x, s_y, s_xy = r_x.sum(), r_y.sum(), c0.sum()
-    q_x, q_y, q_xy = (K_XX * K_XX).sum() - sdg2_x, (K_YY * K_YY).sum() - sdg2_y, (K_XY * K_XY).sum()
-    if biased:
-        mmd2_val = (s_x + sdg_x) / (m * m) + (s_y + sdg_y) / (m * m) - 2 * s_xy / (m * m)
-    else:
-        mmd2_val = (s_x + sdg_x) / (m * (m - 1)) + (s_y + sdg_y) / (m * (m - 1)) - 2 * s_xy / (m * m)
-    var_est = (2 / (m ** 2 * (m - 1) ** 2) * (2 * (r_x * r_x).sum() - q_x + 2 * (r_y * r_y).sum() - q_y)
-               - (4 * m - 6) / (m ** 3 * (m - 1) ** 3) * (s_x ** 2 + s_y ** 2)
-               + 4 * (m - 2) / (m ** 3 * (m - 1) ** 2) * ((c1 * c1).sum() + (c0 * c0).sum())
-               - 4 * (m - 3) / (m ** 3 * (m - 1) ** 2) * q_xy
-               - (8 * m - 12) / (m ** 5 * (m - 1)) * s_xy ** 2
-               + 8 / (m ** 3 * (m - 1)) * (1 / m * (s_x + s_y) * s_xy - (r_x * c1).sum() - (r_y * c0).sum()))
-    return mmd2_val, var_est
+    """mmd.py:236-293 on caller-materialised dense blocks (CUDA tensors): (mmd2, var_est), including the reference's
+    quirk that the unbiased estimate keeps the diagonal (:273-276)."""
+    sc = _ratio_scalars_from_blocks(K_XX, K_XY, K_YY, const_diagonal, biased, _eps)
+    return sc[_lib.S_MMD2].to(K_XX.dtype), sc[_lib.S_VAR].to(K_XX.dtype)
 
 
 def _mmd2_and_ratio(K_XX, K_XY, K_YY, const_diagonal=False, biased=False, min_var_est=_eps):
     """mmd.py:228-233 on dense blocks: (mmd2, ratio = mmd2 / sqrt(max(var_est, min_var_est)), var_est)."""
-    mmd2_val, var_est = _mmd2_and_variance(K_XX, K_XY, K_YY, const_diagonal=const_diagonal, biased=biased)
-    ratio = mmd2_val / torch.sqrt(torch.clamp(var_est, min=min_var_est))
-    return mmd2_val, ratio, var_est
+    sc = _ratio_scalars_from_blocks(K_XX, K_XY, K_YY, const_diagonal, biased, min_var_est)
+    return sc[_lib.S_MMD2].to(K_XX.dtype), sc[_lib.S_RATIO].to(K_XX.dtype), sc[_lib.S_VAR].to(K_XX.dtype)
 
 
 # ---------------------------------------------------------------------------------------------------

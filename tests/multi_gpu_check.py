@@ -24,7 +24,11 @@ def main():
     # bf16 path: shards cut the tile stream elsewhere -> fp32 accumulation order differs, amplified by the
     # cancellation in r*z - O (measured 3-5e-5 of max|g|; the bf16 tier itself is 4e-3)
     # d = 512 takes the two-pass path (W row panels + GEMM) on the gathered layout
-    for (b, d, precision, gtol) in ((64, 16, "fp32", 1e-5), (1024, 128, "bf16", 2e-4), (768, 512, "bf16", 2e-4)):
+    # the last two are sizes at which the UNSHARDED reference takes the symmetric paths (tc_bf16_symf / tc_bf16_sym: every
+    # unordered pair once, different r_i bookkeeping) while the shards run the row-stacked kernels: both are bf16
+    # evaluations within 4e-3 max|g| of the oracle, they agree to ~1e-3
+    for (b, d, precision, gtol, vtol) in ((64, 16, "fp32", 1e-5, 1e-6), (1024, 128, "bf16", 2e-4, 1e-6), (768, 512, "bf16", 2e-4, 1e-6),
+                                          (16384 // world, 256, "bf16", 2e-3, 1e-4), (8192 // world, 512, "bf16", 2e-3, 1e-4)):
         rng = np.random.RandomState(100 + rank)
         Xl = torch.tensor((rng.randn(b, d) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
         Yl = torch.tensor(((1.05 * rng.randn(b, d) + 0.1) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
@@ -39,7 +43,7 @@ def main():
         Ya = torch.cat(Ys).requires_grad_(True)
         ref = mmd.mmd2(mmd._mix_rq_kernel(Xa, Ya), precision=precision)
         ref.backward()
-        c1 = abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-12
+        c1 = abs(loss.item() - ref.item()) <= vtol * abs(ref.item()) + 1e-12
         ex = (Xl.grad - Xa.grad[rank * b:(rank + 1) * b]).abs().max().item() / Xa.grad.abs().max().item()
         ey = (Yl.grad - Ya.grad[rank * b:(rank + 1) * b]).abs().max().item() / Ya.grad.abs().max().item()
         if not (c1 and ex <= gtol and ey <= gtol):

@@ -253,3 +253,28 @@ def test_general_exact_path_on_the_same_golden_cases():
                         "test_fp32_path_matches_reference_golden", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_dense_block_ratio_helpers_match_oracle():
+    """smmd.mmd._mmd2_and_variance / _mmd2_and_ratio (mmd.py:228-293) on dense torch blocks vs the numpy oracle: the
+    blocks are reduced to row statistics and finished by the library's own ratio finalizer (smmd_ratio_from_row_stats)."""
+    import torch
+
+    from smmd import mmd
+
+    rng = np.random.RandomState(5)
+    X = rng.randn(40, 6)
+    Y = 1.1 * rng.randn(40, 6) + 0.1
+    for name, kw in (("mix_rbf", {"sigmas": [1.0, 2.0, 4.0]}), ("distance", {}), ("mix_rq_1dot", {})):
+        Kxx, Kxy, Kyy, cd = mmd_oracle.kernel_matrices(name, X, Y, np.float64, **kw)
+        for biased in (False, True):
+            v, ratio, var = mmd_oracle.mmd2_and_ratio(name, X, Y, biased, 1e-5, np.float64, **kw)
+            blocks = [torch.tensor(K, device=DEV) for K in (Kxx, Kxy, Kyy)]
+            gv, gvar = mmd._mmd2_and_variance(*blocks, const_diagonal=cd, biased=biased)
+            gv2, gr, gvar2 = mmd._mmd2_and_ratio(*blocks, const_diagonal=cd, biased=biased)   # 3-tuple: mmd.py:233
+            assert abs(float(gv) - v) <= 1e-11 * abs(v) and abs(float(gvar) - var) <= 1e-9 * abs(var) + 1e-18
+            assert abs(float(gv2) - v) <= 1e-11 * abs(v) and abs(float(gr) - ratio) <= 1e-9 * abs(ratio)
+            assert float(gvar2) == float(gvar)
+            # mmd2_and_ratio takes the explicit 4-tuple as well (mmd.py:224-225)
+            tv, tr, tvar = mmd.mmd2_and_ratio((blocks[0], blocks[1], blocks[2], cd), biased=biased)
+            assert float(tv) == float(gv2) and float(tr) == float(gr) and float(tvar) == float(gvar)

@@ -124,30 +124,6 @@ def test_kid_rejects_non_square():
         kid_oracle.mmd2_and_variance(K, np.ones((4, 5)), K)
 
 
-def test_dense_block_ratio_helpers_match_oracle():
-    """smmd.mmd._mmd2_and_variance / _mmd2_and_ratio (mmd.py:228-293) on dense torch blocks vs the numpy oracle."""
-    import torch
-
-    from smmd import mmd
-
-    rng = np.random.RandomState(5)
-    X = rng.randn(40, 6)
-    Y = 1.1 * rng.randn(40, 6) + 0.1
-    for name, kw in (("mix_rbf", {"sigmas": [1.0, 2.0, 4.0]}), ("distance", {}), ("mix_rq_1dot", {})):
-        Kxx, Kxy, Kyy, cd = mmd_oracle.kernel_matrices(name, X, Y, np.float64, **kw)
-        for biased in (False, True):
-            v, ratio, var = mmd_oracle.mmd2_and_ratio(name, X, Y, biased, 1e-5, np.float64, **kw)
-            blocks = [torch.tensor(K) for K in (Kxx, Kxy, Kyy)]
-            gv, gvar = mmd._mmd2_and_variance(*blocks, const_diagonal=cd, biased=biased)
-            gv2, gr, gvar2 = mmd._mmd2_and_ratio(*blocks, const_diagonal=cd, biased=biased)   # 3-tuple: mmd.py:233
-            assert abs(float(gv) - v) <= 1e-12 * abs(v) and abs(float(gvar) - var) <= 1e-9 * abs(var) + 1e-18
-            assert abs(float(gv2) - v) <= 1e-12 * abs(v) and abs(float(gr) - ratio) <= 1e-9 * abs(ratio)
-            assert float(gvar2) == float(gvar)
-            # mmd2_and_ratio takes the explicit 4-tuple as well (mmd.py:224-225)
-            tv, tr, tvar = mmd.mmd2_and_ratio((blocks[0], blocks[1], blocks[2], cd), biased=biased)
-            assert float(tv) == float(gv2) and float(tr) == float(gr) and float(tvar) == float(gvar)
-
-
 def test_cpu_port_matches_reference_golden():
     """oracle/cpu_port.py (the bench's fallback CPU arm when the reference sources are not staged) against the
     reference-minted golden values and gradients of the mix_rq cases."""
