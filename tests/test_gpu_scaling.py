@@ -49,9 +49,13 @@ def test_scaled_loss_parameter_gradients_vs_oracle(kernel, dof, variant):
     assert abs(float(scale) - float(rscale)) <= 1e-4 * float(rscale)
     assert abs(float(unscaled) - float(rmmd2)) <= 1e-5 * abs(float(rmmd2)) + 1e-7
     assert abs(float(g_loss) - float(rg)) <= 1e-4 * abs(float(rg)) + 1e-7
+    # (the last bias has an exactly zero gradient for distance-based kernels -- a common shift of all features changes
+    # nothing -- so every parameter is compared on the scale of the largest gradient of its kind, not its own)
+    gmax = max(float(q.grad.abs().max()) for q in ref_net.parameters())
     for (name, p), q in zip(net.named_parameters(), ref_net.parameters()):
         got, ref = p.grad.double().cpu(), q.grad
-        assert (got - ref).abs().max() <= 2e-4 * ref.abs().max() + 1e-9, (name, float((got - ref).abs().max()), float(ref.abs().max()))
+        tol = 2e-4 * max(float(ref.abs().max()), 1e-3 * gmax)
+        assert (got - ref).abs().max() <= tol, (name, float((got - ref).abs().max()), float(ref.abs().max()), gmax)
 
 
 def test_scaled_mmd2_backward_is_scale_times_dx_and_mmd2():
