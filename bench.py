@@ -375,6 +375,11 @@ def run_ours(args):
                 "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_rank,
                 "frac_from_step_loop": 14.0 * n * n * d / world / (ms_per_step * 1e-3) / 1e12 / peak}
+    try:   # informational: the same achieved rate against the SUSTAINED cuBLAS peak (this loop runs power-capped)
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            roofline["frac_of_sustained_peak"] = achieved / float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        pass
     if kernels:
         roofline["kernels"] = kernels
 

@@ -103,10 +103,10 @@ struct SymWgenArgs {
   double* partials;              // [gridDim.x][6]: (sxx, syy, sxy, syx, 0, 0) of this CTA
 };
 
-__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -453,7 +453,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmap_w, stg_ptr, c0, rb * BM + q * 32);
+          tma_store_2d_hint(&tmap_w, stg_ptr, c0, rb * BM + q * 32, kL2EvictFirst);
           bulk_commit();
         }
         stored = true;
@@ -815,7 +815,7 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
             // 32-column halves of a row quarter interleave into one contiguous 4 KB region and pass 2 reads a transposed
             // 64 x 64 operand box as 8 KB of consecutive memory (row-major W made every 128-byte row segment a separate
             // DRAM page visit: the mirrored pass ran at 66% of the HBM rate)
-            tma_store_2d(&tmap_w, stg_ptr, cb & 63, (cb >> 6) * (int32_t)a.Mp + rb * BM + q * 32);
+            tma_store_2d_hint(&tmap_w, stg_ptr, cb & 63, (cb >> 6) * (int32_t)a.Mp + rb * BM + q * 32, kL2EvictFirst);
             bulk_commit();
           }
           stored = true;
@@ -986,18 +986,20 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
           const int R = 2 * mb + h;
           uint8_t* dst = sa + h * (BM * 128);
           if (ks >= (h ? hlim1 : hlim0)) continue;
+          // W streams through once per direction (evict-first: it must not displace Z, which every CTA re-reads)
           if (!a.tonly && J >= R) {   // stored tile W[R, J]: 128 rows x 64 columns, K-major A
-            tma_load_2d(dst, &tmap_wd, &full[st], ks * 64, R * BM);
+            tma_load_2d_hint(dst, &tmap_wd, &full[st], ks * 64, R * BM, kL2EvictFirst);
           } else if (!a.tonly) {   // stored tile W[J, R] read transposed: 64 K-rows x 128 columns = two 64 x 64 boxes, MN-major A
-            tma_load_2d(dst, &tmap_wt, &full[st], R * BM, ks * 64);
-            tma_load_2d(dst + 64 * 128, &tmap_wt, &full[st], R * BM + 64, ks * 64);
+            tma_load_2d_hint(dst, &tmap_wt, &full[st], R * BM, ks * 64, kL2EvictFirst);
+            tma_load_2d_hint(dst + 64 * 128, &tmap_wt, &full[st], R * BM + 64, ks * 64, kL2EvictFirst);
           } else {                 // same operand from the column-group-major W of the fused variant (see tc_symf_kernel)
-            tma_load_2d(dst, &tmap_wt, &full[st], 0, (2 * R) * a.Mp + ks * 64);
-            tma_load_2d(dst + 64 * 128, &tmap_wt, &full[st], 0, (2 * R + 1) * a.Mp + ks * 64);
+            tma_load_2d_hint(dst, &tmap_wt, &full[st], 0, (2 * R) * a.Mp + ks * 64, kL2EvictFirst);
+            tma_load_2d_hint(dst + 64 * 128, &tmap_wt, &full[st], 0, (2 * R + 1) * a.Mp + ks * 64, kL2EvictFirst);
           }
         }
         uint8_t* sb = sa + 2 * BM * 128;
-        for (int p = 0; p < npan; ++p) tma_load_2d(sb + p * (BNF * 128), &tmap_z, &full[st], fb * 256 + p * 64, ks * 64);
+        for (int p = 0; p < npan; ++p)
+          tma_load_2d_hint(sb + p * (BNF * 128), &tmap_z, &full[st], fb * 256 + p * 64, ks * 64, kL2EvictLast);
       }
       __syncwarp();
       if (++st == kSzStages) {
