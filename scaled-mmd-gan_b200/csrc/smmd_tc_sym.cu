@@ -1248,20 +1248,23 @@ struct SymPlan {
   size_t off_Z, off_norm, off_csum, off_W, off_racc, off_O, off_stats, off_end;
 };
 
-// K splits per unit so that units * S fills whole waves of SMs (>= 8 K steps per piece, <= 16 splits)
+// K splits per unit, chosen by a small cost model (cycles): a piece costs its K steps (8 UMMAs of 128 x 256 x 16 = 1024
+// tensor cycles per step) plus a fixed ~14K cycles (TMEM allocation, pipeline fill, 256 KB drain); pieces run in waves of
+// #SMs; every piece also adds 512 KB of slab traffic (written here, read by the finalize kernel).  The first version
+// maximised wave occupancy alone and cut N = 8192, d = 512 into 1920 pieces of 17 K steps: 273 us for a 140 us GEMM.
 int sym_choose_split(int units, int KT) {
   const int sm = sm_count();
   int best = 1;
-  double best_eff = 0.0;
+  double best_cost = 1e300;
   for (int S = 1; S <= 16 && KT / S >= 8; ++S) {
     const int64_t pieces = (int64_t)units * S;
     const int64_t waves = (pieces + sm - 1) / sm;
-    const double eff = (double)pieces / (double)(waves * sm);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
+    const double ksteps = (double)((KT + S - 1) / S);
+    const double cost = (double)waves * (ksteps * 1024.0 + 14000.0) + (double)pieces * 153.0;
+    if (cost < best_cost) {
+      best_cost = cost;
       best = S;
     }
-    if (eff >= 0.92) return S;
   }
   return best;
 }
