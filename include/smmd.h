@@ -244,7 +244,7 @@ SMMD_API int smmd_profile_last_split_ms(float* first_ms, float* second_ms);
 
 /* Path-selection options (process-wide; set them before concurrent use).  Values are validated and clamped to what
  * the kernels support.  Names: "sym" (0/1: symmetric two-pass path), "sym_min_rows" (stacked rows from which it is
- * used; 0 = measured default), "sym_max_w_mb", "fused_pair", "fused_lockstep", "fused_ksplit", "wz_pair",
+ * used; 0 = measured default), "symf" / "symf_min_rows" (fused variant for d <= 256), "sym_max_w_mb", "fused_pair", "fused_lockstep", "fused_ksplit", "wz_pair",
  * "wz_min_d" (clamped to [0, 256]), "wz_panel_mb", "disable_small".  Tests use them to run a given code path on a
  * small shape; there is no reference counterpart.  Returns SMMD_EINVAL for an unknown name. */
 SMMD_API int smmd_set_option(const char* name, long long value);

@@ -213,6 +213,7 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 constexpr uint32_t kFmtBF16 = 1;
+constexpr uint32_t kFmtF16 = 0;
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05: MMA, commit
@@ -322,6 +323,22 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// same for fp16 (IEEE half: 11-bit significand, range 6e-5 .. 65504)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t packed) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}\n" : "=f"(r) : "r"(packed));
+  return r;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t packed) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}\n" : "=f"(r) : "r"(packed));
   return r;
 }
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }

@@ -59,10 +59,12 @@ __host__ __device__ inline int64_t src_row(int64_t i, bool in_x, int64_t blk_x, 
 struct Coefs {
   double a_xx, a_yy, a_xy;  // a_xy = -1/(m n)
   int diag_in_sum;          // 1 if K_ii enters the estimator (biased, or unbiased + const-diag quirk)
+  int f16;                  // tensor-core gradient paths: fp16 operands (SMMD_PREC_FP16) instead of bf16
 };
 
 inline Coefs make_coefs(const Geometry& g, const KernelFn& k) {
   Coefs c;
+  c.f16 = 0;
   double m = (double)g.m, n = (double)g.n;
   if (g.biased) {
     c.a_xx = 1.0 / (m * m);

@@ -24,6 +24,7 @@
 // workspace slabs and are reduced in a fixed order by the finalisation kernel (deterministic).  The Gram + reduction
 // kernels deal tiles round-robin (L2 residency) and accumulate row statistics with fp64 atomics.
 // Shared pieces (constants, tuning knobs, PrepTcArgs, the 16-column epilogue step): smmd_tc_common.cuh.
+#include <cuda_fp16.h>
 #include "smmd_tc_common.cuh"
 
 namespace smmd {
@@ -49,7 +50,25 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
   // per step (2 x LDG.128 -> 1 x STG.128), several independent loads in flight
   const bool vec = a.dtype == SMMD_F32 && !a.split && (ld % 4 == 0) && (a.d % 8 == 0) &&
                    ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-  if (vec) {
+  if (a.f16) {
+    // fp16 operand tier: IEEE half operands (11-bit significand); norms from exactly the rounded values
+    for (int64_t c = 2 * lane; c < a.dp; c += 64) {
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (valid && c + e < a.d) {
+          v[e] = a.dtype == SMMD_F32 ? reinterpret_cast<const float*>(base)[src * ld + c + e]
+                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[src * ld + c + e]);
+          if (a.tanh_features) v[e] = tanhf(v[e]);
+        }
+      }
+      const __half2 h2 = __floats2half2_rn(v[0], v[1]);
+      const float2 f2 = __half22float2(h2);
+      *reinterpret_cast<__half2*>(zrow + c) = h2;
+      acc = fmaf(f2.x, f2.x, acc);
+      acc = fmaf(f2.y, f2.y, acc);
+    }
+  } else if (vec) {
     const float* srow = reinterpret_cast<const float*>(base) + src * ld;
     for (int64_t c = 8 * lane; c < a.dp; c += 256) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include "sm100_ptx.cuh"
 #include "smmd_kfun.cuh"
@@ -40,7 +41,8 @@ struct Tuning {
   int sym;              // symmetric two-pass path for whole problems (default 1)
   int symf;             // d <= 256: fused variant of the symmetric path (direct products inside pass 1; default 1)
   int sym_only;         // DEV timing knob: 1 = pass 1 only, 2 = pass 2 only; results are meaningless
-  int64_t sym_min_rows;      // stacked rows from which the symmetric path is used (0 = the measured per-d default)
+  int64_t sym_min_rows;      // stacked rows from which the symmetric paths are used (0 = the measured default)
+  int64_t symf_min_rows;     // stacked rows from which d <= 256 takes the fused variant (0 = the measured default)
   int64_t sym_max_w_bytes;   // largest W (Mp x Mp bf16) the symmetric path may place in the workspace
   int disable_small;    // exact path: skip the one-launch small-problem kernel (tests: force the general kernels)
 };
@@ -56,6 +58,7 @@ inline bool tuning_set(Tuning& v, const char* name, int64_t x) {
   else if (!strcmp(name, "sym")) v.sym = x != 0;
   else if (!strcmp(name, "symf")) v.symf = x != 0;
   else if (!strcmp(name, "sym_min_rows")) v.sym_min_rows = clamp_i64(x, 0, (int64_t)1 << 40);
+  else if (!strcmp(name, "symf_min_rows")) v.symf_min_rows = clamp_i64(x, 0, (int64_t)1 << 40);
   else if (!strcmp(name, "sym_max_w_mb")) v.sym_max_w_bytes = clamp_i64(x, 0, (int64_t)1 << 24) << 20;
   else if (!strcmp(name, "disable_small")) v.disable_small = x != 0;
 #ifdef SMMD_DEV_KNOBS
@@ -79,10 +82,11 @@ inline Tuning& tuning_mut() {
     v.symf = 1;
     v.sym_only = 0;
     v.sym_min_rows = 0;
+    v.symf_min_rows = 0;
     v.sym_max_w_bytes = (int64_t)48 << 30;
     v.disable_small = 0;
     static const char* const names[] = {"fused_ksplit", "fused_pair", "fused_lockstep", "wz_min_d", "wz_panel_mb", "wz_pair",
-                                        "sym", "symf", "sym_min_rows", "sym_max_w_mb", "disable_small", "debug_nullmath", "sym_only"};
+                                        "sym", "symf", "sym_min_rows", "symf_min_rows", "sym_max_w_mb", "disable_small", "debug_nullmath", "sym_only"};
     for (const char* nm : names) {
       char env[64] = "SMMD_";
       size_t k = 5;
@@ -128,6 +132,7 @@ struct PrepTcArgs {
   double* stats;  // optional [batch][m+n][RS_COUNT]: zeroed, RS_DIAG set analytically
   KernelFn kf;
   int64_t blk_a, blk_b;  // gathered block layout (0 = plain), see SrcLayout
+  int f16;               // write IEEE half instead of bf16 (fp16 operand tier; not with `split`)
 };
 
 // launch wrappers (kernels live in smmd_tc.cu): grid = (ceil(rows / 8), batch)
@@ -176,9 +181,35 @@ __device__ __forceinline__ void fused_chunk16(const Math& math, const uint32_t (
       tsum = add2(tsum, k[e]);
       const float2 ww = mul2(kd[e], cw);
       rsum = add2(rsum, ww);
-      wpk[(c >> 1) + e] = pack_bf16x2(ww.x, ww.y);
+      wpk[(c >> 1) + e] = pack_w<Math::kF16>(ww.x, ww.y);
     }
   }
+}
+
+// bound of |dk/dD| over D >= 0 (sizes the fixed-point accumulator of the row sums of W and the fp16 scale of W)
+inline double kd_abs_bound(const KernelFn& kf) {
+  double b = 0.0;
+  switch (kf.family) {
+    case FAM_RBF:
+      for (int i = 0; i < kf.np; ++i) b += fabs((double)kf.w[i]) * (double)kf.p0[i];
+      break;
+    case FAM_RQ:
+      for (int i = 0; i < kf.np; ++i) b += 0.5 * fabs((double)kf.w[i]);
+      break;
+    case FAM_DISTANCE: b = 0.5 / sqrt(1.0e-7); break;
+    default: b = 1.0;
+  }
+  return b > 0.0 ? b : 1.0;
+}
+// fp16 operand tier: W = 4 a k'(D) is ~1/N^2 and would underflow IEEE half, so it is carried times a power of two chosen
+// from its bound (largest |W| lands near 2^12; half keeps 11 significant bits down to 2^-14, i.e. over 26 binades below
+// the largest weight) and the gradient rows are multiplied back in the finalize kernels.  bf16 tier: scale 1.
+inline double w_scale_for(const Coefs& c, const KernelFn& kf) {
+  if (!c.f16) return 1.0;
+  const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
+  int ex = 0;
+  frexp(cmax * kd_abs_bound(kf), &ex);   // bound < 2^ex
+  return ldexp(1.0, std::max(-120, std::min(120, 12 - ex)));
 }
 
 // ---- per-path entry points (one translation unit each); `variant` = select_tc_variant(kf) ----

@@ -468,8 +468,8 @@ tc_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_c
     }
   } else if (warp == EPI_WARPS + 1) {
     // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, kFmtBF16, false, false);
-    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
+    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, operand_fmt<Math>(), false, false);
+    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, operand_fmt<Math>(), false, true);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
     const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);                 // K-major B of UMMA #1 (two stages = 128 rows)
@@ -654,6 +654,7 @@ struct FinRowsArgs {
   float* dX;
   float* dY;
   double* partials;  // [gridDim.x][6] per-CTA block sums (second stage: launch_finalize_partials)
+  float gscale;      // 1 / (power-of-two scale W was carried with): 1 for bf16 operands, see w_scale_for()
 };
 
 constexpr int kFinRowsPerWarp = 4;
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
-            gv[e] = rs * zz[e] - oo[e];                      // W already carries the factor 4 a_ij
+            gv[e] = (rs * zz[e] - oo[e]) * a.gscale;         // W already carries the factor 4 a_ij
             if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
           }
           *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
@@ -770,7 +771,7 @@ __global__ void __launch_bounds__(256) tc_finalize_rows_kernel(FinRowsArgs a) {
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
         if (a.kf.tanh_features) z = tanhf(z);
         if (out) {
-          float gv = rs * z - oacc[t];
+          float gv = (rs * z - oacc[t]) * a.gscale;
           if (dot) {
             const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
             gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a_xy * co));
@@ -899,8 +900,19 @@ cudaError_t launch_fused_pair_t(const CUtensorMap& tzi, const CUtensorMap& tzj, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_fused_pair(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
+cudaError_t launch_fused_pair(TcVariant v, bool f16, const CUtensorMap& tzi, const CUtensorMap& tzj, const FusedArgs& a, int grid,
                               cudaStream_t s) {
+  if (f16) {
+    switch (v) {
+      case TV_RBF1: return launch_fused_pair_t<F16Of<MathRbf1>>(tzi, tzj, a, grid, s);
+      case TV_RBF_LADDER5: return launch_fused_pair_t<F16Of<MathRbfLadder<5>>>(tzi, tzj, a, grid, s);
+      case TV_RBF_GENERIC: return launch_fused_pair_t<F16Of<MathGeneric<FAM_RBF>>>(tzi, tzj, a, grid, s);
+      case TV_RQ3_DEFAULT: return launch_fused_pair_t<F16Of<MathRq3Default>>(tzi, tzj, a, grid, s);
+      case TV_RQ_GENERIC: return launch_fused_pair_t<F16Of<MathGeneric<FAM_RQ>>>(tzi, tzj, a, grid, s);
+      case TV_DISTANCE: return launch_fused_pair_t<F16Of<MathDistance>>(tzi, tzj, a, grid, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (v) {
     case TV_RBF1: return launch_fused_pair_t<MathRbf1>(tzi, tzj, a, grid, s);
     case TV_RBF_LADDER5: return launch_fused_pair_t<MathRbfLadder<5>>(tzi, tzj, a, grid, s);
@@ -964,6 +976,8 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   double* csum = reinterpret_cast<double*>(w + p.off_csum);
   PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  pa.f16 = c.f16;
+  const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
@@ -980,9 +994,9 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   fa.n = g.n;
   fa.mp = p.mp;
   fa.np = p.np;
-  fa.c_xx = (float)(4.0 * c.a_xx);
-  fa.c_yy = (float)(4.0 * c.a_yy);
-  fa.c_xy = (float)(4.0 * c.a_xy);
+  fa.c_xx = (float)(4.0 * c.a_xx * wscale);
+  fa.c_yy = (float)(4.0 * c.a_yy * wscale);
+  fa.c_xy = (float)(4.0 * c.a_xy * wscale);
   fa.norms = norms;
   fa.nrb_x = p.nrb_x;
   fa.rb_x0 = p.rb_x0;
@@ -1000,7 +1014,9 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   fa.rpart = reinterpret_cast<float*>(w + p.off_r);
   fa.spart = reinterpret_cast<double*>(w + p.off_s);
   prof_begin(s);
-  e = tuning().fused_pair ? launch_fused_pair(variant, tzi, tzj, fa, p.grid, s) : launch_fused(variant, tzi, tzj, fa, p.grid, s);
+  // (the fp16 operand tier exists for the tile-pair kernel only)
+  e = (tuning().fused_pair || c.f16) ? launch_fused_pair(variant, c.f16 != 0, tzi, tzj, fa, p.grid, s)
+                                     : launch_fused(variant, tzi, tzj, fa, p.grid, s);
   prof_end(s);
   if (e != cudaSuccess) return e;
   ++*launches;
@@ -1038,6 +1054,7 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   fr.dX = dX;
   fr.dY = dY;
   fr.partials = reinterpret_cast<double*>(w + p.off_stats);
+  fr.gscale = (float)(1.0 / wscale);
   const unsigned fin_blocks = (unsigned)((fr.ox + fr.oy + kFinRowsPerCta - 1) / kFinRowsPerCta);
   tc_finalize_rows_kernel<<<fin_blocks, 256, 0, s>>>(fr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

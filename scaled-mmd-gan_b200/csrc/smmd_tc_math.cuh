@@ -18,6 +18,7 @@
 // are computed from the same bf16 operands the MMA sees), and a slightly negative D is harmless for every
 // transform below, so it is dropped; an upper cap keeps products of bases finite for absurd distances.
 #pragma once
+#include "sm100_ptx.cuh"
 #include "smmd_kfun.cuh"
 
 namespace smmd {
@@ -42,6 +43,7 @@ __device__ __forceinline__ float2 rcp_2(float2 x) { return make_float2(fast_rcp(
 
 struct MathRbf1 {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   float c1, w, g;
@@ -59,6 +61,7 @@ struct MathRbf1 {
 template <int NP>
 struct MathRbfLadder {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   float c1, w[NP], g[NP];
@@ -120,6 +123,7 @@ __device__ __forceinline__ void eval_pairs_pt(const Math& m, const float2 (&S)[N
 
 struct MathRq3Default {
   static constexpr bool kHasEvalN = true;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = true;
 #ifdef SMMD_SYM_NOSPLIT
   static constexpr bool kHasSplit = false;
@@ -258,6 +262,7 @@ struct MathRq3Default {
 template <int FAM>
 struct MathGeneric {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   const float* sp;
@@ -289,6 +294,7 @@ struct MathGeneric {
 
 struct MathDistance {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   __device__ explicit MathDistance(const KernelFn&, const float*) {}
@@ -303,6 +309,7 @@ struct MathDistance {
 
 struct MathNull {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   __device__ explicit MathNull(const KernelFn&, const float*) {}
@@ -316,6 +323,7 @@ struct MathNull {
 
 struct MathPoly3 {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   float gamma, c0;
@@ -331,6 +339,7 @@ struct MathPoly3 {
 
 struct MathPolyN {
   static constexpr bool kHasEvalN = false;
+  static constexpr bool kF16 = false;
   static constexpr bool kHasPt = false;
   static constexpr bool kHasSplit = false;
   float gamma, c0;
@@ -393,5 +402,26 @@ inline TcVariant select_tc_variant(KernelFn& kf) {
     default: return TV_NONE;
   }
 }
+
+// ---- fp16 operand tier (SMMD_PREC_FP16): the same epilogue math, W packed to IEEE half instead of bf16 ------------------
+// F16Of<Math> only flips the compile-time flag the kernels read (operand format of the UMMA descriptors, W packing,
+// unpacking of the staged W block); the kernels stay templated on one Math parameter.
+template <class Base>
+struct F16Of : Base {
+  static constexpr bool kF16 = true;
+  using Base::Base;
+};
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_w(float lo, float hi) {
+  if constexpr (F16) return sm100::pack_f16x2(lo, hi);
+  else return sm100::pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_w(uint32_t w) {
+  if constexpr (F16) return make_float2(sm100::f16_lo_to_f32(w), sm100::f16_hi_to_f32(w));
+  else return make_float2(sm100::bf16_lo_to_f32(w), sm100::bf16_hi_to_f32(w));
+}
+template <class Math>
+__host__ __device__ constexpr uint32_t operand_fmt() { return Math::kF16 ? 0u : 1u; }   // kFmtF16 : kFmtBF16
 
 }  // namespace smmd

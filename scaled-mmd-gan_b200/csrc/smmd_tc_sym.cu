@@ -1592,15 +1592,21 @@ bool tc_sym_eligible(const Geometry& g) {
   if (!tuning().sym) return false;
   if (!(g.x0 == 0 && g.x1 == g.m && g.y0 == 0 && g.y1 == g.n)) return false;   // whole problem on this GPU
   const int64_t Mp = round_up(g.m, BM) + round_up(g.n, BM);
-  // measured cross-over against the row-stacked fused kernel (d <= 256: N = 8192 per side 0.48 vs 0.34 ms, 16384: 1.15 vs
-  // 1.17 ms, 32768: 3.93 vs 4.38 ms) and against the row-stacked two-pass path (d > 256: wins from N = 4096 per side on)
-  const int64_t min_rows = tuning().sym_min_rows > 0 ? tuning().sym_min_rows : (g.d <= 256 ? 32768 : 8192);
+  // measured cross-over against the row-stacked kernels (warm single calls, mix_rq): d = 256: N = 2048 per side 0.073 vs
+  // 0.079 ms, 8192: 0.331 vs 0.346, 16384: 1.055 vs 1.165; d = 512: N = 2048 0.085 vs 0.099, N = 1024 0.066 vs 0.071
+  const int64_t min_rows = tuning().sym_min_rows > 0 ? tuning().sym_min_rows : 4096;
   if (Mp < min_rows) return false;
   return Mp * Mp * 2 <= tuning().sym_max_w_bytes;
 }
 
 // d <= 256: the fused variant (direct products inside pass 1, mirrored products in pass 2)
-static bool use_symf(const Geometry& g) { return tuning().symf && round_up(g.d, 64) <= 256; }
+// (from ~20K rows per side on: N = 16384 1.139 vs 1.055 ms for the unfused pair, 24576: 2.29 vs 2.39, 65536: 14.7 vs 16.7;
+// below that the 128 KB O drain per unit and the short mirrored pieces cost more than the halved second pass saves)
+static bool use_symf(const Geometry& g) {
+  if (!tuning().symf || round_up(g.d, 64) > 256) return false;
+  const int64_t Mp = round_up(g.m, BM) + round_up(g.n, BM);
+  return Mp >= (tuning().symf_min_rows > 0 ? tuning().symf_min_rows : 40960);
+}
 
 size_t tc_sym_workspace_bytes(const Geometry& g) {
   return use_symf(g) ? symf_plan(g.m, g.n, g.d).off_end : sym_plan(g.m, g.n, g.d).off_end;

@@ -28,7 +28,7 @@ def main():
     # unordered pair once, different r_i bookkeeping) while the shards run the row-stacked kernels: both are bf16
     # evaluations within 4e-3 max|g| of the oracle, they agree to ~1e-3
     for (b, d, precision, gtol, vtol) in ((64, 16, "fp32", 1e-5, 1e-6), (1024, 128, "bf16", 2e-4, 1e-6), (768, 512, "bf16", 2e-4, 1e-6),
-                                          (16384 // world, 256, "bf16", 2e-3, 1e-4), (8192 // world, 512, "bf16", 2e-3, 1e-4)):
+                                          (20480 // world, 256, "bf16", 2e-3, 1e-4), (8192 // world, 512, "bf16", 2e-3, 1e-4)):
         rng = np.random.RandomState(100 + rank)
         Xl = torch.tensor((rng.randn(b, d) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
         Yl = torch.tensor(((1.05 * rng.randn(b, d) + 0.1) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)

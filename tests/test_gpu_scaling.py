@@ -54,7 +54,7 @@ def test_scaled_loss_parameter_gradients_vs_oracle(kernel, dof, variant):
     gmax = max(float(q.grad.abs().max()) for q in ref_net.parameters())
     for (name, p), q in zip(net.named_parameters(), ref_net.parameters()):
         got, ref = p.grad.double().cpu(), q.grad
-        tol = 2e-4 * max(float(ref.abs().max()), 1e-3 * gmax)
+        tol = 2e-4 * float(ref.abs().max()) + 2e-5 * gmax   # (second term: fp32 noise of the critic's backward)
         assert (got - ref).abs().max() <= tol, (name, float((got - ref).abs().max()), float(ref.abs().max()), gmax)
 
 
@@ -69,7 +69,7 @@ def test_scaled_mmd2_backward_is_scale_times_dx_and_mmd2():
     loss, unscaled = scaling.scaled_mmd2(mmd._mix_rq_kernel(X, Y), scale, precision="bf16")
     loss.backward()
     sc, dX, dY = mmd.fused_mmd2_raw(mmd._mix_rq_kernel(X, Y).spec, X, Y, precision="bf16")
-    assert _lib.last_path() == "tc_bf16_fused"
+    assert _lib.last_path() in ("tc_bf16_fused", "tc_bf16_sym")   # 4224 stacked rows: the symmetric path by default
     assert torch.allclose(X.grad, 0.37 * dX, rtol=1e-6, atol=0) and torch.allclose(Y.grad, 0.37 * dY, rtol=1e-6, atol=0)
     assert abs(float(scale.grad) - float(sc[_lib.S_MMD2])) <= 1e-6 * abs(float(sc[_lib.S_MMD2]))
     assert abs(float(loss) - 0.37 * float(unscaled)) <= 1e-6 * abs(float(loss))

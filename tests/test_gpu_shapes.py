@@ -9,6 +9,17 @@ import torch
 from oracle import mmd_oracle
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _row_stacked_kernels():
+    """This module pins the row-stacked kernels (fused tile-pair kernel, W row panels + GEMM): whole problems of >= 4096
+    stacked rows would otherwise take the symmetric paths, which tests/test_gpu_sym.py covers."""
+    from smmd import _lib
+
+    _lib.set_option("sym", 0)
+    yield
+    _lib.set_option("sym", 1)
 DEV = "cuda"
 
 SHAPES = [

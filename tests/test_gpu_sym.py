@@ -53,8 +53,10 @@ def force_sym():
     from smmd import _lib
 
     _lib.set_option("sym_min_rows", 1)
+    _lib.set_option("symf_min_rows", 1)
     yield
     _lib.set_option("sym_min_rows", 0)
+    _lib.set_option("symf_min_rows", 0)
 
 
 SYM_SHAPES = [(300, 200, 100), (1000, 1100, 256), (513, 700, 256), (129, 127, 64), (700, 900, 512), (257, 255, 600),
@@ -146,17 +148,17 @@ def test_c4_sizes_vs_fp64_oracle(cell):
     loss = mmd.mmd2(mmd._mix_rq_kernel(Xt, Yt), precision="bf16")
     loss.backward()
     path = _lib.last_path()
-    assert path == ("tc_bf16_sym" if d > 256 else "tc_bf16_fused"), path   # the paths bench.py --sweep runs at these cells
+    assert path == "tc_bf16_sym", path   # the path bench.py --sweep runs at these cells
     _check("mix_rq", {}, X, Y, False, loss.item(), Xt.grad.cpu().numpy(), Yt.grad.cpu().numpy())
 
 
 def test_c4_symmetric_path_at_bench_row_count():
     """The bench.py headline workload (N = 65536, d = 256) takes the symmetric path; the fp64 oracle cannot hold it.
-    Here: the same path at the smallest size it is selected for by default (Mp = 32768) against the exact fp32
+    Here: the same path at the smallest size it is selected for by default (Mp = 40960) against the exact fp32
     SIMT path (itself oracle-pinned at 1e-5), value and every gradient element."""
     from smmd import _lib, mmd
 
-    n, d = 16384, 256
+    n, d = 20480, 256
     g = torch.Generator(device=DEV).manual_seed(7)
     Xt = torch.randn(n, d, device=DEV, generator=g) / d ** 0.5
     Yt = (1.05 * torch.randn(n, d, device=DEV, generator=g) + 0.1) / d ** 0.5

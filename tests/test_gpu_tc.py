@@ -15,6 +15,17 @@ import torch
 from oracle import kid_oracle, mmd_oracle
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _row_stacked_kernels():
+    """This module pins the row-stacked kernels (fused tile-pair kernel, W row panels + GEMM): whole problems of >= 4096
+    stacked rows would otherwise take the symmetric paths, which tests/test_gpu_sym.py covers."""
+    from smmd import _lib
+
+    _lib.set_option("sym", 0)
+    yield
+    _lib.set_option("sym", 1)
 DEV = "cuda:0"
 
 CASES = [
@@ -115,7 +126,7 @@ def test_tc_wide_long_stream_and_shards():
         assert _lib.last_path() == "tc_bf16_wz"
         full2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
     finally:
-        _lib.set_option("sym", 1)
+        _lib.set_option("sym", 0)   # (module default, see _row_stacked_kernels)
     ref, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
     assert abs(full[_lib.S_MMD2].item() - ref[_lib.S_MMD2].item()) <= 1e-3 * abs(ref[_lib.S_MMD2].item())
     assert (gX - rX).abs().max() <= 4e-3 * rX.abs().max()
@@ -153,7 +164,7 @@ def test_tc_wide_cta_pair_path():
         assert _lib.last_path() == "tc_bf16_wz_pair"
         sc2, gX2, gY2 = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="bf16")
     finally:
-        _lib.set_option("sym", 1)
+        _lib.set_option("sym", 0)   # (module default, see _row_stacked_kernels)
     rs, rX, rY = mmd.fused_mmd2_raw(spec, Xt, Yt, precision="fp32")
     assert abs(sc[_lib.S_MMD2].item() - rs[_lib.S_MMD2].item()) <= 1e-3 * abs(rs[_lib.S_MMD2].item())
     for i in (_lib.S_SUM_XX, _lib.S_SUM_YY, _lib.S_SUM_XY, _lib.S_SUM_YX):
