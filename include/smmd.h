@@ -70,6 +70,10 @@ typedef enum smmd_kernel_id {
  * BF16: tcgen05 tensor cores, bf16 operands / fp32 accumulate (tier rel 1e-3).
  * BF16X3: tcgen05 with a 3-term split-bf16 Gram (hi*hi + lo*hi + hi*lo), forward-only paths
  * (KID, value-only MMD^2); ~fp32-accurate Gram at 3x the tensor work.
+ * FP16: the BF16 gradient paths with IEEE-half operands (features and the weight matrix W; W is carried times a power of two
+ * derived from its bound): 11 significant bits instead of 8 -- gradients within 3e-4 of max|g| instead of 1e-3..2e-3 (bf16),
+ * same speed -- for features inside half's range (6e-5 <= |z| <= 6e4; a larger |z| becomes inf and raises
+ * SMMD_S_NONFINITE).  Explicit request only (AUTO never picks it); forward-only calls return SMMD_EUNSUPPORTED.
  * AUTO: FP32 for small problems (m + n < 1024 or d < 32) and for combinations the tensor-core kernels do not
  * cover (dot kernel), BF16 otherwise.  The exact gradient kernel keeps a feature row in registers and supports
  * d <= 2048: with gradients and a wider d, AUTO takes BF16 whatever the size, and an explicit FP32 request returns
@@ -78,7 +82,8 @@ typedef enum smmd_precision {
   SMMD_PREC_FP32 = 0,
   SMMD_PREC_BF16 = 1,
   SMMD_PREC_BF16X3 = 2,
-  SMMD_PREC_AUTO = 3
+  SMMD_PREC_AUTO = 3,
+  SMMD_PREC_FP16 = 4
 } smmd_precision;
 
 /* One MMD^2 problem: X = generated/fake features [m,d], Y = real features [n,d] -- the reference's

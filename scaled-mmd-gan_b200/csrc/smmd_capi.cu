@@ -109,7 +109,7 @@ int validate_problem(const smmd_problem* p) {
   if (p->m + p->n > (int64_t)1 << 24 || p->d > 1 << 16) return SMMD_ESHAPE;
   if (p->dtype != SMMD_F32 && p->dtype != SMMD_BF16) return SMMD_EDTYPE;
   if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return SMMD_EINVAL;
-  if (p->precision < SMMD_PREC_FP32 || p->precision > SMMD_PREC_AUTO) return SMMD_EINVAL;
+  if (p->precision < SMMD_PREC_FP32 || p->precision > SMMD_PREC_FP16) return SMMD_EINVAL;
   if (p->kernel_id < 0 || p->kernel_id > SMMD_K_POLY) return SMMD_EINVAL;
   return SMMD_OK;
 }
@@ -269,9 +269,12 @@ static int mmd2_fwd_bwd_impl(const smmd_problem* p, const SrcLayout& src, double
     return SMMD_OK;
   }
   if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
+  if (prec == SMMD_PREC_FP16 && !want_grad) return SMMD_EUNSUPPORTED;   // the fp16 operand tier exists for the gradient paths
   if (!tc_mmd2_covers(kf, g, want_grad)) return SMMD_EUNSUPPORTED;
   int launches = 0;
-  cudaError_t e = tc_mmd2_run(kf, g, c, src, prec, scalars, dX, dY, workspace, workspace_bytes, s, &launches, &g_path);
+  Coefs ct = c;
+  ct.f16 = prec == SMMD_PREC_FP16 ? 1 : 0;
+  cudaError_t e = tc_mmd2_run(kf, g, ct, src, prec, scalars, dX, dY, workspace, workspace_bytes, s, &launches, &g_path);
   g_launches += launches;
   if (e != cudaSuccess) return cuda_fail(e);
   return SMMD_OK;

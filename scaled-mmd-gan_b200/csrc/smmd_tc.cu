@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
 
 // column sums of the X block and of the Y block (needed by the add_dot terms): csum[2][dp] double
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* Z, int64_t dpz, int64_t dp, int64_t m,
-                                                     int64_t mp, int64_t n, double* csum) {
+                                                     int64_t mp, int64_t n, double* csum, int f16) {
   const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   const int which = blockIdx.y;  // 0 = X, 1 = Y
   const int rl = threadIdx.x >> 5;
@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* Z, int
   double s = 0.0;
   const int64_t r0 = which ? mp : 0, cnt = which ? n : m;
   if (c < dp)
-    for (int64_t r = rl; r < cnt; r += 8) s += (double)__bfloat162float(Z[(r0 + r) * dpz + c]);
+    for (int64_t r = rl; r < cnt; r += 8)
+      s += f16 ? (double)__half2float(reinterpret_cast<const __half*>(Z)[(r0 + r) * dpz + c])
+               : (double)__bfloat162float(Z[(r0 + r) * dpz + c]);
   sh[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && c < dp) {
@@ -177,8 +179,8 @@ cudaError_t launch_prep_tc(const PrepTcArgs& a, int64_t rows, unsigned batch, cu
   return cudaGetLastError();
 }
 cudaError_t launch_colsum_tc(const __nv_bfloat16* Z, int64_t dpz, int64_t dp, int64_t m, int64_t mp, int64_t n,
-                             double* csum, cudaStream_t s) {
-  colsum_kernel<<<dim3((unsigned)((dp + 31) / 32), 2), 256, 0, s>>>(Z, dpz, dp, m, mp, n, csum);
+                             double* csum, int f16, cudaStream_t s) {
+  colsum_kernel<<<dim3((unsigned)((dp + 31) / 32), 2), 256, 0, s>>>(Z, dpz, dp, m, mp, n, csum, f16);
   return cudaGetLastError();
 }
 

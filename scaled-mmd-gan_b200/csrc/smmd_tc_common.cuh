@@ -138,7 +138,7 @@ struct PrepTcArgs {
 // launch wrappers (kernels live in smmd_tc.cu): grid = (ceil(rows / 8), batch)
 cudaError_t launch_prep_tc(const PrepTcArgs& a, int64_t rows, unsigned batch, cudaStream_t s);
 cudaError_t launch_colsum_tc(const __nv_bfloat16* Z, int64_t dpz, int64_t dp, int64_t m, int64_t mp, int64_t n,
-                             double* csum, cudaStream_t s);
+                             double* csum, int f16, cudaStream_t s);
 
 // copy the mixture parameters to shared memory for the generic math variants: sp[0..7]=p0, [8..15]=p1, [16..23]=w
 __device__ __forceinline__ void stage_params(const KernelFn& kf, float* sp) {

@@ -982,7 +982,7 @@ cudaError_t tc_run_fused(const KernelFn& kf, TcVariant variant, const Geometry& 
   ++*launches;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
   if (dot) {
-    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, c.f16, s)) != cudaSuccess) return e;
     ++*launches;
   }
   CUtensorMap tzi, tzj;

@@ -161,7 +161,7 @@ __device__ __forceinline__ void sym_chunk16(const Math& math, const uint32_t (&v
       tsum = add2(tsum, k[e]);
       const float2 ww = mul2(kd[e], cw);
       rsum = add2(rsum, ww);
-      wpk[(c >> 1) + e] = pack_bf16x2(ww.x, ww.y);
+      wpk[(c >> 1) + e] = pack_w<Math::kF16>(ww.x, ww.y);
     }
   }
 }
@@ -216,7 +216,7 @@ __device__ __forceinline__ void sym_quarter_split(const Math& math, uint32_t tba
         tsum = add2(tsum, k[e]);
         const float2 ww = mul2(kd[e], cw);
         rsum = add2(rsum, ww);
-        wpk[2 * g + e] = pack_bf16x2(ww.x, ww.y);
+        wpk[2 * g + e] = pack_w<Math::kF16>(ww.x, ww.y);
       }
     }
     // chunk ch is consumed: its TMEM buffer takes chunk ch + 2 (the load of chunk ch + 1 was waited for above)
@@ -313,7 +313,7 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
     }
   } else if (warp == kSyEpiWarps + 1) {
     // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BM, BNW, kFmtBF16, false, false);
+    constexpr uint32_t idesc = make_idesc(BM, BNW, operand_fmt<Math>(), false, false);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
@@ -466,8 +466,8 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
           for (int i = 0; i < 32; i += 2) {
             const uint32_t p0 = ld_shared_u32(stg + i * 128 + ((wch ^ (uint32_t)(i & 7)) << 4) + wofs);
             const uint32_t p1 = ld_shared_u32(stg + (i + 1) * 128 + ((wch ^ (uint32_t)((i + 1) & 7)) << 4) + wofs);
-            acc0 = add2(acc0, make_float2(bf16_lo_to_f32(p0), bf16_hi_to_f32(p0)));
-            acc1 = add2(acc1, make_float2(bf16_lo_to_f32(p1), bf16_hi_to_f32(p1)));
+            acc0 = add2(acc0, unpack_w<Math::kF16>(p0));
+            acc1 = add2(acc1, unpack_w<Math::kF16>(p1));
           }
           const float2 t = add2(acc0, acc1);
           fixed_add(a.racc + c0 + 2 * lane, t.x, a.rscale, a.rclamp);
@@ -668,8 +668,8 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
     }
   } else if (warp == EPI_WARPS + 1) {
     // ===================== UMMA issuer (as tc_fused_pair_kernel) =====================
-    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, kFmtBF16, false, false);
-    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, kFmtBF16, false, true);
+    constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, operand_fmt<Math>(), false, false);
+    const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, operand_fmt<Math>(), false, true);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t zi_lo = desc_lo(smem_u32(sZi), 16);
     const uint32_t zj_lo1 = desc_lo(smem_u32(sZj), 16);
@@ -826,7 +826,7 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
           for (int i = 0; i < 16; ++i) {
             const uint32_t rr = 2 * i + hrow;
             const uint32_t wv = ld_shared_u32(stg + rr * 64 + ((((pcol >> 2) ^ ((uint32_t)i & 3u))) << 4) + (pcol & 3u) * 4);
-            acc = add2(acc, make_float2(bf16_lo_to_f32(wv), bf16_hi_to_f32(wv)));
+            acc = add2(acc, unpack_w<Math::kF16>(wv));
           }
           acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
           acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
@@ -909,6 +909,7 @@ struct SymWzArgs {
   // pieces are numbered mb-major: piece = (P(mb) + s) * FB + fb, P(mb) = sum_{i < mb} (i / ell + 1).
   int tonly, ell;
   int Mp;         // stacked padded rows (tonly: row stride of a column group of W)
+  int f16;        // operands are IEEE half (fp16 tier) instead of bf16
 };
 __host__ __device__ inline int64_t symt_prefix(int mb, int ell) {   // P(mb)
   const int64_t q = mb / ell, r = mb % ell;
@@ -1008,8 +1009,9 @@ tc_sym_wz_kernel(const __grid_constant__ CUtensorMap tmap_wd, const __grid_const
       }
     }
   } else if (warp == 9) {
-    const uint32_t idesc_d = make_idesc(BM, (uint32_t)nf, kFmtBF16, false, true);   // A K-major, B = Z tile MN-major
-    const uint32_t idesc_t = make_idesc(BM, (uint32_t)nf, kFmtBF16, true, true);    // A MN-major (transposed tile)
+    const uint32_t fmt = a.f16 ? kFmtF16 : kFmtBF16;
+    const uint32_t idesc_d = make_idesc(BM, (uint32_t)nf, fmt, false, true);   // A K-major, B = Z tile MN-major
+    const uint32_t idesc_t = make_idesc(BM, (uint32_t)nf, fmt, true, true);    // A MN-major (transposed tile)
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t ad_lo0 = desc_lo(smem_u32(smem), 16);
     const uint32_t at_lo0 = desc_lo(smem_u32(smem), 64 * 128);   // LBO = distance between the two 64-wide M panels
@@ -1095,6 +1097,7 @@ struct SymFinArgs {
   int symf, ell;
   SymfGeo fgeo;
   const float* Odir;         // [nunits][128][dp]
+  float gscale;              // 1 / (power-of-two scale W was carried with), see w_scale_for()
 };
 
 // sum of the partial O values of one row at features [c, c + 4) (c % 4 == 0, inside one 256-feature block), fixed order
@@ -1173,7 +1176,7 @@ __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
-          gv[e] = rs * zz[e] - oo[e];
+          gv[e] = (rs * zz[e] - oo[e]) * a.gscale;
           if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
         }
         *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
@@ -1187,7 +1190,7 @@ __global__ void __launch_bounds__(256) sym_finalize_rows_kernel(SymFinArgs a) {
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
         if (a.kf.tanh_features) z = tanhf(z);
         if (out) {
-          float gv = rs * z - o;
+          float gv = (rs * z - o) * a.gscale;
           if (dot) {
             const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
             gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
@@ -1322,22 +1325,6 @@ SymPlan sym_plan(int64_t m, int64_t n, int64_t d) {
   return p;
 }
 
-// bound of |dk/dD| over D >= 0 (sizes the fixed-point accumulator of the row sums of W)
-double kd_abs_bound(const KernelFn& kf) {
-  double b = 0.0;
-  switch (kf.family) {
-    case FAM_RBF:
-      for (int i = 0; i < kf.np; ++i) b += fabs((double)kf.w[i]) * (double)kf.p0[i];
-      break;
-    case FAM_RQ:
-      for (int i = 0; i < kf.np; ++i) b += 0.5 * fabs((double)kf.w[i]);
-      break;
-    case FAM_DISTANCE: b = 0.5 / sqrt(1.0e-7); break;
-    default: b = 1.0;
-  }
-  return b > 0.0 ? b : 1.0;
-}
-
 template <class Math>
 cudaError_t launch_sym_wgen_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymWgenArgs& a,
                               int grid, cudaStream_t s) {
@@ -1347,8 +1334,19 @@ cudaError_t launch_sym_wgen_t(const CUtensorMap& tzi, const CUtensorMap& tzj, co
   kern<<<grid, kSyThreads, kSySmem, s>>>(tzi, tzj, tw, a);
   return cudaGetLastError();
 }
-cudaError_t launch_sym_wgen(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw,
+cudaError_t launch_sym_wgen(TcVariant v, bool f16, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw,
                             const SymWgenArgs& a, int grid, cudaStream_t s) {
+  if (f16) {
+    switch (v) {
+      case TV_RBF1: return launch_sym_wgen_t<F16Of<MathRbf1>>(tzi, tzj, tw, a, grid, s);
+      case TV_RBF_LADDER5: return launch_sym_wgen_t<F16Of<MathRbfLadder<5>>>(tzi, tzj, tw, a, grid, s);
+      case TV_RBF_GENERIC: return launch_sym_wgen_t<F16Of<MathGeneric<FAM_RBF>>>(tzi, tzj, tw, a, grid, s);
+      case TV_RQ3_DEFAULT: return launch_sym_wgen_t<F16Of<MathRq3Default>>(tzi, tzj, tw, a, grid, s);
+      case TV_RQ_GENERIC: return launch_sym_wgen_t<F16Of<MathGeneric<FAM_RQ>>>(tzi, tzj, tw, a, grid, s);
+      case TV_DISTANCE: return launch_sym_wgen_t<F16Of<MathDistance>>(tzi, tzj, tw, a, grid, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (v) {
     case TV_RBF1: return launch_sym_wgen_t<MathRbf1>(tzi, tzj, tw, a, grid, s);
     case TV_RBF_LADDER5: return launch_sym_wgen_t<MathRbfLadder<5>>(tzi, tzj, tw, a, grid, s);
@@ -1450,8 +1448,19 @@ cudaError_t launch_symf_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const 
   kern<<<grid, 576, smem, s>>>(tzi, tzj, tw, a);
   return cudaGetLastError();
 }
-cudaError_t launch_symf(TcVariant v, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymfArgs& a,
+cudaError_t launch_symf(TcVariant v, bool f16, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymfArgs& a,
                         int grid, cudaStream_t s) {
+  if (f16) {
+    switch (v) {
+      case TV_RBF1: return launch_symf_t<F16Of<MathRbf1>>(tzi, tzj, tw, a, grid, s);
+      case TV_RBF_LADDER5: return launch_symf_t<F16Of<MathRbfLadder<5>>>(tzi, tzj, tw, a, grid, s);
+      case TV_RBF_GENERIC: return launch_symf_t<F16Of<MathGeneric<FAM_RBF>>>(tzi, tzj, tw, a, grid, s);
+      case TV_RQ3_DEFAULT: return launch_symf_t<F16Of<MathRq3Default>>(tzi, tzj, tw, a, grid, s);
+      case TV_RQ_GENERIC: return launch_symf_t<F16Of<MathGeneric<FAM_RQ>>>(tzi, tzj, tw, a, grid, s);
+      case TV_DISTANCE: return launch_symf_t<F16Of<MathDistance>>(tzi, tzj, tw, a, grid, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (v) {
     case TV_RBF1: return launch_symf_t<MathRbf1>(tzi, tzj, tw, a, grid, s);
     case TV_RBF_LADDER5: return launch_symf_t<MathRbfLadder<5>>(tzi, tzj, tw, a, grid, s);
@@ -1480,12 +1489,14 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   double* partials = reinterpret_cast<double*>(w + p.off_stats);
   PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  pa.f16 = c.f16;
+  const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;
   if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
   if (dot) {
-    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, c.f16, s)) != cudaSuccess) return e;
     ++*launches;
   }
   CUtensorMap tzi, tzj, tz, twd, twt, tws;
@@ -1497,7 +1508,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   if (!smmd_host::make_tmap_bf16_2d(&twd, Wb, wrows, 64, 64, BM)) return cudaErrorUnknown;   // (unused by the mirrored pass)
   if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, wrows, 64, 64, 64)) return cudaErrorUnknown;
   if (!smmd_host::make_tmap_bf16_2d_box32(&tws, Wb, wrows, 64, 64, 32)) return cudaErrorUnknown;   // pass-1 stores
-  const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
+  const double cmax = 4.0 * wscale * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
   const double wb = cmax * kd_abs_bound(kf);
   int ex = 0;
   frexp(wb * (double)p.Mp, &ex);
@@ -1510,9 +1521,9 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   fa.mp = p.mp;
   fa.np = p.np;
   fa.Mp = p.Mp;
-  fa.c_xx = (float)(4.0 * c.a_xx);
-  fa.c_yy = (float)(4.0 * c.a_yy);
-  fa.c_xy = (float)(4.0 * c.a_xy);
+  fa.c_xx = (float)(4.0 * c.a_xx * wscale);
+  fa.c_yy = (float)(4.0 * c.a_yy * wscale);
+  fa.c_xy = (float)(4.0 * c.a_xy * wscale);
   fa.norms = norms;
   fa.dp = (int)p.dp;
   fa.npanel = (int)(p.dp / 64);
@@ -1528,7 +1539,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   const int only = 0;
 #endif
   if (only != 2) {
-    if ((e = launch_symf(variant, tzi, tzj, tws, fa, p.grid1, s)) != cudaSuccess) return e;
+    if ((e = launch_symf(variant, c.f16 != 0, tzi, tzj, tws, fa, p.grid1, s)) != cudaSuccess) return e;
     ++*launches;
   }
   prof_mark(s);
@@ -1543,6 +1554,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   za.tonly = 1;
   za.ell = p.ell;
   za.Mp = (int)p.Mp;
+  za.f16 = c.f16;
   if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
     return e;
   if (only != 1) {
@@ -1577,6 +1589,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   fr.ell = p.ell;
   fr.fgeo = p.geo;
   fr.Odir = fa.Opart;
+  fr.gscale = (float)(1.0 / wscale);
   sym_finalize_rows_kernel<<<(unsigned)p.fin_blocks, 256, 0, s>>>(fr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;
@@ -1629,12 +1642,14 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   double* partials = reinterpret_cast<double*>(w + p.off_stats);
   PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  pa.f16 = c.f16;
+  const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;
   if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
   if (dot) {
-    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, c.f16, s)) != cudaSuccess) return e;
     ++*launches;
   }
   CUtensorMap tzi, tzj, tz, twd, twt, tws;
@@ -1645,7 +1660,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   if (!smmd_host::make_tmap_bf16_2d(&twt, Wb, p.Mp, p.Mp, p.Mp, 64)) return cudaErrorUnknown;
   if (!smmd_host::make_tmap_bf16_2d(&tws, Wb, p.Mp, p.Mp, p.Mp, 32)) return cudaErrorUnknown;   // pass-1 stores
   // fixed-point scale of the row sums of W: |W| <= cmax * kd bound, |r_i| <= that * Mp < 2^61 after scaling
-  const double cmax = 4.0 * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
+  const double cmax = 4.0 * wscale * std::max(std::max(fabs(c.a_xx), fabs(c.a_yy)), fabs(c.a_xy));
   const double wb = cmax * kd_abs_bound(kf);
   int ex = 0;
   frexp(wb * (double)p.Mp, &ex);           // wb * Mp < 2^ex
@@ -1658,9 +1673,9 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   ga.mp = p.mp;
   ga.np = p.np;
   ga.Mp = p.Mp;
-  ga.c_xx = (float)(4.0 * c.a_xx);
-  ga.c_yy = (float)(4.0 * c.a_yy);
-  ga.c_xy = (float)(4.0 * c.a_xy);
+  ga.c_xx = (float)(4.0 * c.a_xx * wscale);
+  ga.c_yy = (float)(4.0 * c.a_yy * wscale);
+  ga.c_xy = (float)(4.0 * c.a_xy * wscale);
   ga.norms = norms;
   ga.nkp = (int)(p.dp / 64);
   ga.rscale = (float)ldexp(1.0, shift);
@@ -1670,7 +1685,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   prof_begin(s);
   const int only = tuning().sym_only;   // developer timing knob: 1 = pass 1 only, 2 = pass 2 only (results meaningless)
   if (only != 2) {
-    if ((e = launch_sym_wgen(variant, tzi, tzj, tws, ga, p.grid1, s)) != cudaSuccess) return e;
+    if ((e = launch_sym_wgen(variant, c.f16 != 0, tzi, tzj, tws, ga, p.grid1, s)) != cudaSuccess) return e;
     ++*launches;
   }
   prof_mark(s);
@@ -1685,6 +1700,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   za.tonly = 0;
   za.ell = 1;
   za.Mp = (int)p.Mp;
+  za.f16 = c.f16;
   if ((e = cudaFuncSetAttribute(tc_sym_wz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSzSmem)) != cudaSuccess)
     return e;
   if (only != 1) {
@@ -1719,6 +1735,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   fr.ell = 1;
   fr.fgeo = SymfGeo{};
   fr.Odir = nullptr;
+  fr.gscale = (float)(1.0 / wscale);
   sym_finalize_rows_kernel<<<(unsigned)p.fin_blocks, 256, 0, s>>>(fr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++*launches;

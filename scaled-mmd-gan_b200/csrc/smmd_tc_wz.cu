@@ -166,7 +166,7 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
   } else if (warp == kWgEpiWarps + 1) {
     // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BNW, kFmtBF16, false, false);
+    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BNW, operand_fmt<Math>(), false, false);
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     uint32_t st = 0, ph = 0, ab = 0, aph = 0;
@@ -342,6 +342,7 @@ struct WzArgs {
   int S;          // K splits per unit
   int ksteps;     // K steps per piece
   float* Opart;   // [unit = mb * FB + fb][S][256][256]
+  int f16;        // operands are IEEE half (fp16 tier) instead of bf16
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -401,7 +402,7 @@ tc_wz_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    const uint32_t idesc = make_idesc(BM, (uint32_t)nf, kFmtBF16, false, true);   // B = Z tile, MN-major
+    const uint32_t idesc = make_idesc(BM, (uint32_t)nf, a.f16 ? kFmtF16 : kFmtBF16, false, true);   // B = Z tile, MN-major
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem + 2 * BM * 128), BNF * 128);
@@ -478,6 +479,7 @@ struct WzFinArgs {
   float* dX;
   float* dY;
   double* partials;          // [gridDim.x][6] of this panel
+  float gscale;              // 1 / (power-of-two scale W was carried with), see w_scale_for()
 };
 
 __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (a.kf.tanh_features) zz[e] = tanhf(zz[e]);
-          gv[e] = rs * zz[e] - oo[e];
+          gv[e] = (rs * zz[e] - oo[e]) * a.gscale;
           if (a.kf.tanh_features) gv[e] *= (1.f - zz[e] * zz[e]);
         }
         *reinterpret_cast<float4*>(out + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(256) wz_finalize_rows_kernel(WzFinArgs a) {
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sidx]);
         if (a.kf.tanh_features) z = tanhf(z);
         if (out) {
-          float gv = rs * z - o;
+          float gv = (rs * z - o) * a.gscale;
           if (dot) {
             const double cs = a.csum[(rowX ? 0 : 1) * a.dp + c], co = a.csum[(rowX ? 1 : 0) * a.dp + c];
             gv += (float)(2.0 * (double)a.kf.add_dot * (a_same * cs + a.a_xy * co));
@@ -758,8 +760,19 @@ cudaError_t launch_wgen_t(const CUtensorMap& tm, const CUtensorMap& tb, const Wg
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, tm, tb, a);
 }
-cudaError_t launch_wgen(TcVariant v, const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid,
+cudaError_t launch_wgen(TcVariant v, bool f16, const CUtensorMap& tm, const CUtensorMap& tb, const WgenArgs& a, int grid,
                         int pair, cudaStream_t s) {
+  if (f16) {
+    switch (v) {
+      case TV_RBF1: return launch_wgen_t<F16Of<MathRbf1>>(tm, tb, a, grid, pair, s);
+      case TV_RBF_LADDER5: return launch_wgen_t<F16Of<MathRbfLadder<5>>>(tm, tb, a, grid, pair, s);
+      case TV_RBF_GENERIC: return launch_wgen_t<F16Of<MathGeneric<FAM_RBF>>>(tm, tb, a, grid, pair, s);
+      case TV_RQ3_DEFAULT: return launch_wgen_t<F16Of<MathRq3Default>>(tm, tb, a, grid, pair, s);
+      case TV_RQ_GENERIC: return launch_wgen_t<F16Of<MathGeneric<FAM_RQ>>>(tm, tb, a, grid, pair, s);
+      case TV_DISTANCE: return launch_wgen_t<F16Of<MathDistance>>(tm, tb, a, grid, pair, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (v) {
     case TV_RBF1: return launch_wgen_t<MathRbf1>(tm, tb, a, grid, pair, s);
     case TV_RBF_LADDER5: return launch_wgen_t<MathRbfLadder<5>>(tm, tb, a, grid, pair, s);
@@ -799,11 +812,13 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
   __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(w + p.off_W);
   PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
+  pa.f16 = c.f16;
+  const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
   if (dot) {
-    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, s)) != cudaSuccess) return e;
+    if ((e = launch_colsum_tc(Z, p.dp, p.dp, g.m, p.mp, g.n, csum, c.f16, s)) != cudaSuccess) return e;
     ++*launches;
   }
   CUtensorMap t1, t1b, tz, tw;
@@ -821,9 +836,9 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
     ga.n = g.n;
     ga.mp = p.mp;
     ga.np = p.np;
-    ga.c_xx = (float)(4.0 * c.a_xx);
-    ga.c_yy = (float)(4.0 * c.a_yy);
-    ga.c_xy = (float)(4.0 * c.a_xy);
+    ga.c_xx = (float)(4.0 * c.a_xx * wscale);
+    ga.c_yy = (float)(4.0 * c.a_yy * wscale);
+    ga.c_xy = (float)(4.0 * c.a_xy * wscale);
     ga.norms = norms;
     ga.nrb_x = p.nrb_x;
     ga.rb_x0 = p.rb_x0;
@@ -844,7 +859,7 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
     ga.rpart = reinterpret_cast<float*>(w + p.off_r);
     ga.spart = reinterpret_cast<double*>(w + p.off_s);
     if (q.pair) *path = "tc_bf16_wz_pair";   // at least one panel ran pass 1 as CTA pairs (cta_group::2)
-    if ((e = launch_wgen(variant, t1, t1b, ga, q.grid1, q.pair, s)) != cudaSuccess) return e;
+    if ((e = launch_wgen(variant, c.f16 != 0, t1, t1b, ga, q.grid1, q.pair, s)) != cudaSuccess) return e;
     ++*launches;
     WzArgs za;
     za.nmb = q.nmb;
@@ -854,6 +869,7 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
     za.S = q.S;
     za.ksteps = q.ksteps;
     za.Opart = reinterpret_cast<float*>(w + p.off_O);
+    za.f16 = c.f16;
     if ((e = launch_wz(tw, tz, za, q.grid2, s)) != cudaSuccess) return e;
     ++*launches;
     WzFinArgs fr;
@@ -894,6 +910,7 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
     fr.dX = dX;
     fr.dY = dY;
     fr.partials = partials + (int64_t)q.fin_block0 * 6;
+    fr.gscale = (float)(1.0 / wscale);
     wz_finalize_rows_kernel<<<(unsigned)q.fin_blocks, 256, 0, s>>>(fr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;

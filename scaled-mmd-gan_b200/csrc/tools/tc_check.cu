@@ -97,14 +97,18 @@ static void warm_and_report(const char* tag) {
 // fused symmetric path (tc_symf_kernel + mirrored pass), the plain symmetric path (d > 256), the row-stacked fused
 // tile-pair kernel and the row-stacked two-pass path, each against the exact fp32 path.
 static int run_suite() {
-  struct Case { const char* label; const char* k; int64_t m, n, d; long long sym, min_rows; };
-  const Case cases[] = {{"symf", "mix_rq", 1500, 1400, 256, 1, 1}, {"sym", "mix_rq", 1200, 1300, 320, 1, 1},
-                        {"fused_pair", "mix_rq", 1500, 1400, 256, 0, 0}, {"wz", "mix_rq", 1200, 1300, 320, 0, 0},
-                        {"symf_rbf_d64", "rbf", 700, 900, 64, 1, 1}};
+  struct Case { const char* label; const char* k; int64_t m, n, d; long long sym, min_rows; int prec; };
+  const Case cases[] = {{"symf", "mix_rq", 1500, 1400, 256, 1, 1, SMMD_PREC_BF16}, {"sym", "mix_rq", 1200, 1300, 320, 1, 1, SMMD_PREC_BF16},
+                        {"fused_pair", "mix_rq", 1500, 1400, 256, 0, 0, SMMD_PREC_BF16}, {"wz", "mix_rq", 1200, 1300, 320, 0, 0, SMMD_PREC_BF16},
+                        {"symf_rbf_d64", "rbf", 700, 900, 64, 1, 1, SMMD_PREC_BF16},
+                        {"symf_f16", "mix_rq", 1500, 1400, 256, 1, 1, SMMD_PREC_FP16}, {"sym_f16", "mix_rq", 1200, 1300, 320, 1, 1, SMMD_PREC_FP16},
+                        {"fused_f16", "mix_rq", 1500, 1400, 256, 0, 0, SMMD_PREC_FP16}, {"wz_f16", "mix_rq", 1200, 1300, 320, 0, 0, SMMD_PREC_FP16},
+                        {"symf_f16_rbf", "mix_rbf", 700, 900, 64, 1, 1, SMMD_PREC_FP16}, {"sym_f16_dist", "distance", 900, 800, 512, 1, 1, SMMD_PREC_FP16}};
   int bad = 0;
   for (const Case& c : cases) {
     smmd_set_option("sym", c.sym);
     smmd_set_option("sym_min_rows", c.min_rows);
+    smmd_set_option("symf_min_rows", c.min_rows);
     std::mt19937 rng(99);
     std::normal_distribution<float> nd(0.f, 1.f);
     std::vector<float> hX(c.m * c.d), hY(c.n * c.d);
@@ -116,13 +120,13 @@ static int run_suite() {
     CK(cudaMemcpy(dXin, hX.data(), hX.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dYin, hY.data(), hY.size() * 4, cudaMemcpyHostToDevice));
     smmd_problem p; fill_problem(&p, c.k, c.m, c.n, c.d);
-    Result tc = run_mmd(p, SMMD_PREC_BF16, dXin, dYin, 1, true);
+    Result tc = run_mmd(p, c.prec, dXin, dYin, 1, true);
     Result ex = run_mmd(p, SMMD_PREC_FP32, dXin, dYin, 1, true);
     double gmax = 0, emax = 0;
     for (size_t i = 0; i < tc.gx.size(); ++i) { gmax = fmax(gmax, fabs((double)ex.gx[i])); emax = fmax(emax, fabs((double)tc.gx[i] - ex.gx[i])); }
     for (size_t i = 0; i < tc.gy.size(); ++i) { gmax = fmax(gmax, fabs((double)ex.gy[i])); emax = fmax(emax, fabs((double)tc.gy[i] - ex.gy[i])); }
     const double vrel = fabs(tc.sc[0] - ex.sc[0]) / fabs(ex.sc[0]);
-    const bool ok = vrel <= 1e-3 && emax <= 4e-3 * gmax;
+    const bool ok = vrel <= 1e-3 && emax <= (c.prec == SMMD_PREC_FP16 ? 1e-3 : 4e-3) * gmax;
     printf("[suite %-12s %s %lldx%lldx%lld] path=%s launches=%d  mmd2 rel %.2e  grad err/max %.2e  %s\n", c.label, c.k,
            (long long)c.m, (long long)c.n, (long long)c.d, tc.path, tc.launches, vrel, emax / gmax, ok ? "ok" : "MISMATCH");
     bad += !ok;
@@ -151,7 +155,8 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dXin, hX.data(), hX.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dYin, hY.data(), hY.size() * 4, cudaMemcpyHostToDevice));
     smmd_problem p; fill_problem(&p, kname, m, n, d);
-    Result tc = run_mmd(p, SMMD_PREC_BF16, dXin, dYin, reps, true);
+    const int tcprec = getenv("TC_CHECK_FP16") ? SMMD_PREC_FP16 : SMMD_PREC_BF16;   // fp16 operand tier
+    Result tc = run_mmd(p, tcprec, dXin, dYin, reps, true);
     const double pairs = (double)m * n * d;  // N^2 d (m = n)
     printf("[%s m=%lld n=%lld d=%lld] TC  path=%s launches=%d  %.3f ms  mmd2=%.9g  nonfinite=%g  -> %.3e pairs/s, %.1f TFLOP/s (14 N^2 d)\n",
            kname, (long long)m, (long long)n, (long long)d, tc.path, tc.launches, tc.ms, tc.sc[0], tc.sc[7],

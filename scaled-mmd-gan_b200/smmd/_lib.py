@@ -14,11 +14,11 @@ NUM_SCALARS = 16
 # enums (include/smmd.h)
 F32, BF16 = 0, 1
 K_DISTANCE, K_TANH_DISTANCE, K_DOT, K_RBF, K_MIX_RBF, K_MIX_RQ, K_TANH_MIX_RQ, K_POLY = range(8)
-PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_AUTO = range(4)
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_AUTO, PREC_FP16 = range(5)
 EST_UNBIASED, EST_BIASED, EST_USTAT = range(3)
 S_MMD2, S_SUM_XX, S_SUM_YY, S_SUM_XY, S_SUM_YX, S_DIAG_X, S_DIAG_Y, S_NONFINITE, S_VAR, S_RATIO = range(10)
 
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "auto": PREC_AUTO}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "auto": PREC_AUTO, "fp16": PREC_FP16}
 ESTIMATORS = {"unbiased": EST_UNBIASED, "biased": EST_BIASED, "u-statistic": EST_USTAT}
 
 EXPORTS = [

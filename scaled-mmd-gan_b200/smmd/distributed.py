@@ -30,7 +30,7 @@ def shard_rows(total, rank, world):
 
 def _tc_eligible(spec, m, n, d, precision):
     """Mirror of the library's AUTO rule: will this global problem run on the bf16 tensor-core path?"""
-    if precision == "bf16":
+    if precision in ("bf16", "fp16"):
         return True
     if precision in (None, "auto"):
         covered = spec.kernel_id in (_lib.K_DISTANCE, _lib.K_TANH_DISTANCE, _lib.K_RBF, _lib.K_MIX_RBF, _lib.K_MIX_RQ,
@@ -87,7 +87,9 @@ def sharded_mmd2_raw(spec, Xl, Yl, biased=False, precision=None, group=None, loc
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     ml, nl, d = Xl.shape[0], Yl.shape[0], Xl.shape[1]
     m, n = ml * world, nl * world
-    gdtype = torch.bfloat16 if (Xl.is_cuda and _tc_eligible(spec, m, n, d, precision)) else torch.float32
+    # bf16 tier: gather bf16 rows (the operand format, half the bytes).  fp16 tier: gather fp32 -- the C ABI takes f32 / bf16
+    # sources only, and rounding to bf16 first would throw away the three extra bits that tier exists for.
+    gdtype = torch.bfloat16 if (Xl.is_cuda and precision != "fp16" and _tc_eligible(spec, m, n, d, precision)) else torch.float32
     # this rank's block goes straight into its slot of the gather buffer (one converting copy per set, no cat + cast)
     gathered = torch.empty((world * (ml + nl), d), dtype=gdtype, device=Xl.device)
     local = gathered[rank * (ml + nl):(rank + 1) * (ml + nl)]
