@@ -15,6 +15,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// warpgroup register reallocation (all warps of a warpgroup execute the same instruction; N a multiple of 8 in [24, 256])
+template <uint32_t N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -81,8 +90,16 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_t parity) {
+// A timed-out wait traps (the launch fails with an illegal-instruction error instead of hanging).  No printf here in the
+// shipping build: a call into vprintf is an ABI call, and ptxas then stops allocating registers per setmaxnreg region
+// (the whole kernel is held to the smallest region's count).  `make DEV=1` keeps the message.
+__device__ __forceinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_t parity) {
+#ifdef SMMD_DEV_KNOBS
   printf("smmd: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+#else
+  (void)bar_addr;
+  (void)parity;
+#endif
   __trap();
 }
 // The poll loop proper is try_wait + branch (+ optional sleep): the timer is read once per 1024 polls in an outer

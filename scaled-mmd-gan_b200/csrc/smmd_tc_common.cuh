@@ -19,6 +19,11 @@ using namespace sm100;
 
 constexpr int BM = 128;            // rows per row block (UMMA M)
 constexpr int BNF = 64;            // fused kernel: columns per tile
+// Kernels with 16 epilogue warps + producer + issuer launch 20 warps (two idle ones complete the fifth warpgroup) at 96
+// registers and re-split them with setmaxnreg: 16 x kEpiRegs + 4 x kCtlRegs = 20 x 96 (the CTA's pool is what it
+// launched with; asking for more than that fails the launch).
+constexpr int kRoleThreads = 640;
+constexpr uint32_t kEpiRegs = 104, kCtlRegs = 64;
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue groups
 constexpr int kMaxSmem = 232448;   // 227 KB
 

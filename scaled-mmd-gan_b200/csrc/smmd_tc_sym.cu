@@ -25,7 +25,7 @@ namespace {
 
 constexpr int BNW = 256;                                   // pass-1 tile width
 constexpr int kSyEpiWarps = 16;                            // 4 TMEM lane quarters x 4 column quarters
-constexpr int kSyThreads = (kSyEpiWarps + 2) * 32;
+constexpr int kSyThreads = kRoleThreads;
 constexpr int kSyStages = 3;
 constexpr int kSyStageBytes = BM * 128 + BNW * 128;        // Z_i panel + Z_j tile per 64-deep step = 48 KB
 constexpr int kSyStagingBytes = kSyEpiWarps * 4096;        // 64 KB: one 32-row x 64-column bf16 block per epilogue warp
@@ -236,7 +236,7 @@ __device__ __forceinline__ void sym_quarter_split(const Math& math, uint32_t tba
 }
 
 template <class Math>
-__global__ void __launch_bounds__(kSyThreads, 1)   // 18 warps: 5 on two sub-partitions -> 16384 / (5 * 32) = 102 -> 96 registers is the cap
+__global__ void __launch_bounds__(kSyThreads, 1)   // 20 warps at 96 registers, re-split by role (kEpiRegs / kCtlRegs)
 tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SymWgenArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -278,6 +278,9 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const SymGeo& geo = a.geo;
 
+  // (nested on purpose: ptxas allocates registers per setmaxnreg region only when each region is a branch of its own)
+  if (warp >= kSyEpiWarps) {
+  reg_dec<kCtlRegs>();
   if (warp == kSyEpiWarps) {
     // ===================== TMA producer =====================
     // The column norms of tile t go to nbuf[t % 8] with one 1 KB bulk copy.  Buffer reuse needs no barrier: the
@@ -346,7 +349,9 @@ tc_sym_wgen_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_con
         ab ^= 1;
       }
     }
+  }
   } else {
+    reg_inc<kEpiRegs>();
     // ===================== epilogue: 16 warps = 4 TMEM lane quarters x 4 column quarters (64 columns each) =====
     // Every warp is self-contained: it owns 32 rows x 64 columns of each tile, stages its bf16 W block in its own
     // 4 KB of shared memory (SW128 atoms of 8 rows), stores it with its own TMA store and takes the column sums of
@@ -577,10 +582,11 @@ constexpr int kSfStages = 4;
 constexpr int kSfZjBytes = BNF * 128;           // one 64-wide k-panel of a 64-row column tile
 constexpr int kSfZiBytes = BM * 128;
 constexpr int kSfStagingBytes = 16 * 2048;      // one 32-row x 32-column bf16 block per epilogue warp
+constexpr int kSfThreads = kRoleThreads;
 inline int symf_smem(int npanel) { return 1024 + npanel * kSfZiBytes + kSfStages * npanel * kSfZjBytes + kSfStagingBytes + 1536; }
 
 template <class Math>
-__global__ void __launch_bounds__(576, 1)   // 18 warps: 5 on two sub-partitions -> 16384 / (5 * 32) = 102 -> 96 registers is the cap
+__global__ void __launch_bounds__(kSfThreads, 1)   // 20 warps (two idle, they complete the last warpgroup): 96 registers at launch, see reg_inc below
 tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constant__ CUtensorMap tmap_zj,
                const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SymfArgs a) {
   constexpr int KSPLIT = 2, NPART = 4, EPI_WARPS = 16, NST = kSfStages;
@@ -640,7 +646,12 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const SymfGeo& geo = a.geo;
 
-  if (warp == EPI_WARPS) {
+  // Register budget: 20 warps launch with 96 registers each; the control warpgroup (producer, issuer, two idle warps) hands
+  // registers back and the four epilogue warpgroups take them (setmaxnreg): the epilogue's per-tile state then stays in
+  // registers instead of being re-derived under the 96-register cap.
+  if (warp >= EPI_WARPS) {
+   reg_dec<kCtlRegs>();
+   if (warp == EPI_WARPS) {
     // ===================== TMA producer =====================
     uint32_t unit = 0, st = 0, ph = 0;
     for (int64_t u = blockIdx.x; u < geo.nunits; u += gridDim.x, ++unit) {
@@ -666,7 +677,7 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
         }
       }
     }
-  } else if (warp == EPI_WARPS + 1) {
+   } else if (warp == EPI_WARPS + 1) {
     // ===================== UMMA issuer (as tc_fused_pair_kernel) =====================
     constexpr uint32_t idesc1 = make_idesc(BM, 2 * BNF, operand_fmt<Math>(), false, false);
     const uint32_t idesc2 = make_idesc(BM, (uint32_t)DP, operand_fmt<Math>(), false, true);
@@ -734,7 +745,9 @@ tc_symf_kernel(const __grid_constant__ CUtensorMap tmap_zi, const __grid_constan
         }
       }
     }
+   }
   } else {
+    reg_inc<kEpiRegs>();
     // ===================== epilogue: group g takes tile g of every pair; warp = 32 rows x 32 columns =====================
     const int grp = warp >> 3;
     const int half = (warp >> 2) & 1;
@@ -1445,7 +1458,7 @@ cudaError_t launch_symf_t(const CUtensorMap& tzi, const CUtensorMap& tzj, const 
   auto kern = tc_symf_kernel<Math>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, 576, smem, s>>>(tzi, tzj, tw, a);
+  kern<<<grid, kSfThreads, smem, s>>>(tzi, tzj, tw, a);
   return cudaGetLastError();
 }
 cudaError_t launch_symf(TcVariant v, bool f16, const CUtensorMap& tzi, const CUtensorMap& tzj, const CUtensorMap& tw, const SymfArgs& a,

@@ -60,7 +60,7 @@ struct WgCfg {
 };
 
 constexpr int kWgEpiWarps = 16;                           // 4 TMEM lane quarters x 4 column quarters
-constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
+constexpr int kWgThreads = kRoleThreads;                   // 16 epilogue warps + producer + issuer + 2 idle (setmaxnreg works per warpgroup)
 
 // PAIR: the kernel runs as clusters of two CTAs that take the two row blocks of a row-block pair through the same
 // column tiles with ONE UMMA stream: `tcgen05.mma.cta_group::2` (M = 256: 128 rows per CTA, each CTA supplies half
@@ -129,6 +129,9 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   auto rbl_of = [&](int u) -> int { return PAIR ? 2 * u + rank : u; };
   auto rbl_ld = [&](int u) -> int { const int b = rbl_of(u); return b < a.nrb_p ? b : a.nrb_p - 1; };
 
+  // (nested on purpose: ptxas allocates registers per setmaxnreg region only when each region is a branch of its own)
+  if (warp >= kWgEpiWarps) {
+  reg_dec<kCtlRegs>();
   if (warp == kWgEpiWarps) {
     // ===================== TMA producer =====================
     uint32_t st = 0, ph = 0;
@@ -230,7 +233,9 @@ tc_wgen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       printf("[wgen issuer] tiles %lld  cycles/tile: total %lld  wait acc_empty %lld  wait full %lld\n", wg_tiles,
              (clock64() - wg_start) / wg_tiles, wg_acc / wg_tiles, wg_full / wg_tiles);
 #endif
+  }
   } else {
+    reg_inc<kEpiRegs>();
     // ===================== epilogue: all 16 warps on every tile (TMEM lane quarter x column quarter) ==========
     // With only two accumulators the issuer can start tile t+2 as soon as tile t is drained, so the drain latency
     // of ONE tile is what matters: 16 warps on one tile halve it compared with two groups on alternate tiles

@@ -23,6 +23,43 @@ import torch.distributed as dist
 from . import _lib
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa(device=None, sysfs="/sys"):
+    """One process per GPU: pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers
+    allocated afterwards (first touch) and the threads that feed the copies are local to that GPU's PCIe root.  With eight
+    ranks staging their inputs / results through host memory, buffers that all sit on one socket push half of the copies
+    across the inter-socket link.  Returns the node id, or None when the topology is unknown (single node, no sysfs
+    entry, no CUDA device) -- then nothing is changed."""
+    import os
+
+    try:
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        props = torch.cuda.get_device_properties(idx)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)       # never widen what the launcher allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+
+
 def shard_rows(total, rank, world):
     """Rows [lo, hi) owned by `rank` -- the same split the C ABI uses (include/smmd.h smmd_problem)."""
     return total * rank // world, total * (rank + 1) // world
