@@ -152,6 +152,34 @@ SMMD_API int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathe
  * (same arithmetic as the single-GPU finalisation).  sums/out are device pointers; out[0] = MMD^2. */
 SMMD_API int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream);
 
+/* Peer-memory variant of the sharded loss (one process per GPU, all GPUs of one NVLink / NVSwitch domain): the exchange
+ * steps of the path run INSIDE the library's kernels over peer-mapped memory instead of as NCCL collectives around them.
+ *   - every rank owns an exchange buffer of smmd_peer_buffer_bytes() bytes, zero-filled once, mapped into every other
+ *     rank's address space by the caller (CUDA IPC / VMM / torch symmetric memory); peers->base[r] is rank r's buffer as
+ *     seen from THIS process (base[rank] is the own buffer);
+ *   - a call publishes the local rows into the own buffer and raises a flag in every peer's buffer (release, system
+ *     scope); the operand-preparation kernel pulls each peer's rows over NVLink as soon as that peer's flag is up
+ *     (the all_gather, fused into the copy / convert / norm pass that had to read those rows anyway); the partial sums
+ *     are written into every peer's buffer the same way and each rank combines them in rank order (the all_reduce +
+ *     smmd_mmd2_combine, fused into one kernel).  Latency-bound shapes (<= 1024 global rows, d <= 64, fp32 tier) run
+ *     publish + pull + loss + gradients + sum exchange + combine as ONE launch.
+ * `step` is the collective's sequence number: 1 for the first call after the buffers were zeroed, +1 per call, the same
+ * on every rank (two slots alternate, so a rank may be at most one call ahead of its slowest peer -- which the flag waits
+ * enforce).  p describes the GLOBAL problem (m, n = total rows, p->rank / p->world = this shard; m and n multiples of
+ * world); X_local / Y_local are this rank's fp32 rows (pitch ld_local); scalars receives the COMBINED result (identical on
+ * every rank), dX / dY the gradients of the local rows.  Every wait is bounded (a missing peer traps after 4 s).
+ * New capability without a reference counterpart (the reference's towers never exchange features,
+ * gan/core/model.py:186-218); parity target = the single-device result on the concatenated batch. */
+#define SMMD_MAX_PEERS 16
+typedef struct smmd_peer_table {
+  int32_t world, rank;
+  void* base[SMMD_MAX_PEERS];
+} smmd_peer_table;
+SMMD_API size_t smmd_peer_buffer_bytes(int64_t rows_local, int64_t d);
+SMMD_API int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers, uint64_t step,
+                                     const float* X_local, const float* Y_local, int64_t ld_local, double* scalars,
+                                     float* dX, float* dY, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Replaces: mmd2_and_ratio(K, biased, min_var_est) -- gan/core/mmd.py:223-293 (+ ops.sq_sum / ops.dot,
  * gan/core/ops.py:209-225).  Requires m == n (mmd.py:237).  Reproduces the reference's unbiased
  * branch that keeps the diagonal (mmd.py:273-276).  scalars[MMD2, VAR, RATIO] are written. */

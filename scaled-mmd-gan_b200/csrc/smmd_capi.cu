@@ -297,6 +297,73 @@ int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathered, int6
   return mmd2_fwd_bwd_impl(p, src, scalars, dX, dY, workspace, workspace_bytes, stream);
 }
 
+size_t smmd_peer_buffer_bytes(int64_t rows_local, int64_t d) {
+  if (rows_local <= 0 || d <= 0) return 0;
+  return peer_buffer_bytes(rows_local, d);
+}
+
+int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers, uint64_t step, const float* X_local,
+                            const float* Y_local, int64_t ld_local, double* scalars, float* dX, float* dY,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_path = "none";
+  if (!p || !peers || !X_local || !Y_local || !scalars) return SMMD_EINVAL;
+  int st = validate_problem(p);
+  if (st != SMMD_OK) return st;
+  if (peers->world != p->world || peers->rank != p->rank || p->world > SMMD_MAX_PEERS || step == 0) return SMMD_EINVAL;
+  for (int r = 0; r < p->world; ++r)
+    if (!peers->base[r] || !aligned(peers->base[r], 256)) return SMMD_EINVAL;
+  if (p->m % p->world || p->n % p->world || ld_local < p->d) return SMMD_ESHAPE;
+  if ((dX == nullptr) != (dY == nullptr)) return SMMD_EINVAL;
+  if (p->kernel_id == SMMD_K_POLY) return SMMD_EUNSUPPORTED;
+  if (!device_ok()) return SMMD_EARCH;
+  const int want_grad = dX != nullptr;
+  KernelFn kf;
+  st = build_kernel_fn(p->kernel_id, p->nparams, p->params, p->wts, p->add_dot, p->degree, p->d, &kf);
+  if (st != SMMD_OK) return st;
+  const size_t need = smmd_mmd2_workspace_bytes(p, want_grad);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 256)) return SMMD_EWORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Geometry g = make_geometry(p);
+  const Coefs c = make_coefs(g, kf);
+  const int prec = resolve_precision(p, want_grad);
+  const int64_t blk_x = p->m / p->world, blk_y = p->n / p->world;
+  char* ws = static_cast<char*>(workspace);
+
+  if (prec == SMMD_PREC_FP32) {
+    // latency-bound shapes: one launch does the whole sharded step.  (Mid-size exact problems have no peer variant:
+    // the caller uses the collective-based path for those.)
+    if (!peer_small_eligible(kf, g)) return SMMD_EUNSUPPORTED;
+    const SimtPlan pl = simt_plan(p->m, p->n, p->d, 1);
+    g_path = "simt_fp32_small_peer";
+    prof_begin(s);
+    SMMD_CUDA(launch_peer_small_mmd2(kf, g, c, X_local, Y_local, ld_local, dX, dY, reinterpret_cast<double*>(ws + pl.off_stats),
+                                     reinterpret_cast<unsigned int*>(ws + pl.off_norm), scalars, *peers, step, s));
+    prof_end(s);
+    g_launches = 1;
+    return SMMD_OK;
+  }
+  if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
+  if (prec == SMMD_PREC_FP16 && !want_grad) return SMMD_EUNSUPPORTED;
+  if (!tc_mmd2_covers(kf, g, want_grad)) return SMMD_EUNSUPPORTED;
+  // 1. publish the local rows in the operand format (bf16; the fp16 tier publishes fp32) and raise the data flags
+  const int to_bf16 = prec == SMMD_PREC_FP16 ? 0 : 1;
+  SMMD_CUDA(launch_peer_publish(X_local, Y_local, ld_local, blk_x, blk_y, p->d, to_bf16, *peers, step, s));
+  // 2. the tensor-core path on the owned rows; its operand preparation pulls every peer's rows over NVLink
+  const PeerSrc ps = make_peer_src(*peers, blk_x + blk_y, p->d, step);
+  SrcLayout src{ps.data[p->rank], ps.data[p->rank], to_bf16 ? SMMD_BF16 : SMMD_F32, p->d, p->d, blk_x, blk_y,
+                X_local, Y_local, ld_local, &ps};
+  int launches = 0;
+  Coefs ct = c;
+  ct.f16 = prec == SMMD_PREC_FP16 ? 1 : 0;
+  cudaError_t e = tc_mmd2_run(kf, g, ct, src, prec, scalars, dX, dY, workspace, workspace_bytes, s, &launches, &g_path);
+  g_launches = launches + (p->world > 1 ? 3 : 2);
+  if (e != cudaSuccess) return cuda_fail(e);
+  // 3. partial sums -> every peer, wait, add in rank order, MMD^2 (replaces all_reduce + smmd_mmd2_combine)
+  SMMD_CUDA(launch_peer_combine(kf, g, scalars, *peers, step, s));
+  return SMMD_OK;
+}
+
 int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double* out, void* stream) {
   g_launches = 0;
   int st = validate_problem(p);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/smmd.h"
+#include "smmd_peer.cuh"
 
 namespace smmd {
 
@@ -48,6 +49,7 @@ struct SrcLayout {
   const float* Xo;
   const float* Yo;
   int64_t ldo;
+  const PeerSrc* peers;   // non-null: the blocks are the peers' published rows (smmd_peer.cuh), pulled over NVLink
 };
 __host__ __device__ inline int64_t src_row(int64_t i, bool in_x, int64_t blk_x, int64_t blk_y) {
   if (blk_x <= 0) return i;
@@ -93,6 +95,17 @@ enum RowStat : int {
 void prof_begin(cudaStream_t s);
 void prof_end(cudaStream_t s);
 void prof_mark(cudaStream_t s);   // boundary between the two kernels of a two-pass path
+
+// ---- peer-memory exchange (smmd_peer.cu) -----------------------------------------------------------------
+cudaError_t launch_peer_publish(const float* X, const float* Y, int64_t ld, int64_t blk_x, int64_t blk_y, int64_t d,
+                                int to_bf16, const smmd_peer_table& pt, uint64_t step, cudaStream_t s);
+PeerSrc make_peer_src(const smmd_peer_table& pt, int64_t rows_local, int64_t d, uint64_t step);
+cudaError_t launch_peer_combine(const KernelFn& kf, const Geometry& g, double* scalars, const smmd_peer_table& pt,
+                                uint64_t step, cudaStream_t s);
+bool peer_small_eligible(const KernelFn& kf, const Geometry& g);
+cudaError_t launch_peer_small_mmd2(const KernelFn& kf, const Geometry& g, const Coefs& c, const float* X, const float* Y,
+                                   int64_t ld, float* dX, float* dY, double* partials, unsigned int* counters,
+                                   double* scalars, const smmd_peer_table& pt, uint64_t step, cudaStream_t s);
 
 // ---- launches implemented in smmd_simt.cu -------------------------------------------------------
 struct SimtPlan {

@@ -233,4 +233,25 @@ __device__ __forceinline__ void eval_fast(const KernelFn& f, float D, float& k, 
   }
 }
 
+// final assembly of MMD^2 from the six block sums (gan/core/mmd.py:194-220), fp64
+__device__ __forceinline__ double mmd2_from_sums(const KernelFn& kf, double m, double n, int biased, double sxx,
+                                                 double syy, double sxy, double syx, double dgx, double dgy) {
+  double a_xx, a_yy;
+  const double a_xy = -1.0 / (m * n);
+  if (biased) {
+    a_xx = 1.0 / (m * m);
+    a_yy = 1.0 / (n * n);
+    return a_xx * (sxx + dgx) + a_yy * (syy + dgy) + a_xy * (sxy + syx);
+  }
+  a_xx = 1.0 / (m * (m - 1.0));
+  a_yy = 1.0 / (n * (n - 1.0));
+  double ex = 0.0, ey = 0.0;
+  if (kf.has_const_diag) {  // trace := m * const_diagonal (mmd.py:209-212), whatever the true diagonal is
+    ex = dgx - m * (double)kf.const_diag;
+    ey = dgy - n * (double)kf.const_diag;
+  }
+  return a_xx * (sxx + ex) + a_yy * (syy + ey) + a_xy * (sxy + syx);
+}
+
+
 }  // namespace smmd

@@ -1,0 +1,80 @@
+// smmd_peer.cuh -- exchange over peer-mapped memory (NVLink / NVSwitch) for the sharded loss: buffer layout, the
+// system-scope flag protocol, and the description of the peers' published rows that the operand preparation reads.
+//
+// Every rank owns one exchange buffer (include/smmd.h, smmd_peer_buffer_bytes), mapped into all peers:
+//   [0, 128)        data_flag[16]  u64: data_flag[r] = last step whose rows rank r has published (written BY rank r)
+//   [128, 256)      sums_flag[16]  u64: same for rank r's partial sums
+//   [1024, 5120)    sums[2][16][16] f64: slot (step & 1), source rank r, the 16 scalars of smmd_scalar
+//   [8192, ...)     two data slots (step & 1) of rows_local x d elements (sized for fp32): the rank's own rows
+// Protocol per step (all stores that cross GPUs are followed by a system-scope fence and a release store of the flag;
+// readers poll the flag in their OWN memory with acquire loads and then pull the data over NVLink):
+//   publish rows -> raise data_flag[self] in every peer -> each peer's preparation pulls the rows once the flag is up
+//   write sums into every peer's slot -> raise sums_flag[self] there -> every rank adds the slots in rank order.
+// Slot reuse needs no extra barrier: a rank can only reach step k + 2 after every peer has raised its step k + 1 flags,
+// which each peer does after it has finished reading step k's slots (stream order on the peer).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include "../../include/smmd.h"
+
+namespace smmd {
+
+constexpr int kPeerMax = SMMD_MAX_PEERS;
+constexpr size_t kPeerOffDataFlag = 0;
+constexpr size_t kPeerOffSumsFlag = 128;
+constexpr size_t kPeerOffSums = 1024;
+constexpr size_t kPeerOffData = 8192;
+
+__host__ __device__ inline size_t peer_slot_bytes(int64_t rows_local, int64_t d) {
+  return ((size_t)rows_local * (size_t)d * 4 + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t peer_buffer_bytes(int64_t rows_local, int64_t d) {
+  return kPeerOffData + 2 * peer_slot_bytes(rows_local, d);
+}
+
+// The rows every rank has published for this step, as the operand preparation sees them: block r of the global X (Y)
+// rows lives in data[r] at rows [0, blk_x) ([blk_x, blk_x + blk_y)), pitch = d elements.  Passed by value to kernels.
+struct PeerSrc {
+  int on;                               // 0 = not a peer call
+  int world, self;
+  const void* data[kPeerMax];           // this step's data slot of every rank
+  const unsigned long long* flags;      // data_flag array of the OWN buffer
+  unsigned long long step;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for flag >= step (a peer that never arrives is an error, not a hang): ~4 s of polling, then trap.
+__device__ __forceinline__ void peer_wait_flag(const unsigned long long* flag, unsigned long long step) {
+  if (ld_acquire_sys(flag) >= step) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i) {
+      __nanosleep(64);
+      if (ld_acquire_sys(flag) >= step) return;
+    }
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();
+  }
+}
+#endif
+
+}  // namespace smmd

@@ -42,8 +42,21 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
   int64_t src = loc;
   if (valid && a.idxA) src = inA ? a.idxA[(a.first_batch + b) * a.m + loc] : a.idxB[(a.first_batch + b) * a.n + loc];
   else src = src_row(src, inA, a.blk_a, a.blk_b);
-  const int64_t ld = inA ? a.lda : a.ldb;
+  int64_t ld = inA ? a.lda : a.ldb;
   const void* base = inA ? a.A : a.B;
+  if (a.peer.on) {
+    // the all_gather, fused: block r of the global rows is read straight from rank r's exchange buffer over NVLink, as
+    // soon as that rank's data flag for this step is up (own block: no wait, it was published earlier on this stream)
+    const int64_t blk = inA ? a.blk_a : a.blk_b;
+    const int64_t r = valid ? loc / blk : (int64_t)a.peer.self;
+    base = a.peer.data[r];
+    src = (inA ? 0 : a.blk_a) + (valid ? loc - r * blk : 0);
+    ld = a.d;
+    if (valid && r != a.peer.self) {
+      if (lane == 0) peer_wait_flag(a.peer.flags + r, a.peer.step);
+      __syncwarp();
+    }
+  }
   __nv_bfloat16* zrow = a.Z + (b * Mp + p) * a.dpz;
   float acc = 0.f;
   // fast path: fp32 rows, 16-B aligned, no split/tanh tail handling needed per element: 8 features per lane

@@ -138,7 +138,13 @@ struct PrepTcArgs {
   KernelFn kf;
   int64_t blk_a, blk_b;  // gathered block layout (0 = plain), see SrcLayout
   int f16;               // write IEEE half instead of bf16 (fp16 operand tier; not with `split`)
+  PeerSrc peer;          // peer.on: block r of A / B is pulled from rank r's exchange buffer once its flag is up
 };
+// (SrcLayout -> PrepTcArgs: the peer description rides along when the call came through smmd_mmd2_fwd_bwd_peers)
+inline void prep_set_peers(PrepTcArgs& pa, const SrcLayout& src) {
+  if (src.peers) pa.peer = *src.peers;
+  else pa.peer.on = 0;
+}
 
 // launch wrappers (kernels live in smmd_tc.cu): grid = (ceil(rows / 8), batch)
 cudaError_t launch_prep_tc(const PrepTcArgs& a, int64_t rows, unsigned batch, cudaStream_t s);

@@ -1503,6 +1503,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
   pa.f16 = c.f16;
+  prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;
@@ -1656,6 +1657,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   PrepTcArgs pa{src.X, src.Y, src.dtype, src.ldx, src.ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
   pa.f16 = c.f16;
+  prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;

@@ -818,6 +818,7 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
   PrepTcArgs pa{X, Y, dtype, ldx, ldy, g.m, g.n, p.mp, p.np, g.d, p.dp, p.dp, nullptr, nullptr, 0,
                 kf.tanh_features, 0, Z, norms, nullptr, kf, src.blk_x, src.blk_y};
   pa.f16 = c.f16;
+  prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
   ++*launches;

@@ -31,7 +31,10 @@ def main():
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps * 1e3
-    nbuf = 2
+    nbuf = 3 if "--nbuf3" in sys.argv else 2
+    d2hs = "--d2hstream" in sys.argv
+    cp_stream = torch.cuda.Stream(dev)
+    done_ev = [None] * 8
     gXh = [torch.empty((nl, d)).pin_memory() for _ in range(nbuf)]; gYh = [torch.empty((nl, d)).pin_memory() for _ in range(nbuf)]
     lossh = [torch.empty(1).pin_memory() for _ in range(nbuf)]
     streams = [torch.cuda.Stream(dev) for _ in range(nbuf)]
@@ -68,6 +71,66 @@ def main():
             loss = loss_of(X, Y); loss.backward()
             gXh[0].copy_(X.grad, non_blocking=True); gYh[0].copy_(Y.grad, non_blocking=True)
             lossh[0].copy_(loss.detach().reshape(1), non_blocking=True)
+    # ---- timeline of the two-stream loop: CUDA events per phase, times relative to a base event (rank 0 prints) ----
+    if "--timeline" in sys.argv:
+        evs = []
+        def ev():
+            e = torch.cuda.Event(enable_timing=True); e.record(); return e
+        marks = []
+        _ag, _ar = dist.all_gather_into_tensor, dist.all_reduce
+        def ag(*a, **k):
+            e_a = ev(); r = _ag(*a, **k); e_b = ev(); marks.append(("ag", e_a, e_b)); return r
+        def ar(*a, **k):
+            e_a = ev(); r = _ar(*a, **k); e_b = ev(); marks.append(("ar", e_a, e_b)); return r
+        if world > 1:
+            dist.all_gather_into_tensor, dist.all_reduce = ag, ar
+        def full_tl(i):
+            b = i % nbuf; st = streams[b]
+            if d2hs:
+                if done_ev[b] is not None: done_ev[b].synchronize()
+            else:
+                st.synchronize()
+            t_host = time.perf_counter()
+            with torch.cuda.stream(st):
+                e0 = ev()
+                X = Xh.to(dev, non_blocking=True).requires_grad_(True); Y = Yh.to(dev, non_blocking=True).requires_grad_(True)
+                e1 = ev()
+                loss = loss_of(X, Y)
+                e2 = ev()
+                loss.backward()
+                e3 = ev()
+                if d2hs:
+                    gx, gy, lv = X.grad, Y.grad, loss.detach().reshape(1)
+                    cp_stream.wait_event(e3)
+                    with torch.cuda.stream(cp_stream):
+                        gXh[b].copy_(gx, non_blocking=True); gYh[b].copy_(gy, non_blocking=True); lossh[b].copy_(lv, non_blocking=True)
+                        gx.record_stream(cp_stream); gy.record_stream(cp_stream); lv.record_stream(cp_stream)
+                        e4 = ev()
+                    done_ev[b] = e4
+                else:
+                    gXh[b].copy_(X.grad, non_blocking=True); gYh[b].copy_(Y.grad, non_blocking=True)
+                    lossh[b].copy_(loss.detach().reshape(1), non_blocking=True)
+                    e4 = ev()
+            evs.append((i, t_host, time.perf_counter(), e0, e1, e2, e3, e4))
+        for i in range(6): full_tl(i)
+        evs.clear(); marks.clear()
+        barrier()
+        base = torch.cuda.Event(enable_timing=True); base.record(); tb = time.perf_counter()
+        t0 = time.perf_counter()
+        for i in range(12): full_tl(i)
+        barrier()
+        dist.all_gather_into_tensor, dist.all_reduce = _ag, _ar
+        if rank == 0:
+            print("TL variant nbuf=%d d2hstream=%s: %.3f ms/step" % (nbuf, d2hs, (time.perf_counter() - t0) / 12 * 1e3), flush=True)
+            for (nm, e_a, e_b) in marks[:24]:
+                print("TL   %s  [%.2f .. %.2f]" % (nm, base.elapsed_time(e_a), base.elapsed_time(e_b)), flush=True)
+            for (i, th0, th1, e0, e1, e2, e3, e4) in evs:
+                print("TL step %d host[%.2f..%.2f] start %.2f | h2d_end %.2f | fwd_end %.2f | bwd_end %.2f | d2h_end %.2f" % (
+                    i, (th0 - tb) * 1e3, (th1 - tb) * 1e3, base.elapsed_time(e0), base.elapsed_time(e1), base.elapsed_time(e2),
+                    base.elapsed_time(e3), base.elapsed_time(e4)), flush=True)
+    if "--timeline" in sys.argv:
+        if world > 1: dist.destroy_process_group()
+        return
     res = {}
     for name, fn in (("h2d", h2d), ("d2h", d2h), ("compute", compute), ("full_2streams", full), ("full_1stream", full_1stream)):
         res[name] = timed(fn)

@@ -24,6 +24,7 @@ ESTIMATORS = {"unbiased": EST_UNBIASED, "biased": EST_BIASED, "u-statistic": EST
 EXPORTS = [
     "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
+    "smmd_peer_buffer_bytes", "smmd_mmd2_fwd_bwd_peers",
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_poly_sums_workspace_bytes", "smmd_poly_sums", "smmd_kid_from_row_stats", "smmd_ratio_from_row_stats",
@@ -40,6 +41,14 @@ class Problem(C.Structure):
         ("add_dot", C.c_float), ("degree", C.c_int32), ("biased", C.c_int32), ("precision", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32),
     ]
+
+
+MAX_PEERS = 16
+
+
+class PeerTable(C.Structure):
+    """smmd_peer_table (include/smmd.h): every rank's exchange buffer as mapped into this process."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("base", C.c_void_p * MAX_PEERS)]
 
 
 class KidProblem(C.Structure):
@@ -90,6 +99,11 @@ def load():
     lib.smmd_mmd2_fwd_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.smmd_mmd2_fwd_bwd_gathered.restype = C.c_int
     lib.smmd_mmd2_fwd_bwd_gathered.argtypes = [C.POINTER(Problem), vp, i64, vp, vp, i64, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_peer_buffer_bytes.restype = C.c_size_t
+    lib.smmd_peer_buffer_bytes.argtypes = [i64, i64]
+    lib.smmd_mmd2_fwd_bwd_peers.restype = C.c_int
+    lib.smmd_mmd2_fwd_bwd_peers.argtypes = [C.POINTER(Problem), C.POINTER(PeerTable), C.c_uint64, vp, vp, i64, vp, vp, vp, vp,
+                                            C.c_size_t, vp]
     lib.smmd_mmd2_combine.restype = C.c_int
     lib.smmd_mmd2_combine.argtypes = [C.POINTER(Problem), vp, vp, vp]
     lib.smmd_mmd2_and_ratio.restype = C.c_int

@@ -139,10 +139,98 @@ def sharded_mmd2_raw(spec, Xl, Yl, biased=False, precision=None, group=None, loc
     return value, dX, dY, sums
 
 
+class PeerExchange:
+    """Exchange buffers for the peer-memory variant of the sharded loss (``smmd_mmd2_fwd_bwd_peers``): one buffer per
+    rank, mapped into every other rank of the NVLink domain through torch symmetric memory (plumbing only: the data
+    moves inside the library's own kernels).  Create it ONCE per (group, local shape) -- the rendezvous is a collective --
+    and pass it to ``sharded_mmd2(..., exchange=px)``; every rank must then make the same sequence of calls on it.
+
+    ``map_buffers`` (tests): callable(nbytes, device, group) -> (own uint8 tensor, [base address of every rank]).
+    """
+
+    def __init__(self, rows_local, d, device, group=None, map_buffers=None):
+        import ctypes as C
+
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("PeerExchange supports up to %d ranks" % _lib.MAX_PEERS)
+        self.rows_local, self.d = int(rows_local), int(d)
+        lib = _lib.load()
+        self.nbytes = int(lib.smmd_peer_buffer_bytes(self.rows_local, self.d))
+        if map_buffers is None:
+            map_buffers = _symmetric_buffers
+        self.buffer, ptrs, self._keepalive = map_buffers(self.nbytes, torch.device(device), group)
+        self.table = _lib.PeerTable()
+        self.table.world, self.table.rank = self.world, self.rank
+        for r in range(self.world):
+            self.table.base[r] = C.c_void_p(int(ptrs[r]))
+        self.step = 0
+
+    def next_step(self):
+        self.step += 1
+        return self.step
+
+    def fits(self, rows_local, d):
+        return int(_lib.load().smmd_peer_buffer_bytes(int(rows_local), int(d))) <= self.nbytes
+
+
+def _symmetric_buffers(nbytes, device, group):
+    """Allocate + zero the own exchange buffer in symmetric memory and rendezvous (collective over `group`)."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+    hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+    buf.zero_()
+    torch.cuda.synchronize(device)
+    hdl.barrier()            # every buffer is zero before anybody raises a flag in it
+    torch.cuda.synchronize(device)
+    return buf, [int(p) for p in hdl.buffer_ptrs], hdl
+
+
+def _peer_local_compute(spec, px, Xl, Yl, m, n, biased, precision):
+    """smmd_mmd2_fwd_bwd_peers: publish + pull + kernels + sum exchange + combine, no collective call on the data path.
+    Returns (combined scalars[16] f64, dX_local, dY_local)."""
+    import ctypes as C
+
+    from .mmd import _as_ptr, _stream_ptr, _workspace
+
+    lib = _lib.load()
+    d = Xl.shape[1]
+    Xo = Xl.detach().float().contiguous()
+    Yo = Yl.detach().float().contiguous()
+    prob = spec.problem(m, n, d, d, d, torch.float32, biased, precision, px.rank, px.world)
+    dev = Xl.device
+    with torch.cuda.device(dev):
+        nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1)
+        if nbytes == 0:
+            raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
+        ws = _workspace(nbytes, dev)
+        scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
+        dX = torch.empty((m // px.world, d), dtype=torch.float32, device=dev)
+        dY = torch.empty((n // px.world, d), dtype=torch.float32, device=dev)
+        st = lib.smmd_mmd2_fwd_bwd_peers(C.byref(prob), C.byref(px.table), px.next_step(), _as_ptr(Xo), _as_ptr(Yo), d,
+                                         _as_ptr(scalars), _as_ptr(dX), _as_ptr(dY), _as_ptr(ws), nbytes, _stream_ptr(dev))
+        _lib.check(st, "smmd_mmd2_fwd_bwd_peers")
+    return scalars, dX, dY
+
+
+def sharded_mmd2_raw_peers(spec, Xl, Yl, px, biased=False, precision=None):
+    """One sharded evaluation over peer memory.  Returns (mmd2 f64 scalar tensor, dX_local, dY_local, combined scalars)."""
+    ml, nl, d = Xl.shape[0], Yl.shape[0], Xl.shape[1]
+    if not px.fits(ml + nl, d):
+        raise ValueError("PeerExchange was created for %d x %d local rows; got %d x %d" % (px.rows_local, px.d, ml + nl, d))
+    sums, dX, dY = _peer_local_compute(spec, px, Xl, Yl, ml * px.world, nl * px.world, biased, precision)
+    return sums[_lib.S_MMD2], dX, dY, sums
+
+
 class _ShardedMMD2(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, X_local, Y_local, spec, biased, precision, group, local_compute, combine):
-        value, dX, dY, sums = sharded_mmd2_raw(spec, X_local, Y_local, biased, precision, group, local_compute, combine)
+    def forward(ctx, X_local, Y_local, spec, biased, precision, group, local_compute, combine, exchange=None):
+        if exchange is not None:
+            value, dX, dY, sums = sharded_mmd2_raw_peers(spec, X_local, Y_local, exchange, biased, precision)
+        else:
+            value, dX, dY, sums = sharded_mmd2_raw(spec, X_local, Y_local, biased, precision, group, local_compute, combine)
         ctx.save_for_backward(dX, dY)
         ctx.in_dtypes = (X_local.dtype, Y_local.dtype)
         ctx.nonfinite = sums[_lib.S_NONFINITE]
@@ -152,7 +240,7 @@ class _ShardedMMD2(torch.autograd.Function):
     def backward(ctx, grad_out):
         dX, dY = ctx.saved_tensors
         g = grad_out.to(dX.dtype)
-        return (g * dX).to(ctx.in_dtypes[0]), (g * dY).to(ctx.in_dtypes[1]), None, None, None, None, None, None
+        return (g * dX).to(ctx.in_dtypes[0]), (g * dY).to(ctx.in_dtypes[1]), None, None, None, None, None, None, None
 
 
 def check_equal_shards(ml, nl, device, group=None):
@@ -165,7 +253,8 @@ def check_equal_shards(ml, nl, device, group=None):
                          % (mn_m, mx_m, mn_n, mx_n))
 
 
-def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=None, _combine=None, check_sizes=False):
+def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=None, _combine=None, check_sizes=False,
+                 exchange=None):
     """Global-batch ``mmd2(kernel(G, images))`` where ``K = mmd._<name>_kernel(G_local, images_local)`` holds
     this rank's rows.  Returns the same scalar on every rank; backward yields gradients for the local rows.
 
@@ -178,6 +267,11 @@ def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=Non
         / world), the result is (1 / world) x the true parameter gradient: scale the loss by `world` or use a SUM
         reduction of parameter gradients to reproduce single-device training.
 
+    ``exchange``: a :class:`PeerExchange` -- the gather of the features and the reduction of the partial sums then run
+    inside the library's kernels over NVLink peer memory (no NCCL call on the data path; one launch in total for
+    latency-bound shapes).  Combinations the peer entry point does not cover (mid-size exact-path problems) raise
+    ``SmmdError``; call without ``exchange`` for those.
+
     ``_local_compute`` / ``_combine`` are injection points for the CPU tests of the host-side logic."""
     from .mmd import KernelHandle
 
@@ -185,7 +279,7 @@ def sharded_mmd2(K, biased=False, precision=None, group=None, _local_compute=Non
         raise TypeError("sharded_mmd2 expects the handle returned by a _<name>_kernel(X_local, Y_local) call")
     if check_sizes:
         check_equal_shards(K.X.shape[0], K.Y.shape[0], K.X.device, group)
-    return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group, _local_compute, _combine)
+    return _ShardedMMD2.apply(K.X, K.Y, K.spec, bool(biased), precision, group, _local_compute, _combine, exchange)
 
 
 def kid_shard(n_subsets, rank, world):

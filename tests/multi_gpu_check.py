@@ -56,6 +56,54 @@ def main():
             print("rank %d MISMATCH mmd2 b=%d d=%d %s: loss %.10g ref %.10g  grad rel err %.3e %.3e" %
                   (rank, b, d, precision, loss.item(), ref.item(), ex, ey), flush=True)
         ok &= c1 and ex <= gtol and ey <= gtol
+    # peer-memory exchange (smmd_mmd2_fwd_bwd_peers: gather + reduction inside the library's kernels over NVLink) against
+    # the collective-based path on the same shards.  Tensor-core tiers run the same kernels on the same operand values:
+    # identical results expected; the one-launch small kernel differs from the general exact path by fp32 rounding order.
+    from smmd.distributed import PeerExchange
+    for (b, d, precision, gtol, vtol) in ((64, 1, "fp32", 1e-5, 1e-6), (64, 16, "fp32", 1e-5, 1e-6), (1024, 128, "bf16", 1e-7, 1e-9),
+                                          (768, 512, "bf16", 1e-7, 1e-9), (1024, 192, "fp16", 1e-7, 1e-9)):
+        px = PeerExchange(2 * b, d, dev)
+        for it in range(4):                       # several steps on one exchange: both slots, flags that keep counting
+            rng = np.random.RandomState(1000 + 10 * it + rank)
+            Xl = torch.tensor((rng.randn(b, d) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
+            Yl = torch.tensor(((1.05 * rng.randn(b, d) + 0.1) / np.sqrt(d)).astype(np.float32), device=dev, requires_grad=True)
+            lp = sharded_mmd2(mmd._mix_rq_kernel(Xl, Yl), precision=precision, exchange=px)
+            path = _lib.last_path()
+            lp.backward()
+            gxp, gyp = Xl.grad.clone(), Yl.grad.clone()
+            Xl.grad = None
+            Yl.grad = None
+            ln = sharded_mmd2(mmd._mix_rq_kernel(Xl, Yl), precision=precision)
+            ln.backward()
+            c1 = abs(lp.item() - ln.item()) <= vtol * abs(ln.item()) + 1e-12
+            ex = (gxp - Xl.grad).abs().max().item() / Xl.grad.abs().max().item()
+            ey = (gyp - Yl.grad).abs().max().item() / Yl.grad.abs().max().item()
+            good = c1 and ex <= gtol and ey <= gtol and ("peer" in path or precision != "fp32")
+            if not good or (rank == 0 and it == 0):
+                print("rank %d peers b=%d d=%d %s step %d path=%s: loss %.10g vs %.10g  grad rel diff %.3e %.3e %s" %
+                      (rank, b, d, precision, it, path, lp.item(), ln.item(), ex, ey, "ok" if good else "MISMATCH"), flush=True)
+            ok &= good
+    # latency of the C5-sized global-batch loss (64 + 64 rows x 1 per rank): one launch over peer memory vs collectives
+    b, d = 64, 1
+    px = PeerExchange(2 * b, d, dev)
+    Xl = torch.randn(b, d, device=dev)
+    Yl = torch.randn(b, d, device=dev) * 1.1
+    spec = mmd._mix_rq_kernel(Xl, Yl).spec
+    from smmd.distributed import sharded_mmd2_raw, sharded_mmd2_raw_peers
+    for name, fn in (("peers", lambda: sharded_mmd2_raw_peers(spec, Xl, Yl, px, precision="fp32")),
+                     ("nccl", lambda: sharded_mmd2_raw(spec, Xl, Yl, precision="fp32"))):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print("C5-size loss fwd+bwd via %s: %.1f us per evaluation (stream launches, world %d)" % (name, e0.elapsed_time(e1) * 5.0, world), flush=True)
     # KID
     gen = torch.Generator(device=dev).manual_seed(7)     # same seed on every rank -> replicated codes
     g = torch.relu(torch.randn(4000, 256, device=dev, generator=gen))
