@@ -289,6 +289,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     launches = [0]
+    # N GPUs: how the features and the partial sums cross the GPUs -- "peer": inside the library's kernels over
+    # peer-mapped memory (smmd_mmd2_fwd_bwd_peers), "nccl": all_gather + all_reduce around them
+    px = None
+    if world > 1:
+        from smmd.distributed import PeerExchange, sharded_mmd2_raw, sharded_mmd2_raw_peers
+        if args.exchange == "peer":
+            px = PeerExchange(2 * nl, d, dev)
 
     def device_step():
         """inputs resident in HBM.  1 GPU: the fused call.  N GPUs: one bf16 all_gather of the local blocks + fused
@@ -297,7 +304,10 @@ def run_ours(args):
             sc, dX, dY = mmd.fused_mmd2_raw(spec, Xd, Yd, biased=False, want_grad=True, precision="bf16")
             launches[0] += _lib.last_launch_count()
             return sc[_lib.S_MMD2], dX, dY
-        from smmd.distributed import sharded_mmd2_raw
+        if px is not None:   # gather + reduction inside the library's kernels over NVLink peer memory
+            val, dX, dY, _ = sharded_mmd2_raw_peers(spec, Xd, Yd, px, biased=False, precision="bf16")
+            launches[0] += _lib.last_launch_count()
+            return val, dX, dY
         val, dX, dY, _ = sharded_mmd2_raw(spec, Xd, Yd, biased=False, precision="bf16")
         launches[0] += _lib.last_launch_count() + 1
         return val, dX, dY
@@ -387,9 +397,10 @@ def run_ours(args):
     # Two steps are kept in flight on two streams (double-buffered pinned result buffers), so one step's PCIe copies
     # overlap the other's kernels; every step still copies its inputs in and its loss + gradients out.
     nbuf = 2
-    gXh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    gYh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    lossh = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    nhost = 3 if px is not None else nbuf    # pinned result buffers (peer loop: one more, its copy-out trails by a step)
+    gXh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nhost)]
+    gYh = [torch.empty((nl, d), dtype=torch.float32).pin_memory() for _ in range(nhost)]
+    lossh = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(nhost)]
     # (N > 1: NCCL collectives are enqueued in program order on every rank, whichever stream they wait on)
     streams = [torch.cuda.Stream(dev) for _ in range(nbuf)]
 
@@ -408,12 +419,70 @@ def run_ours(args):
             gYh[b].copy_(Y.grad, non_blocking=True)
             lossh[b].copy_(loss.detach().reshape(1), non_blocking=True)   # device -> host read of the step's result
 
+    # Peer exchange (N > 1): the same per-step work, but the PCIe copies are ordered behind the step's NVLink phase.
+    # Measured on this pool's 8-GPU boxes: a device->host copy that runs next to the pull of the peers' rows stalls the
+    # NVLink traffic for its whole duration (the gather phase grows from ~0.1 to ~1.4 ms per step, with NCCL's all_gather
+    # just the same), while next to the kernels it is free.  So step i's inputs go up once step i-1's pull has completed,
+    # and step i-1's results come down once step i's pull has (PeerExchange.last_pull_event): both overlap kernels only.
+    # Two streams (the exchange allows two calls in flight), three pinned result buffers.
+    cp_stream = torch.cuda.Stream(dev)
+    done_ev = [None] * nhost
+    state = {"pending": None, "prev_pull": None}
+    if px is not None:
+        px.enable_pull_events()
+
+    def copy_out(pending, after):
+        b, gx, gy, lv, bwd_ev = pending
+        if after is not None:
+            cp_stream.wait_event(after)
+        cp_stream.wait_event(bwd_ev)
+        with torch.cuda.stream(cp_stream):
+            gXh[b].copy_(gx, non_blocking=True)
+            gYh[b].copy_(gy, non_blocking=True)
+            lossh[b].copy_(lv, non_blocking=True)
+            for t in (gx, gy, lv):
+                t.record_stream(cp_stream)
+            done_ev[b] = torch.cuda.Event()
+            done_ev[b].record(cp_stream)
+
+    def e2e_step_peer(i):
+        b = i % nhost
+        st = streams[i % nbuf]
+        if done_ev[b] is not None:
+            done_ev[b].synchronize()     # the results that last used these host buffers (step i - nbuf) have landed
+        with torch.cuda.stream(st):
+            flush.zero_()
+            if state["prev_pull"] is not None:
+                st.wait_event(state["prev_pull"])      # inputs go up next to the previous step's kernels
+            X = Xh.to(dev, non_blocking=True).requires_grad_(True)
+            Y = Yh.to(dev, non_blocking=True).requires_grad_(True)
+            K = mmd._mix_rq_kernel(X, Y)
+            loss = sharded_mmd2(K, precision="bf16", exchange=px)
+            pull = px.last_pull_event
+            loss.backward()
+            bwd_ev = torch.cuda.Event()
+            bwd_ev.record(st)
+        if state["pending"] is not None:
+            copy_out(state["pending"], pull)           # step i-1's results come down next to step i's kernels
+        state["pending"] = (b, X.grad, Y.grad, loss.detach().reshape(1), bwd_ev)
+        state["prev_pull"] = pull
+
+    def e2e_drain():
+        if state["pending"] is not None:
+            copy_out(state["pending"], None)
+            state["pending"] = None
+
+    step_fn = e2e_step_peer if px is not None else e2e_step
     for i in range(4):
-        e2e_step(i)
+        step_fn(i)
+    if px is not None:
+        e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        e2e_step(i)
+        step_fn(i)
+    if px is not None:
+        e2e_drain()                 # every timed step's results are on the host before the clock stops
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -422,13 +491,14 @@ def run_ours(args):
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * nl * d * 4 * world,
            "d2h_bytes_per_step": (2 * nl * d * 4 + 4) * world, "ms_per_step": t_e2e.item() / args.steps * 1e3,
            "api": "smmd.mmd.mmd2(smmd.mmd._mix_rq_kernel(G, images)).backward() on tensors copied from pinned host memory; "
-                  "loss + both gradients copied back every step; %d step(s) in flight" % nbuf}
+                  "loss + both gradients copied back every step; %d step(s) in flight%s" % (
+                      nbuf, "; copies ordered behind each step's NVLink pull (PeerExchange.last_pull_event)" if px is not None else "")}
 
     # ---- KID (configs[2]): 50k vs 50k x 2048, 100 subsets of 1000, subsets split across ranks ----
-    kid = run_kid(dev, rank, world, args, compute_scores, lib, dist, peak)
+    kid = None if args.mmd_only else run_kid(dev, rank, world, args, compute_scores, lib, dist, peak)
 
     # ---- latency-bound shapes (configs[0] and the shipped YAML shape): microseconds per loss fwd+bwd ----
-    small = run_small(dev, mmd, args) if (rank == 0 and world == 1) else None
+    small = run_small(dev, mmd, args) if (rank == 0 and world == 1 and not args.mmd_only) else None
 
     # ---- parity of the sharded path, visible to the driver (its GPU-test box has one GPU): every rank's owned-row
     #      gradients and the combined scalar against the SAME problem evaluated unsharded on rank 0 (outside all timed
@@ -478,7 +548,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "C4 large-batch Gram: mix_rq MMD^2 fwd+bwd, N=%d fake + %d real, d=%d, alphas (.1,1,10), unbiased"
                                    % (n, n, d),
-                       "parallelism": "row-sharded Gram x%d (all_gather features, all_reduce 7 fp64 sums)" % world,
+                       "parallelism": ("row-sharded Gram x%d (features pulled from peer memory over NVLink inside the operand "
+                                       "preparation, 7 fp64 sums exchanged + combined in one kernel; no NCCL call on the data path)" % world
+                                       if px is not None else
+                                       "row-sharded Gram x%d (all_gather features, all_reduce 7 fp64 sums)" % world),
                        "l2": "flushed between timed iterations (256 MiB write, outside the per-step event pair)",
                        "path": path, "mmd2": mmd2_val},
             "clocks": clocks.summary(), "gpu_launches": n_launch, "roofline": roofline, "e2e": e2e, "kid": kid,
@@ -779,6 +852,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
     ap.add_argument("--no-kid", action="store_true", help="reference arm: skip the KID line")
     ap.add_argument("--ref-n", type=int, default=0, help="reference arm: fixed sample N (default: chosen from time / memory)")
+    ap.add_argument("--mmd-only", action="store_true", help="quick A/B runs: skip the KID object and the latency-bound shapes")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: features / partial sums cross the GPUs inside the library's kernels over peer memory, or as NCCL collectives")
     ap.add_argument("--workload", default="mmd", choices=["mmd", "kid"], help="kid: the KID half of the metric as its own line")
     ap.add_argument("--sweep", action="store_true", help="C4 grid (N x d) instead of the headline line")
     ap.add_argument("--sweep-n", default="4096,8192,16384,32768,65536")

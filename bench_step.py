@@ -169,7 +169,7 @@ def run_c5(args):
     import torch.distributed as dist
 
     from smmd import _lib, mmd
-    from smmd.distributed import sharded_mmd2_raw
+    from smmd.distributed import PeerExchange, sharded_mmd2_raw, sharded_mmd2_raw_peers
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     lr = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,6 +187,11 @@ def run_c5(args):
     def loss():
         return sharded_mmd2_raw(spec, f, r, biased=False, precision="fp32")[0]
 
+    px = PeerExchange(128, 1, dev)
+
+    def loss_peers():   # the same loss with the gather + reduction inside ONE kernel over NVLink peer memory
+        return sharded_mmd2_raw_peers(spec, f, r, px, biased=False, precision="fp32")[0]
+
     def collectives_only():
         dist.all_gather_into_tensor(buf, buf[rank * 128:(rank + 1) * 128])
         dist.all_reduce(sc)
@@ -196,6 +201,8 @@ def run_c5(args):
 
     res = {"config": "C5 imagenet_smmd.yml loss: %d ranks x (64 fake + 64 real) x dof_dim 1, rbf, global-batch MMD^2 "
                      "(all_gather + owned-row kernel + all_reduce of 7 sums)" % world, "n_gpus": world,
+           "sharded_loss_peer_memory_us": timed(loss_peers, 200, 20), "mmd2_peer_memory": float(loss_peers()),
+           "path_peer_memory": _lib.last_path(),
            "sharded_loss_us": timed(loss, 200, 20), "collectives_only_us": timed(collectives_only, 200, 20),
            "local_64x1_loss_us": timed(local_only, 200, 20), "sharded_loss_us_cuda_graph": graphed(loss),
            "collectives_only_us_cuda_graph": graphed(collectives_only), "mmd2": float(loss()), "path": _lib.last_path()}

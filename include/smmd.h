@@ -164,8 +164,8 @@ SMMD_API int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double
  *     smmd_mmd2_combine, fused into one kernel).  Latency-bound shapes (<= 1024 global rows, d <= 64, fp32 tier) run
  *     publish + pull + loss + gradients + sum exchange + combine as ONE launch.
  * `step` is the collective's sequence number: 1 for the first call after the buffers were zeroed, +1 per call, the same
- * on every rank (two slots alternate, so a rank may be at most one call ahead of its slowest peer -- which the flag waits
- * enforce).  p describes the GLOBAL problem (m, n = total rows, p->rank / p->world = this shard; m and n multiples of
+ * on every rank (two slots and two sets of flags alternate: a rank may be one call ahead of its slowest peer, and two
+ * consecutive calls may be in flight on two streams; calls of the same parity must be stream-ordered).  p describes the GLOBAL problem (m, n = total rows, p->rank / p->world = this shard; m and n multiples of
  * world); X_local / Y_local are this rank's fp32 rows (pitch ld_local); scalars receives the COMBINED result (identical on
  * every rank), dX / dY the gradients of the local rows.  Every wait is bounded (a missing peer traps after 4 s).
  * New capability without a reference counterpart (the reference's towers never exchange features,
@@ -175,6 +175,12 @@ typedef struct smmd_peer_table {
   int32_t world, rank;
   void* base[SMMD_MAX_PEERS];
 } smmd_peer_table;
+/* Optional: a cudaEvent_t (NULL to clear; per calling thread) that the following smmd_mmd2_fwd_bwd_peers calls record on
+ * their stream as soon as the peers' rows have been pulled (after the operand preparation; at the end of the call for
+ * the one-launch path).  Lets a pipelined caller order host<->device copies behind the NVLink phase of a step: on the
+ * measured 8-GPU boxes a PCIe device->host copy running next to the pull stalls the NVLink traffic for its whole
+ * duration (0.1 ms -> 1.4 ms per step), while the same copy next to the kernels costs nothing. */
+SMMD_API int smmd_peer_set_pull_event(void* cuda_event);
 SMMD_API size_t smmd_peer_buffer_bytes(int64_t rows_local, int64_t d);
 SMMD_API int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers, uint64_t step,
                                      const float* X_local, const float* Y_local, int64_t ld_local, double* scalars,

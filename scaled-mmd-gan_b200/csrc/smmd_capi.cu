@@ -15,6 +15,8 @@ thread_local char g_cuda_err[256] = "";
 thread_local int g_launches = 0;
 thread_local const char* g_path = "none";
 
+thread_local cudaEvent_t g_pull_event = nullptr;   // smmd_peer_set_pull_event
+thread_local int g_in_peer_call = 0;
 thread_local int g_prof_on = 0;
 thread_local int g_prof_recorded = 0;
 thread_local cudaEvent_t g_prof_ev[3] = {nullptr, nullptr, nullptr};   // begin, end, mid (two-kernel paths)
@@ -151,6 +153,9 @@ bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) %
 }  // namespace
 
 namespace smmd {
+void peer_after_pull(cudaStream_t s) {
+  if (g_in_peer_call && g_pull_event) cudaEventRecord(g_pull_event, s);
+}
 void prof_begin(cudaStream_t s) {
   if (!g_prof_on) return;
   if (!g_prof_ev[0]) {
@@ -297,6 +302,11 @@ int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathered, int6
   return mmd2_fwd_bwd_impl(p, src, scalars, dX, dY, workspace, workspace_bytes, stream);
 }
 
+int smmd_peer_set_pull_event(void* cuda_event) {
+  g_pull_event = static_cast<cudaEvent_t>(cuda_event);
+  return SMMD_OK;
+}
+
 size_t smmd_peer_buffer_bytes(int64_t rows_local, int64_t d) {
   if (rows_local <= 0 || d <= 0) return 0;
   return peer_buffer_bytes(rows_local, d);
@@ -341,6 +351,7 @@ int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers,
                                      reinterpret_cast<unsigned int*>(ws + pl.off_norm), scalars, *peers, step, s));
     prof_end(s);
     g_launches = 1;
+    if (g_pull_event) cudaEventRecord(g_pull_event, s);
     return SMMD_OK;
   }
   if (prec == SMMD_PREC_BF16X3 && want_grad) return SMMD_EUNSUPPORTED;
@@ -356,7 +367,9 @@ int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers,
   int launches = 0;
   Coefs ct = c;
   ct.f16 = prec == SMMD_PREC_FP16 ? 1 : 0;
+  g_in_peer_call = 1;
   cudaError_t e = tc_mmd2_run(kf, g, ct, src, prec, scalars, dX, dY, workspace, workspace_bytes, s, &launches, &g_path);
+  g_in_peer_call = 0;
   g_launches = launches + (p->world > 1 ? 3 : 2);
   if (e != cudaSuccess) return cuda_fail(e);
   // 3. partial sums -> every peer, wait, add in rank order, MMD^2 (replaces all_reduce + smmd_mmd2_combine)

@@ -97,6 +97,7 @@ void prof_end(cudaStream_t s);
 void prof_mark(cudaStream_t s);   // boundary between the two kernels of a two-pass path
 
 // ---- peer-memory exchange (smmd_peer.cu) -----------------------------------------------------------------
+void peer_after_pull(cudaStream_t s);   // smmd_capi.cu: records the caller's event once the peers' rows have been pulled
 cudaError_t launch_peer_publish(const float* X, const float* Y, int64_t ld, int64_t blk_x, int64_t blk_y, int64_t d,
                                 int to_bf16, const smmd_peer_table& pt, uint64_t step, cudaStream_t s);
 PeerSrc make_peer_src(const smmd_peer_table& pt, int64_t rows_local, int64_t d, uint64_t step);

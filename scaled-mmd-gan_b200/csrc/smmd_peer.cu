@@ -64,7 +64,7 @@ __global__ void peer_signal_kernel(PeerBases pb, int world, int self, size_t fla
   __threadfence_system();
   const int t = threadIdx.x;
   if (t < world && t != self)
-    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(pb.base[t]) + flag_off) + self, step);
+    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(pb.base[t]) + flag_off) + peer_flag_index(step, self), step);
 }
 
 // ---- partial sums: exchange + combine (the all_reduce of 7 doubles and smmd_mmd2_combine in one kernel) -------
@@ -82,10 +82,10 @@ __device__ __forceinline__ void peer_exchange_and_combine(const KernelFn& kf, do
 #pragma unroll
     for (int i = 0; i < SMMD_NUM_SCALARS; ++i) st_relaxed_sys_f64(dst + i, mine[i]);
     __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(dst_base + kPeerOffSumsFlag) + self, step);
+    st_release_sys(reinterpret_cast<unsigned long long*>(dst_base + kPeerOffSumsFlag) + peer_flag_index(step, self), step);
   }
   char* own = static_cast<char*>(pb.base[self]);
-  if (lane < world) peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffSumsFlag) + lane, step);
+  if (lane < world) peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffSumsFlag) + peer_flag_index(step, lane), step);
   __syncwarp();
   if (lane == 0) {
     const double* in = reinterpret_cast<const double*>(own + kPeerOffSums + slot);
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(256) peer_small_mmd2_kernel(PeerSmallArgs a) {
     if (is_last) {
       __threadfence_system();
       if (tid < a.world && tid != a.self)
-        st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(a.pb.base[tid]) + kPeerOffDataFlag) + a.self,
-                       a.step);
+        st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(a.pb.base[tid]) + kPeerOffDataFlag) +
+                           peer_flag_index(a.step, a.self), a.step);
     }
     // 2. every peer's rows are published
     if (tid < a.world && tid != a.self)
-      peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffDataFlag) + tid, a.step);
+      peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffDataFlag) + peer_flag_index(a.step, tid), a.step);
     __syncthreads();
   }
   // 3. pull the global batch into shared memory (independent loads: one NVLink round trip, not one per column)
@@ -321,7 +321,8 @@ PeerSrc make_peer_src(const smmd_peer_table& pt, int64_t rows_local, int64_t d, 
   ps.self = pt.rank;
   const size_t off = kPeerOffData + (size_t)(step & 1) * peer_slot_bytes(rows_local, d);
   for (int i = 0; i < kPeerMax; ++i) ps.data[i] = i < pt.world ? static_cast<const char*>(pt.base[i]) + off : nullptr;
-  ps.flags = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(pt.base[pt.rank]) + kPeerOffDataFlag);
+  ps.flags = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(pt.base[pt.rank]) + kPeerOffDataFlag) +
+             peer_flag_index(step, 0);
   ps.step = (unsigned long long)step;
   return ps;
 }

@@ -2,16 +2,19 @@
 // system-scope flag protocol, and the description of the peers' published rows that the operand preparation reads.
 //
 // Every rank owns one exchange buffer (include/smmd.h, smmd_peer_buffer_bytes), mapped into all peers:
-//   [0, 128)        data_flag[16]  u64: data_flag[r] = last step whose rows rank r has published (written BY rank r)
-//   [128, 256)      sums_flag[16]  u64: same for rank r's partial sums
+//   [0, 256)        data_flag[2][16] u64: data_flag[step & 1][r] = last step of that parity whose rows rank r has published
+//                   (written BY rank r)
+//   [256, 512)      sums_flag[2][16] u64: same for rank r's partial sums
 //   [1024, 5120)    sums[2][16][16] f64: slot (step & 1), source rank r, the 16 scalars of smmd_scalar
 //   [8192, ...)     two data slots (step & 1) of rows_local x d elements (sized for fp32): the rank's own rows
 // Protocol per step (all stores that cross GPUs are followed by a system-scope fence and a release store of the flag;
 // readers poll the flag in their OWN memory with acquire loads and then pull the data over NVLink):
 //   publish rows -> raise data_flag[self] in every peer -> each peer's preparation pulls the rows once the flag is up
 //   write sums into every peer's slot -> raise sums_flag[self] there -> every rank adds the slots in rank order.
-// Slot reuse needs no extra barrier: a rank can only reach step k + 2 after every peer has raised its step k + 1 flags,
-// which each peer does after it has finished reading step k's slots (stream order on the peer).
+// Slot reuse needs no extra barrier: step k + 2 of a rank follows its step k in stream order, step k completes only after
+// every peer has raised its step-k sums flag, and a peer does that after it has finished reading step k's rows.  Flags are
+// kept per slot parity, so two consecutive steps of one rank may be in flight on two streams (step k + 1's flags say
+// nothing about step k); calls of the same parity must be stream-ordered.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -21,10 +24,11 @@ namespace smmd {
 
 constexpr int kPeerMax = SMMD_MAX_PEERS;
 constexpr size_t kPeerOffDataFlag = 0;
-constexpr size_t kPeerOffSumsFlag = 128;
+constexpr size_t kPeerOffSumsFlag = 256;
 constexpr size_t kPeerOffSums = 1024;
 constexpr size_t kPeerOffData = 8192;
 
+__host__ __device__ inline size_t peer_flag_index(unsigned long long step, int r) { return (size_t)(step & 1) * kPeerMax + (size_t)r; }
 __host__ __device__ inline size_t peer_slot_bytes(int64_t rows_local, int64_t d) {
   return ((size_t)rows_local * (size_t)d * 4 + 255) / 256 * 256;
 }
@@ -38,7 +42,7 @@ struct PeerSrc {
   int on;                               // 0 = not a peer call
   int world, self;
   const void* data[kPeerMax];           // this step's data slot of every rank
-  const unsigned long long* flags;      // data_flag array of the OWN buffer
+  const unsigned long long* flags;      // data_flag[step & 1] array of the OWN buffer
   unsigned long long step;
 };
 

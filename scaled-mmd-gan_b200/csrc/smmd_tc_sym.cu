@@ -1506,6 +1506,7 @@ cudaError_t run_symf(const KernelFn& kf, TcVariant variant, const Geometry& g, c
   prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
+  peer_after_pull(s);   // (peer calls: the caller's "rows pulled" event, see smmd_peer_set_pull_event)
   ++*launches;
   if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
@@ -1660,6 +1661,7 @@ cudaError_t tc_run_sym(const KernelFn& kf, TcVariant variant, const Geometry& g,
   prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
+  peer_after_pull(s);   // (peer calls: the caller's "rows pulled" event, see smmd_peer_set_pull_event)
   ++*launches;
   if ((e = cudaMemsetAsync(racc, 0, (size_t)p.Mp * 8, s)) != cudaSuccess) return e;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;

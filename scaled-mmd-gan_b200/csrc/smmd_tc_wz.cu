@@ -821,6 +821,7 @@ cudaError_t tc_run_wz(const KernelFn& kf, TcVariant variant, const Geometry& g, 
   prep_set_peers(pa, src);
   const double wscale = w_scale_for(c, kf);
   if ((e = launch_prep_tc(pa, p.Mp, 1, s)) != cudaSuccess) return e;
+  peer_after_pull(s);   // (peer calls: the caller's "rows pulled" event, see smmd_peer_set_pull_event)
   ++*launches;
   const bool dot = kf.family == FAM_RQ && kf.add_dot > 0.f;
   if (dot) {

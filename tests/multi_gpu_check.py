@@ -58,9 +58,10 @@ def main():
         ok &= c1 and ex <= gtol and ey <= gtol
     # peer-memory exchange (smmd_mmd2_fwd_bwd_peers: gather + reduction inside the library's kernels over NVLink) against
     # the collective-based path on the same shards.  Tensor-core tiers run the same kernels on the same operand values:
-    # identical results expected; the one-launch small kernel differs from the general exact path by fp32 rounding order.
+    # identical results expected; the one-launch small kernel differs from the general exact path by fp32 rounding order
+    # (each is within 1e-5 of fp64: 3e-5 between the two).
     from smmd.distributed import PeerExchange
-    for (b, d, precision, gtol, vtol) in ((64, 1, "fp32", 1e-5, 1e-6), (64, 16, "fp32", 1e-5, 1e-6), (1024, 128, "bf16", 1e-7, 1e-9),
+    for (b, d, precision, gtol, vtol) in ((64, 1, "fp32", 3e-5, 1e-6), (64, 16, "fp32", 3e-5, 1e-6), (1024, 128, "bf16", 1e-7, 1e-9),
                                           (768, 512, "bf16", 1e-7, 1e-9), (1024, 192, "fp16", 1e-7, 1e-9)):
         px = PeerExchange(2 * b, d, dev)
         for it in range(4):                       # several steps on one exchange: both slots, flags that keep counting

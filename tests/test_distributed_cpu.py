@@ -174,3 +174,90 @@ def test_unequal_shards_raise_on_every_rank():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all("different numbers of rows" in msg for _, msg in res), res
+
+
+def _emulated_peer_compute(spec, px, Xl, Yl, m, n, biased, precision):
+    """What smmd_mmd2_fwd_bwd_peers leaves on every rank (COMBINED scalars + local gradients), with the kernels' exchange
+    over peer memory emulated by gloo collectives and the arithmetic by the fp64 oracle."""
+    from smmd import _lib
+
+    world, rank = px.world, px.rank
+    step = px.next_step()
+    Xs = [torch.empty_like(Xl) for _ in range(world)]
+    Ys = [torch.empty_like(Yl) for _ in range(world)]
+    dist.all_gather(Xs, Xl.detach())
+    dist.all_gather(Ys, Yl.detach())
+    X, Y = torch.cat(Xs).numpy().astype(np.float64), torch.cat(Ys).numpy().astype(np.float64)
+    v, gX, gY = mmd_oracle.mmd2_and_grads("mix_rq_dot", X, Y, biased, np.float64)
+    ml, nl = m // world, n // world
+    sc = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64)
+    sc[_lib.S_MMD2] = v
+    sc[_lib.S_VAR] = float(step)       # (smuggles the step number out for the sequencing assertion)
+    return (sc, torch.tensor(gX[rank * ml:(rank + 1) * ml].astype(np.float32)),
+            torch.tensor(gY[rank * nl:(rank + 1) * nl].astype(np.float32)))
+
+
+def _peer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "scaled-mmd-gan_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smmd import _lib, mmd
+        from smmd.distributed import PeerExchange, sharded_mmd2
+
+        def fake_map(nbytes, device, group):     # every rank "maps" buffers at made-up, 256-aligned addresses
+            own = torch.zeros(nbytes, dtype=torch.uint8)
+            mine = torch.tensor([0x10000000 * (rank + 1)], dtype=torch.int64)
+            ptrs = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(ptrs, mine)
+            return own, [int(p) for p in ptrs], None
+
+        b, d = 12, 5
+        px = PeerExchange(2 * b, d, "cpu", map_buffers=fake_map, _compute=_emulated_peer_compute)
+        table = (px.table.world, px.table.rank, [int(px.table.base[r] or 0) for r in range(world)])
+        assert px.fits(2 * b, d) and not px.fits(2 * b + 1, d + 60)
+        out = []
+        for it in range(3):
+            rng = np.random.RandomState(100 + 7 * it + rank)
+            Xl = torch.tensor(rng.randn(b, d).astype(np.float32), requires_grad=True)
+            Yl = torch.tensor((1.1 * rng.randn(b, d) + 0.1).astype(np.float32), requires_grad=True)
+            spec = mmd.KernelSpec(_lib.K_MIX_RQ, [0.1, 1.0, 10.0], [1.0, 1.0, 1.0], add_dot=0.1, const_diagonal=3.0)
+            K = mmd.KernelHandle.__new__(mmd.KernelHandle)
+            K.spec, K.X, K.Y, K._dense = spec, Xl, Yl, None
+            loss = sharded_mmd2(K, exchange=px)
+            (loss * 3.0).backward()
+            out.append((float(loss), Xl.grad.numpy(), Yl.grad.numpy(), Xl.detach().numpy(), Yl.detach().numpy()))
+        q.put((rank, table, px.step, px.nbytes, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_host_logic_world2():
+    """PeerExchange: table construction from the mapped addresses, buffer size from the library, one step number per
+    call (the same on every rank), and the autograd plumbing of sharded_mmd2(..., exchange=px)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, table, step, nbytes, out in res:
+        assert table == (world, rank, [0x10000000, 0x20000000])
+        assert step == 3                                   # three calls -> steps 1, 2, 3
+        assert nbytes == 8192 + 2 * 256 * ((24 * 5 * 4 + 255) // 256)
+    for it in range(3):
+        X = np.concatenate([r[4][it][3] for r in res])
+        Y = np.concatenate([r[4][it][4] for r in res])
+        v, gX, gY = mmd_oracle.mmd2_and_grads("mix_rq_dot", X, Y, False, np.float64)
+        for rank, _, _, _, out in res:
+            loss, gx, gy = out[it][:3]
+            assert abs(loss - v) <= 1e-6 * abs(v)
+            assert np.allclose(gx, 3.0 * gX[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
+            assert np.allclose(gy, 3.0 * gY[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
