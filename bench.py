@@ -295,7 +295,18 @@ def run_ours(args):
     if world > 1:
         from smmd.distributed import PeerExchange, sharded_mmd2_raw, sharded_mmd2_raw_peers
         if args.exchange == "peer":
-            px = PeerExchange(2 * nl, d, dev)
+            # (a box whose ranks cannot map each other's memory falls back to the collective-based exchange -- on every
+            # rank or on none -- and the line's `parallelism` says which one ran)
+            try:
+                px = PeerExchange(2 * nl, d, dev)
+                okf = torch.ones(1, device=dev)
+            except Exception as e:   # noqa: BLE001
+                print("bench: peer-memory exchange unavailable on rank %d (%s: %s); using NCCL" % (rank, type(e).__name__, e),
+                      file=sys.stderr)
+                px, okf = None, torch.zeros(1, device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if okf.item() == 0.0:
+                px = None
 
     def device_step():
         """inputs resident in HBM.  1 GPU: the fused call.  N GPUs: one bf16 all_gather of the local blocks + fused
