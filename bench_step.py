@@ -192,6 +192,11 @@ def run_c5(args):
     def loss_peers():   # the same loss with the gather + reduction inside ONE kernel over NVLink peer memory
         return sharded_mmd2_raw_peers(spec, f, r, px, biased=False, precision="fp32")[0]
 
+    pxg = PeerExchange(128, 1, dev, device_steps=True)   # steps counted on the device: capturable
+
+    def loss_peers_graphable():
+        return sharded_mmd2_raw_peers(spec, f, r, pxg, biased=False, precision="fp32")[0]
+
     def collectives_only():
         dist.all_gather_into_tensor(buf, buf[rank * 128:(rank + 1) * 128])
         dist.all_reduce(sc)
@@ -203,6 +208,7 @@ def run_c5(args):
                      "(all_gather + owned-row kernel + all_reduce of 7 sums)" % world, "n_gpus": world,
            "sharded_loss_peer_memory_us": timed(loss_peers, 200, 20), "mmd2_peer_memory": float(loss_peers()),
            "path_peer_memory": _lib.last_path(),
+           "sharded_loss_peer_memory_us_cuda_graph": graphed(loss_peers_graphable), "mmd2_peer_memory_graphable": float(loss_peers_graphable()),
            "sharded_loss_us": timed(loss, 200, 20), "collectives_only_us": timed(collectives_only, 200, 20),
            "local_64x1_loss_us": timed(local_only, 200, 20), "sharded_loss_us_cuda_graph": graphed(loss),
            "collectives_only_us_cuda_graph": graphed(collectives_only), "mmd2": float(loss()), "path": _lib.last_path()}

@@ -164,7 +164,9 @@ SMMD_API int smmd_mmd2_combine(const smmd_problem* p, const double* sums, double
  *     smmd_mmd2_combine, fused into one kernel).  Latency-bound shapes (<= 1024 global rows, d <= 64, fp32 tier) run
  *     publish + pull + loss + gradients + sum exchange + combine as ONE launch.
  * `step` is the collective's sequence number: 1 for the first call after the buffers were zeroed, +1 per call, the same
- * on every rank (two slots and two sets of flags alternate: a rank may be one call ahead of its slowest peer, and two
+ * on every rank; step = 0 lets the kernels count on the device (last completed step of this rank + 1, kept in the own
+ * buffer) -- the call sequence then contains no host-side state and can be captured into a CUDA graph and replayed (calls
+ * must be stream-ordered in that mode) (two slots and two sets of flags alternate: a rank may be one call ahead of its slowest peer, and two
  * consecutive calls may be in flight on two streams; calls of the same parity must be stream-ordered).  p describes the GLOBAL problem (m, n = total rows, p->rank / p->world = this shard; m and n multiples of
  * world); X_local / Y_local are this rank's fp32 rows (pitch ld_local); scalars receives the COMBINED result (identical on
  * every rank), dX / dY the gradients of the local rows.  Every wait is bounded (a missing peer traps after 4 s).

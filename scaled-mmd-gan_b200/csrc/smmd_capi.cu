@@ -320,7 +320,7 @@ int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers,
   if (!p || !peers || !X_local || !Y_local || !scalars) return SMMD_EINVAL;
   int st = validate_problem(p);
   if (st != SMMD_OK) return st;
-  if (peers->world != p->world || peers->rank != p->rank || p->world > SMMD_MAX_PEERS || step == 0) return SMMD_EINVAL;
+  if (peers->world != p->world || peers->rank != p->rank || p->world > SMMD_MAX_PEERS) return SMMD_EINVAL;
   for (int r = 0; r < p->world; ++r)
     if (!peers->base[r] || !aligned(peers->base[r], 256)) return SMMD_EINVAL;
   if (p->m % p->world || p->n % p->world || ld_local < p->d) return SMMD_ESHAPE;
@@ -362,8 +362,8 @@ int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_table* peers,
   SMMD_CUDA(launch_peer_publish(X_local, Y_local, ld_local, blk_x, blk_y, p->d, to_bf16, *peers, step, s));
   // 2. the tensor-core path on the owned rows; its operand preparation pulls every peer's rows over NVLink
   const PeerSrc ps = make_peer_src(*peers, blk_x + blk_y, p->d, step);
-  SrcLayout src{ps.data[p->rank], ps.data[p->rank], to_bf16 ? SMMD_BF16 : SMMD_F32, p->d, p->d, blk_x, blk_y,
-                X_local, Y_local, ld_local, &ps};
+  SrcLayout src{peers->base[p->rank], peers->base[p->rank], to_bf16 ? SMMD_BF16 : SMMD_F32, p->d, p->d, blk_x, blk_y,
+                X_local, Y_local, ld_local, &ps};   // (X / Y only have to be non-null: the preparation reads the peers' slots)
   int launches = 0;
   Coefs ct = c;
   ct.f16 = prec == SMMD_PREC_FP16 ? 1 : 0;

@@ -25,8 +25,10 @@ struct PeerBases {
 // rows [0, blk_x) = X_local, [blk_x, blk_x + blk_y) = Y_local, pitch d; bf16 (the tensor-core operand format: half
 // the NVLink bytes, and exactly the values every rank will multiply) or fp32 (fp16 operand tier).
 __global__ void __launch_bounds__(256) peer_publish_kernel(const float* X, const float* Y, int64_t ld, int64_t blk_x,
-                                                           int64_t blk_y, int64_t d, int to_bf16, void* slot) {
+                                                           int64_t blk_y, int64_t d, int to_bf16, void* own,
+                                                           size_t slot_bytes, unsigned long long step_arg) {
   const int64_t rows = blk_x + blk_y;
+  void* slot = peer_data_slot(own, peer_step_of(step_arg, own), slot_bytes);
   const bool vec = (d % 8 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   if (vec) {
@@ -60,11 +62,11 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const float* X, const
 
 // The publish kernel has completed (stream order): its rows sit in this GPU's memory, which is where a peer's NVLink read
 // looks.  Raise data_flag[self] = step in every peer's buffer.
-__global__ void peer_signal_kernel(PeerBases pb, int world, int self, size_t flag_off, unsigned long long step) {
+__global__ void peer_signal_kernel(PeerBases pb, int world, int self, size_t flag_off, unsigned long long step_arg) {
+  const unsigned long long step = peer_step_of(step_arg, pb.base[self]);
   __threadfence_system();
   const int t = threadIdx.x;
-  if (t < world && t != self)
-    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(pb.base[t]) + flag_off) + peer_flag_index(step, self), step);
+  if (t < world && t != self) st_release_sys(peer_flag(pb.base[t], flag_off, step, self), step);
 }
 
 // ---- partial sums: exchange + combine (the all_reduce of 7 doubles and smmd_mmd2_combine in one kernel) -------
@@ -82,10 +84,10 @@ __device__ __forceinline__ void peer_exchange_and_combine(const KernelFn& kf, do
 #pragma unroll
     for (int i = 0; i < SMMD_NUM_SCALARS; ++i) st_relaxed_sys_f64(dst + i, mine[i]);
     __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(dst_base + kPeerOffSumsFlag) + peer_flag_index(step, self), step);
+    st_release_sys(peer_flag(pb.base[lane], kPeerOffSumsFlag, step, self), step);
   }
   char* own = static_cast<char*>(pb.base[self]);
-  if (lane < world) peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffSumsFlag) + peer_flag_index(step, lane), step);
+  if (lane < world) peer_wait_flag(peer_flag(pb.base[self], kPeerOffSumsFlag, step, lane), step);
   __syncwarp();
   if (lane == 0) {
     const double* in = reinterpret_cast<const double*>(own + kPeerOffSums + slot);
@@ -97,11 +99,14 @@ __device__ __forceinline__ void peer_exchange_and_combine(const KernelFn& kf, do
                                     t[SMMD_S_SUM_YX], t[SMMD_S_DIAG_X], t[SMMD_S_DIAG_Y]);
     t[SMMD_S_NONFINITE] = t[SMMD_S_NONFINITE] != 0.0 ? 1.0 : 0.0;
     for (int i = 0; i < SMMD_NUM_SCALARS; ++i) scalars[i] = t[i];
+    // this rank has completed `step` (last action of the call: the next call with step = 0 reads counter + 1)
+    *reinterpret_cast<volatile unsigned long long*>(own + kPeerOffStep) = step;
   }
 }
 
 __global__ void __launch_bounds__(32) peer_combine_kernel(KernelFn kf, int64_t m, int64_t n, int biased, double* scalars,
-                                                          PeerBases pb, int world, int self, unsigned long long step) {
+                                                          PeerBases pb, int world, int self, unsigned long long step_arg) {
+  const unsigned long long step = peer_step_of(step_arg, pb.base[self]);
   double mine[SMMD_NUM_SCALARS];
 #pragma unroll
   for (int i = 0; i < SMMD_NUM_SCALARS; ++i) mine[i] = scalars[i];
@@ -127,8 +132,8 @@ struct PeerSmallArgs {
   double* scalars;
   PeerBases pb;
   int world, self;
-  unsigned long long step;
-  size_t slot_off;           // offset of this step's data slot in every exchange buffer
+  unsigned long long step;   // 0: read on the device (own counter + 1)
+  size_t slot_bytes;
 };
 
 template <int DMAX>
@@ -141,10 +146,12 @@ __global__ void __launch_bounds__(256) peer_small_mmd2_kernel(PeerSmallArgs a) {
   __shared__ double red[kPeerRowsPerCta][6];
   __shared__ int is_last;
   char* own = static_cast<char*>(a.pb.base[a.self]);
+  const unsigned long long step = peer_step_of(a.step, own);
+  const size_t slot_off = kPeerOffData + (size_t)(step & 1) * a.slot_bytes;
 
   // 1. publish: this CTA's share of the local rows -> own slot (fp32, pitch d); the last CTA to finish raises the flags
   if (a.world > 1) {
-    float* slot = reinterpret_cast<float*>(own + a.slot_off);
+    float* slot = reinterpret_cast<float*>(own + slot_off);
     const int total = rows_local * a.d;
     for (int e = blockIdx.x * 256 + tid; e < total; e += gridDim.x * 256) {
       const int r = e / a.d, c = e - r * a.d;
@@ -157,12 +164,11 @@ __global__ void __launch_bounds__(256) peer_small_mmd2_kernel(PeerSmallArgs a) {
     if (is_last) {
       __threadfence_system();
       if (tid < a.world && tid != a.self)
-        st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(a.pb.base[tid]) + kPeerOffDataFlag) +
-                           peer_flag_index(a.step, a.self), a.step);
+        st_release_sys(peer_flag(a.pb.base[tid], kPeerOffDataFlag, step, a.self), step);
     }
     // 2. every peer's rows are published
     if (tid < a.world && tid != a.self)
-      peer_wait_flag(reinterpret_cast<const unsigned long long*>(own + kPeerOffDataFlag) + peer_flag_index(a.step, tid), a.step);
+      peer_wait_flag(peer_flag(own, kPeerOffDataFlag, step, tid), step);
     __syncthreads();
   }
   // 3. pull the global batch into shared memory (independent loads: one NVLink round trip, not one per column)
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(256) peer_small_mmd2_kernel(PeerSmallArgs a) {
     const int r = idx / blk, loc = idx - r * blk;
     float v;
     if (r == a.self) v = inX ? a.X[(int64_t)loc * a.ld + c] : a.Y[(int64_t)loc * a.ld + c];
-    else v = __ldcg(reinterpret_cast<const float*>(static_cast<const char*>(a.pb.base[r]) + a.slot_off) +
+    else v = __ldcg(reinterpret_cast<const float*>(static_cast<const char*>(a.pb.base[r]) + slot_off) +
                     (size_t)((inX ? 0 : a.blk_x) + loc) * a.d + c);
     Zs[j * a.pitch + c] = v;
   }
@@ -285,8 +291,7 @@ __global__ void __launch_bounds__(256) peer_small_mmd2_kernel(PeerSmallArgs a) {
       bad = bad || !isfinite(red[0][i]);
     }
     mine[SMMD_S_NONFINITE] = bad ? 1.0 : 0.0;
-    peer_exchange_and_combine(a.kf, (double)a.m, (double)a.n, a.biased, mine, a.scalars, a.pb, a.world, a.self, a.step,
-                              lane);
+    peer_exchange_and_combine(a.kf, (double)a.m, (double)a.n, a.biased, mine, a.scalars, a.pb, a.world, a.self, step, lane);
   }
 }
 
@@ -300,11 +305,10 @@ PeerBases bases_of(const smmd_peer_table& pt) {
 
 cudaError_t launch_peer_publish(const float* X, const float* Y, int64_t ld, int64_t blk_x, int64_t blk_y, int64_t d,
                                 int to_bf16, const smmd_peer_table& pt, uint64_t step, cudaStream_t s) {
-  char* own = static_cast<char*>(pt.base[pt.rank]);
-  void* slot = own + kPeerOffData + (size_t)(step & 1) * peer_slot_bytes(blk_x + blk_y, d);
   const int64_t work = (blk_x + blk_y) * d / 8 + 1;
   const unsigned grid = (unsigned)std::min<int64_t>((work + 255) / 256, 148 * 8);
-  peer_publish_kernel<<<grid, 256, 0, s>>>(X, Y, ld, blk_x, blk_y, d, to_bf16, slot);
+  peer_publish_kernel<<<grid, 256, 0, s>>>(X, Y, ld, blk_x, blk_y, d, to_bf16, pt.base[pt.rank],
+                                          peer_slot_bytes(blk_x + blk_y, d), (unsigned long long)step);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (pt.world > 1) {
@@ -319,10 +323,8 @@ PeerSrc make_peer_src(const smmd_peer_table& pt, int64_t rows_local, int64_t d, 
   ps.on = 1;
   ps.world = pt.world;
   ps.self = pt.rank;
-  const size_t off = kPeerOffData + (size_t)(step & 1) * peer_slot_bytes(rows_local, d);
-  for (int i = 0; i < kPeerMax; ++i) ps.data[i] = i < pt.world ? static_cast<const char*>(pt.base[i]) + off : nullptr;
-  ps.flags = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(pt.base[pt.rank]) + kPeerOffDataFlag) +
-             peer_flag_index(step, 0);
+  for (int i = 0; i < kPeerMax; ++i) ps.base[i] = i < pt.world ? pt.base[i] : nullptr;
+  ps.slot_bytes = peer_slot_bytes(rows_local, d);
   ps.step = (unsigned long long)step;
   return ps;
 }
@@ -373,7 +375,7 @@ cudaError_t launch_peer_small_mmd2(const KernelFn& kf, const Geometry& g, const 
   a.world = pt.world;
   a.self = pt.rank;
   a.step = (unsigned long long)step;
-  a.slot_off = kPeerOffData + (size_t)(step & 1) * peer_slot_bytes(a.blk_x + a.blk_y, g.d);
+  a.slot_bytes = peer_slot_bytes(a.blk_x + a.blk_y, g.d);
   cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   const int rows_local = a.blk_x + a.blk_y;

@@ -5,6 +5,8 @@
 //   [0, 256)        data_flag[2][16] u64: data_flag[step & 1][r] = last step of that parity whose rows rank r has published
 //                   (written BY rank r)
 //   [256, 512)      sums_flag[2][16] u64: same for rank r's partial sums
+//   [512, 520)      step counter u64 (local use only): the last step this rank has completed; a call made with step = 0
+//                   takes "counter + 1" on the device, which makes the call sequence CUDA-graph capturable
 //   [1024, 5120)    sums[2][16][16] f64: slot (step & 1), source rank r, the 16 scalars of smmd_scalar
 //   [8192, ...)     two data slots (step & 1) of rows_local x d elements (sized for fp32): the rank's own rows
 // Protocol per step (all stores that cross GPUs are followed by a system-scope fence and a release store of the flag;
@@ -25,6 +27,7 @@ namespace smmd {
 constexpr int kPeerMax = SMMD_MAX_PEERS;
 constexpr size_t kPeerOffDataFlag = 0;
 constexpr size_t kPeerOffSumsFlag = 256;
+constexpr size_t kPeerOffStep = 512;
 constexpr size_t kPeerOffSums = 1024;
 constexpr size_t kPeerOffData = 8192;
 
@@ -37,12 +40,13 @@ __host__ __device__ inline size_t peer_buffer_bytes(int64_t rows_local, int64_t 
 }
 
 // The rows every rank has published for this step, as the operand preparation sees them: block r of the global X (Y)
-// rows lives in data[r] at rows [0, blk_x) ([blk_x, blk_x + blk_y)), pitch = d elements.  Passed by value to kernels.
+// rows lives in rank r's data slot (step & 1) at rows [0, blk_x) ([blk_x, blk_x + blk_y)), pitch = d elements.
+// Passed by value to kernels.  step = 0: the step number is read on the device (own counter + 1).
 struct PeerSrc {
   int on;                               // 0 = not a peer call
   int world, self;
-  const void* data[kPeerMax];           // this step's data slot of every rank
-  const unsigned long long* flags;      // data_flag[step & 1] array of the OWN buffer
+  void* base[kPeerMax];                 // every rank's exchange buffer as mapped here
+  size_t slot_bytes;                    // peer_slot_bytes(rows_local, d)
   unsigned long long step;
 };
 
@@ -62,6 +66,17 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   double v;
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
+}
+// step of this call: given by the host, or (step == 0) one more than the last step this rank completed
+__device__ __forceinline__ unsigned long long peer_step_of(unsigned long long step, void* own_base) {
+  if (step) return step;
+  return *reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(own_base) + kPeerOffStep) + 1ull;
+}
+__device__ __forceinline__ char* peer_data_slot(void* base, unsigned long long step, size_t slot_bytes) {
+  return static_cast<char*>(base) + kPeerOffData + (size_t)(step & 1) * slot_bytes;
+}
+__device__ __forceinline__ unsigned long long* peer_flag(void* base, size_t flag_off, unsigned long long step, int r) {
+  return reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + flag_off) + peer_flag_index(step, r);
 }
 // Bounded wait for flag >= step (a peer that never arrives is an error, not a hang): ~4 s of polling, then trap.
 __device__ __forceinline__ void peer_wait_flag(const unsigned long long* flag, unsigned long long step) {

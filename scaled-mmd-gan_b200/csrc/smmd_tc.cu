@@ -49,11 +49,12 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(PrepTcArgs a) {
     // soon as that rank's data flag for this step is up (own block: no wait, it was published earlier on this stream)
     const int64_t blk = inA ? a.blk_a : a.blk_b;
     const int64_t r = valid ? loc / blk : (int64_t)a.peer.self;
-    base = a.peer.data[r];
+    const unsigned long long step = peer_step_of(a.peer.step, a.peer.base[a.peer.self]);
+    base = peer_data_slot(a.peer.base[r], step, a.peer.slot_bytes);
     src = (inA ? 0 : a.blk_a) + (valid ? loc - r * blk : 0);
     ld = a.d;
     if (valid && r != a.peer.self) {
-      if (lane == 0) peer_wait_flag(a.peer.flags + r, a.peer.step);
+      if (lane == 0) peer_wait_flag(peer_flag(a.peer.base[a.peer.self], kPeerOffDataFlag, step, (int)r), step);
       __syncwarp();
     }
   }

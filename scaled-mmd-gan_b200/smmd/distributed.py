@@ -145,10 +145,11 @@ class PeerExchange:
     moves inside the library's own kernels).  Create it ONCE per (group, local shape) -- the rendezvous is a collective --
     and pass it to ``sharded_mmd2(..., exchange=px)``; every rank must then make the same sequence of calls on it.
 
+    ``device_steps=True``: step numbers are kept on the device (CUDA-graph capturable; calls must be stream-ordered).
     ``map_buffers`` (tests): callable(nbytes, device, group) -> (own uint8 tensor, [base address of every rank]).
     """
 
-    def __init__(self, rows_local, d, device, group=None, map_buffers=None, _compute=None):
+    def __init__(self, rows_local, d, device, group=None, map_buffers=None, _compute=None, device_steps=False):
         import ctypes as C
 
         self.group = group
@@ -166,6 +167,9 @@ class PeerExchange:
         for r in range(self.world):
             self.table.base[r] = C.c_void_p(int(ptrs[r]))
         self.step = 0
+        # device_steps: the kernels count the steps themselves (smmd_mmd2_fwd_bwd_peers with step = 0): no host state in
+        # the call, so a sequence of calls can be captured into a CUDA graph; calls must then be stream-ordered
+        self.device_steps = bool(device_steps)
         self._cache = {}
         self._compute = _compute     # injection point for the CPU tests of the host-side logic
         self._pull_events = None
@@ -238,7 +242,7 @@ def _peer_local_compute(spec, px, Xl, Yl, m, n, biased, precision):
         if px._pull_events is not None:
             px.last_pull_event = px._pull_events[step % len(px._pull_events)]
             lib.smmd_peer_set_pull_event(px.last_pull_event.cuda_event)
-        st = lib.smmd_mmd2_fwd_bwd_peers(prob_ref, table_ref, step, Xo.data_ptr(), Yo.data_ptr(), d,
+        st = lib.smmd_mmd2_fwd_bwd_peers(prob_ref, table_ref, 0 if px.device_steps else step, Xo.data_ptr(), Yo.data_ptr(), d,
                                          scalars.data_ptr(), dX.data_ptr(), dY.data_ptr(), ws.data_ptr(), nbytes,
                                          _stream_ptr(dev))
         if px._pull_events is not None:

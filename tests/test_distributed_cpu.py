@@ -261,3 +261,15 @@ def test_peer_exchange_host_logic_world2():
             assert abs(loss - v) <= 1e-6 * abs(v)
             assert np.allclose(gx, 3.0 * gX[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
             assert np.allclose(gy, 3.0 * gY[rank * 12:(rank + 1) * 12], rtol=1e-5, atol=1e-9)
+
+
+def test_numa_binding_helper_is_inert_without_topology():
+    """bind_to_device_numa: cpulist parsing, and no change of the affinity mask when the topology is unknown (no GPU here)."""
+    sys.path.insert(0, os.path.join(ROOT, "scaled-mmd-gan_b200"))
+    from smmd.distributed import _parse_cpulist, bind_to_device_numa
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_device_numa(sysfs="/nonexistent") is None
+    assert os.sched_getaffinity(0) == before

@@ -89,5 +89,47 @@ def test_peers_rejects_bad_tables_and_uncovered_shapes():
     buf = torch.zeros(int(lib.smmd_peer_buffer_bytes(4000, 16)), dtype=torch.uint8, device=DEV)
     with pytest.raises(_lib.SmmdError):           # exact tier beyond the one-launch kernel: no peer variant
         _peers_call(spec, X, Y, "fp32", buf, 1)
-    with pytest.raises(_lib.SmmdError):           # step 0 is reserved for "nothing published yet"
-        _peers_call(spec, X[:64], Y[:64], "fp32", buf, 0)
+
+
+def test_peers_device_counted_steps():
+    """step = 0: the kernels take (last completed step + 1) from the own buffer -- same results, counter advances, and the
+    call can be captured into a CUDA graph and replayed."""
+    from smmd import _lib, mmd
+
+    rng = np.random.RandomState(5)
+    X = torch.tensor(rng.randn(64, 16).astype(np.float32), device=DEV)
+    Y = torch.tensor((1.1 * rng.randn(64, 16) + 0.1).astype(np.float32), device=DEV)
+    spec = mmd._mix_rq_kernel(X, Y).spec
+    lib = _lib.load()
+    buf = torch.zeros(int(lib.smmd_peer_buffer_bytes(128, 16)), dtype=torch.uint8, device=DEV)
+    counter = buf[512:520].view(torch.int64)
+    ref = _peers_call(spec, X, Y, "fp32", buf, 1)            # host-given step 1
+    assert counter.item() == 1
+    for k in (2, 3, 4):
+        sc, dX, dY, path = _peers_call(spec, X, Y, "fp32", buf, 0)
+        assert path == "simt_fp32_small_peer" and counter.item() == k
+        assert sc[_lib.S_MMD2].item() == ref[0][_lib.S_MMD2].item() and torch.equal(dX, ref[1]) and torch.equal(dY, ref[2])
+    # tensor-core tier, device-counted
+    Xb = torch.tensor((rng.randn(700, 128) / 11).astype(np.float32), device=DEV)
+    Yb = torch.tensor((rng.randn(600, 128) / 11 + 0.01).astype(np.float32), device=DEV)
+    specb = mmd._mix_rq_kernel(Xb, Yb).spec
+    bufb = torch.zeros(int(lib.smmd_peer_buffer_bytes(1300, 128)), dtype=torch.uint8, device=DEV)
+    r1 = _peers_call(specb, Xb, Yb, "bf16", bufb, 0)
+    r2 = _peers_call(specb, Xb, Yb, "bf16", bufb, 0)
+    assert bufb[512:520].view(torch.int64).item() == 2
+    assert r1[0][_lib.S_MMD2].item() == r2[0][_lib.S_MMD2].item() and torch.equal(r1[1], r2[1])
+    # CUDA-graph capture + replay of the one-launch loss
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        _peers_call(spec, X, Y, "fp32", buf, 0)              # warm the workspace cache of this stream
+        torch.cuda.synchronize()
+        before = counter.item()
+        with torch.cuda.graph(g, stream=s):
+            out = _peers_call(spec, X, Y, "fp32", buf, 0)
+        for _ in range(5):
+            g.replay()
+    torch.cuda.synchronize()
+    assert counter.item() == before + 5
+    assert out[0][_lib.S_MMD2].item() == ref[0][_lib.S_MMD2].item() and torch.equal(out[1], ref[1])
