@@ -438,7 +438,7 @@ def run_ours(args):
     # Two streams (the exchange allows two calls in flight), three pinned result buffers.
     cp_stream = torch.cuda.Stream(dev)
     done_ev = [None] * nhost
-    state = {"pending": None, "prev_pull": None}
+    state = {"pending": None, "prev_pull": None, "last_done": None}
     if px is not None:
         px.enable_pull_events()
 
@@ -455,6 +455,7 @@ def run_ours(args):
                 t.record_stream(cp_stream)
             done_ev[b] = torch.cuda.Event()
             done_ev[b].record(cp_stream)
+            state["last_done"] = done_ev[b]
 
     def e2e_step_peer(i):
         b = i % nhost
@@ -467,6 +468,10 @@ def run_ours(args):
                 st.wait_event(state["prev_pull"])      # inputs go up next to the previous step's kernels
             X = Xh.to(dev, non_blocking=True).requires_grad_(True)
             Y = Yh.to(dev, non_blocking=True).requires_grad_(True)
+            if state["last_done"] is not None:
+                # this rank publishes (and its peers start pulling from it) only after its latest copy-out has left the
+                # PCIe link: the stall is at the GPU that SERVES the NVLink reads while it copies to the host
+                st.wait_event(state["last_done"])
             K = mmd._mix_rq_kernel(X, Y)
             loss = sharded_mmd2(K, precision="bf16", exchange=px)
             pull = px.last_pull_event
