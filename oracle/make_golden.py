@@ -145,6 +145,38 @@ def make_kid_golden(path):
     np.savez_compressed(path, **out)
 
 
+def fid_codes(tag):
+    """Seeded synthetic "Inception" codes / class probabilities of the FID fixtures (regenerated by the tests)."""
+    ng, nr, d = {"a": (900, 960, 48), "b": (1500, 1500, 96)}[tag]
+    g = np.maximum(np.random.RandomState(4321).randn(ng, d) * np.linspace(0.5, 1.5, d), 0).astype(np.float32)
+    r = np.maximum(np.random.RandomState(4322).randn(nr, d) * np.linspace(0.6, 1.4, d) + 0.05, 0).astype(np.float32)
+    logits = np.random.RandomState(4323).randn(ng, 10).astype(np.float64) * 2.0
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    return g, r, (p / p.sum(1, keepdims=True)).astype(np.float32)
+
+
+def make_fid_golden(path):
+    """Reference fid_score / inception_score (compute_scores.py:158-208) on seeded codes: 'openai' splits and 'bootstrap'
+    splits (numpy global RNG seeded with 0 right before the call)."""
+    import io
+    import warnings
+
+    cs = ref_loader.load_reference_compute_scores()
+    out = {}
+    for tag in ("a", "b"):
+        g, r, p = fid_codes(tag)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")       # ComplexWarning when the reference stores a complex trace
+            out["fid_openai_%s" % tag] = cs.fid_score(g, r, output=io.StringIO(), splits=3)
+            out["fid64_openai_%s" % tag] = cs.fid_score(g.astype(np.float64), r.astype(np.float64), output=io.StringIO(), splits=3)
+            np.random.seed(0)
+            out["fid_bootstrap_%s" % tag] = cs.fid_score(g, r, output=io.StringIO(), splits=2, split_method="bootstrap")
+        out["is_openai_%s" % tag] = cs.inception_score(p, splits=4)
+        np.random.seed(0)
+        out["is_bootstrap_%s" % tag] = cs.inception_score(p, splits=3, split_method="bootstrap")
+    np.savez_compressed(path, **out)
+
+
 def make_three_sample_golden(path):
     """Reference numpy 3-sample test (mmd.py:429-539) on seeded synthetic codes; fp32 (as the scorer feeds it) and
     fp64.  Inputs are regenerated from the seeds by the tests (tests/golden_util.py:three_sample_codes)."""
@@ -178,6 +210,10 @@ if __name__ == "__main__":
         sys.exit("reference not found at %s" % ref_loader.REFERENCE_ROOT)
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
+    if "--fid" in sys.argv:   # only the FID / inception-score fixture
+        make_fid_golden(os.path.join(gdir, "fid_golden.npz"))
+        print("wrote FID fixtures to %s" % gdir)
+        sys.exit(0)
     if "--three-sample" in sys.argv:   # only the 3-sample fixture (leaves the committed mmd/kid files untouched)
         make_three_sample_golden(os.path.join(gdir, "three_sample_golden.npz"))
         print("wrote 3-sample fixtures to %s" % gdir)
@@ -185,4 +221,5 @@ if __name__ == "__main__":
     n = make_mmd_golden(os.path.join(gdir, "mmd_golden.npz"))
     make_kid_golden(os.path.join(gdir, "kid_golden.npz"))
     make_three_sample_golden(os.path.join(gdir, "three_sample_golden.npz"))
+    make_fid_golden(os.path.join(gdir, "fid_golden.npz"))
     print("wrote %d mmd cases + kid fixtures to %s" % (n, gdir))

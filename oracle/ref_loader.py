@@ -184,7 +184,29 @@ def load_reference_compute_scores():
     finally:
         if saved is None:
             sys.modules.pop("tensorflow", None)
+    _patch_sqrtm(mod)
     return mod
+
+
+def _patch_sqrtm(mod):
+    """The reference calls ``scipy.linalg.sqrtm(A, disp=False)`` (compute_scores.py:199, scipy==1.0.1 in its
+    requirements.txt:9: returns ``(sqrtm, errest)``); the scipy installed here dropped the ``disp`` argument.  The
+    reference source stays untouched: its module-level ``linalg`` name is re-bound to a namespace whose ``sqrtm``
+    accepts the old signature and calls the installed (same Schur-method) implementation."""
+    import inspect
+
+    import scipy.linalg as sl
+
+    if "disp" in inspect.signature(sl.sqrtm).parameters:
+        return
+
+    def sqrtm(A, disp=True, blocksize=64):
+        out = sl.sqrtm(A)
+        return out if disp else (out, 0.0)
+
+    ns = types.SimpleNamespace(**{k: getattr(sl, k) for k in dir(sl) if not k.startswith("_")})
+    ns.sqrtm = sqrtm
+    mod.linalg = ns
 
 
 def reference_loss_and_grads(kernel_name, X, Y, biased=False, dtype_name="float32", **kernel_kwargs):

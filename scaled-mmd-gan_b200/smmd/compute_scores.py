@@ -1,5 +1,7 @@
 """Drop-in for the KID part of the reference's ``gan/compute_scores.py`` (lines 211-335): same
-function names, kwargs and RNG draw order, backed by libsmmd.so.
+function names, kwargs and RNG draw order, backed by libsmmd.so.  (``get_splits`` / ``inception_score`` / ``fid_score``,
+compute_scores.py:158-208, are provided at the end of the module as device-resident library math: fp64 covariance GEMMs
+and symmetric eigendecompositions on the GPU -- plain library calls, no kernel of this repo.)
 
 ``polynomial_mmd_averages`` accepts numpy arrays (like the reference: host codes in, numpy float64
 arrays out -- the codes are copied to the GPU once per call) or torch CUDA tensors (device in, torch
@@ -175,3 +177,83 @@ def _mmd2_and_variance(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est='unbiased'
     _lib.check(st, "smmd_kid_from_row_stats")
     fin = (lambda t: float(t.item())) if host_in else (lambda t: t)
     return (fin(out[0]), fin(out[1])) if ret_var else fin(out[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# compute_scores.py:158-208 -- splits, inception score, FID.  Not part of the MMD hot path: plain library math kept on
+# the device (the reference spends 34-56 s per scoring pass in scipy's sqrtm of three 2048 x 2048 products).
+# ------------------------------------------------------------------------------------------------------------------
+def get_splits(n, splits=10, split_method='openai'):
+    """compute_scores.py:158-165; 'bootstrap' draws from numpy's global RNG exactly like the reference."""
+    if split_method == 'openai':
+        return [slice(i * n // splits, (i + 1) * n // splits) for i in range(splits)]
+    elif split_method == 'bootstrap':
+        return [np.random.choice(n, n) for _ in range(splits)]
+    else:
+        raise ValueError("bad split_method {}".format(split_method))
+
+
+def _score_device(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("smmd.compute_scores needs a CUDA device (there is no CPU path in this package)")
+    return torch.device(device if device is not None else "cuda")
+
+
+def _take(t, inds):
+    if isinstance(inds, slice):
+        return t[inds]
+    return t.index_select(0, torch.as_tensor(np.asarray(inds), dtype=torch.int64, device=t.device))
+
+
+def inception_score(preds, device=None, **split_args):
+    """compute_scores.py:168-176: exp(mean_i KL(p(y|x_i) || p(y))) per split; numpy float64 array out."""
+    dev = preds.device if (torch.is_tensor(preds) and preds.is_cuda) else _score_device(device)
+    p = torch.as_tensor(preds).to(dev, torch.float64)
+    scores = []
+    for inds in get_splits(p.shape[0], **split_args):
+        part = _take(p, inds)
+        kl = part * (torch.log(part) - torch.log(part.mean(0, keepdim=True)))
+        scores.append(torch.exp(kl.sum(1).mean()))
+    return torch.stack(scores).cpu().numpy()
+
+
+def _mean_cov(part):
+    """mean and np.cov(part, rowvar=False) (unbiased, n - 1) in fp64 on the device: one centred Gram X_c^T X_c."""
+    mn = part.mean(0)
+    xc = part - mn
+    return mn, (xc.t() @ xc) / (part.shape[0] - 1)
+
+
+def _trace_sqrt_product(cov_g, cov_r):
+    """tr sqrtm(cov_g cov_r) for symmetric PSD factors = sum_i sqrt(lambda_i(cov_g^(1/2) cov_r cov_g^(1/2))): two symmetric
+    eigendecompositions instead of the reference's complex Schur form (scipy.linalg.sqrtm, compute_scores.py:199); equal to
+    the real part of the trace the reference keeps."""
+    w, v = torch.linalg.eigh(cov_g)
+    root = (v * w.clamp_min(0).sqrt()) @ v.t()
+    m = root @ cov_r @ root
+    lam = torch.linalg.eigvalsh(0.5 * (m + m.t()))
+    return lam.clamp_min(0).sqrt().sum()
+
+
+def fid_score(codes_g, codes_r, eps=1e-6, output=sys.stdout, device=None, **split_args):
+    """compute_scores.py:179-208: per split |mu_g - mu_r|^2 + tr(cov_g) + tr(cov_r) - 2 tr sqrtm(cov_g cov_r); the g splits
+    are drawn before the r splits.  numpy float64 array out (one score per split)."""
+    dev = codes_g.device if (torch.is_tensor(codes_g) and codes_g.is_cuda) else _score_device(device)
+    g = torch.as_tensor(codes_g).to(dev)
+    r = torch.as_tensor(codes_r).to(dev)
+    splits_g = get_splits(g.shape[0], **split_args)
+    splits_r = get_splits(r.shape[0], **split_args)
+    assert len(splits_g) == len(splits_r)
+    d = g.shape[1]
+    assert r.shape[1] == d
+    scores = []
+    for w_g, w_r in zip(splits_g, splits_r):
+        mn_g, cov_g = _mean_cov(_take(g, w_g).to(torch.float64))
+        mn_r, cov_r = _mean_cov(_take(r, w_r).to(torch.float64))
+        tr = _trace_sqrt_product(cov_g, cov_r)
+        if not bool(torch.isfinite(tr)):
+            cov_g = cov_g + eps * torch.eye(d, dtype=cov_g.dtype, device=dev)
+            cov_r = cov_r + eps * torch.eye(d, dtype=cov_r.dtype, device=dev)
+            tr = _trace_sqrt_product(cov_g, cov_r)
+        scores.append(((mn_g - mn_r) ** 2).sum() + cov_g.trace() + cov_r.trace() - 2 * tr)
+    return torch.stack(scores).cpu().numpy()
