@@ -224,7 +224,7 @@ def _peer_local_compute(spec, px, Xl, Yl, m, n, biased, precision):
     if Yo.dtype != torch.float32 or not Yo.is_contiguous():
         Yo = Yo.float().contiguous()
     dev = Xl.device
-    key = (id(spec), m, n, d, bool(biased), precision)
+    key = (spec._key, m, n, d, bool(biased), precision)   # value key: kernel handles build a fresh spec per call
     ent = px._cache.get(key)
     with torch.cuda.device(dev):
         if ent is None:    # (latency-bound shapes: the struct, its byref and the workspace size are built once per signature)
@@ -232,8 +232,8 @@ def _peer_local_compute(spec, px, Xl, Yl, m, n, biased, precision):
             nbytes = lib.smmd_mmd2_workspace_bytes(C.byref(prob), 1)
             if nbytes == 0:
                 raise _lib.SmmdError(-1, "smmd_mmd2_workspace_bytes", "problem rejected (shape/params)")
-            ent = px._cache[key] = (prob, C.byref(prob), nbytes, C.byref(px.table), spec)
-        prob, prob_ref, nbytes, table_ref, _ = ent
+            ent = px._cache[key] = (prob, C.byref(prob), nbytes, C.byref(px.table))
+        prob, prob_ref, nbytes, table_ref = ent
         ws = _workspace(nbytes, dev)
         scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float64, device=dev)
         dX = torch.empty((m // px.world, d), dtype=torch.float32, device=dev)
@@ -248,6 +248,7 @@ def _peer_local_compute(spec, px, Xl, Yl, m, n, biased, precision):
         if px._pull_events is not None:
             lib.smmd_peer_set_pull_event(None)
         if st != 0:
+            px.step -= 1      # nothing was launched (every rank refuses the same problem): the sequence number is not used up
             _lib.check(st, "smmd_mmd2_fwd_bwd_peers")
     return scalars, dX, dY
 
