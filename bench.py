@@ -730,9 +730,10 @@ def run_kid(dev, rank, world, args, compute_scores, lib, dist, peak):
                       "host_subset_draw_ms": t_draw * 1e3,
                       "kid_mean": float(np.mean(np.asarray(mmh))),
                       "api": "smmd.compute_scores.polynomial_mmd_averages(codes_g, codes_r, n_subsets=100, subset_size=1000, "
-                             "ret_var=False) with pinned HOST codes: 200 np.random.choice(50000, 1000, replace=False) draws in "
-                             "the reference's order (host, numpy's global RNG: %.0f ms of the call), H2D of both code "
-                             "matrices, one batched kernel pass, D2H of the estimates" % (t_draw * 1e3)}
+                             "ret_var=False) with pinned HOST codes: the 200 np.random.choice(50000, 1000, replace=False) draws of "
+                             "the reference, reproduced bit for bit from numpy's global RNG state by the library's host helper "
+                             "(smmd_draw_subsets_mt19937: %.0f ms, running under the asynchronous H2D of both code matrices), "
+                             "one batched kernel pass, D2H of the estimates" % (t_draw * 1e3)}
         del gh, rh
     if rank == 0 and world == 1 and not args.no_cpu:
         kind, loader = _reference_kind()

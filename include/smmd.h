@@ -188,6 +188,17 @@ SMMD_API int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_tabl
                                      const float* X_local, const float* Y_local, int64_t ld_local, double* scalars,
                                      float* dX, float* dY, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-side helper (no GPU work): the subset draw of polynomial_mmd_averages, gan/compute_scores.py:219-222 --
+ *   for each subset: np.random.choice(len(codes_g), subset_size, replace=False), then the same for codes_r --
+ * reproduced bit for bit from numpy's legacy global RNG state: choice(n, m, replace=False) is permutation(n)[:m], i.e. a
+ * Fisher-Yates shuffle of arange(n) from the top with one rejection-sampled `random_interval(i)` (masked 32-bit MT19937
+ * outputs) per position.  key[624] / pos are np.random.get_state()[1:3]; they are advanced in place, so that
+ * np.random.set_state afterwards leaves the global stream exactly where the reference's loop would have left it.
+ * idx_g / idx_r: host int32 [n_subsets][subset_size].  ~3x faster than the numpy loop (the draw is 107 of the 124 ms of
+ * a host-codes KID call at 100 x 1000 of 50k). */
+SMMD_API int smmd_draw_subsets_mt19937(uint32_t* key, int32_t* pos, int64_t len_g, int64_t len_r, int32_t n_subsets,
+                                       int32_t subset_size, int32_t* idx_g, int32_t* idx_r);
+
 /* Replaces: mmd2_and_ratio(K, biased, min_var_est) -- gan/core/mmd.py:223-293 (+ ops.sq_sum / ops.dot,
  * gan/core/ops.py:209-225).  Requires m == n (mmd.py:237).  Reproduces the reference's unbiased
  * branch that keeps the diagonal (mmd.py:273-276).  scalars[MMD2, VAR, RATIO] are written. */

@@ -24,7 +24,7 @@ ESTIMATORS = {"unbiased": EST_UNBIASED, "biased": EST_BIASED, "u-statistic": EST
 EXPORTS = [
     "smmd_version", "smmd_strerror", "smmd_last_cuda_error", "smmd_device_supported",
     "smmd_mmd2_workspace_bytes", "smmd_mmd2_fwd_bwd", "smmd_mmd2_fwd_bwd_gathered", "smmd_mmd2_combine",
-    "smmd_peer_buffer_bytes", "smmd_mmd2_fwd_bwd_peers", "smmd_peer_set_pull_event",
+    "smmd_peer_buffer_bytes", "smmd_mmd2_fwd_bwd_peers", "smmd_peer_set_pull_event", "smmd_draw_subsets_mt19937",
     "smmd_mmd2_and_ratio",
     "smmd_kernel_xy", "smmd_kernel_xy_bwd", "smmd_kernel_xy_bwd2", "smmd_kid_workspace_bytes", "smmd_kid_subsets",
     "smmd_poly_sums_workspace_bytes", "smmd_poly_sums", "smmd_kid_from_row_stats", "smmd_ratio_from_row_stats",
@@ -99,6 +99,8 @@ def load():
     lib.smmd_mmd2_fwd_bwd.argtypes = [C.POINTER(Problem), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.smmd_mmd2_fwd_bwd_gathered.restype = C.c_int
     lib.smmd_mmd2_fwd_bwd_gathered.argtypes = [C.POINTER(Problem), vp, i64, vp, vp, i64, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.smmd_draw_subsets_mt19937.restype = C.c_int
+    lib.smmd_draw_subsets_mt19937.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, C.c_int32, C.c_int32, vp, vp]
     lib.smmd_peer_set_pull_event.restype = C.c_int
     lib.smmd_peer_set_pull_event.argtypes = [vp]
     lib.smmd_peer_buffer_bytes.restype = C.c_size_t

@@ -46,14 +46,35 @@ def _to_device_codes(a, device):
     return t
 
 
-def draw_subsets(len_g, len_r, n_subsets, subset_size):
-    """np.random.choice(..., replace=False) in the reference's order (compute_scores.py:219-222)."""
+def _draw_subsets_numpy(len_g, len_r, n_subsets, subset_size):
     choice = np.random.choice
     ig = np.empty((n_subsets, subset_size), dtype=np.int32)
     ir = np.empty((n_subsets, subset_size), dtype=np.int32)
     for i in range(n_subsets):
         ig[i] = choice(len_g, subset_size, replace=False)
         ir[i] = choice(len_r, subset_size, replace=False)
+    return ig, ir
+
+
+def draw_subsets(len_g, len_r, n_subsets, subset_size):
+    """np.random.choice(..., replace=False) in the reference's order (compute_scores.py:219-222), from numpy's GLOBAL
+    RNG and leaving it in the state the reference's loop would: the draw itself runs in the library
+    (smmd_draw_subsets_mt19937: numpy's legacy permutation, bit for bit, ~3x faster than the numpy loop, which is most of
+    a host-codes KID call).  Anything unusual (a sample larger than the population, a non-MT19937 state) goes through
+    numpy itself, so errors and results are numpy's."""
+    state = np.random.get_state()
+    if (state[0] != "MT19937" or subset_size > min(len_g, len_r) or n_subsets < 1 or subset_size < 1
+            or max(len_g, len_r) >= 2 ** 31):
+        return _draw_subsets_numpy(len_g, len_r, n_subsets, subset_size)
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(state[2]))
+    ig = np.empty((n_subsets, subset_size), dtype=np.int32)
+    ir = np.empty((n_subsets, subset_size), dtype=np.int32)
+    st = _lib.load().smmd_draw_subsets_mt19937(key.ctypes.data_as(C.c_void_p), C.byref(pos), int(len_g), int(len_r),
+                                               int(n_subsets), int(subset_size), ig.ctypes.data_as(C.c_void_p),
+                                               ir.ctypes.data_as(C.c_void_p))
+    _lib.check(st, "smmd_draw_subsets_mt19937")
+    np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
     return ig, ir
 
 
@@ -103,9 +124,9 @@ def polynomial_mmd_averages(codes_g, codes_r, n_subsets=50, subset_size=1000, re
     host_in = isinstance(codes_g, np.ndarray) or (isinstance(codes_g, torch.Tensor) and not codes_g.is_cuda)
     dev = codes_g.device if (isinstance(codes_g, torch.Tensor) and codes_g.is_cuda) else torch.device("cuda")
     m = min(codes_g.shape[0], codes_r.shape[0])
-    ig, ir = draw_subsets(len(codes_g), len(codes_r), n_subsets, subset_size)
-    g = _to_device_codes(codes_g, dev)
+    g = _to_device_codes(codes_g, dev)          # (pinned host codes: the copy is asynchronous and runs under the draw)
     r = _to_device_codes(codes_r, dev)
+    ig, ir = draw_subsets(len(codes_g), len(codes_r), n_subsets, subset_size)
     igd = torch.from_numpy(ig).to(dev, non_blocking=True)
     ird = torch.from_numpy(ir).to(dev, non_blocking=True)
     mm, vv = kid_subsets(g, r, igd, ird, var_at_m=m, ret_var=ret_var, precision=precision, **kernel_args)

@@ -113,3 +113,32 @@ def test_set_option_validates_names_and_clamps():
     assert lib.smmd_set_option(b"wz_min_d", 256) == 0
     assert lib.smmd_set_option(b"sym_min_rows", 0) == 0
     assert lib.smmd_set_option(b"debug_nullmath", 1) == -1   # ablation knobs exist only in developer builds
+
+
+def test_subset_draw_is_numpys_bit_for_bit():
+    """smmd_draw_subsets_mt19937 (host helper behind compute_scores.draw_subsets): the same indices as the reference's
+    np.random.choice(n, m, replace=False) loop (gan/compute_scores.py:219-222) AND the same global RNG state afterwards,
+    for several population / sample sizes, stream positions and cached-gaussian states."""
+    import numpy as np
+
+    from smmd import compute_scores as cs
+
+    cases = [(5000, 6000, 7, 300, 0), (400, 500, 6, 100, 1), (7, 9, 5, 7, 3), (1000, 1000, 3, 1, 5), (65537, 70000, 2, 33, 9),
+             (1, 1, 2, 1, 1), (2, 3, 4, 2, 2), (1024, 1025, 3, 1000, 4), (50000, 50000, 2, 1000, 6)]
+    for (lg, lr, S, m, seed) in cases:
+        for burn in (0, 3):                      # burn = 3 leaves a cached gaussian and an odd stream position behind
+            np.random.seed(seed)
+            if burn:
+                np.random.randn(burn)
+            a = cs._draw_subsets_numpy(lg, lr, S, m)
+            sa = np.random.get_state()
+            np.random.seed(seed)
+            if burn:
+                np.random.randn(burn)
+            b = cs.draw_subsets(lg, lr, S, m)
+            sb = np.random.get_state()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (lg, lr, S, m, seed)
+            assert sa[0] == sb[0] and np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:], (lg, lr, S, m, seed)
+    # a sample larger than the population: numpy's own error, raised by numpy
+    with pytest.raises(ValueError):
+        cs.draw_subsets(10, 20, 2, 11)
