@@ -302,101 +302,6 @@ int smmd_mmd2_fwd_bwd_gathered(const smmd_problem* p, const void* gathered, int6
   return mmd2_fwd_bwd_impl(p, src, scalars, dX, dY, workspace, workspace_bytes, stream);
 }
 
-// ---- host helper: numpy's legacy subset draw (compute_scores.py:219-222), bit for bit -------------------------
-namespace {
-struct Mt19937 {
-  uint32_t key[624];   // a private copy: through a pointer the compiler must assume that the shuffle's stores alias the state
-  int pos;
-  void refill() {
-    constexpr int N = 624, M = 397;
-    constexpr uint32_t A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
-    int i = 0;
-    for (; i < N - M; ++i) {
-      const uint32_t y = (key[i] & UP) | (key[i + 1] & LO);
-      key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
-    }
-    for (; i < N - 1; ++i) {
-      const uint32_t y = (key[i] & UP) | (key[i + 1] & LO);
-      key[i] = key[i + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
-    }
-    const uint32_t y = (key[N - 1] & UP) | (key[0] & LO);
-    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
-    pos = 0;
-  }
-  inline uint32_t next() {
-    if (pos == 624) refill();
-    uint32_t y = key[pos++];
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
-  }
-};
-// numpy random_interval(max) for max < 2^32: smallest all-ones mask >= max, reject masked draws above max
-inline uint32_t mt_interval(Mt19937& g, uint32_t max) {
-  if (max == 0) return 0;
-  uint32_t mask = max;
-  mask |= mask >> 1;
-  mask |= mask >> 2;
-  mask |= mask >> 4;
-  mask |= mask >> 8;
-  mask |= mask >> 16;
-  uint32_t v;
-  while ((v = (g.next() & mask)) > max) {
-  }
-  return v;
-}
-// permutation(n)[:m]: shuffle arange(n) from the top (numpy _shuffle_raw), keep the first m entries.
-// Same draws as mt_interval per position, but without a data-dependent branch: numpy's loop spends most of its time
-// in mispredicted rejections (a masked draw exceeds i 25-50% of the time); here a rejected draw swaps position i with
-// itself and does not advance, so the instruction stream is the same for accepted and rejected candidates.
-void mt_choice_no_replace(Mt19937& gref, int32_t* __restrict__ scratch, int64_t n, int32_t m, int32_t* __restrict__ out) {
-  Mt19937 g = gref;   // a local the compiler can keep in registers / knows not to alias the shuffle's stores
-  for (int64_t i = 0; i < n; ++i) scratch[i] = (int32_t)i;
-  uint32_t i = (uint32_t)(n - 1);
-  uint32_t mask = i;
-  mask |= mask >> 1;
-  mask |= mask >> 2;
-  mask |= mask >> 4;
-  mask |= mask >> 8;
-  mask |= mask >> 16;
-  while (i >= 1) {
-    const uint32_t v = g.next() & mask;
-    const uint32_t acc = v <= i ? 1u : 0u;
-    const uint32_t j = i ^ ((v ^ i) & (0u - acc));   // acc ? v : i, without a branch
-    const int32_t a = scratch[i], b = scratch[j];
-    scratch[i] = b;
-    scratch[j] = a;
-    i -= acc;
-    mask >>= (i <= (mask >> 1)) ? 1 : 0;             // smallest all-ones mask >= i
-  }
-  for (int32_t k = 0; k < m; ++k) out[k] = scratch[k];
-  gref = g;
-}
-}  // namespace
-
-int smmd_draw_subsets_mt19937(uint32_t* key, int32_t* pos, int64_t len_g, int64_t len_r, int32_t n_subsets,
-                              int32_t subset_size, int32_t* idx_g, int32_t* idx_r) {
-  if (!key || !pos || !idx_g || !idx_r) return SMMD_EINVAL;
-  if (*pos < 0 || *pos > 624 || n_subsets < 0 || subset_size < 0) return SMMD_EINVAL;
-  if (len_g < 1 || len_r < 1 || len_g >= ((int64_t)1 << 31) || len_r >= ((int64_t)1 << 31)) return SMMD_ESHAPE;
-  if (subset_size > len_g || subset_size > len_r) return SMMD_ESHAPE;   // numpy: "Cannot take a larger sample than population"
-  Mt19937 g;
-  memcpy(g.key, key, sizeof(g.key));
-  g.pos = *pos;
-  int32_t* scratch = static_cast<int32_t*>(malloc(sizeof(int32_t) * (size_t)(len_g > len_r ? len_g : len_r)));
-  if (!scratch) return SMMD_EWORKSPACE;
-  for (int32_t s = 0; s < n_subsets; ++s) {
-    mt_choice_no_replace(g, scratch, len_g, subset_size, idx_g + (size_t)s * subset_size);
-    mt_choice_no_replace(g, scratch, len_r, subset_size, idx_r + (size_t)s * subset_size);
-  }
-  free(scratch);
-  memcpy(key, g.key, sizeof(g.key));
-  *pos = g.pos;
-  return SMMD_OK;
-}
-
 int smmd_peer_set_pull_event(void* cuda_event) {
   g_pull_event = static_cast<cudaEvent_t>(cuda_event);
   return SMMD_OK;

@@ -124,8 +124,13 @@ def test_subset_draw_is_numpys_bit_for_bit():
     from smmd import compute_scores as cs
 
     cases = [(5000, 6000, 7, 300, 0), (400, 500, 6, 100, 1), (7, 9, 5, 7, 3), (1000, 1000, 3, 1, 5), (65537, 70000, 2, 33, 9),
-             (1, 1, 2, 1, 1), (2, 3, 4, 2, 2), (1024, 1025, 3, 1000, 4), (50000, 50000, 2, 1000, 6)]
-    for (lg, lr, S, m, seed) in cases:
+             (1, 1, 2, 1, 1), (2, 3, 4, 2, 2), (1024, 1025, 3, 1000, 4), (50000, 50000, 2, 1000, 6),
+             (50000, 49999, 6, 1000, 7), (70000, 300000, 3, 50, 8)]     # the last two take the scan + threaded-shuffle path
+    for (lg, lr, S, m, seed), threads in [(c, t) for c in cases for t in ("1", "3", None)]:
+        if threads is None:
+            os.environ.pop("SMMD_DRAW_THREADS", None)
+        else:
+            os.environ["SMMD_DRAW_THREADS"] = threads
         for burn in (0, 3):                      # burn = 3 leaves a cached gaussian and an odd stream position behind
             np.random.seed(seed)
             if burn:
@@ -139,6 +144,7 @@ def test_subset_draw_is_numpys_bit_for_bit():
             sb = np.random.get_state()
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (lg, lr, S, m, seed)
             assert sa[0] == sb[0] and np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:], (lg, lr, S, m, seed)
+    os.environ.pop("SMMD_DRAW_THREADS", None)
     # a sample larger than the population: numpy's own error, raised by numpy
     with pytest.raises(ValueError):
         cs.draw_subsets(10, 20, 2, 11)
