@@ -197,7 +197,7 @@ SMMD_API int smmd_mmd2_fwd_bwd_peers(const smmd_problem* p, const smmd_peer_tabl
  * idx_g / idx_r: host int32 [n_subsets][subset_size].  The stream is walked twice: a sequential scan that only counts
  * what each shuffle consumes (16 outputs classified at a time) and remembers the generator state it starts from, then the
  * shuffles themselves, branch-free, on up to 16 threads (SMMD_DRAW_THREADS overrides; 1 = one thread, no scan).  The
- * numpy loop takes 107 ms at 100 x 1000 of 50k on the bench box's host -- most of a host-codes KID call. */
+ * numpy loop takes 107-136 ms at 100 x 1000 of 50k on the bench box's host (most of a host-codes KID call), this 11.8 ms. */
 SMMD_API int smmd_draw_subsets_mt19937(uint32_t* key, int32_t* pos, int64_t len_g, int64_t len_r, int32_t n_subsets,
                                        int32_t subset_size, int32_t* idx_g, int32_t* idx_r);
 
