@@ -461,7 +461,7 @@ def run_ours(args):
         b = i % nhost
         st = streams[i % nbuf]
         if done_ev[b] is not None:
-            done_ev[b].synchronize()     # the results that last used these host buffers (step i - nbuf) have landed
+            done_ev[b].synchronize()     # the results that last used these host buffers (step i - nhost) have landed
         with torch.cuda.stream(st):
             flush.zero_()
             if state["prev_pull"] is not None:
